@@ -1,0 +1,86 @@
+"""Deterministic inputs for the golden fixtures (shared by oracle/gen_golden.py and the tests).
+
+Inputs are regenerated from seeds with the CPU generator (bit-stable for a given torch build; the
+GPU box runs the same image), so the committed fixtures only hold the reference's OUTPUTS.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+# name -> dict(B, T, N, Ce, p, tau, flip, seed)           patch-walk cases (model.py:334-415)
+WALK_CASES = {
+    "w_cfg1like": dict(B=2, T=4, N=49, Ce=32, p=0.1, tau=0.07, flip=False, seed=11),
+    "w_b3t5":     dict(B=3, T=5, N=49, Ce=32, p=0.1, tau=0.07, flip=False, seed=12),
+    "w_nodrop":   dict(B=2, T=4, N=49, Ce=32, p=0.0, tau=0.07, flip=False, seed=13),
+    "w_flip":     dict(B=2, T=4, N=25, Ce=16, p=0.2, tau=0.05, flip=True,  seed=14),
+    "w_t3":       dict(B=2, T=3, N=49, Ce=16, p=0.1, tau=0.07, flip=False, seed=15),
+    "w_n16t8":    dict(B=2, T=8, N=16, Ce=16, p=0.3, tau=0.07, flip=False, seed=16),
+    "w_n100t4":   dict(B=1, T=4, N=100, Ce=16, p=0.1, tau=0.07, flip=False, seed=17),
+}
+
+# superpixel cases (model.py:260-332): SP labels on 256x256, maps 32x32
+SP_CASES = {
+    "sp_16":      dict(B=1, T=3, SP=16, Ce=32, one_based=False, p=0.1, tau=0.07, seed=21),
+    "sp_40_empty": dict(B=2, T=3, SP=40, Ce=16, one_based=True, p=0.1, tau=0.07, seed=22),
+}
+
+# label-propagation cases (test_utils.py:148-179, test.py:141-160)
+LP_CASES = {
+    "lp_small":   dict(C=16, h=12, w=17, n_ctx=4, n_tgt=6, long_mem=[0], radius=3, k=5, tau=0.07, L=3,
+                       dyadic=False, repeat_first=False, seed=31),
+    "lp_dyadic":  dict(C=8, h=10, w=13, n_ctx=3, n_tgt=5, long_mem=[0], radius=4, k=4, tau=0.07, L=4,
+                       dyadic=True, repeat_first=False, seed=32),
+    "lp_repeat":  dict(C=16, h=9, w=11, n_ctx=5, n_tgt=7, long_mem=[0], radius=12, k=10, tau=0.05, L=2,
+                       dyadic=False, repeat_first=True, seed=33),
+    "lp_long2":   dict(C=16, h=8, w=9, n_ctx=3, n_tgt=8, long_mem=[0, 2], radius=2, k=3, tau=0.07, L=2,
+                       dyadic=False, repeat_first=False, seed=34),
+}
+
+
+def walk_inputs(c):
+    """-> maps (B*N, Ce, T, 8, 8), head_w (128, Ce).  The walk RNG seed is c['seed'] + 1000."""
+    g = torch.Generator().manual_seed(c["seed"])
+    maps = torch.randn(c["B"] * c["N"], c["Ce"], c["T"], 8, 8, generator=g)
+    head_w = torch.randn(128, c["Ce"], generator=g) / c["Ce"] ** 0.5
+    return maps, head_w
+
+
+def voronoi_labels(B, T, SP, size, g, one_based):
+    ys, xs = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
+    out = torch.empty(B, T, size, size, dtype=torch.long)
+    for b in range(B):
+        for t in range(T):
+            n_real = SP - 1 if one_based else SP
+            pts = torch.rand(n_real, 2, generator=g) * size
+            d = (ys[None] - pts[:, 0, None, None]) ** 2 + (xs[None] - pts[:, 1, None, None]) ** 2
+            out[b, t] = d.argmin(0) + (1 if one_based else 0)
+    return out
+
+
+def sp_inputs(c):
+    """-> maps (B, Ce, T, 32, 32), labels3 (B, T, 3, 256, 256) int64, head_w (128, Ce)."""
+    g = torch.Generator().manual_seed(c["seed"])
+    maps = torch.randn(c["B"], c["Ce"], c["T"], 32, 32, generator=g)
+    head_w = torch.randn(128, c["Ce"], generator=g) / c["Ce"] ** 0.5
+    lab = voronoi_labels(c["B"], c["T"], c["SP"], 256, g, c["one_based"])
+    return maps, lab[:, :, None].repeat(1, 1, 3, 1, 1), head_w
+
+
+def lp_inputs(c):
+    """-> feats (1, C, Nf, h, w) unit-norm over C, lbls (Nf, h, w, L) with frame 0 one-hot blobs."""
+    g = torch.Generator().manual_seed(c["seed"])
+    Nf = c["n_ctx"] + c["n_tgt"]
+    if c["dyadic"]:
+        # multiples of 2^-6 in [-1,1]: every dot product is exact in fp32 in any summation order
+        feats = torch.randint(-64, 65, (1, c["C"], Nf, c["h"], c["w"]), generator=g).float() / 64.0
+    else:
+        feats = F.normalize(torch.randn(1, c["C"], Nf, c["h"], c["w"], generator=g), dim=1)
+    if c["repeat_first"]:
+        feats[:, :, : c["n_ctx"] + 1] = feats[:, :, :1]        # vos.py:148-149 replicates frame 0
+    lbls = torch.zeros(Nf, c["h"], c["w"], c["L"])
+    seg = torch.randint(0, c["L"], (c["h"], c["w"]), generator=g)
+    first = F.one_hot(seg, c["L"]).float()
+    lbls[: c["n_ctx"] + 1] = first                              # replicated first frame carries GT
+    lbls[c["n_ctx"] + 1:] = torch.rand(c["n_tgt"] - 1, c["h"], c["w"], c["L"], generator=g)  # junk, zeroed by test.py:142
+    return feats, lbls

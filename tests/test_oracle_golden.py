@@ -1,0 +1,99 @@
+"""The oracle (oracle/crw_oracle.py) is pinned here against outputs of the UNMODIFIED reference
+(tests/golden/*.pt, produced by oracle/gen_golden.py in the authoring container)."""
+import os
+
+import pytest
+import torch
+
+from oracle import crw_oracle as O
+from tests.golden import cases
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(G, name + ".pt"), weights_only=False)
+
+
+def oracle_walk_from_maps(c, maps, head_w):
+    maps = maps.clone().requires_grad_(True)
+    head_w = head_w.clone().requires_grad_(True)
+    q = O.patch_nodes(maps, head_w, c["B"])
+    torch.manual_seed(c["seed"] + 1000)
+    u12, u21p = O.draw_uniforms(c["B"], c["N"], c["T"]) if c["p"] > 0 else (None, None)
+    loss, xents, accs, names = O.walk_loss(q, c["tau"], c["p"], u12, u21p, flip=c["flip"])
+    loss.mean().backward()
+    return q, loss, xents, accs, names, maps.grad, head_w.grad, (u12, u21p)
+
+
+@pytest.mark.parametrize("name", list(cases.WALK_CASES))
+def test_walk_matches_reference(name):
+    c = cases.WALK_CASES[name]
+    fx = load(name)
+    maps, head_w = cases.walk_inputs(c)
+    q, loss, xents, accs, names, gmaps, ghead, (u12, u21p) = oracle_walk_from_maps(c, maps, head_w)
+    assert q.shape == fx["q"].shape
+    torch.testing.assert_close(q, fx["q"], rtol=1e-5, atol=1e-6)
+    assert loss.shape == fx["loss"].shape == (1,)
+    torch.testing.assert_close(loss, fx["loss"], rtol=2e-6, atol=0)
+    for n, xe, ac in zip(names, xents, accs):
+        torch.testing.assert_close(xe, fx["diags"]["64 xent cyc %s" % n], rtol=2e-6, atol=0)
+        torch.testing.assert_close(ac, fx["diags"]["64 acc cyc %s" % n], rtol=0, atol=1e-6)
+    assert len(fx["diags"]) == 2 * len(names)
+    torch.testing.assert_close(ghead, fx["grad_head"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(gmaps[..., 0, 0], fx["grad_maps00"], rtol=1e-4, atol=1e-8)
+    # the transition matrices themselves, including the in-place union-mask artefact (F4) and the
+    # transposed physical layout of the backward draws (F6)
+    A12, A21 = O.walk_matrices(q.detach(), c["tau"], c["p"], u12, u21p)
+    torch.testing.assert_close(torch.stack(A12), fx["A12"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(torch.stack(A21), fx["A21"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(cases.SP_CASES))
+def test_superpixel_matches_reference(name):
+    c = cases.SP_CASES[name]
+    fx = load(name)
+    maps, lab3, head_w = cases.sp_inputs(c)
+    maps = maps.clone().requires_grad_(True)
+    head_w = head_w.clone().requires_grad_(True)
+    # segment_mean runs in float64 without autograd; rebuild it differentiably for the grad check
+    q = O.superpixel_nodes(maps.detach(), lab3[:, :, 0], c["SP"], head_w.detach())
+    torch.testing.assert_close(q, fx["sp_feats"], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(q, fx["q"], rtol=1e-4, atol=2e-6)
+    if c["one_based"]:
+        assert q[:, :, :, 0].abs().max() == 0          # empty node -> zero embedding (F5)
+    torch.manual_seed(c["seed"] + 1000)
+    u12, u21p = O.draw_uniforms(c["B"], c["SP"], c["T"])
+    loss, xents, accs, names = O.walk_loss(q, c["tau"], c["p"], u12, u21p)
+    torch.testing.assert_close(loss, fx["loss"], rtol=1e-5, atol=0)
+    for n, xe in zip(names, xents):
+        torch.testing.assert_close(xe, fx["diags"]["256 xent cyc %s" % n], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("name", list(cases.LP_CASES))
+def test_label_prop_matches_reference(name):
+    c = cases.LP_CASES[name]
+    fx = load(name)
+    feats, lbls = cases.lp_inputs(c)
+    n_tgt = c["n_tgt"]
+    ki = O.context_index_bank(c["n_ctx"], c["long_mem"], n_tgt)
+    f = feats[0].flatten(-2)                                   # (C, Nf, hw)
+    Ws, Is = O.lp_topk(f, ki, c["n_ctx"], len(c["long_mem"]), c["h"], c["w"], c["radius"], c["tau"], c["k"])
+    assert Is.dtype == torch.int64 and Is.shape == fx["Is"].shape
+    if not c["repeat_first"]:
+        assert torch.equal(Is, fx["Is"])
+    torch.testing.assert_close(Ws, fx["Ws"], rtol=1e-5, atol=1e-7)
+    preds = O.lp_propagate(lbls, ki, Ws, Is, c["n_ctx"])
+    torch.testing.assert_close(preds, fx["preds"], rtol=1e-5, atol=1e-6)
+
+
+def test_misc_known_answers():
+    fx = load("misc")
+    torch.testing.assert_close(O.zero_softmax(fx["zs_in"]), fx["zs_out"], rtol=1e-6, atol=0)
+    assert torch.equal(O.radius_mask_additive(5, 6, 3), fx["mask_5x6_r3"])
+    for (nc, lm, N), bank in fx["banks"].items():
+        assert torch.equal(O.context_index_bank(nc, list(lm), N), bank)
+    # ZeroSoftmax artefacts the kernels must reproduce (F5): dropped edge -> numerator 1, zero logit -> 0
+    x = torch.tensor([[-1e20 / 0.07, 0.0, 0.5 / 0.07]])
+    e = (torch.exp(x) - 1) ** 2
+    assert e[0, 0] == 1 and e[0, 1] == 0
