@@ -1,0 +1,115 @@
+/* crw_b200.h - C ABI of libcrw_b200.so (sm_100a only).
+ *
+ * The reference (paolomandica/sapienza-video-contrastive) has no FFI layer: its hot path is a chain of
+ * PyTorch ATen calls inside code/model.py and code/utils/test_utils.py.  This header is the boundary a
+ * binding for that path targets instead.  Every entry point cites the reference lines it replaces
+ * (paths relative to the reference root).  Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name says host;
+ *   - the caller owns every buffer, including workspaces (query the size with *_workspace_bytes);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises or allocates;
+ *   - return value: CRW_OK or a negative error; crw_last_error() gives a thread-local message;
+ *   - fp32 arithmetic throughout; indices int64.
+ */
+#ifndef CRW_B200_H
+#define CRW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRW_OK 0
+#define CRW_ERR_SHAPE (-1)
+#define CRW_ERR_UNSUPPORTED (-2)
+#define CRW_ERR_CUDA (-3)
+
+/* walk flags */
+#define CRW_WALK_SOFTMAX 1u   /* F.softmax rows (teacherstudent.py:80) instead of ZeroSoftmax (model.py:90) */
+#define CRW_WALK_FLIP 2u      /* args.flip: reversed product order, model.py:380-382 */
+#define CRW_WALK_FORCE_GENERAL 4u /* skip the single-CTA fused kernel even when the clip fits shared memory */
+
+typedef void* crw_stream_t;
+
+int crw_version(void);
+const char* crw_last_error(void);
+
+/* ---- a1: patch mean pooling, model.py:116  (feats = maps.sum(-1).sum(-1) / (H*W)) -------------------
+ * maps (rows, hw) contiguous fp32 with rows = B*N*C*T; pooled (rows).  bwd broadcasts g/hw. */
+int crw_pool_patch_fwd(const float* maps, float* pooled, int64_t rows, int hw, crw_stream_t stream);
+int crw_pool_patch_bwd(const float* grad_pooled, float* grad_maps, int64_t rows, int hw, crw_stream_t stream);
+
+/* ---- a2/a3: superpixel segment-mean pooling, model.py:296-325 + utils/__init__.py:433-584 -------------
+ * maps (B,C,T,Hm,Wm) contiguous; labels int64 addressed as labels[b*ls_b + t*ls_t + y*ls_y + x*ls_x]
+ * (so channel 0 of the (B,T,3,h,w) mask is passed without a copy, model.py:298); h = sy*Hm, w = sx*Wm.
+ * out (B,T,SP,C): mean of maps[b,:,t,y/sy,x/sx] over pixels labelled s; labels outside [0,SP) ignored;
+ * empty segments -> 0.  The workspace keeps the per-cell label histogram for the backward. */
+size_t crw_segmean_workspace_bytes(int B, int T, int Hm, int Wm, int h, int w, int SP);
+int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t ls_b, int64_t ls_t, int64_t ls_y, int64_t ls_x,
+                    int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
+                    float* out, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+int crw_segmean_bwd(const float* grad_out, const void* workspace, size_t workspace_bytes,
+                    int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
+                    float* grad_maps, crw_stream_t stream);
+
+/* ---- a4: affinity, model.py:63-72  (einsum 'bctn,bctm->btnm') ----------------------------------------
+ * x1, x2 node-major: x1[(b*T + t)*N1*D + n*D + d] (unit-norm or not), out (B*T, N1, N2). */
+int crw_affinity(const float* x1, const float* x2, int BT, int N1, int N2, int D, float* out, crw_stream_t stream);
+
+/* ---- a5: stoch_mat, model.py:74-90 + utils/__init__.py:414-422 ----------------------------------------
+ * A (R, N, M) contiguous.  If drop_uniform != NULL, entries with u < rate are overwritten IN PLACE with
+ * -1e20 (the reference mutates its argument).  out = ZeroSoftmax(A / temperature) (or softmax)
+ * along the last dim. */
+int crw_stoch_mat(float* A, const float* drop_uniform, float rate, float temperature, unsigned flags,
+                  int64_t R, int N, int M, float* out, crw_stream_t stream);
+
+/* ---- a5/a6: the walk, model.py:366-413, forward AND backward in one call -------------------------------
+ * feats (B,N,T,D) fp32, NOT yet normalised (output of selfsim_fc, model.py:117); the L2 normalisation of
+ * model.py:118 is folded in.  Edge dropout: either u12/u21p (each (T-1,B,N,N), the reference's rand_like
+ * draws in its order, u21p in its physical = transposed layout) or, if both are NULL and
+ * rate > 0, an in-kernel Philox4x32-10 replay of torch's CUDA generator: draw j (0 <= j < 2(T-1)) uses
+ * (philox_seed, philox_offset + inc*j), inc = 4*ceil(B*N*N / (4*philox_threads)), with torch's
+ * element->thread mapping for `philox_threads` = grid*block threads of torch's rand kernel.
+ * The workspace must be zero-filled once after allocation; every call leaves it reusable.
+ * Outputs: q (B,N,T,D) unit-norm nodes; xent (T-2) mean cross-entropies and acc (T-2) argmax accuracies
+ * of walks i = 1..T-2; grad_feats (B,N,T,D) = d(sum_i xent_i / max(1,T-2)) / d feats, or NULL
+ * to skip the backward. */
+size_t crw_walk_workspace_bytes(int B, int N, int T, int D, unsigned flags);
+int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,
+                     const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
+                     uint32_t philox_threads, unsigned flags, float* q, float* xent, float* acc,
+                     float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+
+/* torch-compatible uniform draw (same Philox stream as torch.rand on CUDA); used by tests to pin the
+ * in-kernel replay.  out (n). */
+int crw_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, uint32_t philox_threads,
+                       crw_stream_t stream);
+
+/* ---- a9-a11: label-propagation affinity + top-k, utils/test_utils.py:148-179 (+ mask test.py:118-122) --
+ * feats (Nf, hw, C) fp32, channel-last, already L2-normalised if the caller wants cosine affinities
+ * (test.py:93).  key_frames (Nt, S) int64: context frame ids of target n (context_index_bank); the first
+ * n_long slots are long-memory (unmasked), the rest are radius-restricted: key (ky,kx) is admissible for
+ * query (qy,qx) iff (ky-qy)^2 + (kx-qx)^2 < radius^2 (float32 sqrt(d2) < radius in the reference).
+ * radius <= 0 disables the restriction.  Target n's query frame is query_frames[n].
+ * Ws (Nt,k,hw) fp32 softmax over the k best scores / temperature; Is (Nt,k,hw) int64 = slot*hw + key_pos,
+ * sorted by descending score, ties broken by ascending index. */
+size_t crw_lp_topk_workspace_bytes(int Nt, int S, int h, int w, int C, int k);
+int crw_lp_topk(const float* feats, const int64_t* key_frames, const int64_t* query_frames, int Nt, int S,
+                int n_long, int h, int w, int C, float radius, float temperature, int k,
+                float* Ws, int64_t* Is, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+
+/* feats (C, Nf, hw) channel-first (the encoder's layout, test.py:90-93) -> (Nf, hw, C) channel-last with
+ * optional L2 normalisation over C (eps 1e-12). */
+int crw_lp_prepare(const float* feats_cf, int C, int Nf, int hw, int normalize, float* feats_cl, crw_stream_t stream);
+
+/* ---- a12: one step of the label gather, test.py:147-154 ----------------------------------------------
+ * lbls (Nf, hw, L) soft labels; pred[q,l] = sum_k lbls[key_frames_n[Is[k,q] / hw], Is[k,q] % hw, l] * Ws[k,q],
+ * written to lbls[out_frame] (test.py:157).  Sequential in the target index by construction. */
+int crw_lp_gather(float* lbls, const int64_t* key_frames_n, const float* Ws_n, const int64_t* Is_n,
+                  int hw, int L, int k, int64_t out_frame, crw_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRW_B200_H */

@@ -1,0 +1,70 @@
+// walk_api.cu - C ABI of the walk (include/crw_b200.h): workspace carve-up and dispatch between the single-CTA
+// fused kernel (walk_fused.cu) and the batched multi-kernel path (walk_general.cu).
+#include "walk.cuh"
+
+using namespace crw;
+
+namespace {
+
+struct WsLayout {
+    size_t o_counter, o_partial, o_araw, o_codes, o_mats, o_stat, total;
+    bool fused;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
+    WsLayout w;
+    w.fused = !(flags & CRW_WALK_FORCE_GENERAL) && fused_fits(N, T, D);
+    const size_t t1 = T > 1 ? T - 1 : 0, t2 = T >= 3 ? T - 2 : 0;
+    size_t o = 0;
+    w.o_counter = o; o += 256;
+    w.o_partial = o; o = align_up(o + sizeof(float) * B * t2 * 2, 256);
+    w.o_araw = o; o = align_up(o + (w.fused ? sizeof(float) * B * t1 * N * N : 0), 256);
+    w.o_codes = o; o = align_up(o + (size_t)B * t1 * N * N * (w.fused ? 1 : 2), 256);
+    w.o_mats = o; o = align_up(o + (w.fused ? 0 : sizeof(float) * walk_general_mats_floats(B, N, T)), 256);
+    w.o_stat = o; o = align_up(o + (w.fused ? 0 : sizeof(float) * walk_general_stat_floats(B, N, T)), 256);
+    w.total = o;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t crw_walk_workspace_bytes(int B, int N, int T, int D, unsigned flags) {
+    if (B <= 0 || N <= 0 || T <= 0 || D <= 0) return 0;
+    return ws_layout(B, N, T, D, flags).total;
+}
+
+extern "C" int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,
+                                const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
+                                uint32_t philox_threads, unsigned flags, float* q, float* xent, float* acc,
+                                float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
+    if (B <= 0 || N <= 0 || T <= 0 || D <= 0) { set_error("walk: bad shape B=%d N=%d T=%d D=%d", B, N, T, D); return CRW_ERR_SHAPE; }
+    if (!(temperature > 0.f)) { set_error("walk: temperature must be > 0"); return CRW_ERR_SHAPE; }
+    if ((u12 == nullptr) != (u21p == nullptr)) { set_error("walk: u12 and u21p must both be given or both be NULL"); return CRW_ERR_SHAPE; }
+    if (rate > 0.f && !u12 && philox_threads == 0) { set_error("walk: in-kernel dropout needs philox_threads"); return CRW_ERR_SHAPE; }
+    const WsLayout w = ws_layout(B, N, T, D, flags);
+    if (workspace_bytes < w.total || !workspace) {
+        set_error("walk: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+        return CRW_ERR_SHAPE;
+    }
+    if ((((uintptr_t)feats | (uintptr_t)q | (uintptr_t)grad_feats) & 15) != 0 || D % 4 != 0) {
+        if (w.fused) { set_error("walk: fused path needs 16-byte aligned feats/q/grad and D %% 4 == 0"); return CRW_ERR_UNSUPPORTED; }
+    }
+    char* ws = (char*)workspace;
+    WalkParams p{};
+    p.feats = feats; p.q = q; p.xent = xent; p.acc = acc; p.grad = grad_feats;
+    p.u12 = u12; p.u21p = u21p;
+    p.seed = philox_seed; p.offset = philox_offset; p.pthreads = philox_threads ? philox_threads : 256;
+    // torch advances the Philox offset by 4 * ceil(numel / (threads * 4)) per rand call (DistributionTemplates.h)
+    const int64_t numel = (int64_t)B * N * N;
+    p.pinc = (uint32_t)(4 * ((numel - 1) / ((int64_t)p.pthreads * 4) + 1));
+    p.B = B; p.N = N; p.T = T; p.D = D; p.tau = temperature; p.rate = rate; p.flags = flags;
+    p.ws_counter = (unsigned*)(ws + w.o_counter);
+    p.ws_partial = (float*)(ws + w.o_partial);
+    p.ws_araw = (float*)(ws + w.o_araw);
+    p.ws_codes = (unsigned char*)(ws + w.o_codes);
+    p.ws_mats = (float*)(ws + w.o_mats);
+    p.ws_stat = (float*)(ws + w.o_stat);
+    return w.fused ? launch_walk_fused(p, stream) : launch_walk_general(p, stream);
+}
