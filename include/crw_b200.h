@@ -43,7 +43,7 @@ int crw_pool_patch_bwd(const float* grad_pooled, float* grad_maps, int64_t rows,
 /* ---- a2/a3: superpixel segment-mean pooling, model.py:296-325 + utils/__init__.py:433-584 -------------
  * maps (B,C,T,Hm,Wm) contiguous; labels int64 addressed as labels[b*ls_b + t*ls_t + y*ls_y + x*ls_x]
  * (so channel 0 of the (B,T,3,h,w) mask is passed without a copy, model.py:298); h = sy*Hm, w = sx*Wm.
- * out (B,T,SP,C): mean of maps[b,:,t,y/sy,x/sx] over pixels labelled s; labels outside [0,SP) ignored;
+ * out (B,SP,T,C) (node-major, the layout the walk consumes): mean of maps[b,:,t,y/sy,x/sx] over pixels labelled s; labels outside [0,SP) ignored;
  * empty segments -> 0.  The workspace keeps the per-cell label histogram for the backward. */
 size_t crw_segmean_workspace_bytes(int B, int T, int Hm, int Wm, int h, int w, int SP);
 int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t ls_b, int64_t ls_t, int64_t ls_y, int64_t ls_x,
@@ -81,6 +81,12 @@ int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float tempe
                      uint32_t philox_threads, unsigned flags, float* q, float* xent, float* acc,
                      float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
+/* L2 normalisation of rows (F.normalize, eps 1e-12; model.py:118,329): q = f / max(|f|, eps).  inv_norm and norm
+ * (rows each) are kept for the backward, which overwrites grad in place: g <- (g - q (q.g)) * inv_norm. */
+int crw_l2norm_fwd(const float* f, float* q, float* inv_norm, float* norm, int64_t rows, int D, crw_stream_t stream);
+int crw_l2norm_bwd(const float* q, float* grad_inout, const float* inv_norm, const float* norm, int64_t rows, int D,
+                   crw_stream_t stream);
+
 /* torch-compatible uniform draw (same Philox stream as torch.rand on CUDA); used by tests to pin the
  * in-kernel replay.  out (n). */
 int crw_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, uint32_t philox_threads,
@@ -92,11 +98,14 @@ int crw_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, ui
  * n_long slots are long-memory (unmasked), the rest are radius-restricted: key (ky,kx) is admissible for
  * query (qy,qx) iff (ky-qy)^2 + (kx-qx)^2 < radius^2 (float32 sqrt(d2) < radius in the reference).
  * radius <= 0 disables the restriction.  Target n's query frame is query_frames[n].
+ * dense_mask (optional, (hw_keys, hw_queries) additive fp32 as built by test.py:118-122): when non-NULL the
+ * restricted slots instead visit every key and add dense_mask[key, query] to the score - the reference's literal
+ * semantics for an arbitrary mask, without the window skipping.
  * Ws (Nt,k,hw) fp32 softmax over the k best scores / temperature; Is (Nt,k,hw) int64 = slot*hw + key_pos,
  * sorted by descending score, ties broken by ascending index. */
 size_t crw_lp_topk_workspace_bytes(int Nt, int S, int h, int w, int C, int k);
 int crw_lp_topk(const float* feats, const int64_t* key_frames, const int64_t* query_frames, int Nt, int S,
-                int n_long, int h, int w, int C, float radius, float temperature, int k,
+                int n_long, int h, int w, int C, float radius, const float* dense_mask, float temperature, int k,
                 float* Ws, int64_t* Is, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
 /* feats (C, Nf, hw) channel-first (the encoder's layout, test.py:90-93) -> (Nf, hw, C) channel-last with

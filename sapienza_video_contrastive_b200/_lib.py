@@ -40,8 +40,10 @@ _SIGNATURES = {
                                  c_size_t, c_void_p]),
     "crw_philox_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint32, c_void_p]),
     "crw_lp_topk_workspace_bytes": (c_size_t, [c_int] * 6),
-    "crw_lp_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
-                            c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crw_lp_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                            c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crw_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "crw_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_lp_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "crw_lp_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
 }

@@ -52,10 +52,11 @@ __host__ __device__ __forceinline__ FusedLayout fused_layout(int N, int T, int D
     return L;
 }
 
+constexpr int kFusedMaxT = 32;
 constexpr size_t kMaxDynSmem = 232448;            // 227 KB opt-in limit per CTA on sm_100
 
 inline bool fused_fits(int N, int T, int D) {
-    return N <= 64 && T >= 2 && D % 4 == 0 && D <= 256 && fused_layout(N, T, D).bytes <= kMaxDynSmem;
+    return N <= 64 && T >= 2 && T <= kFusedMaxT && D % 4 == 0 && D <= 256 && fused_layout(N, T, D).bytes <= kMaxDynSmem;
 }
 
 int launch_walk_fused(const WalkParams& p, crw_stream_t stream);

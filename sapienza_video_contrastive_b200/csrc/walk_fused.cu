@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams
     }
 
     // ---- phase 3: losses and the reverse sweep -------------------------------------------------------------
-    float* freeb[8];
+    float* freeb[2 * kFusedMaxT + 4];   // grows by two buffers per level (P_j, S_j are recycled)
     int nfree = 0;
     freeb[nfree++] = scratch;
     freeb[nfree++] = scratch + MS;

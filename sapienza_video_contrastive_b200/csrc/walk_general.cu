@@ -568,6 +568,21 @@ extern "C" int crw_stoch_mat(float* A, const float* drop_uniform, float rate, fl
     return check_launch("stoch_mat");
 }
 
+extern "C" int crw_l2norm_fwd(const float* f, float* q, float* inv_norm, float* norm, int64_t rows, int D, crw_stream_t stream) {
+    if (rows < 0 || D <= 0) { set_error("l2norm_fwd: bad shape"); return CRW_ERR_SHAPE; }
+    if (rows == 0) return CRW_OK;
+    CRW_LAUNCH(gnorm_kernel, rows_grid(rows), 256, 0, stream, f, q, inv_norm, norm, rows, D);
+    return check_launch("l2norm_fwd");
+}
+
+extern "C" int crw_l2norm_bwd(const float* q, float* grad_inout, const float* inv_norm, const float* norm, int64_t rows, int D,
+                              crw_stream_t stream) {
+    if (rows < 0 || D <= 0) { set_error("l2norm_bwd: bad shape"); return CRW_ERR_SHAPE; }
+    if (rows == 0) return CRW_OK;
+    CRW_LAUNCH(gnorm_bwd_kernel, rows_grid(rows), 256, 0, stream, q, grad_inout, inv_norm, norm, rows, D);
+    return check_launch("l2norm_bwd");
+}
+
 namespace crw {
 __global__ void __launch_bounds__(256) philox_uniform_kernel(float* out, int64_t n, uint64_t seed, uint64_t offset, uint32_t threads) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
