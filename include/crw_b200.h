@@ -71,6 +71,9 @@ int crw_stoch_mat(float* A, const float* drop_uniform, float rate, float tempera
  * rate > 0, an in-kernel Philox4x32-10 replay of torch's CUDA generator: draw j (0 <= j < 2(T-1)) uses
  * (philox_seed, philox_offset + inc*j), inc = 4*ceil(B*N*N / (4*philox_threads)), with torch's
  * element->thread mapping for `philox_threads` = grid*block threads of torch's rand kernel.
+ * If philox_state_dev != NULL it points to DEVICE memory {seed, offset}: the kernel reads the state from there and
+ * advances the offset by 2(T-1)*inc when it is done, so a launch captured in a CUDA graph draws fresh dropout
+ * masks on every replay (philox_seed / philox_offset are then ignored).
  * The workspace must be zero-filled once after allocation; every call leaves it reusable.
  * Outputs: q (B,N,T,D) unit-norm nodes; xent (T-2) mean cross-entropies and acc (T-2) argmax accuracies
  * of walks i = 1..T-2; grad_feats (B,N,T,D) = d(sum_i xent_i / max(1,T-2)) / d feats, or NULL
@@ -78,7 +81,7 @@ int crw_stoch_mat(float* A, const float* drop_uniform, float rate, float tempera
 size_t crw_walk_workspace_bytes(int B, int N, int T, int D, unsigned flags);
 int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,
                      const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
-                     uint32_t philox_threads, unsigned flags, float* q, float* xent, float* acc,
+                     uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
                      float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
 /* L2 normalisation of rows (F.normalize, eps 1e-12; model.py:118,329): q = f / max(|f|, eps).  inv_norm and norm

@@ -47,6 +47,14 @@ __device__ __forceinline__ float ld_cg(const float* p) {     // L2-coherent load
 #endif
 }
 
+__device__ __forceinline__ uint64_t ld_cg64(const uint64_t* p) {
+#ifdef CRW_SIM
+    return *p;
+#else
+    return (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p));
+#endif
+}
+
 // ---- Philox4x32-10, bit-compatible with curand / torch's CUDA generator -----------------------------
 struct Philox4 { uint32_t x, y, z, w; };
 

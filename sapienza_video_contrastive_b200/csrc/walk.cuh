@@ -14,6 +14,7 @@ struct WalkParams {
     const float* u21p;         // (T-1,B,N,N) physical layout, or nullptr
     uint64_t seed, offset;     // torch Philox state for the in-kernel replay
     uint32_t pthreads, pinc;   // torch rand launch threads; offset increment per draw
+    uint64_t* dev_state;       // optional device {seed, offset}, advanced after the launch
     int B, N, T, D;
     float tau, rate;
     unsigned flags;

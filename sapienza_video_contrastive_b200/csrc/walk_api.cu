@@ -37,7 +37,7 @@ extern "C" size_t crw_walk_workspace_bytes(int B, int N, int T, int D, unsigned 
 
 extern "C" int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,
                                 const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
-                                uint32_t philox_threads, unsigned flags, float* q, float* xent, float* acc,
+                                uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
                                 float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
     if (B <= 0 || N <= 0 || T <= 0 || D <= 0) { set_error("walk: bad shape B=%d N=%d T=%d D=%d", B, N, T, D); return CRW_ERR_SHAPE; }
     if (!(temperature > 0.f)) { set_error("walk: temperature must be > 0"); return CRW_ERR_SHAPE; }
@@ -55,6 +55,7 @@ extern "C" int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, 
     WalkParams p{};
     p.feats = feats; p.q = q; p.xent = xent; p.acc = acc; p.grad = grad_feats;
     p.u12 = u12; p.u21p = u21p;
+    p.dev_state = (rate > 0.f && !u12) ? philox_state_dev : nullptr;
     p.seed = philox_seed; p.offset = philox_offset; p.pthreads = philox_threads ? philox_threads : 256;
     // torch advances the Philox offset by 4 * ceil(numel / (threads * 4)) per rand call (DistributionTemplates.h)
     const int64_t numel = (int64_t)B * N * N;

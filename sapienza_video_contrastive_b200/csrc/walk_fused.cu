@@ -158,6 +158,7 @@ __device__ __forceinline__ void dq_update(float* G, const float* Q, int64_t gs, 
 
 __global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams p) {
     CRW_DYN_SMEM(smem_raw);
+    if (p.dev_state) { p.seed = ld_cg64(p.dev_state); p.offset = ld_cg64(p.dev_state + 1); }
     float* smem = reinterpret_cast<float*>(smem_raw);
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -321,7 +322,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams
         }
     }
 
-    if (T < 3) return;
+    if (T < 3) {
+        if (p.dev_state && tid == 0) {       // still consume the 2(T-1) draws
+            __threadfence();
+            if (atomicAdd(p.ws_counter, 1u) == (unsigned)p.B - 1u) {
+                p.dev_state[1] = p.offset + (uint64_t)p.pinc * 2u * (unsigned)(T - 1);
+                *p.ws_counter = 0u;
+            }
+        }
+        return;
+    }
 
     // ---- phase 2: prefix / suffix chains ---------------------------------------------------------------------
     // X_i / Y_i: forward / backward lists (swapped by --flip, model.py:380-382)
@@ -533,6 +543,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams
                 p.xent[j] = l * inv;
                 p.acc[j] = a * inv;
             }
+            if (p.dev_state) p.dev_state[1] = p.offset + (uint64_t)p.pinc * 2u * (unsigned)(T - 1);
             *p.ws_counter = 0u;
         }
     }

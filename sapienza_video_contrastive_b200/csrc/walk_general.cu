@@ -150,6 +150,7 @@ struct StochArgs {
     const float* u2;
     uint64_t seed, offset;
     uint32_t pthreads, pinc;
+    const uint64_t* dev_state;
     int mode, softmax;
     int64_t rows;
     int N, M, T, B;
@@ -157,6 +158,7 @@ struct StochArgs {
 };
 
 __global__ void __launch_bounds__(256) stoch_rows_kernel(StochArgs s) {
+    if (s.dev_state) { s.seed = ld_cg64(s.dev_state); s.offset = ld_cg64(s.dev_state + 1); }
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -307,6 +309,10 @@ static int rows_grid(int64_t rows) {
     return (int)(blocks > 0 ? blocks : 1);
 }
 
+__global__ void advance_state_kernel(uint64_t* state, uint64_t inc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) state[1] += inc;
+}
+
 // copies B matrices of MS floats between strided stacks (dX_0 = gP_0, dY_0 = gS_0)
 __global__ void __launch_bounds__(256) copy_mats_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t dsb,
                                                         int64_t ssb, int64_t MS, int B) {
@@ -404,11 +410,16 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
         s.codes = dir == 1 ? codesF : codesG;
         s.u1 = p.u12; s.u2 = p.u21p;
         s.seed = p.seed; s.offset = p.offset; s.pthreads = p.pthreads; s.pinc = p.pinc;
+        s.dev_state = p.dev_state;
         s.mode = dir; s.softmax = softmax;
         s.rows = (int64_t)B * t1 * N; s.N = N; s.M = N; s.T = T; s.B = B;
         s.tau = p.tau; s.rate = p.rate;
         CRW_LAUNCH(stoch_rows_kernel, rows_grid(s.rows), 256, 0, stream, s);
         CRW_TRY(check_launch("stoch_rows"));
+    }
+    if (p.dev_state && p.rate > 0.f) {       // both row passes have consumed the state: advance it for the next launch
+        CRW_LAUNCH(advance_state_kernel, 1, 32, 0, stream, p.dev_state, (uint64_t)p.pinc * 2u * (unsigned)(T - 1));
+        CRW_TRY(check_launch("advance_state"));
     }
     if (T < 3) return CRW_OK;
 

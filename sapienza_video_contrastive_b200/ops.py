@@ -1,0 +1,439 @@
+"""Host-side operators: thin torch.autograd wrappers over the C ABI (include/crw_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every arithmetic step of the hot path
+is a kernel in libcrw_b200.so.  All functions require CUDA fp32 tensors and raise otherwise - there is no CPU or
+PyTorch fallback.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import WALK_FLIP, WALK_FORCE_GENERAL, WALK_SOFTMAX  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("crw_b200 operators run on CUDA tensors only (got %s); there is no CPU path" % t.device)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError("crw_b200 computes in fp32 (got %s)" % t.dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_checked_devices = set()
+
+
+def check_device(device) -> None:
+    """sm_100a code only: refuse anything but a compute-capability-10.x GPU."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx in _checked_devices:
+        return
+    cap = torch.cuda.get_device_capability(idx)
+    if cap[0] != 10:
+        raise RuntimeError("libcrw_b200.so is built for sm_100a only; device %d has compute capability %d.%d" % (idx, *cap))
+    _checked_devices.add(idx)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# workspaces: cached per (device, stream, key); zero-filled once (the walk's ticket counter relies on it)
+# ------------------------------------------------------------------------------------------------------------------
+_ws_cache = {}
+_ws_lock = threading.Lock()
+
+
+def _workspace(key, nbytes: int, device) -> torch.Tensor:
+    k = (torch.device(device).index, _stream(), key)
+    with _ws_lock:
+        ws = _ws_cache.get(k)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)
+            _ws_cache[k] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# a1: patch mean pooling (model.py:116)
+# ------------------------------------------------------------------------------------------------------------------
+class _PoolPatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, maps):
+        _need_cuda(maps)
+        check_device(maps.device)
+        maps = _f32c(maps)
+        hw = maps.shape[-1] * maps.shape[-2]
+        rows = maps.numel() // hw
+        out = torch.empty(maps.shape[:-2], dtype=torch.float32, device=maps.device)
+        L = _lib.lib()
+        L.check(L.crw_pool_patch_fwd(maps.data_ptr(), out.data_ptr(), rows, hw, _stream()), "pool_patch_fwd")
+        ctx.shape = maps.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        shape = ctx.shape
+        hw = shape[-1] * shape[-2]
+        gm = torch.empty(shape, dtype=torch.float32, device=g.device)
+        L = _lib.lib()
+        L.check(L.crw_pool_patch_bwd(g.data_ptr(), gm.data_ptr(), g.numel(), hw, _stream()), "pool_patch_bwd")
+        return gm
+
+
+def pool_patch(maps: torch.Tensor) -> torch.Tensor:
+    """(..., H, W) -> (...) spatial mean.  model.py:116."""
+    return _PoolPatch.apply(maps)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# a2/a3: superpixel segment-mean pooling (model.py:296-325)
+# ------------------------------------------------------------------------------------------------------------------
+class _SegMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, maps, labels, SP):
+        _need_cuda(maps, labels)
+        check_device(maps.device)
+        maps = _f32c(maps)
+        if labels.dtype != torch.int64:
+            labels = labels.long()
+        B, C, T, Hm, Wm = maps.shape
+        if labels.dim() != 4 or labels.shape[0] != B or labels.shape[1] != T:
+            raise ValueError("labels must be (B,T,h,w), got %s" % (tuple(labels.shape),))
+        h, w = labels.shape[-2:]
+        L = _lib.lib()
+        nbytes = L.crw_segmean_workspace_bytes(B, T, Hm, Wm, h, w, SP)
+        if nbytes == 0:
+            raise _lib.CrwError("segmean: %s" % L.crw_last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=maps.device)     # kept for the backward
+        out = torch.empty(B, SP, T, C, dtype=torch.float32, device=maps.device)
+        sb, st, sy, sx = labels.stride()
+        L.check(L.crw_segmean_fwd(maps.data_ptr(), labels.data_ptr(), sb, st, sy, sx, B, C, T, Hm, Wm, h, w, SP,
+                                  out.data_ptr(), ws.data_ptr(), nbytes, _stream()), "segmean_fwd")
+        ctx.ws = ws
+        ctx.dims = (B, C, T, Hm, Wm, h, w, SP)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        B, C, T, Hm, Wm, h, w, SP = ctx.dims
+        gm = torch.empty(B, C, T, Hm, Wm, dtype=torch.float32, device=g.device)
+        L = _lib.lib()
+        L.check(L.crw_segmean_bwd(g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), B, C, T, Hm, Wm, h, w, SP,
+                                  gm.data_ptr(), _stream()), "segmean_bwd")
+        return gm, None, None
+
+
+def segment_mean(maps: torch.Tensor, labels: torch.Tensor, SP: int) -> torch.Tensor:
+    """maps (B,C,T,Hm,Wm), labels (B,T,h,w) integer (any strides) -> (B,SP,T,C) per-superpixel feature means."""
+    return _SegMean.apply(maps, labels, int(SP))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# L2 normalisation (model.py:118)
+# ------------------------------------------------------------------------------------------------------------------
+class _L2Norm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f):
+        _need_cuda(f)
+        check_device(f.device)
+        f = _f32c(f)
+        D = f.shape[-1]
+        rows = f.numel() // D
+        q = torch.empty_like(f)
+        inv = torch.empty(rows, dtype=torch.float32, device=f.device)
+        nrm = torch.empty_like(inv)
+        L = _lib.lib()
+        L.check(L.crw_l2norm_fwd(f.data_ptr(), q.data_ptr(), inv.data_ptr(), nrm.data_ptr(), rows, D, _stream()), "l2norm_fwd")
+        ctx.save_for_backward(q, inv, nrm)
+        return q
+
+    @staticmethod
+    def backward(ctx, g):
+        q, inv, nrm = ctx.saved_tensors
+        g = g.contiguous().clone()
+        L = _lib.lib()
+        L.check(L.crw_l2norm_bwd(q.data_ptr(), g.data_ptr(), inv.data_ptr(), nrm.data_ptr(), inv.numel(), q.shape[-1], _stream()),
+                "l2norm_bwd")
+        return g
+
+
+def l2_normalize_last(f: torch.Tensor) -> torch.Tensor:
+    """F.normalize(f, p=2, dim=-1, eps=1e-12) on contiguous rows."""
+    return _L2Norm.apply(f)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# torch-compatible Philox replay
+# ------------------------------------------------------------------------------------------------------------------
+def torch_rand_threads(numel: int, device) -> int:
+    """grid*block of torch's CUDA rand kernel for `numel` elements (ATen DistributionTemplates.h: block 256)."""
+    p = torch.cuda.get_device_properties(device)
+    grid = min((numel + 255) // 256, p.multi_processor_count * (p.max_threads_per_multi_processor // 256))
+    return max(grid, 1) * 256
+
+
+def torch_rand_offset_increment(numel: int, threads: int) -> int:
+    return 4 * ((numel - 1) // (threads * 4) + 1)
+
+
+def philox_uniform(n: int, seed: int, offset: int, threads: int, device) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    L = _lib.lib()
+    L.check(L.crw_philox_uniform(out.data_ptr(), n, seed, offset, threads, _stream()), "philox_uniform")
+    return out
+
+
+_philox_ok = {}
+
+
+def philox_replay_ok(device) -> bool:
+    """One-time self check per device: does the in-kernel Philox replay reproduce torch.rand bit-for-bit?
+    (It must, for the in-kernel edge dropout to be a drop-in for the reference's rand_like draws.)"""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _philox_ok:
+        gen = torch.cuda.default_generators[idx]
+        state = gen.get_state()
+        try:
+            ok = True
+            for numel in (1000, 48020, 700001):
+                seed, off = gen.initial_seed(), gen.get_offset()
+                ref = torch.rand(numel, device="cuda:%d" % idx)
+                thr = torch_rand_threads(numel, idx)
+                mine = philox_uniform(numel, seed, off, thr, "cuda:%d" % idx)
+                ok = ok and bool(torch.equal(ref, mine)) and gen.get_offset() == off + torch_rand_offset_increment(numel, thr)
+        finally:
+            gen.set_state(state)
+        _philox_ok[idx] = ok
+    return _philox_ok[idx]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# a4-a6: the walk (model.py:366-413)
+# ------------------------------------------------------------------------------------------------------------------
+class _Walk(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, tau, rate, flags, rng, u12, u21p, rng_state):
+        _need_cuda(feats, u12, u21p)
+        check_device(feats.device)
+        feats = _f32c(feats)
+        B, N, T, D = feats.shape
+        dev = feats.device
+        L = _lib.lib()
+        need_grad = ctx.needs_input_grad[0]
+        seed = off = thr = 0
+        if rate > 0 and T > 1:
+            if rng == "torch":
+                if u12 is None:
+                    # the reference's 2(T-1) rand_like draws, in its order; the backward ones are physically transposed
+                    u12 = torch.stack([torch.rand(B, N, N, device=dev) for _ in range(T - 1)])
+                    u21p = torch.stack([torch.rand(B, N, N, device=dev) for _ in range(T - 1)])
+            elif rng == "philox":
+                idx = dev.index if dev.index is not None else torch.cuda.current_device()
+                gen = torch.cuda.default_generators[idx]
+                numel = B * N * N
+                thr = torch_rand_threads(numel, idx)
+                seed, off = gen.initial_seed(), gen.get_offset()
+                gen.set_offset(off + 2 * (T - 1) * torch_rand_offset_increment(numel, thr))
+                u12 = u21p = None
+            elif rng == "device":
+                # graph-safe: {seed, offset} live in device memory and the kernel advances them itself
+                if rng_state is None or rng_state.dtype != torch.int64 or rng_state.numel() != 2 or not rng_state.is_cuda:
+                    raise ValueError("rng='device' needs rng_state: a CUDA int64 tensor {seed, offset}")
+                thr = torch_rand_threads(B * N * N, dev)
+                u12 = u21p = None
+            else:
+                raise ValueError("rng must be 'torch', 'philox' or 'device'")
+            if u12 is not None:
+                u12, u21p = _f32c(u12), _f32c(u21p)
+                if tuple(u12.shape) != (T - 1, B, N, N) or tuple(u21p.shape) != (T - 1, B, N, N):
+                    raise ValueError("dropout uniforms must be (T-1,B,N,N)")
+        else:
+            u12 = u21p = None
+            rate = 0.0
+        nbytes = L.crw_walk_workspace_bytes(B, N, T, D, flags)
+        ws = _workspace(("walk", B, N, T, D, flags), nbytes, dev)
+        q = torch.empty_like(feats)
+        nw = max(T - 2, 0)
+        xent = torch.zeros(max(nw, 1), dtype=torch.float32, device=dev)
+        acc = torch.zeros(max(nw, 1), dtype=torch.float32, device=dev)
+        grad = torch.empty_like(feats) if (need_grad and nw > 0) else None
+        L.check(L.crw_walk_fwd_bwd(feats.data_ptr(), B, N, T, D, float(tau), float(rate),
+                                   u12.data_ptr() if u12 is not None else None,
+                                   u21p.data_ptr() if u21p is not None else None,
+                                   seed, off, thr, rng_state.data_ptr() if (rng == "device" and rate > 0) else None,
+                                   flags, q.data_ptr(), xent.data_ptr(), acc.data_ptr(),
+                                   grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(), _stream()),
+                "walk_fwd_bwd")
+        xent, acc = xent[:nw], acc[:nw]
+        loss = (xent.sum() / max(1, nw)).reshape(1)            # model.py:413
+        ctx.save_for_backward(grad if grad is not None else torch.empty(0, device=dev), q, feats)
+        ctx.has_grad = grad is not None
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(xent, acc)
+        return q, loss, xent, acc
+
+    @staticmethod
+    def backward(ctx, gq, gloss, gxent, gacc):
+        grad, q, feats = ctx.saved_tensors
+        out = None
+        if ctx.has_grad and gloss is not None:
+            out = grad * gloss.reshape(())                     # d loss / d feats was produced by the forward launch
+        if gq is not None:
+            # gradient arriving through the returned node embeddings (not used by the reference's training loop):
+            # normalisation backward with the l2norm kernels
+            L = _lib.lib()
+            D = feats.shape[-1]
+            rows = feats.numel() // D
+            inv = torch.empty(rows, dtype=torch.float32, device=feats.device)
+            nrm = torch.empty_like(inv)
+            tmp = torch.empty_like(feats)
+            L.check(L.crw_l2norm_fwd(feats.data_ptr(), tmp.data_ptr(), inv.data_ptr(), nrm.data_ptr(), rows, D, _stream()), "l2norm_fwd")
+            extra = gq.contiguous().clone()
+            L.check(L.crw_l2norm_bwd(q.data_ptr(), extra.data_ptr(), inv.data_ptr(), nrm.data_ptr(), rows, D, _stream()), "l2norm_bwd")
+            out = extra if out is None else out + extra
+        if out is None:
+            out = torch.zeros_like(feats)
+        return out, None, None, None, None, None, None, None
+
+
+def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = False, softmax: bool = False,
+         rng: str = "philox", u12: Optional[torch.Tensor] = None, u21p: Optional[torch.Tensor] = None,
+         force_general: bool = False, rng_state: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """feats (B,N,T,D) pre-normalisation node vectors -> (q (B,N,T,D) unit-norm, loss [1], xent (T-2), acc (T-2)).
+
+    One launch computes the forward AND d loss / d feats; backward() only scales it by the incoming gradient.
+    `rng`: 'philox' replays torch's CUDA generator inside the kernel (advancing it exactly as the reference's
+    2(T-1) rand_like calls would); 'torch' draws the uniforms with torch.rand and hands them to the kernel;
+    'device' reads {seed, offset} from the CUDA int64 tensor `rng_state` and advances it on the device (CUDA-graph
+    safe: every replay draws fresh masks); explicit (u12, u21p) override all of these.
+    """
+    flags = (WALK_FLIP if flip else 0) | (WALK_SOFTMAX if softmax else 0) | (WALK_FORCE_GENERAL if force_general else 0)
+    if u12 is not None:
+        rng = "torch"
+    return _Walk.apply(feats, float(temperature), float(rate), flags, rng, u12, u21p, rng_state)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# a4 / a5 as standalone operators (CRW.affinity, CRW.stoch_mat)
+# ------------------------------------------------------------------------------------------------------------------
+def _affinity_raw(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """x1 (R,N1,D), x2 (R,N2,D) contiguous -> (R,N1,N2)."""
+    R, N1, D = x1.shape
+    N2 = x2.shape[1]
+    out = torch.empty(R, N1, N2, dtype=torch.float32, device=x1.device)
+    L = _lib.lib()
+    L.check(L.crw_affinity(x1.data_ptr(), x2.data_ptr(), R, N1, N2, D, out.data_ptr(), _stream()), "affinity")
+    return out
+
+
+class _Affinity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2):
+        _need_cuda(x1, x2)
+        check_device(x1.device)
+        x1, x2 = _f32c(x1), _f32c(x2)
+        ctx.save_for_backward(x1, x2)
+        return _affinity_raw(x1, x2)
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2 = ctx.saved_tensors
+        g = _f32c(g)
+        # dX1 = G X2 = G (X2^T)^T ; dX2 = G^T X1
+        g1 = _affinity_raw(g, x2.transpose(1, 2).contiguous())
+        g2 = _affinity_raw(g.transpose(1, 2).contiguous(), x1.transpose(1, 2).contiguous())
+        return g1, g2
+
+
+def affinity_nodes(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """node-major affinity: x1 (R,N1,D), x2 (R,N2,D) -> (R,N1,N2) = x1 x2^T (differentiable)."""
+    return _Affinity.apply(x1, x2)
+
+
+def stoch_mat_(A: torch.Tensor, temperature: float, rate: float = 0.0, softmax: bool = False,
+               uniform: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """model.py:74-90 on a contiguous (..., N, M) stack: in-place dropout to -1e20 where uniform < rate, then
+    ZeroSoftmax (or softmax) of A / temperature along the last dim.  Forward only."""
+    _need_cuda(A, uniform)
+    check_device(A.device)
+    if A.dtype != torch.float32 or not A.is_contiguous():
+        raise ValueError("stoch_mat_ needs a contiguous fp32 tensor")
+    N, M = A.shape[-2:]
+    R = A.numel() // (N * M)
+    out = torch.empty_like(A)
+    if uniform is not None:
+        uniform = _f32c(uniform)
+    L = _lib.lib()
+    L.check(L.crw_stoch_mat(A.data_ptr(), uniform.data_ptr() if uniform is not None else None, float(rate),
+                            float(temperature), WALK_SOFTMAX if softmax else 0, R, N, M, out.data_ptr(), _stream()), "stoch_mat")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# a9-a12: label propagation
+# ------------------------------------------------------------------------------------------------------------------
+def lp_prepare(feats_cf: torch.Tensor, normalize: bool) -> torch.Tensor:
+    """(C, Nf, hw) channel-first -> (Nf, hw, C) channel-last, optionally L2-normalised over C (test.py:93)."""
+    _need_cuda(feats_cf)
+    check_device(feats_cf.device)
+    feats_cf = _f32c(feats_cf)
+    C, Nf, hw = feats_cf.shape
+    out = torch.empty(Nf, hw, C, dtype=torch.float32, device=feats_cf.device)
+    L = _lib.lib()
+    L.check(L.crw_lp_prepare(feats_cf.data_ptr(), C, Nf, hw, 1 if normalize else 0, out.data_ptr(), _stream()), "lp_prepare")
+    return out
+
+
+def lp_topk(feats_cl: torch.Tensor, key_frames: torch.Tensor, query_frames: torch.Tensor, n_long: int, h: int, w: int,
+            radius: float, temperature: float, k: int, dense_mask: Optional[torch.Tensor] = None):
+    """feats_cl (Nf,hw,C); key_frames (Nt,S) int64; query_frames (Nt) int64 -> Ws (Nt,k,hw) fp32, Is (Nt,k,hw) int64."""
+    _need_cuda(feats_cl, key_frames, query_frames, dense_mask)
+    check_device(feats_cl.device)
+    feats_cl = _f32c(feats_cl)
+    key_frames = key_frames.to(torch.int64).contiguous()
+    query_frames = query_frames.to(torch.int64).contiguous()
+    Nf, hw, C = feats_cl.shape
+    if hw != h * w:
+        raise ValueError("feats have %d positions, expected %d x %d" % (hw, h, w))
+    Nt, S = key_frames.shape
+    if Nt and (int(key_frames.max()) >= Nf or int(query_frames.max()) >= Nf or int(key_frames.min()) < 0):
+        raise ValueError("frame index out of range")
+    if dense_mask is not None:
+        dense_mask = _f32c(dense_mask).reshape(hw, hw)
+    dev = feats_cl.device
+    Ws = torch.empty(Nt, k, hw, dtype=torch.float32, device=dev)
+    Is = torch.empty(Nt, k, hw, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    nbytes = L.crw_lp_topk_workspace_bytes(Nt, S, h, w, C, k)
+    ws = _workspace(("lp", Nt, S, h, w, C, k), nbytes, dev)
+    L.check(L.crw_lp_topk(feats_cl.data_ptr(), key_frames.data_ptr(), query_frames.data_ptr(), Nt, S, n_long, h, w, C,
+                          float(radius), dense_mask.data_ptr() if dense_mask is not None else None, float(temperature), k,
+                          Ws.data_ptr(), Is.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "lp_topk")
+    return Ws, Is
+
+
+def lp_gather_(lbls: torch.Tensor, key_frames_n: torch.Tensor, Ws_n: torch.Tensor, Is_n: torch.Tensor, out_frame: int) -> None:
+    """One step of test.py:147-157 in place: lbls (Nf,hw,L); writes lbls[out_frame]."""
+    _need_cuda(lbls, key_frames_n, Ws_n, Is_n)
+    if lbls.dtype != torch.float32 or not lbls.is_contiguous():
+        raise ValueError("lbls must be contiguous fp32 (Nf,hw,L)")
+    Nf, hw, Lc = lbls.shape
+    k = Ws_n.shape[0]
+    L = _lib.lib()
+    L.check(L.crw_lp_gather(lbls.data_ptr(), key_frames_n.contiguous().data_ptr(), _f32c(Ws_n).data_ptr(),
+                            Is_n.contiguous().data_ptr(), hw, Lc, k, int(out_frame), _stream()), "lp_gather")

@@ -1,0 +1,197 @@
+"""Drop-in for the evaluator functions of the reference (code/utils/test_utils.py:129-209, the radius mask of
+code/utils/__init__.py:354-411 and the propagation loop of code/test.py:141-160), on the sm_100a kernels.
+
+Two levels:
+  * the reference's own signatures - `context_index_bank`, `mem_efficient_batched_affinity`, `batched_affinity`,
+    `MaskedAttention` - accepting the tensors test.py builds (materialised key bank, dense additive mask) and
+    returning what it returns (lists of per-frame CPU tensors);
+  * `LabelPropagator`, the native entry point: features stay on the device in channel-last layout, the 21x key
+    copy and the 165 MB mask are never built, and the whole video is one top-k launch plus one gather per frame.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def context_index_bank(n_context: int, long_mem: Sequence[int], N: int) -> List[torch.Tensor]:
+    """test_utils.py:129-145: per target frame, the long-memory frame ids then the n_context preceding frames."""
+    bank = []
+    for t in long_mem:
+        assert 0 <= t < N, "context frame out of bounds"
+        col = torch.zeros(N, 1, dtype=torch.long)
+        if t > 0:
+            col += t + (n_context + 1)
+            col[: n_context + t + 1] = 0
+        bank.append(col)
+    bank.append(torch.arange(N)[:, None] + torch.arange(n_context)[None, :])
+    return bank
+
+
+class MaskedAttention(nn.Module):
+    """code/utils/__init__.py:354-411.  `mask(H, W)` returns the reference's dense (1,H,W,H,W) 0/1 tensor for callers
+    that want it; the kernels only need `radius` and evaluate dy^2 + dx^2 < radius^2 on the fly."""
+
+    def __init__(self, radius, flat=True):
+        super().__init__()
+        self.radius = radius
+        self.flat = flat
+        self.masks = {}
+
+    def mask(self, H, W):
+        key = "%s-%s" % (H, W)
+        if key not in self.masks:
+            self.make(H, W)
+        return self.masks[key]
+
+    def make(self, H, W):
+        if self.flat:
+            H, W = int(H ** 0.5), int(W ** 0.5)
+        gy, gx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        d2 = (gy[None, None] - gy[:, :, None, None]) ** 2 + (gx[None, None] - gx[:, :, None, None]) ** 2
+        D = (d2.float() ** 0.5 < self.radius)[None].float()
+        if self.flat:
+            D = torch.flatten(torch.flatten(D, 1, 2), -2, -1)
+        self.masks["%s-%s" % (H, W)] = D
+        return D
+
+    def forward(self, x):
+        H, W = x.shape[-2:]
+        return x * self.mask(H, W)[0].to(x.device)
+
+
+class RadiusMask:
+    """Lightweight stand-in for the dense additive mask of test.py:118-122: pass it as `mask` to
+    mem_efficient_batched_affinity to take the window-skipping path without building the (hw,hw) tensor."""
+
+    def __init__(self, radius: float, h: int, w: int):
+        self.radius, self.h, self.w = float(radius), int(h), int(w)
+
+
+_mask_cache = {}
+
+
+def _analyse_dense_mask(mask: torch.Tensor, device) -> Tuple[Optional[RadiusMask], torch.Tensor]:
+    """Recover (h, w, radius) from a dense additive mask when it IS a radius mask (verified exactly on the device);
+    otherwise the caller falls back to the literal dense-mask path."""
+    m = mask.reshape(mask.shape[-2], mask.shape[-1])
+    hw = m.shape[0]
+    key = (mask.data_ptr(), hw, str(mask.device), mask._version)
+    if key in _mask_cache:
+        return _mask_cache[key]
+    md = m.to(device=device, dtype=torch.float32).contiguous()
+    spec = None
+    row0 = md[0] == 0                                     # queries admissible for key (0,0)
+    idx = torch.nonzero(row0).flatten()
+    if idx.numel() > 0 and bool(row0[0]):
+        run = int((idx == torch.arange(idx.numel(), device=device)).sum())          # length of the first run = R + 1 (or w)
+        rest = idx[idx >= run]
+        w = int(rest[0]) if rest.numel() else (hw if run == hw else 0)
+        if run == hw:
+            w = hw
+        if w > 0 and hw % w == 0:
+            h = hw // w
+            ys, xs = idx // w, idx % w
+            d2max = int((ys * ys + xs * xs).max())
+            radius = float(d2max + 0.5) ** 0.5
+            gy, gx = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
+            gy, gx = gy.flatten(), gx.flatten()
+            inside = ((gy[:, None] - gy[None]) ** 2 + (gx[:, None] - gx[None]) ** 2).float() < radius * radius
+            if bool(torch.equal(inside, md == 0)) and bool((md[~inside] <= -1e9).all()):
+                spec = RadiusMask(radius, h, w)
+    _mask_cache.clear()
+    _mask_cache[key] = (spec, md)
+    return spec, md
+
+
+def mem_efficient_batched_affinity(query, keys, mask, temperature, topk, long_mem, device, chunk: int = 8):
+    """test_utils.py:148-179 with the reference's signature and return convention.
+
+    query (1,C,N',hw); keys (1,C,N',S,hw) (the materialised context bank of test.py:115,125); mask: the dense
+    additive (1,1,hw,hw) tensor of test.py:118-122, or a RadiusMask.  Returns (Ws, Is): lists of N' CPU tensors
+    (topk, hw), fp32 / int64, index = slot*hw + key position, sorted by descending score.
+    """
+    assert query.shape[0] == 1 and keys.shape[0] == 1
+    C, Nt, S, hw = keys.shape[1], keys.shape[2], keys.shape[3], keys.shape[4]
+    n_long = len(long_mem)
+    dense = None
+    if isinstance(mask, RadiusMask):
+        spec = mask
+    else:
+        spec, md = _analyse_dense_mask(mask, device)
+        if spec is None:
+            dense = md
+    if spec is not None:
+        h, w, radius = spec.h, spec.w, spec.radius
+    else:
+        h, w, radius = 1, hw, 0.0
+    Ws, Is = [], []
+    for b0 in range(0, Nt, chunk):
+        nb = min(chunk, Nt - b0)
+        k_cf = keys[0, :, b0:b0 + nb].to(device).reshape(C, nb * S, hw)
+        q_cf = query[0, :, b0:b0 + nb].to(device).reshape(C, nb, hw)
+        feats = ops.lp_prepare(torch.cat([k_cf, q_cf], dim=1), normalize=False)          # (nb*S + nb, hw, C)
+        kf = torch.arange(nb * S, device=device).view(nb, S)
+        qf = torch.arange(nb, device=device) + nb * S
+        w_, i_ = ops.lp_topk(feats, kf, qf, n_long, h, w, radius, temperature, topk, dense_mask=dense)
+        Ws += [x for x in w_.cpu()]
+        Is += [x for x in i_.cpu()]
+    return Ws, Is
+
+
+def batched_affinity(query, keys, mask, temperature, topk, long_mem, device):
+    """test_utils.py:182-209 is shape-broken and unused in the reference; exported with the semantics of
+    mem_efficient_batched_affinity, which is what test.py:128 actually calls."""
+    return mem_efficient_batched_affinity(query, keys, mask, temperature, topk, long_mem, device)
+
+
+def propagate_labels(lbls: torch.Tensor, key_indices: torch.Tensor, Ws, Is, n_context: int, device=None) -> torch.Tensor:
+    """test.py:141-160: lbls (Nf,h,w,L) soft labels (rows >= n_context are overwritten, frame 0 is ground truth).
+    Ws / Is: per-target (k,hw) tensors (lists or stacked).  Returns the predictions (Nt,h,w,L) on `device`."""
+    device = device or (Ws[0].device if Ws[0].is_cuda else "cuda")
+    Nf, h, w, L = lbls.shape
+    lb = lbls.to(device=device, dtype=torch.float32).clone()
+    lb[n_context:] = 0
+    lb = lb.view(Nf, h * w, L)
+    ki = key_indices.to(device)
+    preds = []
+    for t in range(ki.shape[0]):
+        if t == 0:
+            lb[n_context] = lb[0]                         # test.py:158-160: the first target keeps the ground truth
+        else:
+            ops.lp_gather_(lb, ki[t], Ws[t].to(device), Is[t].to(device), t + n_context)
+        preds.append(lb[t + n_context])
+    return torch.stack(preds).view(-1, h, w, L)
+
+
+class LabelPropagator:
+    """Native evaluator: encoder features in, propagated soft label maps out, everything on the device.
+
+        lp = LabelPropagator(n_context=20, long_mem=[0], radius=12, topk=10, temperature=0.07)
+        preds, (Ws, Is) = lp(feats, lbls)        # feats (1,C,Nf,h,w) or (C,Nf,h,w); lbls (Nf,h,w,L)
+    """
+
+    def __init__(self, n_context: int, long_mem: Sequence[int], radius: float, topk: int, temperature: float,
+                 normalize: bool = True):
+        self.n_context, self.long_mem = int(n_context), list(long_mem)
+        self.radius, self.topk, self.temperature, self.normalize = float(radius), int(topk), float(temperature), normalize
+
+    def affinity(self, feats: torch.Tensor):
+        if feats.dim() == 5:
+            feats = feats[0]
+        C, Nf, h, w = feats.shape
+        cl = ops.lp_prepare(feats.reshape(C, Nf, h * w), self.normalize)
+        Nt = Nf - self.n_context
+        ki = torch.cat(context_index_bank(self.n_context, self.long_mem, Nt), dim=-1).to(feats.device)
+        qf = torch.arange(Nt, device=feats.device) + self.n_context
+        Ws, Is = ops.lp_topk(cl, ki, qf, len(self.long_mem), h, w, self.radius, self.temperature, self.topk)
+        return ki, Ws, Is
+
+    def __call__(self, feats: torch.Tensor, lbls: torch.Tensor):
+        ki, Ws, Is = self.affinity(feats)
+        preds = propagate_labels(lbls, ki, Ws, Is, self.n_context, device=feats.device)
+        return preds, (Ws, Is)

@@ -1,0 +1,358 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (sapienza_video_contrastive_b200.ops ->
+libcrw_b200.so), against the oracle on identical seeded inputs and against the golden outputs of the unmodified
+reference (tests/golden).  Run on the B200 box: pytest -m gpu.
+
+Tolerances (fp32 everywhere): loss / xent rel 1e-5 vs the reference, gradients rel 1e-4 of the largest entry
+(BASELINE.json north_star: 1e-4), top-k indices bit-exact apart from exact score ties, label maps 1e-5.
+"""
+import argparse
+import os
+
+import pytest
+import torch
+
+from oracle import crw_oracle as O
+from tests.golden import cases
+from tests.test_sim_kernels import check_topk_indices, load
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from sapienza_video_contrastive_b200 import ops as _ops
+    _ops.check_device(DEV)
+    return _ops
+
+
+def relmax(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_library_is_the_cuda_one(ops):
+    from sapienza_video_contrastive_b200 import _lib
+    L = _lib.lib()
+    assert L.path.endswith("libcrw_b200.so") and L.crw_version() >= 100
+    with pytest.raises(RuntimeError):
+        ops.pool_patch(torch.zeros(2, 2, 8, 8))                     # CPU tensors are refused: no fallback
+
+
+def test_philox_replay_matches_torch_rand(ops):
+    assert ops.philox_replay_ok(DEV)
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    torch.manual_seed(1234)
+    for numel in (7, 48020, 20 * 49 * 49, 303104, 303105, 2_000_003):
+        seed, off = gen.initial_seed(), gen.get_offset()
+        ref = torch.rand(numel, device=DEV)
+        thr = ops.torch_rand_threads(numel, DEV)
+        mine = ops.philox_uniform(numel, seed, off, thr, DEV)
+        assert torch.equal(ref, mine), numel
+        assert gen.get_offset() == off + ops.torch_rand_offset_increment(numel, thr)
+    # rand_like of a transposed view keeps the transposed physical layout, also on CUDA
+    torch.manual_seed(5)
+    a = torch.rand(3, 5, 5, device=DEV)
+    torch.manual_seed(5)
+    base = torch.zeros(3, 2, 5, 5, device=DEV)
+    b = torch.rand_like(base[:, 0].transpose(-1, -2))
+    assert torch.equal(a.transpose(-1, -2), b)
+
+
+@pytest.mark.parametrize("rows,hw", [(980 * 32 * 4, 64), (1001, 64), (777, 32), (50, 16), (33, 49)])
+def test_pool_patch(ops, rows, hw):
+    torch.manual_seed(rows)
+    x = torch.randn(rows, hw)
+    xd = x.to(DEV).view(rows, 1, hw).requires_grad_(True)
+    out = ops.pool_patch(xd)
+    torch.testing.assert_close(out.cpu().view(-1), O.patch_pool(x.view(rows, 1, 1, 1, hw)).view(-1), rtol=1e-6, atol=1e-6)
+    g = torch.randn(rows, device=DEV)
+    out.view(-1).backward(g)
+    assert torch.equal(xd.grad.view(rows, hw), (g / hw)[:, None].expand(rows, hw))
+
+
+def test_pool_patch_full_size_linearity(ops):
+    """BASELINE config 2 size (980,512,4,8,8): mean-pool is linear and reproduces constants exactly."""
+    torch.manual_seed(0)
+    a = torch.randn(980, 512, 4, 8, 8, device=DEV)
+    pa = ops.pool_patch(a)
+    assert pa.shape == (980, 512, 4)
+    torch.testing.assert_close(pa, a.double().mean((-1, -2)).float(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ops.pool_patch(2 * a), 2 * pa, rtol=0, atol=0)
+    assert torch.equal(ops.pool_patch(torch.full_like(a, 3.0)), torch.full_like(pa, 3.0))
+
+
+def gpu_walk_from_case(ops, c, rng="explicit", force_general=False):
+    maps, head_w = cases.walk_inputs(c)
+    maps_d = maps.to(DEV).requires_grad_(True)
+    head_d = head_w.to(DEV).requires_grad_(True)
+    pooled = ops.pool_patch(maps_d)                                           # (BN, Ce, T)
+    f = (pooled.transpose(-1, -2) @ head_d.t()).reshape(c["B"], c["N"], c["T"], 128)
+    torch.manual_seed(c["seed"] + 1000)
+    u12 = u21p = None
+    if c["p"] > 0:
+        u12, u21p = O.draw_uniforms(c["B"], c["N"], c["T"])
+        u12, u21p = u12.to(DEV), u21p.to(DEV)
+    q, loss, xent, acc = ops.walk(f, c["tau"], c["p"], flip=c["flip"], u12=u12, u21p=u21p, force_general=force_general)
+    loss.sum().backward()
+    return q, loss, xent, acc, maps_d.grad, head_d.grad
+
+
+@pytest.mark.parametrize("name", list(cases.WALK_CASES))
+@pytest.mark.parametrize("force_general", [False, True])
+def test_walk_matches_reference_golden(ops, name, force_general):
+    c = cases.WALK_CASES[name]
+    fx = load(name)
+    q, loss, xent, acc, gmaps, ghead = gpu_walk_from_case(ops, c, force_general=force_general)
+    torch.testing.assert_close(q.permute(0, 3, 2, 1).cpu(), fx["q"], rtol=1e-5, atol=1e-6)
+    assert loss.shape == (1,)
+    torch.testing.assert_close(loss.cpu(), fx["loss"], rtol=1e-5, atol=0)
+    tag = "l" if c["flip"] else "r"
+    for j in range(c["T"] - 2):
+        torch.testing.assert_close(xent[j].cpu(), fx["diags"]["64 xent cyc %s%d" % (tag, j + 1)], rtol=1e-5, atol=0)
+        torch.testing.assert_close(acc[j].cpu(), fx["diags"]["64 acc cyc %s%d" % (tag, j + 1)], rtol=0, atol=1e-6)
+    assert relmax(ghead.cpu(), fx["grad_head"]) < 1e-4
+    assert relmax(gmaps[..., 0, 0].cpu(), fx["grad_maps00"]) < 1e-4
+    assert float((gmaps - gmaps[..., :1, :1]).abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,N,T,D,p,flip,softmax", [(20, 49, 4, 128, 0.1, False, False), (4, 49, 8, 128, 0.1, False, False),
+                                                    (3, 64, 4, 128, 0.1, True, False), (2, 128, 4, 128, 0.1, False, False),
+                                                    (2, 100, 6, 128, 0.2, False, True), (1, 256, 5, 128, 0.1, False, False),
+                                                    (2, 31, 3, 64, 0.5, False, False), (2, 17, 2, 32, 0.1, False, False)])
+def test_walk_matches_oracle(ops, B, N, T, D, p, flip, softmax):
+    torch.manual_seed(B * 100 + N)
+    f = torch.randn(B, N, T, D)
+    u12, u21p = O.draw_uniforms(B, N, T)
+    fo = f.clone().requires_grad_(True)
+    qo = (fo / fo.norm(dim=-1, keepdim=True).clamp_min(1e-12)).permute(0, 3, 2, 1)
+    loss_o, xents, accs, _ = O.walk_loss(qo, 0.07, p, u12, u21p, flip=flip, softmax=softmax)
+    if T >= 3:
+        loss_o.sum().backward()
+    for fg in (False, True):
+        fd = f.to(DEV).requires_grad_(True)
+        q, loss, xent, acc = ops.walk(fd, 0.07, p, flip=flip, softmax=softmax, u12=u12.to(DEV), u21p=u21p.to(DEV), force_general=fg)
+        torch.testing.assert_close(q.cpu(), qo.detach().permute(0, 3, 2, 1), rtol=1e-5, atol=1e-6)
+        if T >= 3:
+            torch.testing.assert_close(xent.cpu(), torch.stack(xents).detach(), rtol=2e-5, atol=0)
+            # argmax accuracy can flip on a near-tie: allow one row
+            assert float((acc.cpu() - torch.stack(accs)).abs().max()) <= 1.0 / (B * N) + 1e-6
+            loss.sum().backward()
+            assert relmax(fd.grad.cpu(), fo.grad) < 1e-4
+        else:
+            assert float(loss) == 0.0
+
+
+def test_walk_in_kernel_dropout_equals_torch_draws(ops):
+    """rng='philox' (drawn inside the kernel) must give exactly the run that rng='torch' (torch.rand draws handed to
+    the kernel) gives from the same generator state, and leave the generator in the same state."""
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    for (B, N, T, fg) in [(20, 49, 4, False), (3, 100, 5, True), (200, 49, 4, False)]:
+        f = torch.randn(B, N, T, 128, device=DEV)
+        outs = []
+        for rng in ("torch", "philox"):
+            torch.manual_seed(77)
+            fd = f.clone().requires_grad_(True)
+            q, loss, xent, acc = ops.walk(fd, 0.07, 0.1, rng=rng, force_general=fg)
+            loss.sum().backward()
+            outs.append((loss.clone(), xent.clone(), fd.grad.clone(), gen.get_offset(), torch.rand(3, device=DEV)))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert torch.equal(outs[0][2], outs[1][2])
+        assert outs[0][3] == outs[1][3] and torch.equal(outs[0][4], outs[1][4])
+
+
+def test_walk_full_size_config2_fused_vs_general(ops):
+    """BASELINE config 2 shape (B=20,N=49,T=4,D=128): the two implementations agree; loss near log N at random init."""
+    torch.manual_seed(2)
+    f = torch.randn(20, 49, 4, 128, device=DEV)
+    res = []
+    for fg in (False, True):
+        torch.manual_seed(9)
+        fd = f.clone().requires_grad_(True)
+        q, loss, xent, acc = ops.walk(fd, 0.07, 0.1, rng="philox", force_general=fg)
+        loss.sum().backward()
+        res.append((loss, xent, fd.grad))
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-5, atol=0)
+    assert relmax(res[0][2], res[1][2]) < 1e-4
+    assert 1.0 < float(res[0][0]) < 12.0
+
+
+def make_args(**kw):
+    d = dict(device=DEV, dropout=0.1, featdrop=0.0, temp=0.07, head_depth=0, model_type="scratch", remove_layers=[],
+             dilate_superpixels=False, flip=False, sk_targets=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_crw_dropin_config1_matches_reference(ops):
+    """BASELINE config 1 verbatim: CRW with a random ResNet-18 under seed 0, x ~ N(0,1) (2,4,147,64,64), dropout draws
+    under seed 123.  The encoder runs on cuDNN here and on CPU in the reference, so tolerances are those of conv."""
+    from sapienza_video_contrastive_b200 import CRW
+    fx = load("cfg1_resnet18")
+    torch.manual_seed(0)
+    crw = CRW(make_args(device="cpu"))             # build on CPU: identical init stream to the reference
+    assert list(crw.state_dict().keys()) == fx["state_dict_keys"]
+    assert abs(float(sum(p.double().sum() for p in crw.parameters())) - fx["param_checksum"]) < 1e-6
+    x = torch.randn(2, 4, 147, 64, 64)
+    torch.manual_seed(123)
+    u12, u21p = O.draw_uniforms(2, 49, 4)
+    crw = crw.to(DEV)
+    crw.args.device = DEV
+    q, loss, diags = crw(x.to(DEV), None, None, walk_uniforms=(u12.to(DEV), u21p.to(DEV)))
+    assert q.shape == (2, 128, 4, 49) and loss.shape == (1,)
+    assert set(diags) == set(fx["diags"])
+    torch.testing.assert_close(q.cpu(), fx["q"], rtol=1e-3, atol=2e-4)
+    torch.testing.assert_close(loss.cpu(), fx["loss"], rtol=1e-4, atol=0)
+    for k in fx["diags"]:
+        if "xent" in k:
+            torch.testing.assert_close(diags[k].cpu(), fx["diags"][k], rtol=1e-4, atol=0)
+    loss.mean().backward()
+    g = crw.selfsim_fc[0].weight.grad.cpu()
+    assert relmax(g, fx["grad_head"]) < 5e-3
+    assert relmax(crw.encoder.model.conv1.weight.grad.cpu(), fx["grad_conv1"]) < 5e-2
+
+
+def test_crw_dropin_api_surface(ops):
+    from sapienza_video_contrastive_b200 import CRW
+    torch.manual_seed(0)
+    crw = CRW(make_args())
+    # affinity: 4-D and 3-D forms (model.py:63-72)
+    x1, x2 = torch.randn(2, 16, 3, 7, device=DEV), torch.randn(2, 16, 3, 9, device=DEV)
+    torch.testing.assert_close(crw.affinity(x1, x2), torch.einsum("bctn,bctm->btnm", x1, x2), rtol=1e-5, atol=1e-5)
+    assert crw.affinity(x1[:, :, 0], x2[:, :, 0]).shape == (2, 7, 9)
+    # stoch_mat mutates its argument through a transposed view, like the reference (F4)
+    As = torch.randn(2, 3, 6, 6, device=DEV)
+    A0 = As.clone()
+    torch.manual_seed(3)
+    view = As[:, 1].transpose(-1, -2)
+    out = crw.stoch_mat(view, do_dropout=True)
+    torch.manual_seed(3)
+    u = torch.rand_like(A0[:, 1].transpose(-1, -2))
+    exp_view = A0[:, 1].transpose(-1, -2).masked_fill(u < 0.1, -1e20)
+    assert torch.equal(As[:, 1].transpose(-1, -2), exp_view) and torch.equal(As[:, 0], A0[:, 0])
+    torch.testing.assert_close(out.cpu(), O.stoch_rows(A0[:, 1].transpose(-1, -2).cpu(), (u < 0.1).cpu(), 0.07), rtol=1e-5, atol=1e-8)
+    # pixels_to_nodes returns unit-norm (B,128,T,N) and the maps
+    x = torch.randn(1, 4, 3, 2, 64, 64, device=DEV)
+    feats, maps = crw.pixels_to_nodes(x)
+    assert feats.shape == (1, 128, 2, 4) and maps.shape == (1, 4, 512, 2, 8, 8)
+    torch.testing.assert_close(feats.norm(dim=1), torch.ones(1, 2, 4, device=DEV), rtol=1e-5, atol=1e-5)
+    assert torch.equal(crw.xent_targets(torch.zeros(2, 5, 5, device=DEV)).cpu(), torch.arange(5).repeat(2))
+    # default rng mode: a full forward/backward under the module API
+    v = torch.randn(2, 4, 49 * 3, 64, 64, device=DEV)
+    q, loss, diags = crw(v)
+    loss.mean().backward()
+    assert torch.isfinite(loss).all() and crw.selfsim_fc[0].weight.grad is not None
+    assert sorted(diags) == ["64 acc cyc r1", "64 acc cyc r2", "64 xent cyc r1", "64 xent cyc r2"]
+
+
+@pytest.mark.parametrize("name", list(cases.SP_CASES))
+def test_superpixel_nodes_and_walk_match_reference(ops, name):
+    c = cases.SP_CASES[name]
+    fx = load(name)
+    maps, lab3, head_w = cases.sp_inputs(c)
+    md = maps.to(DEV).requires_grad_(True)
+    hd = head_w.to(DEV).requires_grad_(True)
+    lab = lab3.to(DEV)[:, :, 0]
+    pooled = ops.segment_mean(md, lab, c["SP"])                               # (B,SP,T,Ce)
+    torch.testing.assert_close(pooled.detach().cpu().transpose(1, 2), O.segment_mean(maps, lab3[:, :, 0], c["SP"]), rtol=1e-5, atol=1e-6)
+    f = pooled @ hd.t()
+    torch.manual_seed(c["seed"] + 1000)
+    u12, u21p = O.draw_uniforms(c["B"], c["SP"], c["T"])
+    q, loss, xent, acc = ops.walk(f, c["tau"], c["p"], u12=u12.to(DEV), u21p=u21p.to(DEV))
+    torch.testing.assert_close(q.permute(0, 3, 2, 1).cpu(), fx["q"], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(loss.cpu(), fx["loss"], rtol=1e-5, atol=0)
+    loss.sum().backward()
+    assert relmax(hd.grad.cpu(), fx["grad_head"]) < 1e-4
+    assert relmax(md.grad.cpu(), fx["grad_maps"]) < 1e-4
+
+
+def test_segmean_config3_shape_properties(ops):
+    """BASELINE config 3 shape: constants are reproduced, sizes partition the image, empty labels give zero rows."""
+    B, C, T, SP = 2, 512, 8, 196
+    g = torch.Generator().manual_seed(7)
+    lab = cases.voronoi_labels(B, T, SP, 256, g, one_based=True).to(DEV)
+    maps = torch.randn(B, C, T, 32, 32, device=DEV)
+    out = ops.segment_mean(maps, lab, SP)
+    assert out.shape == (B, SP, T, C) and float(out[:, 0].abs().max()) == 0            # label 0 unused -> empty node
+    ones = ops.segment_mean(torch.ones_like(maps), lab, SP)
+    present = torch.zeros(B, T, SP, device=DEV).scatter_(2, lab.flatten(2), 1.0).transpose(1, 2)
+    torch.testing.assert_close(ones[..., 0], present, rtol=1e-6, atol=1e-6)
+    ref = O.segment_mean(maps[:1, :64].cpu(), lab[:1].cpu(), SP)
+    torch.testing.assert_close(out[:1, :, :, :64].cpu().transpose(1, 2), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(cases.LP_CASES))
+def test_label_prop_matches_reference_golden(ops, name):
+    from sapienza_video_contrastive_b200 import LabelPropagator, context_index_bank
+    c = cases.LP_CASES[name]
+    fx = load(name)
+    feats, lbls = cases.lp_inputs(c)
+    lp = LabelPropagator(c["n_ctx"], c["long_mem"], c["radius"], c["k"], c["tau"], normalize=False)
+    preds, (Ws, Is) = lp(feats.to(DEV), lbls)
+    ki = torch.cat(context_index_bank(c["n_ctx"], c["long_mem"], c["n_tgt"]), -1)
+    check_topk_indices(feats, ki, Is.cpu(), fx["Is"], c)
+    torch.testing.assert_close(Ws.cpu(), fx["Ws"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(preds.cpu(), fx["preds"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["lp_small", "lp_long2"])
+@pytest.mark.parametrize("mask_kind", ["dense", "radius_object", "arbitrary_dense"])
+def test_reference_signature_mem_efficient_batched_affinity(ops, name, mask_kind):
+    """The reference's own call (test.py:112-129): materialised key bank + dense additive mask, lists of CPU tensors back."""
+    from sapienza_video_contrastive_b200 import RadiusMask, context_index_bank, mem_efficient_batched_affinity
+    c = cases.LP_CASES[name]
+    fx = load(name)
+    feats, lbls = cases.lp_inputs(c)
+    ki = torch.cat(context_index_bank(c["n_ctx"], c["long_mem"], c["n_tgt"]), -1)
+    keys, query = feats[:, :, ki].flatten(-2), feats[:, :, c["n_ctx"]:].flatten(-2)
+    D = O.radius_mask_additive(c["h"], c["w"], c["radius"])
+    if mask_kind == "radius_object":
+        mask = RadiusMask(c["radius"], c["h"], c["w"])
+    elif mask_kind == "arbitrary_dense":
+        mask = D.clone()
+        mask[0, 0, 0, 1] = -1e10                      # no longer a radius mask -> literal dense path
+        mask[0, 0, 1, 0] = -1e10
+    else:
+        mask = D
+    Ws, Is = mem_efficient_batched_affinity(query, keys, mask, c["tau"], c["k"], c["long_mem"], DEV, chunk=4)
+    assert isinstance(Ws, list) and len(Ws) == c["n_tgt"] and not Ws[0].is_cuda and Is[0].dtype == torch.int64
+    if mask_kind == "arbitrary_dense":
+        Wo, Io = [], []
+        f = feats[0].flatten(-2)
+        for n in range(c["n_tgt"]):
+            sc = torch.cat([f[:, ki[n, s]].t() @ f[:, n + c["n_ctx"]] + (mask[0, 0] if s >= len(c["long_mem"]) else 0)
+                            for s in range(ki.shape[1])], 0) / c["tau"]
+            v, i = torch.topk(sc, c["k"], dim=0)
+            torch.testing.assert_close(torch.gather(sc, 0, Is[n]), v, rtol=0, atol=0)
+    else:
+        check_topk_indices(feats, ki, torch.stack(Is), fx["Is"], c)
+        torch.testing.assert_close(torch.stack(Ws), fx["Ws"], rtol=1e-5, atol=1e-7)
+
+
+def test_label_prop_davis_shape_properties(ops):
+    """BASELINE config 4 shape (C=256, 60x107, 20 context frames + long memory, radius 12, k=10) on a short video:
+    structural properties that do not need the oracle, plus an oracle spot check of two targets."""
+    from sapienza_video_contrastive_b200 import LabelPropagator
+    C, h, w, n_ctx, n_tgt, k, r = 256, 60, 107, 20, 3, 10, 12
+    torch.manual_seed(0)
+    feats = torch.nn.functional.normalize(torch.randn(1, C, n_ctx + n_tgt, h, w), dim=1)
+    lp = LabelPropagator(n_ctx, [0], r, k, 0.07, normalize=True)
+    ki, Ws, Is = lp.affinity(feats.to(DEV))
+    hw = h * w
+    assert Ws.shape == (n_tgt, k, hw) and Is.shape == (n_tgt, k, hw)
+    torch.testing.assert_close(Ws.sum(1), torch.ones(n_tgt, hw, device=DEV), rtol=1e-5, atol=1e-5)
+    assert bool((Ws[:, :-1] >= Ws[:, 1:]).all())
+    assert int(Is.min()) >= 0 and int(Is.max()) < (n_ctx + 1) * hw
+    slot, pos = Is // hw, Is % hw
+    qpos = torch.arange(hw, device=DEV)[None, None]
+    d2 = (pos // w - qpos // w) ** 2 + (pos % w - qpos % w) ** 2
+    assert bool(((slot == 0) | (d2 < r * r)).all())                                  # radius respected outside long memory
+    # oracle spot check on a band of queries of target 1
+    f = feats[0].flatten(-2)
+    for n in (1,):
+        qs = torch.arange(3000, 3000 + 64)
+        sc = torch.cat([f[:, ki[n, s].item()].t() @ f[:, n + n_ctx][:, qs] +
+                        (O.radius_mask_additive(h, w, r)[0, 0][:, qs] if s >= 1 else 0) for s in range(ki.shape[1])], 0) / 0.07
+        v, i = torch.topk(sc, k, dim=0)
+        mine = torch.gather(sc, 0, Is[n][:, qs].cpu())
+        torch.testing.assert_close(mine, v, rtol=1e-5, atol=1e-5)
+        assert float((Is[n][:, qs].cpu() == i).float().mean()) > 0.97

@@ -38,7 +38,7 @@ def run_walk(sim, f, tau, p, u12, u21p, flags=0, need_grad=True):
     g = torch.empty_like(f) if need_grad else None
     for _ in range(2):       # twice: the workspace must be reusable without re-zeroing
         sim.check(sim.crw_walk_fwd_bwd(ptr(f), B, N, T, D, tau, p, ptr(u12) if p > 0 else None,
-                                       ptr(u21p) if p > 0 else None, 0, 0, 0, flags, ptr(q), ptr(xe), ptr(ac), ptr(g),
+                                       ptr(u21p) if p > 0 else None, 0, 0, 0, None, flags, ptr(q), ptr(xe), ptr(ac), ptr(g),
                                        ptr(ws), wsb, None), "walk")
     return q, xe[: max(T - 2, 0)], ac[: max(T - 2, 0)], g
 
@@ -297,3 +297,39 @@ def test_l2norm(sim):
     gi = g.clone()
     sim.check(sim.crw_l2norm_bwd(ptr(q), ptr(gi), ptr(inv), ptr(nr), 37, 48, None))
     torch.testing.assert_close(gi[4:], fo.grad[4:], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("flags", [0, _lib.WALK_FORCE_GENERAL])
+def test_walk_device_rng_state(sim, flags):
+    """in-kernel Philox dropout: host-passed (seed, offset) == device-resident state, which the launch then advances."""
+    torch.manual_seed(4)
+    B, N, T, D = 2, 20, 4, 32
+    f = torch.randn(B, N, T, D)
+    wsb = sim.crw_walk_workspace_bytes(B, N, T, D, flags)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    thr = 256 * ((B * N * N + 255) // 256)
+
+    def run(seed, off, state):
+        q, g = torch.empty_like(f), torch.empty_like(f)
+        xe, ac = torch.zeros(T - 2), torch.zeros(T - 2)
+        sim.check(sim.crw_walk_fwd_bwd(ptr(f), B, N, T, D, 0.07, 0.3, None, None, seed, off, thr, ptr(state), flags, ptr(q),
+                                       ptr(xe), ptr(ac), ptr(g), ptr(ws), wsb, None))
+        return xe, g
+
+    xe1, g1 = run(42, 8, None)
+    state = torch.tensor([42, 8], dtype=torch.int64)
+    xe2, g2 = run(0, 0, state)
+    assert torch.equal(xe1, xe2) and torch.equal(g1, g2)
+    assert state.tolist() == [42, 8 + 4 * 2 * (T - 1)]
+    xe3, _ = run(0, 0, state)                 # second replay: fresh masks
+    assert not torch.equal(xe3, xe2)
+    xe4, _ = run(42, 8 + 4 * 2 * (T - 1), None)
+    assert torch.equal(xe3, xe4)
+    # and the uniforms path agrees with an explicit draw of the same stream
+    u = torch.empty(2 * (T - 1), B * N * N)
+    for j in range(2 * (T - 1)):
+        sim.check(sim.crw_philox_uniform(ptr(u[j]), B * N * N, 42, 8 + 4 * j, thr, None))
+    u12 = u[: T - 1].view(T - 1, B, N, N).contiguous()
+    u21p = u[T - 1:].view(T - 1, B, N, N).contiguous()
+    q, xe5, _, g5 = run_walk(sim, f, 0.07, 0.3, u12, u21p, flags)
+    assert torch.equal(xe5, xe1) and torch.equal(g5, g1)
