@@ -171,20 +171,24 @@ class HotPath:
         return loss
 
     def prepare(self):
-        for _ in range(3):
-            self._step_eager()
-        torch.cuda.synchronize()
-        if self.use_graph:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
+        if not self.use_graph:
+            for _ in range(3):
                 self._step_eager()
-            torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._static_loss = self._step_eager()
-            torch.cuda.synchronize()
+            return
+        # whole-step capture (forward + backward): warm up on a side stream FIRST so that the autograd accumulators
+        # of the leaves are bound to a capturable stream, then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._step_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._static_loss = self._step_eager()
+        torch.cuda.synchronize()
 
     def step(self):
         if self.graph is not None:
