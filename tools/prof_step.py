@@ -1,0 +1,27 @@
+"""Profiling target: a few eager steps of the headline hot path (bench.py's HotPath) and optionally one label-prop call.
+Used under ncu (see profiles/README.md); prints nothing that is a bench number."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--lp", action="store_true")
+ap.add_argument("--walk-general", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(dev)
+if a.lp:
+    bench.LP["n_tgt"] = 2
+    print(bench.label_prop_bench(dev)["ms_per_frame"])
+else:
+    hp = bench.HotPath(dev, 0, use_graph=False)
+    for _ in range(a.steps):
+        hp.step()
+    torch.cuda.synchronize()
+print("ok")
