@@ -112,7 +112,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise CrwError("nvcc failed, see log above")
     tmp = LIB_PATH + ".tmp"
-    subprocess.check_call([NVCC, "-shared", "-o", tmp] + ARCH_FLAGS + objs + ["-lcuda"])
+    subprocess.check_call([NVCC, "-shared", "-o", tmp] + ARCH_FLAGS + objs)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -1,0 +1,84 @@
+"""CPU-side checks: the C ABI library builds, loads and exports every symbol of include/crw_b200.h; the host logic
+(index banks, radius masks, argument checks) matches the reference's golden vectors; the product never touches the
+oracle and has no CPU path."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "sapienza_video_contrastive_b200")
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "crw_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(crw_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from sapienza_video_contrastive_b200 import _lib
+    path = _lib.build()
+    lib = _lib.CrwLib(path)                                   # no compute calls: loading + symbol lookup only
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib._dll, s), s
+    assert sorted(_lib.EXPORTS) == syms                       # the ctypes table and the header agree
+    assert lib.crw_version() >= 100
+    assert lib.crw_walk_workspace_bytes(20, 49, 4, 128, 0) > 0
+    assert lib.crw_walk_workspace_bytes(20, 49, 4, 128, _lib.WALK_FORCE_GENERAL) > lib.crw_walk_workspace_bytes(20, 49, 4, 128, 0)
+    assert lib.crw_segmean_workspace_bytes(2, 3, 32, 32, 256, 256, 100) > 0
+
+
+def test_product_never_imports_the_oracle_or_a_cpu_path():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("crw_oracle", "oracle") or f == "__none__", f
+                assert "cusim" not in txt or f.endswith((".cu", ".cuh")), f
+
+
+def test_ops_refuse_cpu_tensors():
+    from sapienza_video_contrastive_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.pool_patch(torch.zeros(4, 2, 8, 8))
+    with pytest.raises(RuntimeError):
+        ops.walk(torch.zeros(1, 4, 3, 8), 0.07, 0.0)
+    with pytest.raises(RuntimeError):
+        ops.lp_prepare(torch.zeros(4, 2, 6), True)
+
+
+def test_host_index_math_matches_reference_goldens():
+    from sapienza_video_contrastive_b200.test_utils import MaskedAttention, context_index_bank
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "misc.pt"), weights_only=False)
+    for (nc, lm, N), bank in fx["banks"].items():
+        assert torch.equal(torch.cat(context_index_bank(nc, list(lm), N), dim=-1), bank)
+    D = MaskedAttention(3, flat=False).mask(5, 6)[None].clone()
+    D = D.flatten(-4, -3).flatten(-2)
+    D[D == 0] = -1e10
+    D[D == 1] = 0
+    assert torch.equal(D, fx["mask_5x6_r3"])
+    with pytest.raises(AssertionError):
+        context_index_bank(3, [7], 5)
+
+
+def test_crw_module_surface_on_cpu():
+    """Construction is plain PyTorch (stock encoder + head): names, shapes and defaults match the reference's."""
+    import argparse
+    from sapienza_video_contrastive_b200 import CRW
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "cfg1_resnet18.pt"), weights_only=False)
+    torch.manual_seed(0)
+    args = argparse.Namespace(device="cpu", dropout=0.1, featdrop=0.0, temp=0.07, head_depth=0, model_type="scratch",
+                              remove_layers=[], dilate_superpixels=False, flip=False, sk_targets=False)
+    crw = CRW(args)
+    assert list(crw.state_dict().keys()) == fx["state_dict_keys"]
+    assert abs(float(sum(p.double().sum() for p in crw.parameters())) - fx["param_checksum"]) < 1e-6   # same init stream
+    assert crw.enc_hid_dim == 512 and crw.map_scale == 8 and crw.temperature == 0.07 and crw.edgedrop_rate == 0.1
+    assert torch.equal(crw.xent_targets(torch.zeros(2, 5, 5)), torch.arange(5).repeat(2))
+    with pytest.raises(RuntimeError):
+        crw(torch.zeros(1, 4, 6, 64, 64))                       # CPU input: refused, no fallback
+    with pytest.raises(NotImplementedError):
+        CRW(argparse.Namespace(**{**vars(args), "dilate_superpixels": True}))
