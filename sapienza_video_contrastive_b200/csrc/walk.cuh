@@ -25,31 +25,33 @@ struct WalkParams {
     unsigned* ws_counter;      // 1 ticket counter (zero between launches)
     float* ws_mats;            // general path: transition / chain / gradient matrices
     float* ws_stat;            // general path: row denominators, norms
+    // fused (small-N) path exchange buffers, all compact (stride N)
+    float *ws_F, *ws_G, *ws_dF, *ws_dG;        // (B,T-1,N,N)
+    float *ws_s12, *ws_s21;                    // (B,T-1,N) row denominators
+    float *ws_invn, *ws_nrm;                   // (B,T,N)
+    float *ws_dqa, *ws_dqb;                    // (B,T-1,N,D) per-pair contributions to dQ_i / dQ_{i+1}
+    unsigned* ws_clipcnt;                      // (B) tickets of the pair-backward CTAs (zero between launches)
 };
 
 struct FusedLayout {
     int NP, MS, DP;
-    int off_F, off_G, off_R, off_stat, off_codes;   // in floats
-    size_t bytes;
+    size_t pair_bytes;     // walk_pairs_fwd: two staged frames + raw affinity + codes
+    size_t chain_bytes;    // walk_chain: F, G, P, S stacks + 3 scratch matrices + reduction scratch
+    size_t pairb_bytes;    // walk_pairs_bwd: two staged frames + dA + raw affinity + codes + flag
 };
 
 __host__ __device__ __forceinline__ FusedLayout fused_layout(int N, int T, int D) {
     FusedLayout L;
     int np = (N + 3) & ~3;
-    if (((np >> 2) & 1) == 0) np += 4;           // NP/4 odd: conflict-free 128-bit row accesses
+    if (((np >> 2) & 1) == 0) np += 4;           // NP/4 odd: conflict-free 128-bit accesses to neighbouring rows
     L.NP = np;
     L.MS = N * np;
     L.DP = D + 4;
-    L.off_F = 0;
-    L.off_G = (T - 1) * L.MS;
-    L.off_R = 2 * (T - 1) * L.MS;
-    const int chain = (T >= 3 ? (2 * (T - 2) + 3) : 0) * L.MS;
-    const int stage = L.MS + 2 * N * L.DP;
-    const int r = chain > stage ? chain : stage;
-    L.off_stat = L.off_R + r;
-    const int stat = 2 * (T - 1) * N + 2 * T * N + 64;
-    L.off_codes = (L.off_stat + stat + 3) & ~3;
-    L.bytes = (size_t)L.off_codes * 4 + (size_t)((N * N + 15) & ~15);
+    const size_t codes = (size_t)((N * N + 15) & ~15);
+    L.pair_bytes = sizeof(float) * ((size_t)2 * N * L.DP + L.MS) + codes;
+    const int nm = 2 * (T - 1) + (T >= 3 ? 2 * (T - 2) + 3 : 0);
+    L.chain_bytes = sizeof(float) * ((size_t)nm * L.MS + 64);
+    L.pairb_bytes = sizeof(float) * ((size_t)2 * N * L.DP + 2 * L.MS) + codes + 16;
     return L;
 }
 
@@ -57,7 +59,9 @@ constexpr int kFusedMaxT = 32;
 constexpr size_t kMaxDynSmem = 232448;            // 227 KB opt-in limit per CTA on sm_100
 
 inline bool fused_fits(int N, int T, int D) {
-    return N <= 64 && T >= 2 && T <= kFusedMaxT && D % 4 == 0 && D <= 256 && fused_layout(N, T, D).bytes <= kMaxDynSmem;
+    if (!(N <= 64 && T >= 1 && T <= kFusedMaxT && D % 4 == 0 && D <= 256)) return false;
+    const FusedLayout L = fused_layout(N, T, D);
+    return L.pair_bytes <= kMaxDynSmem && L.chain_bytes <= kMaxDynSmem && L.pairb_bytes <= kMaxDynSmem;
 }
 
 int launch_walk_fused(const WalkParams& p, crw_stream_t stream);

@@ -7,23 +7,33 @@ using namespace crw;
 namespace {
 
 struct WsLayout {
-    size_t o_counter, o_partial, o_araw, o_codes, o_mats, o_stat, total;
+    size_t o_counter, o_clipcnt, o_partial, o_araw, o_codes, o_mats, o_stat;
+    size_t o_F, o_G, o_dF, o_dG, o_s12, o_s21, o_invn, o_nrm, o_dqa, o_dqb, total;
     bool fused;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
-    WsLayout w;
+    WsLayout w{};
     w.fused = !(flags & CRW_WALK_FORCE_GENERAL) && fused_fits(N, T, D);
     const size_t t1 = T > 1 ? T - 1 : 0, t2 = T >= 3 ? T - 2 : 0;
+    const size_t mat = sizeof(float) * B * t1 * N * N;
     size_t o = 0;
-    w.o_counter = o; o += 256;
-    w.o_partial = o; o = align_up(o + sizeof(float) * B * t2 * 2, 256);
-    w.o_araw = o; o = align_up(o + (w.fused ? sizeof(float) * B * t1 * N * N : 0), 256);
-    w.o_codes = o; o = align_up(o + (size_t)B * t1 * N * N * (w.fused ? 1 : 2), 256);
-    w.o_mats = o; o = align_up(o + (w.fused ? 0 : sizeof(float) * walk_general_mats_floats(B, N, T)), 256);
-    w.o_stat = o; o = align_up(o + (w.fused ? 0 : sizeof(float) * walk_general_stat_floats(B, N, T)), 256);
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    w.o_counter = take(256);
+    w.o_clipcnt = take(sizeof(unsigned) * B);                  // zero-initialised region ends here (see crw_b200.h)
+    w.o_partial = take(sizeof(float) * B * t2 * 2);
+    w.o_araw = take(w.fused ? mat : 0);
+    w.o_codes = take((size_t)B * t1 * N * N * (w.fused ? 1 : 2));
+    w.o_mats = take(w.fused ? 0 : sizeof(float) * walk_general_mats_floats(B, N, T));
+    w.o_stat = take(w.fused ? 0 : sizeof(float) * walk_general_stat_floats(B, N, T));
+    if (w.fused) {
+        w.o_F = take(mat); w.o_G = take(mat); w.o_dF = take(mat); w.o_dG = take(mat);
+        w.o_s12 = take(sizeof(float) * B * t1 * N); w.o_s21 = take(sizeof(float) * B * t1 * N);
+        w.o_invn = take(sizeof(float) * B * T * N); w.o_nrm = take(sizeof(float) * B * T * N);
+        w.o_dqa = take(sizeof(float) * B * t1 * N * D); w.o_dqb = take(sizeof(float) * B * t1 * N * D);
+    }
     w.total = o;
     return w;
 }
@@ -67,5 +77,13 @@ extern "C" int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, 
     p.ws_codes = (unsigned char*)(ws + w.o_codes);
     p.ws_mats = (float*)(ws + w.o_mats);
     p.ws_stat = (float*)(ws + w.o_stat);
+    p.ws_clipcnt = (unsigned*)(ws + w.o_clipcnt);
+    if (w.fused) {
+        p.ws_F = (float*)(ws + w.o_F); p.ws_G = (float*)(ws + w.o_G);
+        p.ws_dF = (float*)(ws + w.o_dF); p.ws_dG = (float*)(ws + w.o_dG);
+        p.ws_s12 = (float*)(ws + w.o_s12); p.ws_s21 = (float*)(ws + w.o_s21);
+        p.ws_invn = (float*)(ws + w.o_invn); p.ws_nrm = (float*)(ws + w.o_nrm);
+        p.ws_dqa = (float*)(ws + w.o_dqa); p.ws_dqb = (float*)(ws + w.o_dqb);
+    }
     return w.fused ? launch_walk_fused(p, stream) : launch_walk_general(p, stream);
 }

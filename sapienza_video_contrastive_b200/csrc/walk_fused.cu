@@ -1,73 +1,155 @@
-// walk_fused.cu - one CTA per clip: the whole contrastive random walk of code/model.py:366-413, forward and
-// backward, with every N x N transition matrix resident in shared memory.
+// walk_fused.cu - the contrastive random walk of code/model.py:366-413, forward and backward, for clips whose N x N
+// transition matrices fit in shared memory (N <= 64; patch graphs: N = 49).
 //
-//   phase 0  L2-normalise node vectors (model.py:118), write q
-//   phase 1  per frame pair i: A_i = Q_i Q_{i+1}^T (model.py:68), edge dropout (model.py:81, incl. the
-//            in-place union mask of SURVEY F4 and the transposed draw layout of F6), ZeroSoftmax / softmax rows
-//            (utils/__init__.py:418-422) in both directions -> F_i (A12) and G_i (A21)
-//   phase 2  prefix / suffix chains P_j = P_{j-1} X_j, S_j = Y_j S_{j-1}  (model.py:376-380 re-associated)
-//   phase 3  per walk j = T-2..1: W_j = P_j S_j, log-diagonal cross-entropy + argmax accuracy (model.py:395-397),
-//            dW_j, reverse accumulation through the chains, ZeroSoftmax backward, dQ, and finally the
-//            normalisation backward -> grad_feats
+// Three launches, every matrix staged in shared memory inside each, exchanged through the L2-resident workspace:
 //
-// Raw affinities and the dropout codes of each pair go to a small per-clip global workspace (L2 resident)
-// because they are only re-read once, elementwise, in the backward.  Used when the clip fits in 227 KB of
-// shared memory (N <= ~60 at T = 4); larger clips take the multi-kernel path in walk_general.cu.
+//   walk_pairs_fwd   one CTA per (clip, frame pair): L2-normalise the two frames (model.py:118) while staging them,
+//                    A_i = Q_i Q_{i+1}^T (model.py:68), edge dropout codes (model.py:81, in-place union mask F4,
+//                    transposed draw layout F6; in-kernel Philox replay or supplied uniforms), ZeroSoftmax / softmax
+//                    rows in both directions -> F_i (A12), G_i (A21)                       [B*(T-1) CTAs]
+//   walk_chain       one CTA per clip: prefix / suffix chains P_j = P_{j-1} X_j, S_j = Y_j S_{j-1} (model.py:376-380
+//                    re-associated, 3(T-2) products), W_j = P_j S_j, log-diagonal cross-entropy + argmax accuracy
+//                    (model.py:395-397), dW_j and the reverse sweep -> dF_i, dG_i            [B CTAs]
+//   walk_pairs_bwd   one CTA per (clip, pair): transition-matrix backward -> dA_i, dQ_i += dA Q_{i+1},
+//                    dQ_{i+1} += dA^T Q_i; the last CTA of a clip applies the normalisation backward  [B*(T-1) CTAs]
+//
+// The sequential part (the chain) is the only one left on a single SM per clip; the two pair kernels spread the
+// K = 128 contractions over (T-1) times more SMs.  All small products use 128-bit shared-memory operand loads.
 #include "walk.cuh"
 
 namespace crw {
 
 constexpr int kFusedThreads = 512;
+constexpr int NW = kFusedThreads / 32;
 
-// ---- small dense products on shared-memory matrices --------------------------------------------------------
-// C[r][c] (+)= sum_k A(r,k) * B(k,c), 0 <= r,c,k < N.  A(r,k) = A[r*ars + k*aks], B(k,c) = B[k*bks + c*bcs],
-// C row-major with stride NP.  Work is split over `nthr` threads (tid in [0,nthr)); each owns a TM x TN set of
-// outputs with STRIDED rows/columns so neighbouring lanes touch neighbouring columns (bank-conflict free for
-// row-major B, broadcast for A).
-template <int TM, int TN>
-__device__ __forceinline__ void mm_smem(float* C, int NP, const float* A, int ars, int aks, const float* B, int bks,
-                                        int bcs, int N, bool accumulate, int tid, int nthr) {
-    const int RS = (N + TM - 1) / TM, CS = (N + TN - 1) / TN;
-    for (int t = tid; t < RS * CS; t += nthr) {
-        const int tr = t / CS, tc = t - tr * CS;
-        int ro[TM], co[TN];
-#pragma unroll
-        for (int i = 0; i < TM; ++i) ro[i] = min(tr + i * RS, N - 1) * ars;
-#pragma unroll
-        for (int j = 0; j < TN; ++j) co[j] = min(tc + j * CS, N - 1) * bcs;
-        float acc[TM][TN];
+// ---- small dense products on shared-memory matrices (row stride NP, NP % 4 == 0, (NP/4) odd) ------------------------
+enum MmMode { MM_NN = 0, MM_NT = 1, MM_TN = 2 };
+
+// C[r*ldc + c] (+)= sum_k opA(r,k) * opB(k,c)   for 0 <= r,c,k < N
+//   MM_NN: A[r][k] B[k][c]      MM_NT: A[r][k] B[c][k]      MM_TN: A[k][r] B[k][c]
+// A and B live in shared memory (stride NP); C may be shared or global (stride ldc).  Each thread owns a TM x 4 block.
+template <int MODE, int TM>
+__device__ __forceinline__ void mm4(float* C, int ldc, const float* A, const float* B, int N, int NP, bool accumulate,
+                                    int tid, int nthr) {
+    const int RT = (N + TM - 1) / TM, CT = (N + 3) / 4;
+    for (int t = tid; t < RT * CT; t += nthr) {
+        const int tr = t / CT, tc = t - tr * CT;
+        float acc[TM][4];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < N; ++k) {
-            float a[TM], b[TN];
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        int rr[TM], cc[4];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = A[ro[i] + k * aks];
+        for (int i = 0; i < TM; ++i) rr[i] = tr * TM + i;
+        if (MODE == MM_NT) {
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = B[k * bks + co[j]];
+            for (int j = 0; j < 4; ++j) cc[j] = tc + j * CT;      // strided columns: neighbouring lanes read neighbouring rows of B
+        } else {
 #pragma unroll
-            for (int i = 0; i < TM; ++i)
+            for (int j = 0; j < 4; ++j) cc[j] = tc * 4 + j;
+        }
+        if (MODE == MM_TN) {
+            const float* ap = A + tr * TM;
+            const float* bp = B + tc * 4;
+#pragma unroll 4
+            for (int k = 0; k < N; ++k) {
+                float av[4];
+                if (TM == 4) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(ap + k * NP);
+                    av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+                } else {
+                    const float2 a2 = *reinterpret_cast<const float2*>(ap + k * NP);
+                    av[0] = a2.x; av[1] = a2.y; av[2] = 0.f; av[3] = 0.f;
+                }
+                const float4 b4 = *reinterpret_cast<const float4*>(bp + k * NP);
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int i = 0; i < TM; ++i) {
+                    acc[i][0] = fmaf(av[i], b4.x, acc[i][0]);
+                    acc[i][1] = fmaf(av[i], b4.y, acc[i][1]);
+                    acc[i][2] = fmaf(av[i], b4.z, acc[i][2]);
+                    acc[i][3] = fmaf(av[i], b4.w, acc[i][3]);
+                }
+            }
+        } else {
+            const float* arow[TM];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) arow[i] = A + min(rr[i], N - 1) * NP;
+            const int K4 = N >> 2;
+            if (MODE == MM_NN) {
+                const float* bp = B + tc * 4;
+                for (int k4 = 0; k4 < K4; ++k4) {
+                    float4 a4[TM];
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) a4[i] = *reinterpret_cast<const float4*>(arow[i] + k4 * 4);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bp + (k4 * 4 + kk) * NP);
+#pragma unroll
+                        for (int i = 0; i < TM; ++i) {
+                            const float a = kk == 0 ? a4[i].x : kk == 1 ? a4[i].y : kk == 2 ? a4[i].z : a4[i].w;
+                            acc[i][0] = fmaf(a, b4.x, acc[i][0]);
+                            acc[i][1] = fmaf(a, b4.y, acc[i][1]);
+                            acc[i][2] = fmaf(a, b4.z, acc[i][2]);
+                            acc[i][3] = fmaf(a, b4.w, acc[i][3]);
+                        }
+                    }
+                }
+                for (int k = K4 * 4; k < N; ++k) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bp + k * NP);
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        const float a = arow[i][k];
+                        acc[i][0] = fmaf(a, b4.x, acc[i][0]);
+                        acc[i][1] = fmaf(a, b4.y, acc[i][1]);
+                        acc[i][2] = fmaf(a, b4.z, acc[i][2]);
+                        acc[i][3] = fmaf(a, b4.w, acc[i][3]);
+                    }
+                }
+            } else {   // MM_NT
+                const float* brow[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) brow[j] = B + min(cc[j], N - 1) * NP;
+                for (int k4 = 0; k4 < K4; ++k4) {
+                    float4 a4[TM], b4[4];
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) a4[i] = *reinterpret_cast<const float4*>(arow[i] + k4 * 4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4*>(brow[j] + k4 * 4);
+#pragma unroll
+                    for (int i = 0; i < TM; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float s = acc[i][j];
+                            s = fmaf(a4[i].x, b4[j].x, s);
+                            s = fmaf(a4[i].y, b4[j].y, s);
+                            s = fmaf(a4[i].z, b4[j].z, s);
+                            s = fmaf(a4[i].w, b4[j].w, s);
+                            acc[i][j] = s;
+                        }
+                }
+                for (int k = K4 * 4; k < N; ++k) {
+#pragma unroll
+                    for (int i = 0; i < TM; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(arow[i][k], brow[j][k], acc[i][j]);
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-            const int r = tr + i * RS;
-            if (r >= N) continue;
+            if (rr[i] >= N) continue;
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int c = tc + j * CS;
-                if (c >= N) continue;
-                float* p = C + r * NP + c;
+            for (int j = 0; j < 4; ++j) {
+                if (cc[j] >= N) continue;
+                float* p = C + rr[i] * ldc + cc[j];
                 *p = accumulate ? (*p + acc[i][j]) : acc[i][j];
             }
         }
     }
 }
 
-// A_i = Qa Qb^T with rows staged in shared memory (stride DP floats, DP/4 odd, 16-byte aligned), K = D.
+// A = Qa Qb^T with rows staged in shared memory (stride DP floats, DP/4 odd, 16-byte aligned), K = D.
 __device__ __forceinline__ void affinity_smem(float* C, int NP, const float* Qa, const float* Qb, int DP, int D, int N,
                                               int tid, int nthr) {
     constexpr int TM = 2, TN = 4;
@@ -85,6 +167,7 @@ __device__ __forceinline__ void affinity_smem(float* C, int NP, const float* Qa,
         for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
         for (int k = 0; k < D / 4; ++k) {
             float4 a[TM], b[TN];
 #pragma unroll
@@ -116,253 +199,271 @@ __device__ __forceinline__ void affinity_smem(float* C, int NP, const float* Qa,
     }
 }
 
-// dQ accumulation into the global gradient buffer (row stride gs floats between nodes).
-//   transposed == false: G[n][:] += sum_m Z[n][m] * Q[m][:]
-//   transposed == true : G[m][:] += sum_n Z[n][m] * Q[n][:]
-__device__ __forceinline__ void dq_update(float* G, const float* Q, int64_t gs, const float* Z, int NP, int N, int D,
-                                          bool transposed, int tid, int nthr) {
-    constexpr int TM = 2;
-    const int RS = (N + TM - 1) / TM, CS = D / 4;
-    const int zrs = transposed ? 1 : NP, zks = transposed ? NP : 1;
-    for (int t = tid; t < RS * CS; t += nthr) {
-        const int tr = t / CS, d4 = t - tr * CS;
-        int zo[TM];
-#pragma unroll
-        for (int i = 0; i < TM; ++i) zo[i] = min(tr + i * RS, N - 1) * zrs;
+// O[r][:] = sum_k Zop(r,k) * Q[k][:]   (r < N, D columns), Q staged in smem (stride DP), O global (stride D), overwrite.
+//   transposed == false: Zop(r,k) = Z[r][k]       transposed == true: Zop(r,k) = Z[k][r]
+__device__ __forceinline__ void dq_smem(float* O, const float* Z, int NP, const float* Q, int DP, int N, int D, bool transposed,
+                                        int tid, int nthr) {
+    constexpr int TM = 4;
+    const int RT = (N + TM - 1) / TM, CT = D / 4;
+    for (int t = tid; t < RT * CT; t += nthr) {
+        const int tr = t / CT, d4 = t - tr * CT;
         float4 acc[TM];
 #pragma unroll
         for (int i = 0; i < TM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-        for (int k = 0; k < N; ++k) {
-            const float4 qv = *reinterpret_cast<const float4*>(Q + (int64_t)k * gs + d4 * 4);
+        const float* qp = Q + d4 * 4;
+        if (transposed) {
+            const float* zp = Z + tr * TM;
+#pragma unroll 4
+            for (int k = 0; k < N; ++k) {
+                const float4 z4 = *reinterpret_cast<const float4*>(zp + k * NP);
+                const float4 qv = *reinterpret_cast<const float4*>(qp + k * DP);
+                const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-            for (int i = 0; i < TM; ++i) {
-                const float z = Z[zo[i] + k * zks];
-                acc[i].x = fmaf(z, qv.x, acc[i].x);
-                acc[i].y = fmaf(z, qv.y, acc[i].y);
-                acc[i].z = fmaf(z, qv.z, acc[i].z);
-                acc[i].w = fmaf(z, qv.w, acc[i].w);
+                for (int i = 0; i < TM; ++i) {
+                    acc[i].x = fmaf(zz[i], qv.x, acc[i].x);
+                    acc[i].y = fmaf(zz[i], qv.y, acc[i].y);
+                    acc[i].z = fmaf(zz[i], qv.z, acc[i].z);
+                    acc[i].w = fmaf(zz[i], qv.w, acc[i].w);
+                }
+            }
+        } else {
+            const float* zrow[TM];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) zrow[i] = Z + min(tr * TM + i, N - 1) * NP;
+            const int K4 = N >> 2;
+            for (int k4 = 0; k4 < K4; ++k4) {
+                float4 z4[TM];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) z4[i] = *reinterpret_cast<const float4*>(zrow[i] + k4 * 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 qv = *reinterpret_cast<const float4*>(qp + (k4 * 4 + kk) * DP);
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        const float z = kk == 0 ? z4[i].x : kk == 1 ? z4[i].y : kk == 2 ? z4[i].z : z4[i].w;
+                        acc[i].x = fmaf(z, qv.x, acc[i].x);
+                        acc[i].y = fmaf(z, qv.y, acc[i].y);
+                        acc[i].z = fmaf(z, qv.z, acc[i].z);
+                        acc[i].w = fmaf(z, qv.w, acc[i].w);
+                    }
+                }
+            }
+            for (int k = K4 * 4; k < N; ++k) {
+                const float4 qv = *reinterpret_cast<const float4*>(qp + k * DP);
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const float z = zrow[i][k];
+                    acc[i].x = fmaf(z, qv.x, acc[i].x);
+                    acc[i].y = fmaf(z, qv.y, acc[i].y);
+                    acc[i].z = fmaf(z, qv.z, acc[i].z);
+                    acc[i].w = fmaf(z, qv.w, acc[i].w);
+                }
             }
         }
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-            const int r = tr + i * RS;
-            if (r >= N) continue;
-            float4* p = reinterpret_cast<float4*>(G + (int64_t)r * gs + d4 * 4);
-            float4 o = *p;
-            o.x += acc[i].x; o.y += acc[i].y; o.z += acc[i].z; o.w += acc[i].w;
-            *p = o;
+            const int r = tr * TM + i;
+            if (r < N) *reinterpret_cast<float4*>(O + (int64_t)r * D + d4 * 4) = acc[i];
         }
     }
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams p) {
+// row-stochastic pass over one row held as two values per lane (N <= 64)
+__device__ __forceinline__ float stoch_row(float (&xv)[2], float (&ev)[2], int lane, int N, bool softmax) {
+    float s = 0.f;
+    if (softmax) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) if (lane + 32 * h < N) mx = fmaxf(mx, xv[h]);
+        mx = warp_max(mx);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { ev[h] = (lane + 32 * h < N) ? expf(xv[h] - mx) : 0.f; s += ev[h]; }
+        s = warp_sum(s);
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float E = expf(xv[h]) - 1.0f;
+            ev[h] = (lane + 32 * h < N) ? E * E : 0.f;
+            s += ev[h];
+        }
+        s = warp_sum(s) + kEpsZs;
+    }
+    return s;
+}
+
+__device__ __forceinline__ float4 ld_cg4(const float* p) {
+#ifdef CRW_SIM
+    return *reinterpret_cast<const float4*>(p);
+#else
+    return __ldcg(reinterpret_cast<const float4*>(p));
+#endif
+}
+
+// ---- kernel 1: per (clip, pair) -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_fwd_kernel(WalkParams p) {
     CRW_DYN_SMEM(smem_raw);
     if (p.dev_state) { p.seed = ld_cg64(p.dev_state); p.offset = ld_cg64(p.dev_state + 1); }
     float* smem = reinterpret_cast<float*>(smem_raw);
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kFusedThreads / 32;
     const int N = p.N, T = p.T, D = p.D;
     const FusedLayout L = fused_layout(N, T, D);
     const int NP = L.NP, MS = L.MS, DP = L.DP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / (T - 1), i = blockIdx.x - b * (T - 1);
+    float* Qa = smem;                         // N x DP
+    float* Qb = Qa + N * DP;
+    float* At = Qb + N * DP;                  // N x NP raw affinity
+    unsigned char* codes = reinterpret_cast<unsigned char*>(At + MS);
     const bool softmax = (p.flags & CRW_WALK_SOFTMAX) != 0;
-    const bool flip = (p.flags & CRW_WALK_FLIP) != 0;
     const float tau = p.tau;
-
-    float* Fm = smem + L.off_F;                 // F_i = A12_i, i < T-1
-    float* Gm = smem + L.off_G;                 // G_i = A21_i
-    float* R = smem + L.off_R;                  // phase-dependent region
-    float* s12 = smem + L.off_stat;             // (T-1)*N row denominators of F
-    float* s21 = s12 + (T - 1) * N;             // (T-1)*N row denominators of G
-    float* invn = s21 + (T - 1) * N;            // T*N  1/max(norm,eps)
-    float* nrm = invn + T * N;                  // T*N  norm
-    float* red = nrm + T * N;                   // 2*NW scratch for block reductions
-    unsigned char* codes = reinterpret_cast<unsigned char*>(smem + L.off_codes);   // N*N dropout codes of the current pair
-
-    const int64_t gs = (int64_t)T * D;          // stride between nodes in feats / q / grad
+    const int64_t gs = (int64_t)T * D;
     const float* fb = p.feats + (int64_t)b * N * gs;
     float* qb = p.q + (int64_t)b * N * gs;
-    float* gb = p.grad ? p.grad + (int64_t)b * N * gs : nullptr;
-    float* araw = p.ws_araw + (int64_t)b * (T - 1) * N * N;
-    unsigned char* gcodes = p.ws_codes + (int64_t)b * (T - 1) * N * N;
 
-    // ---- phase 0: normalise --------------------------------------------------------------------------------
-    for (int row = warp; row < N * T; row += NW) {           // row = n*T + t
-        const float* src = fb + (int64_t)row * D;
+    // stage + normalise frames i and i+1; the pair owns frame i (and the last pair also frame T-1)
+    for (int row = warp; row < 2 * N; row += NW) {
+        const int which = row >= N, n = row - which * N, t = i + which;
+        const float* src = fb + (int64_t)n * gs + (int64_t)t * D;
+        float4 v[2];
         float ss = 0.f;
-        for (int d = lane * 4; d < D; d += 128) {
-            const float4 v = *reinterpret_cast<const float4*>(src + d);
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        int c = 0;
+        for (int d = lane * 4; d < D; d += 128, ++c) {
+            v[c] = *reinterpret_cast<const float4*>(src + d);
+            ss += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
         }
         ss = warp_sum(ss);
-        const float nr = sqrtf(ss);
-        const float den = fmaxf(nr, kEpsNorm);
-        for (int d = lane * 4; d < D; d += 128) {
-            float4 v = *reinterpret_cast<const float4*>(src + d);
-            v.x /= den; v.y /= den; v.z /= den; v.w /= den;
-            *reinterpret_cast<float4*>(qb + (int64_t)row * D + d) = v;
-            if (gb) *reinterpret_cast<float4*>(gb + (int64_t)row * D + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float nr = sqrtf(ss), den = fmaxf(nr, kEpsNorm);
+        const bool owner = !which || i == T - 2;
+        float* dst = (which ? Qb : Qa) + n * DP;
+        c = 0;
+        for (int d = lane * 4; d < D; d += 128, ++c) {
+            float4 o = v[c];
+            o.x /= den; o.y /= den; o.z /= den; o.w /= den;
+            *reinterpret_cast<float4*>(dst + d) = o;
+            if (owner) *reinterpret_cast<float4*>(qb + (int64_t)n * gs + (int64_t)t * D + d) = o;
         }
-        if (lane == 0) {
-            const int n = row / T, t = row - n * T;
-            invn[t * N + n] = 1.0f / den;
-            nrm[t * N + n] = nr;
+        if (owner && lane == 0) {
+            p.ws_invn[((int64_t)b * T + t) * N + n] = 1.0f / den;
+            p.ws_nrm[((int64_t)b * T + t) * N + n] = nr;
         }
     }
     __syncthreads();
+    affinity_smem(At, NP, Qa, Qb, DP, D, N, tid, kFusedThreads);
+    __syncthreads();
 
-    // ---- phase 1: affinities -> transition matrices -----------------------------------------------------------
-    {
-        float* At = R;                         // raw affinity of the current pair
-        float* Qs0 = R + MS;                   // staged frames, ping-pong
-        float* Qs1 = Qs0 + N * DP;
-        auto stage = [&](float* dst, int t) {
-            for (int v = tid; v < N * (D / 4); v += kFusedThreads) {
-                const int n = v / (D / 4), d4 = v - n * (D / 4);
-                *reinterpret_cast<float4*>(dst + n * DP + d4 * 4) =
-                    *reinterpret_cast<const float4*>(qb + (int64_t)n * gs + (int64_t)t * D + d4 * 4);
-            }
-        };
-        stage(Qs0, 0);
-        const int64_t numel = (int64_t)p.B * N * N;
-        for (int i = 0; i < T - 1; ++i) {
-            float* Qa = (i & 1) ? Qs1 : Qs0;
-            float* Qb = (i & 1) ? Qs0 : Qs1;
-            stage(Qb, i + 1);
-            __syncthreads();
-            affinity_smem(At, NP, Qa, Qb, DP, D, N, tid, kFusedThreads);
-            __syncthreads();
-            // forward rows (A12): row n over m.  Also produces the dropout codes (bit0: forward draw, bit1: backward draw)
-            float* Fi = Fm + i * MS;
-            float* Gi = Gm + i * MS;
-            for (int n = warp; n < N; n += NW) {
-                float xv[2], ev[2];
-                float mx = -INFINITY;
+    const int64_t pm = ((int64_t)b * (T - 1) + i) * N * N;          // this pair's matrices in the workspace (stride N)
+    float* Fg = p.ws_F + pm;
+    float* Gg = p.ws_G + pm;
+    float* araw = p.ws_araw + pm;
+    unsigned char* gcodes = p.ws_codes + pm;
+    const int64_t numel = (int64_t)p.B * N * N;
+    // forward rows (A12): row n over m; also the dropout codes (bit0 forward draw, bit1 backward draw)
+    for (int n = warp; n < N; n += NW) {
+        float xv[2], ev[2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int m = lane + 32 * h;
-                    xv[h] = 0.f;
-                    if (m < N) {
-                        const float a = At[n * NP + m];
-                        unsigned code = 0;
-                        if (p.rate > 0.f) {
-                            const int64_t e = ((int64_t)b * N + n) * N + m;
-                            float u1, u2;
-                            if (p.u12) {
-                                u1 = p.u12[(int64_t)i * numel + e];
-                                u2 = p.u21p[(int64_t)i * numel + e];
-                            } else {
-                                u1 = torch_uniform(p.seed, p.offset + (uint64_t)p.pinc * i, p.pthreads, (uint64_t)e);
-                                u2 = torch_uniform(p.seed, p.offset + (uint64_t)p.pinc * (T - 1 + i), p.pthreads, (uint64_t)e);
-                            }
-                            code = (u1 < p.rate ? 1u : 0u) | (u2 < p.rate ? 2u : 0u);
-                        }
-                        codes[n * N + m] = (unsigned char)code;
-                        gcodes[(int64_t)i * N * N + n * N + m] = (unsigned char)code;
-                        araw[(int64_t)i * N * N + n * N + m] = a;
-                        xv[h] = ((code & 1u) ? kNegDrop : a) / tau;
-                        mx = fmaxf(mx, xv[h]);
+        for (int h = 0; h < 2; ++h) {
+            const int m = lane + 32 * h;
+            xv[h] = 0.f;
+            if (m < N) {
+                const float a = At[n * NP + m];
+                unsigned code = 0;
+                if (p.rate > 0.f) {
+                    const int64_t e = ((int64_t)b * N + n) * N + m;
+                    float u1, u2;
+                    if (p.u12) {
+                        u1 = p.u12[(int64_t)i * numel + e];
+                        u2 = p.u21p[(int64_t)i * numel + e];
+                    } else {
+                        u1 = torch_uniform(p.seed, p.offset + (uint64_t)p.pinc * i, p.pthreads, (uint64_t)e);
+                        u2 = torch_uniform(p.seed, p.offset + (uint64_t)p.pinc * (T - 1 + i), p.pthreads, (uint64_t)e);
                     }
+                    code = (u1 < p.rate ? 1u : 0u) | (u2 < p.rate ? 2u : 0u);
                 }
-                float s = 0.f;
-                if (softmax) {
-                    mx = warp_max(mx);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) { ev[h] = (lane + 32 * h < N) ? expf(xv[h] - mx) : 0.f; s += ev[h]; }
-                    s = warp_sum(s);
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float E = expf(xv[h]) - 1.0f;
-                        ev[h] = (lane + 32 * h < N) ? E * E : 0.f;
-                        s += ev[h];
-                    }
-                    s = warp_sum(s) + kEpsZs;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) { const int m = lane + 32 * h; if (m < N) Fi[n * NP + m] = ev[h] / s; }
-                if (lane == 0) s12[i * N + n] = s;
-            }
-            __syncthreads();
-            // backward rows (A21): row m of G = column m of A over n, union mask
-            for (int m = warp; m < N; m += NW) {
-                float xv[2], ev[2];
-                float mx = -INFINITY;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int n = lane + 32 * h;
-                    xv[h] = 0.f;
-                    if (n < N) {
-                        const float a = At[n * NP + m];
-                        xv[h] = (codes[n * N + m] ? kNegDrop : a) / tau;
-                        mx = fmaxf(mx, xv[h]);
-                    }
-                }
-                float s = 0.f;
-                if (softmax) {
-                    mx = warp_max(mx);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) { ev[h] = (lane + 32 * h < N) ? expf(xv[h] - mx) : 0.f; s += ev[h]; }
-                    s = warp_sum(s);
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float E = expf(xv[h]) - 1.0f;
-                        ev[h] = (lane + 32 * h < N) ? E * E : 0.f;
-                        s += ev[h];
-                    }
-                    s = warp_sum(s) + kEpsZs;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) { const int n = lane + 32 * h; if (n < N) Gi[m * NP + n] = ev[h] / s; }
-                if (lane == 0) s21[i * N + m] = s;
-            }
-            __syncthreads();
-        }
-    }
-
-    if (T < 3) {
-        if (p.dev_state && tid == 0) {       // still consume the 2(T-1) draws
-            __threadfence();
-            if (atomicAdd(p.ws_counter, 1u) == (unsigned)p.B - 1u) {
-                p.dev_state[1] = p.offset + (uint64_t)p.pinc * 2u * (unsigned)(T - 1);
-                *p.ws_counter = 0u;
+                codes[n * N + m] = (unsigned char)code;
+                gcodes[n * N + m] = (unsigned char)code;
+                araw[n * N + m] = a;
+                xv[h] = ((code & 1u) ? kNegDrop : a) / tau;
             }
         }
-        return;
+        const float s = stoch_row(xv, ev, lane, N, softmax);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { const int m = lane + 32 * h; if (m < N) Fg[n * N + m] = ev[h] / s; }
+        if (lane == 0) p.ws_s12[((int64_t)b * (T - 1) + i) * N + n] = s;
     }
+    __syncthreads();
+    // backward rows (A21): row m of G = column m of A over n, union mask
+    for (int m = warp; m < N; m += NW) {
+        float xv[2], ev[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = lane + 32 * h;
+            xv[h] = 0.f;
+            if (n < N) xv[h] = (codes[n * N + m] ? kNegDrop : At[n * NP + m]) / tau;
+        }
+        const float s = stoch_row(xv, ev, lane, N, softmax);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { const int n = lane + 32 * h; if (n < N) Gg[m * N + n] = ev[h] / s; }
+        if (lane == 0) p.ws_s21[((int64_t)b * (T - 1) + i) * N + m] = s;
+    }
+}
 
-    // ---- phase 2: prefix / suffix chains ---------------------------------------------------------------------
-    // X_i / Y_i: forward / backward lists (swapped by --flip, model.py:380-382)
-    float* Xm = flip ? Gm : Fm;
+__global__ void advance_philox_state_kernel(uint64_t* state, uint64_t inc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) state[1] += inc;
+}
+
+// ---- kernel 2: per clip ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams p) {
+    CRW_DYN_SMEM(smem_raw);
+    float* smem = reinterpret_cast<float*>(smem_raw);
+    const int N = p.N, T = p.T;
+    const FusedLayout L = fused_layout(N, T, p.D);
+    const int NP = L.NP, MS = L.MS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const bool flip = (p.flags & CRW_WALK_FLIP) != 0;
+    float* Fm = smem;                               // (T-1) matrices
+    float* Gm = Fm + (T - 1) * MS;
+    float* Pm = Gm + (T - 1) * MS;                  // P_j at Pm + (j-1)*MS, j = 1..T-2 (P_0 = X_0)
+    float* Sm = Pm + (T - 2) * MS;
+    float* scratch = Sm + (T - 2) * MS;             // 3 matrices
+    float* red = scratch + 3 * MS;                  // 2*NW floats
+
+    // load F_i, G_i (global stride N -> smem stride NP)
+    const int64_t cm = (int64_t)b * (T - 1) * N * N;
+    for (int e = tid; e < (T - 1) * N * N; e += kFusedThreads) {
+        const int i = e / (N * N), r = e - i * N * N;
+        const int n = r / N, m = r - n * N;
+        Fm[i * MS + n * NP + m] = ld_cg(p.ws_F + cm + e);
+        Gm[i * MS + n * NP + m] = ld_cg(p.ws_G + cm + e);
+    }
+    __syncthreads();
+
+    float* Xm = flip ? Gm : Fm;                     // forward / backward lists (swapped by --flip, model.py:380-382)
     float* Ym = flip ? Fm : Gm;
-    float* Pm = R;                               // P_j at Pm + (j-1)*MS, j = 1..T-2   (P_0 = X_0)
-    float* Sm = R + (T - 2) * MS;                // S_j at Sm + (j-1)*MS               (S_0 = Y_0)
-    float* scratch = R + 2 * (T - 2) * MS;       // 3 matrices
+    float* dXg = (flip ? p.ws_dG : p.ws_dF) + cm;   // gradients w.r.t. X_j / Y_j go to the F / G slots they came from
+    float* dYg = (flip ? p.ws_dF : p.ws_dG) + cm;
     auto Pj = [&](int j) { return j == 0 ? Xm : Pm + (j - 1) * MS; };
     auto Sj = [&](int j) { return j == 0 ? Ym : Sm + (j - 1) * MS; };
-    const int grp = tid >> 8, gtid = tid & 255;  // two 256-thread groups run independent products
+    const int grp = tid >> 8, gtid = tid & 255;     // two 256-thread groups run independent products
     for (int j = 1; j <= T - 2; ++j) {
-        if (grp == 0) mm_smem<4, 4>(Pj(j), NP, Pj(j - 1), NP, 1, Xm + j * MS, NP, 1, N, false, gtid, 256);
-        else          mm_smem<4, 4>(Sj(j), NP, Ym + j * MS, NP, 1, Sj(j - 1), NP, 1, N, false, gtid, 256);
+        if (grp == 0) mm4<MM_NN, 4>(Pj(j), NP, Pj(j - 1), Xm + j * MS, N, NP, false, gtid, 256);
+        else          mm4<MM_NN, 4>(Sj(j), NP, Ym + j * MS, Sj(j - 1), N, NP, false, gtid, 256);
         __syncthreads();
     }
 
-    // ---- phase 3: losses and the reverse sweep -------------------------------------------------------------
-    float* freeb[2 * kFusedMaxT + 4];   // grows by two buffers per level (P_j, S_j are recycled)
+    float* freeb[2 * kFusedMaxT + 4];
     int nfree = 0;
     freeb[nfree++] = scratch;
     freeb[nfree++] = scratch + MS;
     freeb[nfree++] = scratch + 2 * MS;
     float* gP = nullptr;
     float* gS = nullptr;
+    const bool need_grad = p.grad != nullptr;
     const float cgrad = 1.0f / ((float)(T - 2) * (float)p.B * (float)N);
     for (int j = T - 2; j >= 0; --j) {
         float* dW = nullptr;
         if (j >= 1) {
             dW = freeb[--nfree];
-            mm_smem<2, 4>(dW, NP, Pj(j), NP, 1, Sj(j), NP, 1, N, false, tid, kFusedThreads);
+            mm4<MM_NN, 2>(dW, NP, Pj(j), Sj(j), N, NP, false, tid, kFusedThreads);
             __syncthreads();
             float lsum = 0.f, asum = 0.f;
             for (int n = warp; n < N; n += NW) {
@@ -386,7 +487,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams
                     const int oi = __shfl_xor_sync(kFull, bi, o);
                     if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                 }
-                const float dg = __shfl_sync(kFull, w[n >> 5], n & 31) + kEpsLog;
+                const float dg = __shfl_sync(kFull, (n >> 5) ? w[1] : w[0], n & 31) + kEpsLog;
                 if (lane == 0) {
                     lsum += logf(rs) - logf(dg);
                     asum += (bi == n) ? 1.f : 0.f;
@@ -406,128 +507,36 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams
                 p.ws_partial[((int64_t)b * (T - 2) + (j - 1)) * 2 + 0] = l;
                 p.ws_partial[((int64_t)b * (T - 2) + (j - 1)) * 2 + 1] = a;
             }
-            if (!gb) { freeb[nfree++] = dW; __syncthreads(); continue; }
+            if (!need_grad) { freeb[nfree++] = dW; __syncthreads(); continue; }
         }
-        if (!gb) continue;
-        // gP_j = dW_j S_j^T + gP_{j+1} X_{j+1}^T ;  gS_j = P_j^T dW_j + Y_{j+1}^T gS_{j+1}
-        float* nP = freeb[--nfree];
-        float* nS = freeb[--nfree];
+        if (!need_grad) continue;
+        // gP_j = dW_j S_j^T + gP_{j+1} X_{j+1}^T ;  gS_j = P_j^T dW_j + Y_{j+1}^T gS_{j+1}.  For j = 0 these ARE dX_0 / dY_0.
+        float* nP = j == 0 ? dXg : freeb[--nfree];
+        float* nS = j == 0 ? dYg : freeb[--nfree];
+        const int ld = j == 0 ? N : NP;
         if (grp == 0) {
-            if (dW) mm_smem<4, 4>(nP, NP, dW, NP, 1, Sj(j), 1, NP, N, false, gtid, 256);
-            if (gP) mm_smem<4, 4>(nP, NP, gP, NP, 1, Xm + (j + 1) * MS, 1, NP, N, dW != nullptr, gtid, 256);
+            if (dW) mm4<MM_NT, 4>(nP, ld, dW, Sj(j), N, NP, false, gtid, 256);
+            if (gP) mm4<MM_NT, 4>(nP, ld, gP, Xm + (j + 1) * MS, N, NP, dW != nullptr, gtid, 256);
         } else {
-            if (dW) mm_smem<4, 4>(nS, NP, Pj(j), 1, NP, dW, NP, 1, N, false, gtid, 256);
-            if (gS) mm_smem<4, 4>(nS, NP, Ym + (j + 1) * MS, 1, NP, gS, NP, 1, N, dW != nullptr, gtid, 256);
+            if (dW) mm4<MM_TN, 4>(nS, ld, Pj(j), dW, N, NP, false, gtid, 256);
+            if (gS) mm4<MM_TN, 4>(nS, ld, Ym + (j + 1) * MS, gS, N, NP, dW != nullptr, gtid, 256);
         }
         __syncthreads();
+        if (j == 0) break;
         if (dW) freeb[nfree++] = dW;
         if (gP) freeb[nfree++] = gP;
         if (gS) freeb[nfree++] = gS;
-        if (j >= 1) { freeb[nfree++] = Pj(j); freeb[nfree++] = Sj(j); }
+        freeb[nfree++] = Pj(j);
+        freeb[nfree++] = Sj(j);
         gP = nP;
         gS = nS;
-        // dX_j = P_{j-1}^T gP_j ; dY_j = gS_j S_{j-1}^T   (j = 0: dX_0 = gP_0, dY_0 = gS_0)
-        float* dX = gP;
-        float* dY = gS;
-        if (j >= 1) {
-            dX = freeb[--nfree];
-            dY = freeb[--nfree];
-            if (grp == 0) mm_smem<4, 4>(dX, NP, Pj(j - 1), 1, NP, gP, NP, 1, N, false, gtid, 256);
-            else          mm_smem<4, 4>(dY, NP, gS, NP, 1, Sj(j - 1), 1, NP, N, false, gtid, 256);
-            __syncthreads();
-        }
-        // transition-matrix backward for pair j -> Z = dA_j
-        float* Z = freeb[--nfree];
-        const float* dF = flip ? dY : dX;
-        const float* dG = flip ? dX : dY;
-        const float* Fi = Fm + j * MS;
-        const float* Gi = Gm + j * MS;
-        const float* ar = araw + (int64_t)j * N * N;
-        const unsigned char* gc = gcodes + (int64_t)j * N * N;
-        for (int n = warp; n < N; n += NW) {
-            float y[2], dy[2];
-            float dot = 0.f;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int m = lane + 32 * h;
-                y[h] = dy[h] = 0.f;
-                if (m < N) { y[h] = Fi[n * NP + m]; dy[h] = dF[n * NP + m]; dot += y[h] * dy[h]; }
-            }
-            dot = warp_sum(dot);
-            const float den = s12[j * N + n];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int m = lane + 32 * h;
-                if (m < N) {
-                    float g = 0.f;
-                    if (!(gc[n * N + m] & 1u)) {
-                        if (softmax) g = y[h] * (dy[h] - dot) / tau;
-                        else { const float E = expf(ar[n * N + m] / tau); g = (dy[h] - dot) / den * (2.0f * (E - 1.0f) * E) / tau; }
-                    }
-                    Z[n * NP + m] = g;
-                }
-            }
-        }
+        // dX_j = P_{j-1}^T gP_j ; dY_j = gS_j S_{j-1}^T  -> straight to the workspace (stride N)
+        if (grp == 0) mm4<MM_TN, 4>(dXg + (int64_t)j * N * N, N, Pj(j - 1), gP, N, NP, false, gtid, 256);
+        else          mm4<MM_NT, 4>(dYg + (int64_t)j * N * N, N, gS, Sj(j - 1), N, NP, false, gtid, 256);
         __syncthreads();
-        for (int m = warp; m < N; m += NW) {
-            float y[2], dy[2];
-            float dot = 0.f;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int n = lane + 32 * h;
-                y[h] = dy[h] = 0.f;
-                if (n < N) { y[h] = Gi[m * NP + n]; dy[h] = dG[m * NP + n]; dot += y[h] * dy[h]; }
-            }
-            dot = warp_sum(dot);
-            const float den = s21[j * N + m];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int n = lane + 32 * h;
-                if (n < N && !gc[n * N + m]) {
-                    float g;
-                    if (softmax) g = y[h] * (dy[h] - dot) / tau;
-                    else { const float E = expf(ar[n * N + m] / tau); g = (dy[h] - dot) / den * (2.0f * (E - 1.0f) * E) / tau; }
-                    Z[n * NP + m] += g;
-                }
-            }
-        }
-        __syncthreads();
-        // dQ_j += Z Q_{j+1} ; dQ_{j+1} += Z^T Q_j
-        dq_update(gb + (int64_t)j * D, qb + (int64_t)(j + 1) * D, gs, Z, NP, N, D, false, tid, kFusedThreads);
-        dq_update(gb + (int64_t)(j + 1) * D, qb + (int64_t)j * D, gs, Z, NP, N, D, true, tid, kFusedThreads);
-        __syncthreads();
-        freeb[nfree++] = Z;
-        if (j >= 1) { freeb[nfree++] = dX; freeb[nfree++] = dY; }
     }
 
-    // ---- normalisation backward: df = (dq - q (q . dq)) / max(|f|, eps) --------------------------------------
-    if (gb) {
-        for (int row = warp; row < N * T; row += NW) {
-            const int n = row / T, t = row - n * T;
-            float4 qv[2], gv[2];
-            float dot = 0.f;
-            int c = 0;
-            for (int d = lane * 4; d < D; d += 128, ++c) {
-                qv[c] = *reinterpret_cast<const float4*>(qb + (int64_t)row * D + d);
-                gv[c] = *reinterpret_cast<const float4*>(gb + (int64_t)row * D + d);
-                dot += qv[c].x * gv[c].x + qv[c].y * gv[c].y + qv[c].z * gv[c].z + qv[c].w * gv[c].w;
-            }
-            dot = warp_sum(dot);
-            const float in = invn[t * N + n];
-            if (!(nrm[t * N + n] > kEpsNorm)) dot = 0.f;       // clamp active: q = f / eps, no projection term
-            c = 0;
-            for (int d = lane * 4; d < D; d += 128, ++c) {
-                float4 o;
-                o.x = (gv[c].x - qv[c].x * dot) * in;
-                o.y = (gv[c].y - qv[c].y * dot) * in;
-                o.z = (gv[c].z - qv[c].z * dot) * in;
-                o.w = (gv[c].w - qv[c].w * dot) * in;
-                *reinterpret_cast<float4*>(gb + (int64_t)row * D + d) = o;
-            }
-        }
-    }
-
-    // ---- cross-clip reduction of the per-clip sums by the last CTA to finish, in clip order (deterministic) ---
+    // cross-clip reduction of the per-clip sums by the last CTA to finish, in clip order (deterministic)
     if (tid == 0) {
         __threadfence();
         const unsigned ticket = atomicAdd(p.ws_counter, 1u);
@@ -543,18 +552,177 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_fused_kernel(WalkParams
                 p.xent[j] = l * inv;
                 p.acc[j] = a * inv;
             }
-            if (p.dev_state) p.dev_state[1] = p.offset + (uint64_t)p.pinc * 2u * (unsigned)(T - 1);
             *p.ws_counter = 0u;
         }
     }
 }
 
+// ---- kernel 3: per (clip, pair) ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkParams p) {
+    CRW_DYN_SMEM(smem_raw);
+    float* smem = reinterpret_cast<float*>(smem_raw);
+    const int N = p.N, T = p.T, D = p.D;
+    const FusedLayout L = fused_layout(N, T, D);
+    const int NP = L.NP, MS = L.MS, DP = L.DP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / (T - 1), i = blockIdx.x - b * (T - 1);
+    float* Qa = smem;
+    float* Qb = Qa + N * DP;
+    float* Z = Qb + N * DP;                   // N x NP: dA
+    float* Ar = Z + MS;                       // N x NP: raw affinity
+    unsigned char* codes = reinterpret_cast<unsigned char*>(Ar + MS);
+    unsigned* s_last = reinterpret_cast<unsigned*>(codes + ((N * N + 15) & ~15));
+    const bool softmax = (p.flags & CRW_WALK_SOFTMAX) != 0;
+    const float tau = p.tau;
+    const int64_t gs = (int64_t)T * D;
+    const float* qb = p.q + (int64_t)b * N * gs;
+    const int64_t pm = ((int64_t)b * (T - 1) + i) * N * N;
+
+    for (int v = tid; v < 2 * N * (D / 4); v += kFusedThreads) {
+        const int which = v >= N * (D / 4), r = v - which * N * (D / 4);
+        const int n = r / (D / 4), d4 = r - n * (D / 4);
+        *reinterpret_cast<float4*>((which ? Qb : Qa) + n * DP + d4 * 4) =
+            ld_cg4(qb + (int64_t)n * gs + (int64_t)(i + which) * D + d4 * 4);
+    }
+    for (int e = tid; e < N * N; e += kFusedThreads) {
+        const int n = e / N, m = e - n * N;
+        Ar[n * NP + m] = ld_cg(p.ws_araw + pm + e);
+        codes[e] = p.ws_codes[pm + e];
+    }
+    __syncthreads();
+    const float* Fg = p.ws_F + pm;
+    const float* Gg = p.ws_G + pm;
+    const float* dF = p.ws_dF + pm;
+    const float* dG = p.ws_dG + pm;
+    // rows of F: Z[n][m] = d loss / d A[n][m] through the forward matrix
+    for (int n = warp; n < N; n += NW) {
+        float y[2], dy[2];
+        float dot = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = lane + 32 * h;
+            y[h] = dy[h] = 0.f;
+            if (m < N) { y[h] = ld_cg(Fg + n * N + m); dy[h] = ld_cg(dF + n * N + m); dot += y[h] * dy[h]; }
+        }
+        dot = warp_sum(dot);
+        const float den = ld_cg(p.ws_s12 + ((int64_t)b * (T - 1) + i) * N + n);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = lane + 32 * h;
+            if (m < N) {
+                float g = 0.f;
+                if (!(codes[n * N + m] & 1u)) {
+                    if (softmax) g = y[h] * (dy[h] - dot) / tau;
+                    else { const float E = expf(Ar[n * NP + m] / tau); g = (dy[h] - dot) / den * (2.0f * (E - 1.0f) * E) / tau; }
+                }
+                Z[n * NP + m] = g;
+            }
+        }
+    }
+    __syncthreads();
+    // rows of G (columns of A): Z[n][m] += contribution through the backward matrix
+    for (int m = warp; m < N; m += NW) {
+        float y[2], dy[2];
+        float dot = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = lane + 32 * h;
+            y[h] = dy[h] = 0.f;
+            if (n < N) { y[h] = ld_cg(Gg + m * N + n); dy[h] = ld_cg(dG + m * N + n); dot += y[h] * dy[h]; }
+        }
+        dot = warp_sum(dot);
+        const float den = ld_cg(p.ws_s21 + ((int64_t)b * (T - 1) + i) * N + m);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = lane + 32 * h;
+            if (n < N && !codes[n * N + m]) {
+                float g;
+                if (softmax) g = y[h] * (dy[h] - dot) / tau;
+                else { const float E = expf(Ar[n * NP + m] / tau); g = (dy[h] - dot) / den * (2.0f * (E - 1.0f) * E) / tau; }
+                Z[n * NP + m] += g;
+            }
+        }
+    }
+    __syncthreads();
+    // dQ_i (from this pair) = Z Q_{i+1} ; dQ_{i+1} (from this pair) = Z^T Q_i
+    float* dqa = p.ws_dqa + ((int64_t)b * (T - 1) + i) * N * D;
+    float* dqb = p.ws_dqb + ((int64_t)b * (T - 1) + i) * N * D;
+    dq_smem(dqa, Z, NP, Qb, DP, N, D, false, tid, kFusedThreads);
+    dq_smem(dqb, Z, NP, Qa, DP, N, D, true, tid, kFusedThreads);
+
+    // the last pair of this clip to finish applies the normalisation backward: df = (dq - q (q.dq)) / max(|f|, eps)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(p.ws_clipcnt + b, 1u);
+        *s_last = (t == (unsigned)(T - 2)) ? 1u : 0u;
+        if (*s_last) p.ws_clipcnt[b] = 0u;
+    }
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    float* gb = p.grad + (int64_t)b * N * gs;
+    for (int row = warp; row < N * T; row += NW) {
+        const int n = row / T, t = row - n * T;
+        float4 qv[2], gv[2];
+        float dot = 0.f;
+        int c = 0;
+        for (int d = lane * 4; d < D; d += 128, ++c) {
+            qv[c] = ld_cg4(qb + (int64_t)row * D + d);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < T - 1) {
+                const float4 a = ld_cg4(p.ws_dqa + (((int64_t)b * (T - 1) + t) * N + n) * D + d);
+                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            }
+            if (t > 0) {
+                const float4 a = ld_cg4(p.ws_dqb + (((int64_t)b * (T - 1) + t - 1) * N + n) * D + d);
+                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            }
+            gv[c] = g;
+            dot += qv[c].x * g.x + qv[c].y * g.y + qv[c].z * g.z + qv[c].w * g.w;
+        }
+        dot = warp_sum(dot);
+        const float in = ld_cg(p.ws_invn + ((int64_t)b * T + t) * N + n);
+        if (!(ld_cg(p.ws_nrm + ((int64_t)b * T + t) * N + n) > kEpsNorm)) dot = 0.f;      // clamp active: q = f / eps
+        c = 0;
+        for (int d = lane * 4; d < D; d += 128, ++c) {
+            float4 o;
+            o.x = (gv[c].x - qv[c].x * dot) * in;
+            o.y = (gv[c].y - qv[c].y * dot) * in;
+            o.z = (gv[c].z - qv[c].z * dot) * in;
+            o.w = (gv[c].w - qv[c].w * dot) * in;
+            *reinterpret_cast<float4*>(gb + (int64_t)row * D + d) = o;
+        }
+    }
+}
+
+int launch_l2norm_rows(const float* f, float* q, float* invn, float* nrm, int64_t rows, int D, crw_stream_t stream);
+
 int launch_walk_fused(const WalkParams& p, crw_stream_t stream) {
     const FusedLayout L = fused_layout(p.N, p.T, p.D);
-    auto k = walk_fused_kernel;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes);
-    CRW_LAUNCH(k, p.B, kFusedThreads, L.bytes, stream, p);
-    return check_launch("walk_fused");
+    const int T = p.T;
+    if (T < 2)   // a single frame: only the normalisation exists
+        return launch_l2norm_rows(p.feats, p.q, p.ws_invn, p.ws_nrm, (int64_t)p.B * p.N, p.D, stream);
+    auto k1 = walk_pairs_fwd_kernel;
+    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.pair_bytes);
+    CRW_LAUNCH(k1, p.B * (T - 1), kFusedThreads, L.pair_bytes, stream, p);
+    int e = check_launch("walk_pairs_fwd");
+    if (e != CRW_OK) return e;
+    if (p.dev_state && p.rate > 0.f && !p.u12) {     // every pair has read the device-resident Philox state: advance it
+        CRW_LAUNCH(advance_philox_state_kernel, 1, 32, 0, stream, p.dev_state, (uint64_t)p.pinc * 2u * (unsigned)(T - 1));
+        e = check_launch("advance_philox_state");
+        if (e != CRW_OK) return e;
+    }
+    if (T < 3) return CRW_OK;
+    auto k2 = walk_chain_kernel;
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.chain_bytes);
+    CRW_LAUNCH(k2, p.B, kFusedThreads, L.chain_bytes, stream, p);
+    e = check_launch("walk_chain");
+    if (e != CRW_OK || !p.grad) return e;
+    auto k3 = walk_pairs_bwd_kernel;
+    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.pairb_bytes);
+    CRW_LAUNCH(k3, p.B * (T - 1), kFusedThreads, L.pairb_bytes, stream, p);
+    return check_launch("walk_pairs_bwd");
 }
 
 }  // namespace crw

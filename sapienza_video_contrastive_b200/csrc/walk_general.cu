@@ -303,6 +303,14 @@ __global__ void __launch_bounds__(256) stoch_bwd_rows_kernel(float* __restrict__
     }
 }
 
+static int rows_grid(int64_t rows);
+
+int launch_l2norm_rows(const float* f, float* q, float* invn, float* nrm, int64_t rows, int D, crw_stream_t stream) {
+    if (rows <= 0) return CRW_OK;
+    CRW_LAUNCH(gnorm_kernel, rows_grid(rows), 256, 0, stream, f, q, invn, nrm, rows, D);
+    return check_launch("l2norm_rows");
+}
+
 static int rows_grid(int64_t rows) {
     int64_t blocks = (rows + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
