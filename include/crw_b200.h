@@ -75,8 +75,8 @@ int crw_stoch_mat(float* A, const float* drop_uniform, float rate, float tempera
  * advances the offset by 2(T-1)*inc when it is done, so a launch captured in a CUDA graph draws fresh dropout
  * masks on every replay (philox_seed / philox_offset are then ignored).
  * The workspace must be zero-filled once after allocation; every call leaves it reusable.
- * Outputs: q (B,N,T,D) unit-norm nodes; xent (T-2) mean cross-entropies and acc (T-2) argmax accuracies
- * of walks i = 1..T-2; grad_feats (B,N,T,D) = d(sum_i xent_i / max(1,T-2)) / d feats, or NULL
+ * Outputs: q (B,N,T,D) unit-norm nodes; xent (T-2 + 1): mean cross-entropies of walks i = 1..T-2
+ * followed by their mean, i.e. the loss of model.py:413 (T < 3: untouched); acc (T-2) argmax accuracies; grad_feats (B,N,T,D) = d(sum_i xent_i / max(1,T-2)) / d feats, or NULL
  * to skip the backward. */
 size_t crw_walk_workspace_bytes(int B, int N, int T, int D, unsigned flags);
 int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,

@@ -86,8 +86,11 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 // step (e/threads)/4.  (ATen/native/cuda/DistributionTemplates.h; curand_uniform4 then maps u32 -> (0,1]
 // and torch folds 1.0 back to 0.)
 __host__ __device__ __forceinline__ float torch_uniform(uint64_t seed, uint64_t offset, uint32_t threads, uint64_t e) {
-    const uint64_t idx = e % threads;
-    const uint64_t k = e / threads;
+    uint64_t idx = e, k = 0;
+    if (e >= threads) {                    // (the common case e < threads avoids the 64-bit division)
+        if (e < 0xffffffffull) { idx = (uint32_t)e % threads; k = (uint32_t)e / threads; }
+        else { idx = e % threads; k = e / threads; }
+    }
     const uint64_t ctr = (offset >> 2) + (k >> 2);
     const Philox4 r = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)idx, (uint32_t)(idx >> 32),
                                     (uint32_t)seed, (uint32_t)(seed >> 32));

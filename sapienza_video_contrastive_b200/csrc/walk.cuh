@@ -30,7 +30,7 @@ struct WalkParams {
     float *ws_s12, *ws_s21;                    // (B,T-1,N) row denominators
     float *ws_invn, *ws_nrm;                   // (B,T,N)
     float *ws_dqa, *ws_dqb;                    // (B,T-1,N,D) per-pair contributions to dQ_i / dQ_{i+1}
-    unsigned* ws_clipcnt;                      // (B) tickets of the pair-backward CTAs (zero between launches)
+    unsigned* ws_clipcnt;                      // (B,T) per-frame tickets of the pair-backward CTAs (zero between launches)
 };
 
 struct FusedLayout {
@@ -50,7 +50,7 @@ __host__ __device__ __forceinline__ FusedLayout fused_layout(int N, int T, int D
     const size_t codes = (size_t)((N * N + 15) & ~15);
     L.pair_bytes = sizeof(float) * ((size_t)2 * N * L.DP + L.MS) + codes;
     const int nm = 2 * (T - 1) + (T >= 3 ? 2 * (T - 2) + 3 : 0);
-    L.chain_bytes = sizeof(float) * ((size_t)nm * L.MS + 64);
+    L.chain_bytes = sizeof(float) * ((size_t)nm * L.MS + 64);     // + reduction scratch (32) + mbarrier
     L.pairb_bytes = sizeof(float) * ((size_t)2 * N * L.DP + 2 * L.MS) + codes + 16;
     return L;
 }

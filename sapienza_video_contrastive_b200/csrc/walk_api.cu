@@ -18,11 +18,11 @@ WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
     WsLayout w{};
     w.fused = !(flags & CRW_WALK_FORCE_GENERAL) && fused_fits(N, T, D);
     const size_t t1 = T > 1 ? T - 1 : 0, t2 = T >= 3 ? T - 2 : 0;
-    const size_t mat = sizeof(float) * B * t1 * N * N;
+    const size_t mat = sizeof(float) * B * t1 * (size_t)fused_layout(N, T, D).MS;     // fused path: row stride NP
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     w.o_counter = take(256);
-    w.o_clipcnt = take(sizeof(unsigned) * B);                  // zero-initialised region ends here (see crw_b200.h)
+    w.o_clipcnt = take(sizeof(unsigned) * B * T);                  // zero-initialised region ends here (see crw_b200.h)
     w.o_partial = take(sizeof(float) * B * t2 * 2);
     w.o_araw = take(w.fused ? mat : 0);
     w.o_codes = take((size_t)B * t1 * N * N * (w.fused ? 1 : 2));

@@ -23,224 +23,191 @@ constexpr int kFusedThreads = 512;
 constexpr int NW = kFusedThreads / 32;
 
 // ---- small dense products on shared-memory matrices (row stride NP, NP % 4 == 0, (NP/4) odd) ------------------------
-enum MmMode { MM_NN = 0, MM_NT = 1, MM_TN = 2 };
+// "Warp-row" mapping: a warp owns TMW = ceil(N / nw) consecutive output rows, a lane owns two output columns.  The A
+// operand of a row is then the same address for all 32 lanes (one broadcast wavefront per 128-bit load) and the B
+// operand is a contiguous, conflict-free sweep, which keeps these N ~ 49 products FMA-issue bound instead of
+// shared-memory-bandwidth bound (a 4x4 register tile per thread needs ~2x the wavefronts per FMA).
+// C may live in shared or global memory (row stride ldc).  Warps whose rows fall outside N simply return.
+#define CRW_COMP4(v, kk) ((kk) == 0 ? (v).x : (kk) == 1 ? (v).y : (kk) == 2 ? (v).z : (v).w)
 
-// C[r*ldc + c] (+)= sum_k opA(r,k) * opB(k,c)   for 0 <= r,c,k < N
-//   MM_NN: A[r][k] B[k][c]      MM_NT: A[r][k] B[c][k]      MM_TN: A[k][r] B[k][c]
-// A and B live in shared memory (stride NP); C may be shared or global (stride ldc).  Each thread owns a TM x 4 block.
-template <int MODE, int TM>
-__device__ __forceinline__ void mm4(float* C, int ldc, const float* A, const float* B, int N, int NP, bool accumulate,
-                                    int tid, int nthr) {
-    const int RT = (N + TM - 1) / TM, CT = (N + 3) / 4;
-    for (int t = tid; t < RT * CT; t += nthr) {
-        const int tr = t / CT, tc = t - tr * CT;
-        float acc[TM][4];
+// C[r][c] (+)= sum_k A[r][k] B[k][c]
+template <int TMAX>
+__device__ __forceinline__ void wr_nn(float* C, int ldc, const float* A, const float* B, int N, int NP, bool accumulate,
+                                      int w, int nw, int lane) {
+    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    if (r0 >= N) return;
+    const int c0 = min(2 * lane, NP - 2);
+    float acc[TMAX][2];
+    const float* arow[TMAX];
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+    for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = 0.f; arow[i] = A + min(r0 + i, N - 1) * NP; }
+    const float* bp = B + c0;
+    const int K4 = N >> 2;
+    for (int k4 = 0; k4 < K4; ++k4) {
+        float4 a4[TMAX];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        int rr[TM], cc[4];
+        for (int i = 0; i < TMAX; ++i) a4[i] = *reinterpret_cast<const float4*>(arow[i] + k4 * 4);
 #pragma unroll
-        for (int i = 0; i < TM; ++i) rr[i] = tr * TM + i;
-        if (MODE == MM_NT) {
+        for (int kk = 0; kk < 4; ++kk) {
+            const float2 b2 = *reinterpret_cast<const float2*>(bp + (k4 * 4 + kk) * NP);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cc[j] = tc + j * CT;      // strided columns: neighbouring lanes read neighbouring rows of B
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cc[j] = tc * 4 + j;
-        }
-        if (MODE == MM_TN) {
-            const float* ap = A + tr * TM;
-            const float* bp = B + tc * 4;
-#pragma unroll 4
-            for (int k = 0; k < N; ++k) {
-                float av[4];
-                if (TM == 4) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(ap + k * NP);
-                    av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-                } else {
-                    const float2 a2 = *reinterpret_cast<const float2*>(ap + k * NP);
-                    av[0] = a2.x; av[1] = a2.y; av[2] = 0.f; av[3] = 0.f;
-                }
-                const float4 b4 = *reinterpret_cast<const float4*>(bp + k * NP);
-#pragma unroll
-                for (int i = 0; i < TM; ++i) {
-                    acc[i][0] = fmaf(av[i], b4.x, acc[i][0]);
-                    acc[i][1] = fmaf(av[i], b4.y, acc[i][1]);
-                    acc[i][2] = fmaf(av[i], b4.z, acc[i][2]);
-                    acc[i][3] = fmaf(av[i], b4.w, acc[i][3]);
-                }
-            }
-        } else {
-            const float* arow[TM];
-#pragma unroll
-            for (int i = 0; i < TM; ++i) arow[i] = A + min(rr[i], N - 1) * NP;
-            const int K4 = N >> 2;
-            if (MODE == MM_NN) {
-                const float* bp = B + tc * 4;
-                for (int k4 = 0; k4 < K4; ++k4) {
-                    float4 a4[TM];
-#pragma unroll
-                    for (int i = 0; i < TM; ++i) a4[i] = *reinterpret_cast<const float4*>(arow[i] + k4 * 4);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bp + (k4 * 4 + kk) * NP);
-#pragma unroll
-                        for (int i = 0; i < TM; ++i) {
-                            const float a = kk == 0 ? a4[i].x : kk == 1 ? a4[i].y : kk == 2 ? a4[i].z : a4[i].w;
-                            acc[i][0] = fmaf(a, b4.x, acc[i][0]);
-                            acc[i][1] = fmaf(a, b4.y, acc[i][1]);
-                            acc[i][2] = fmaf(a, b4.z, acc[i][2]);
-                            acc[i][3] = fmaf(a, b4.w, acc[i][3]);
-                        }
-                    }
-                }
-                for (int k = K4 * 4; k < N; ++k) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bp + k * NP);
-#pragma unroll
-                    for (int i = 0; i < TM; ++i) {
-                        const float a = arow[i][k];
-                        acc[i][0] = fmaf(a, b4.x, acc[i][0]);
-                        acc[i][1] = fmaf(a, b4.y, acc[i][1]);
-                        acc[i][2] = fmaf(a, b4.z, acc[i][2]);
-                        acc[i][3] = fmaf(a, b4.w, acc[i][3]);
-                    }
-                }
-            } else {   // MM_NT
-                const float* brow[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) brow[j] = B + min(cc[j], N - 1) * NP;
-                for (int k4 = 0; k4 < K4; ++k4) {
-                    float4 a4[TM], b4[4];
-#pragma unroll
-                    for (int i = 0; i < TM; ++i) a4[i] = *reinterpret_cast<const float4*>(arow[i] + k4 * 4);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4*>(brow[j] + k4 * 4);
-#pragma unroll
-                    for (int i = 0; i < TM; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float s = acc[i][j];
-                            s = fmaf(a4[i].x, b4[j].x, s);
-                            s = fmaf(a4[i].y, b4[j].y, s);
-                            s = fmaf(a4[i].z, b4[j].z, s);
-                            s = fmaf(a4[i].w, b4[j].w, s);
-                            acc[i][j] = s;
-                        }
-                }
-                for (int k = K4 * 4; k < N; ++k) {
-#pragma unroll
-                    for (int i = 0; i < TM; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(arow[i][k], brow[j][k], acc[i][j]);
-                }
+            for (int i = 0; i < TMAX; ++i) {
+                const float a = CRW_COMP4(a4[i], kk);
+                acc[i][0] = fmaf(a, b2.x, acc[i][0]);
+                acc[i][1] = fmaf(a, b2.y, acc[i][1]);
             }
         }
+    }
+    for (int k = K4 * 4; k < N; ++k) {
+        const float2 b2 = *reinterpret_cast<const float2*>(bp + k * NP);
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            if (rr[i] >= N) continue;
+        for (int i = 0; i < TMAX; ++i) {
+            const float a = arow[i][k];
+            acc[i][0] = fmaf(a, b2.x, acc[i][0]);
+            acc[i][1] = fmaf(a, b2.y, acc[i][1]);
+        }
+    }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (cc[j] >= N) continue;
-                float* p = C + rr[i] * ldc + cc[j];
-                *p = accumulate ? (*p + acc[i][j]) : acc[i][j];
-            }
+    for (int i = 0; i < TMAX; ++i) {
+        const int r = r0 + i;
+        if (i >= TMW || r >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = 2 * lane + j;
+            if (c >= N) continue;
+            float* o = C + r * ldc + c;
+            *o = accumulate ? (*o + acc[i][j]) : acc[i][j];
         }
     }
 }
 
-// A = Qa Qb^T with rows staged in shared memory (stride DP floats, DP/4 odd, 16-byte aligned), K = D.
-__device__ __forceinline__ void affinity_smem(float* C, int NP, const float* Qa, const float* Qb, int DP, int D, int N,
-                                              int tid, int nthr) {
-    constexpr int TM = 2, TN = 4;
-    const int RS = (N + TM - 1) / TM, CS = (N + TN - 1) / TN;
-    for (int t = tid; t < RS * CS; t += nthr) {
-        const int tr = t / CS, tc = t - tr * CS;
-        const float4* pa[TM];
-        const float4* pb[TN];
+// C[r][c] (+)= sum_k A[r][k] B[c][k]      (lane's columns: lane and lane + 32 -> neighbouring lanes read neighbouring rows of B)
+template <int TMAX>
+__device__ __forceinline__ void wr_nt(float* C, int ldc, const float* A, int lda, const float* B, int ldb, int K, int N,
+                                      bool accumulate, int w, int nw, int lane) {
+    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    if (r0 >= N) return;
+    float acc[TMAX][2];
+    const float* arow[TMAX];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) pa[i] = reinterpret_cast<const float4*>(Qa + min(tr + i * RS, N - 1) * DP);
+    for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = 0.f; arow[i] = A + min(r0 + i, N - 1) * lda; }
+    const float* brow[2];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) pb[j] = reinterpret_cast<const float4*>(Qb + min(tc + j * CS, N - 1) * DP);
-        float acc[TM][TN];
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 2; ++j) brow[j] = B + min(lane + 32 * j, N - 1) * ldb;
+    const int K4 = K >> 2;
 #pragma unroll 2
-        for (int k = 0; k < D / 4; ++k) {
-            float4 a[TM], b[TN];
+    for (int k4 = 0; k4 < K4; ++k4) {
+        float4 b4[2];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = pa[i][k];
+        for (int j = 0; j < 2; ++j) b4[j] = *reinterpret_cast<const float4*>(brow[j] + k4 * 4);
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = pb[j][k];
+        for (int i = 0; i < TMAX; ++i) {
+            const float4 a4 = *reinterpret_cast<const float4*>(arow[i] + k4 * 4);
 #pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) {
-                    float s = acc[i][j];
-                    s = fmaf(a[i].x, b[j].x, s);
-                    s = fmaf(a[i].y, b[j].y, s);
-                    s = fmaf(a[i].z, b[j].z, s);
-                    s = fmaf(a[i].w, b[j].w, s);
-                    acc[i][j] = s;
-                }
-        }
-#pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            const int r = tr + i * RS;
-            if (r >= N) continue;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int c = tc + j * CS;
-                if (c < N) C[r * NP + c] = acc[i][j];
+            for (int j = 0; j < 2; ++j) {
+                float s = acc[i][j];
+                s = fmaf(a4.x, b4[j].x, s);
+                s = fmaf(a4.y, b4[j].y, s);
+                s = fmaf(a4.z, b4[j].z, s);
+                s = fmaf(a4.w, b4[j].w, s);
+                acc[i][j] = s;
             }
+        }
+    }
+    for (int k = K4 * 4; k < K; ++k) {
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j] = fmaf(arow[i][k], brow[j][k], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        const int r = r0 + i;
+        if (i >= TMW || r >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = lane + 32 * j;
+            if (c >= N) continue;
+            float* o = C + r * ldc + c;
+            *o = accumulate ? (*o + acc[i][j]) : acc[i][j];
         }
     }
 }
 
-// O[r][:] = sum_k Zop(r,k) * Q[k][:]   (r < N, D columns), Q staged in smem (stride DP), O global (stride D), overwrite.
-//   transposed == false: Zop(r,k) = Z[r][k]       transposed == true: Zop(r,k) = Z[k][r]
-__device__ __forceinline__ void dq_smem(float* O, const float* Z, int NP, const float* Q, int DP, int N, int D, bool transposed,
-                                        int tid, int nthr) {
-    constexpr int TM = 4;
-    const int RT = (N + TM - 1) / TM, CT = D / 4;
-    for (int t = tid; t < RT * CT; t += nthr) {
-        const int tr = t / CT, d4 = t - tr * CT;
-        float4 acc[TM];
+// C[r][c] (+)= sum_k A[k][r] B[k][c]
+template <int TMAX>
+__device__ __forceinline__ void wr_tn(float* C, int ldc, const float* A, const float* B, int N, int NP, bool accumulate,
+                                      int w, int nw, int lane) {
+    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    if (r0 >= N) return;
+    const int c0 = min(2 * lane, NP - 2);
+    float acc[TMAX][2];
+    int ro[TMAX];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* qp = Q + d4 * 4;
+    for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = 0.f; ro[i] = min(r0 + i, N - 1); }
+    const float* bp = B + c0;
+#pragma unroll 4
+    for (int k = 0; k < N; ++k) {
+        const float2 b2 = *reinterpret_cast<const float2*>(bp + k * NP);
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i) {
+            const float a = A[k * NP + ro[i]];
+            acc[i][0] = fmaf(a, b2.x, acc[i][0]);
+            acc[i][1] = fmaf(a, b2.y, acc[i][1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        const int r = r0 + i;
+        if (i >= TMW || r >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = 2 * lane + j;
+            if (c >= N) continue;
+            float* o = C + r * ldc + c;
+            *o = accumulate ? (*o + acc[i][j]) : acc[i][j];
+        }
+    }
+}
+
+// O[r][:] = sum_k Zop(r,k) * Q[k][:]   (r < N, D <= 128*? columns: a lane owns 4 columns per 128-column chunk), Q staged in
+// smem (stride DP), O global (stride D), overwrite.  transposed == false: Zop(r,k) = Z[r][k]; true: Zop(r,k) = Z[k][r]
+template <int TMAX>
+__device__ __forceinline__ void dq_wr(float* O, const float* Z, int NP, const float* Q, int DP, int N, int D, bool transposed,
+                                      int w, int nw, int lane) {
+    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    if (r0 >= N) return;
+    for (int d0 = lane * 4; d0 < D; d0 += 128) {
+        float4 acc[TMAX];
+        int ro[TMAX];
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i) { acc[i] = make_float4(0.f, 0.f, 0.f, 0.f); ro[i] = min(r0 + i, N - 1); }
+        const float* qp = Q + d0;
         if (transposed) {
-            const float* zp = Z + tr * TM;
 #pragma unroll 4
             for (int k = 0; k < N; ++k) {
-                const float4 z4 = *reinterpret_cast<const float4*>(zp + k * NP);
                 const float4 qv = *reinterpret_cast<const float4*>(qp + k * DP);
-                const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-                for (int i = 0; i < TM; ++i) {
-                    acc[i].x = fmaf(zz[i], qv.x, acc[i].x);
-                    acc[i].y = fmaf(zz[i], qv.y, acc[i].y);
-                    acc[i].z = fmaf(zz[i], qv.z, acc[i].z);
-                    acc[i].w = fmaf(zz[i], qv.w, acc[i].w);
+                for (int i = 0; i < TMAX; ++i) {
+                    const float z = Z[k * NP + ro[i]];
+                    acc[i].x = fmaf(z, qv.x, acc[i].x);
+                    acc[i].y = fmaf(z, qv.y, acc[i].y);
+                    acc[i].z = fmaf(z, qv.z, acc[i].z);
+                    acc[i].w = fmaf(z, qv.w, acc[i].w);
                 }
             }
         } else {
-            const float* zrow[TM];
-#pragma unroll
-            for (int i = 0; i < TM; ++i) zrow[i] = Z + min(tr * TM + i, N - 1) * NP;
             const int K4 = N >> 2;
             for (int k4 = 0; k4 < K4; ++k4) {
-                float4 z4[TM];
+                float4 z4[TMAX];
 #pragma unroll
-                for (int i = 0; i < TM; ++i) z4[i] = *reinterpret_cast<const float4*>(zrow[i] + k4 * 4);
+                for (int i = 0; i < TMAX; ++i) z4[i] = *reinterpret_cast<const float4*>(Z + ro[i] * NP + k4 * 4);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const float4 qv = *reinterpret_cast<const float4*>(qp + (k4 * 4 + kk) * DP);
 #pragma unroll
-                    for (int i = 0; i < TM; ++i) {
-                        const float z = kk == 0 ? z4[i].x : kk == 1 ? z4[i].y : kk == 2 ? z4[i].z : z4[i].w;
+                    for (int i = 0; i < TMAX; ++i) {
+                        const float z = CRW_COMP4(z4[i], kk);
                         acc[i].x = fmaf(z, qv.x, acc[i].x);
                         acc[i].y = fmaf(z, qv.y, acc[i].y);
                         acc[i].z = fmaf(z, qv.z, acc[i].z);
@@ -251,8 +218,8 @@ __device__ __forceinline__ void dq_smem(float* O, const float* Z, int NP, const 
             for (int k = K4 * 4; k < N; ++k) {
                 const float4 qv = *reinterpret_cast<const float4*>(qp + k * DP);
 #pragma unroll
-                for (int i = 0; i < TM; ++i) {
-                    const float z = zrow[i][k];
+                for (int i = 0; i < TMAX; ++i) {
+                    const float z = Z[ro[i] * NP + k];
                     acc[i].x = fmaf(z, qv.x, acc[i].x);
                     acc[i].y = fmaf(z, qv.y, acc[i].y);
                     acc[i].z = fmaf(z, qv.z, acc[i].z);
@@ -261,11 +228,56 @@ __device__ __forceinline__ void dq_smem(float* O, const float* Z, int NP, const 
             }
         }
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            const int r = tr * TM + i;
-            if (r < N) *reinterpret_cast<float4*>(O + (int64_t)r * D + d4 * 4) = acc[i];
+        for (int i = 0; i < TMAX; ++i) {
+            const int r = r0 + i;
+            if (i < TMW && r < N) *reinterpret_cast<float4*>(O + (int64_t)r * D + d0) = acc[i];
         }
     }
+}
+
+// global -> shared TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: thread 0 announces the total
+// byte count, issues the copies, and the whole CTA waits on the barrier.  Sizes are multiples of 16, both sides aligned.
+__device__ __forceinline__ void bulk_bar_init(uint64_t* bar, int tid) {
+#ifndef CRW_SIM
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#else
+    (void)bar; (void)tid;
+#endif
+    __syncthreads();
+}
+__device__ __forceinline__ void bulk_expect(uint64_t* bar, unsigned total_bytes, int tid) {
+#ifndef CRW_SIM
+    if (tid == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(total_bytes) : "memory");
+#else
+    (void)bar; (void)total_bytes; (void)tid;
+#endif
+}
+__device__ __forceinline__ void bulk_copy(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar, int tid) {
+#ifdef CRW_SIM
+    for (unsigned o = tid * 16; o < bytes; o += blockDim.x * 16)
+        *reinterpret_cast<float4*>((char*)dst_smem + o) = *reinterpret_cast<const float4*>((const char*)src_gmem + o);
+    (void)bar;
+#else
+    if (tid == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem), "r"(bytes),
+                        "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_wait(uint64_t* bar, unsigned phase) {
+#ifdef CRW_SIM
+    (void)bar; (void)phase;
+    __syncthreads();
+#else
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tCRW_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra CRW_DONE_%=;\n\t"
+                 "bra CRW_WAIT_%=;\n\tCRW_DONE_%=:\n\t}" :: "r"(b), "r"(phase) : "memory");
+#endif
 }
 
 // row-stochastic pass over one row held as two values per lane (N <= 64)
@@ -347,14 +359,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_fwd_kernel(WalkPa
         }
     }
     __syncthreads();
-    affinity_smem(At, NP, Qa, Qb, DP, D, N, tid, kFusedThreads);
+    wr_nt<4>(At, NP, Qa, DP, Qb, DP, D, N, false, warp, NW, lane);
     __syncthreads();
 
-    const int64_t pm = ((int64_t)b * (T - 1) + i) * N * N;          // this pair's matrices in the workspace (stride N)
+    const int64_t pm = ((int64_t)b * (T - 1) + i) * MS;             // this pair's matrices in the workspace (stride NP)
+    const int64_t pc = ((int64_t)b * (T - 1) + i) * N * N;          // ... and its codes (stride N)
     float* Fg = p.ws_F + pm;
     float* Gg = p.ws_G + pm;
     float* araw = p.ws_araw + pm;
-    unsigned char* gcodes = p.ws_codes + pm;
+    unsigned char* gcodes = p.ws_codes + pc;
     const int64_t numel = (int64_t)p.B * N * N;
     // forward rows (A12): row n over m; also the dropout codes (bit0 forward draw, bit1 backward draw)
     for (int n = warp; n < N; n += NW) {
@@ -380,13 +393,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_fwd_kernel(WalkPa
                 }
                 codes[n * N + m] = (unsigned char)code;
                 gcodes[n * N + m] = (unsigned char)code;
-                araw[n * N + m] = a;
+                araw[n * NP + m] = a;
                 xv[h] = ((code & 1u) ? kNegDrop : a) / tau;
             }
         }
         const float s = stoch_row(xv, ev, lane, N, softmax);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { const int m = lane + 32 * h; if (m < N) Fg[n * N + m] = ev[h] / s; }
+        for (int h = 0; h < 2; ++h) { const int m = lane + 32 * h; if (m < N) Fg[n * NP + m] = ev[h] / s; }
         if (lane == 0) p.ws_s12[((int64_t)b * (T - 1) + i) * N + n] = s;
     }
     __syncthreads();
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_fwd_kernel(WalkPa
         }
         const float s = stoch_row(xv, ev, lane, N, softmax);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { const int n = lane + 32 * h; if (n < N) Gg[m * N + n] = ev[h] / s; }
+        for (int h = 0; h < 2; ++h) { const int n = lane + 32 * h; if (n < N) Gg[m * NP + n] = ev[h] / s; }
         if (lane == 0) p.ws_s21[((int64_t)b * (T - 1) + i) * N + m] = s;
     }
 }
@@ -426,16 +439,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams
     float* Sm = Pm + (T - 2) * MS;
     float* scratch = Sm + (T - 2) * MS;             // 3 matrices
     float* red = scratch + 3 * MS;                  // 2*NW floats
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * NW + 2);
 
-    // load F_i, G_i (global stride N -> smem stride NP)
-    const int64_t cm = (int64_t)b * (T - 1) * N * N;
-    for (int e = tid; e < (T - 1) * N * N; e += kFusedThreads) {
-        const int i = e / (N * N), r = e - i * N * N;
-        const int n = r / N, m = r - n * N;
-        Fm[i * MS + n * NP + m] = ld_cg(p.ws_F + cm + e);
-        Gm[i * MS + n * NP + m] = ld_cg(p.ws_G + cm + e);
+    // F_i, G_i of this clip: two TMA bulk copies (identical layout in the workspace and in shared memory)
+    const int64_t cm = (int64_t)b * (T - 1) * MS;
+    bulk_bar_init(bar, tid);
+    {
+        const unsigned mbytes = (unsigned)(MS * sizeof(float));
+        bulk_expect(bar, 2u * (unsigned)(T - 1) * mbytes, tid);
+        for (int i = 0; i < T - 1; ++i) {
+            bulk_copy(Fm + i * MS, p.ws_F + cm + (int64_t)i * MS, mbytes, bar, tid);
+            bulk_copy(Gm + i * MS, p.ws_G + cm + (int64_t)i * MS, mbytes, bar, tid);
+        }
+        bulk_wait(bar, 0);
     }
-    __syncthreads();
 
     float* Xm = flip ? Gm : Fm;                     // forward / backward lists (swapped by --flip, model.py:380-382)
     float* Ym = flip ? Fm : Gm;
@@ -443,10 +460,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams
     float* dYg = (flip ? p.ws_dF : p.ws_dG) + cm;
     auto Pj = [&](int j) { return j == 0 ? Xm : Pm + (j - 1) * MS; };
     auto Sj = [&](int j) { return j == 0 ? Ym : Sm + (j - 1) * MS; };
-    const int grp = tid >> 8, gtid = tid & 255;     // two 256-thread groups run independent products
+    const int grp = warp >> 3, gw = warp & 7;       // two 8-warp groups run independent products
     for (int j = 1; j <= T - 2; ++j) {
-        if (grp == 0) mm4<MM_NN, 4>(Pj(j), NP, Pj(j - 1), Xm + j * MS, N, NP, false, gtid, 256);
-        else          mm4<MM_NN, 4>(Sj(j), NP, Ym + j * MS, Sj(j - 1), N, NP, false, gtid, 256);
+        if (grp == 0) wr_nn<8>(Pj(j), NP, Pj(j - 1), Xm + j * MS, N, NP, false, gw, 8, lane);
+        else          wr_nn<8>(Sj(j), NP, Ym + j * MS, Sj(j - 1), N, NP, false, gw, 8, lane);
         __syncthreads();
     }
 
@@ -463,7 +480,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams
         float* dW = nullptr;
         if (j >= 1) {
             dW = freeb[--nfree];
-            mm4<MM_NN, 2>(dW, NP, Pj(j), Sj(j), N, NP, false, tid, kFusedThreads);
+            wr_nn<4>(dW, NP, Pj(j), Sj(j), N, NP, false, warp, NW, lane);
             __syncthreads();
             float lsum = 0.f, asum = 0.f;
             for (int n = warp; n < N; n += NW) {
@@ -513,13 +530,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams
         // gP_j = dW_j S_j^T + gP_{j+1} X_{j+1}^T ;  gS_j = P_j^T dW_j + Y_{j+1}^T gS_{j+1}.  For j = 0 these ARE dX_0 / dY_0.
         float* nP = j == 0 ? dXg : freeb[--nfree];
         float* nS = j == 0 ? dYg : freeb[--nfree];
-        const int ld = j == 0 ? N : NP;
         if (grp == 0) {
-            if (dW) mm4<MM_NT, 4>(nP, ld, dW, Sj(j), N, NP, false, gtid, 256);
-            if (gP) mm4<MM_NT, 4>(nP, ld, gP, Xm + (j + 1) * MS, N, NP, dW != nullptr, gtid, 256);
+            if (dW) wr_nt<8>(nP, NP, dW, NP, Sj(j), NP, N, N, false, gw, 8, lane);
+            if (gP) wr_nt<8>(nP, NP, gP, NP, Xm + (j + 1) * MS, NP, N, N, dW != nullptr, gw, 8, lane);
         } else {
-            if (dW) mm4<MM_TN, 4>(nS, ld, Pj(j), dW, N, NP, false, gtid, 256);
-            if (gS) mm4<MM_TN, 4>(nS, ld, Ym + (j + 1) * MS, gS, N, NP, dW != nullptr, gtid, 256);
+            if (dW) wr_tn<8>(nS, NP, Pj(j), dW, N, NP, false, gw, 8, lane);
+            if (gS) wr_tn<8>(nS, NP, Ym + (j + 1) * MS, gS, N, NP, dW != nullptr, gw, 8, lane);
         }
         __syncthreads();
         if (j == 0) break;
@@ -530,19 +546,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams
         freeb[nfree++] = Sj(j);
         gP = nP;
         gS = nS;
-        // dX_j = P_{j-1}^T gP_j ; dY_j = gS_j S_{j-1}^T  -> straight to the workspace (stride N)
-        if (grp == 0) mm4<MM_TN, 4>(dXg + (int64_t)j * N * N, N, Pj(j - 1), gP, N, NP, false, gtid, 256);
-        else          mm4<MM_NT, 4>(dYg + (int64_t)j * N * N, N, gS, Sj(j - 1), N, NP, false, gtid, 256);
+        // dX_j = P_{j-1}^T gP_j ; dY_j = gS_j S_{j-1}^T  -> straight to the workspace
+        if (grp == 0) wr_tn<8>(dXg + (int64_t)j * MS, NP, Pj(j - 1), gP, N, NP, false, gw, 8, lane);
+        else          wr_nt<8>(dYg + (int64_t)j * MS, NP, gS, NP, Sj(j - 1), NP, N, N, false, gw, 8, lane);
         __syncthreads();
     }
 
-    // cross-clip reduction of the per-clip sums by the last CTA to finish, in clip order (deterministic)
+    // cross-clip reduction of the per-clip sums by the last CTA to finish, in clip order (deterministic);
+    // xent[T-2] receives the loss itself, sum_j xent_j / (T-2) (model.py:413)
     if (tid == 0) {
         __threadfence();
         const unsigned ticket = atomicAdd(p.ws_counter, 1u);
         if (ticket == (unsigned)p.B - 1u) {
             __threadfence();
             const float inv = 1.0f / ((float)p.B * (float)N);
+            float tot = 0.f;
             for (int j = 0; j < T - 2; ++j) {
                 float l = 0.f, a = 0.f;
                 for (int bb = 0; bb < p.B; ++bb) {
@@ -551,7 +569,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams
                 }
                 p.xent[j] = l * inv;
                 p.acc[j] = a * inv;
+                tot += l * inv;
             }
+            p.xent[T - 2] = tot / (float)(T - 2);
+            // every pair CTA of the previous launch has consumed the device-resident Philox state: advance it
+            if (p.dev_state && p.rate > 0.f && !p.u12)
+                p.dev_state[1] = ld_cg64(p.dev_state + 1) + (uint64_t)p.pinc * 2u * (unsigned)(T - 1);
             *p.ws_counter = 0u;
         }
     }
@@ -571,12 +594,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
     float* Z = Qb + N * DP;                   // N x NP: dA
     float* Ar = Z + MS;                       // N x NP: raw affinity
     unsigned char* codes = reinterpret_cast<unsigned char*>(Ar + MS);
-    unsigned* s_last = reinterpret_cast<unsigned*>(codes + ((N * N + 15) & ~15));
+    unsigned* s_last = reinterpret_cast<unsigned*>(codes + ((N * N + 15) & ~15));   // 2 flags
     const bool softmax = (p.flags & CRW_WALK_SOFTMAX) != 0;
     const float tau = p.tau;
     const int64_t gs = (int64_t)T * D;
     const float* qb = p.q + (int64_t)b * N * gs;
-    const int64_t pm = ((int64_t)b * (T - 1) + i) * N * N;
+    const int64_t pm = ((int64_t)b * (T - 1) + i) * MS;
+    const int64_t pc = ((int64_t)b * (T - 1) + i) * N * N;
 
     for (int v = tid; v < 2 * N * (D / 4); v += kFusedThreads) {
         const int which = v >= N * (D / 4), r = v - which * N * (D / 4);
@@ -584,11 +608,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
         *reinterpret_cast<float4*>((which ? Qb : Qa) + n * DP + d4 * 4) =
             ld_cg4(qb + (int64_t)n * gs + (int64_t)(i + which) * D + d4 * 4);
     }
-    for (int e = tid; e < N * N; e += kFusedThreads) {
-        const int n = e / N, m = e - n * N;
-        Ar[n * NP + m] = ld_cg(p.ws_araw + pm + e);
-        codes[e] = p.ws_codes[pm + e];
-    }
+    for (int e = tid; e < MS / 4; e += kFusedThreads)
+        *reinterpret_cast<float4*>(Ar + e * 4) = ld_cg4(p.ws_araw + pm + e * 4);
+    for (int e = tid; e < N * N; e += kFusedThreads) codes[e] = p.ws_codes[pc + e];
     __syncthreads();
     const float* Fg = p.ws_F + pm;
     const float* Gg = p.ws_G + pm;
@@ -602,7 +624,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
         for (int h = 0; h < 2; ++h) {
             const int m = lane + 32 * h;
             y[h] = dy[h] = 0.f;
-            if (m < N) { y[h] = ld_cg(Fg + n * N + m); dy[h] = ld_cg(dF + n * N + m); dot += y[h] * dy[h]; }
+            if (m < N) { y[h] = ld_cg(Fg + n * NP + m); dy[h] = ld_cg(dF + n * NP + m); dot += y[h] * dy[h]; }
         }
         dot = warp_sum(dot);
         const float den = ld_cg(p.ws_s12 + ((int64_t)b * (T - 1) + i) * N + n);
@@ -628,7 +650,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
         for (int h = 0; h < 2; ++h) {
             const int n = lane + 32 * h;
             y[h] = dy[h] = 0.f;
-            if (n < N) { y[h] = ld_cg(Gg + m * N + n); dy[h] = ld_cg(dG + m * N + n); dot += y[h] * dy[h]; }
+            if (n < N) { y[h] = ld_cg(Gg + m * NP + n); dy[h] = ld_cg(dG + m * NP + n); dot += y[h] * dy[h]; }
         }
         dot = warp_sum(dot);
         const float den = ld_cg(p.ws_s21 + ((int64_t)b * (T - 1) + i) * N + m);
@@ -647,28 +669,33 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
     // dQ_i (from this pair) = Z Q_{i+1} ; dQ_{i+1} (from this pair) = Z^T Q_i
     float* dqa = p.ws_dqa + ((int64_t)b * (T - 1) + i) * N * D;
     float* dqb = p.ws_dqb + ((int64_t)b * (T - 1) + i) * N * D;
-    dq_smem(dqa, Z, NP, Qb, DP, N, D, false, tid, kFusedThreads);
-    dq_smem(dqb, Z, NP, Qa, DP, N, D, true, tid, kFusedThreads);
+    dq_wr<4>(dqa, Z, NP, Qb, DP, N, D, false, warp, NW, lane);
+    dq_wr<4>(dqb, Z, NP, Qa, DP, N, D, true, warp, NW, lane);
 
-    // the last pair of this clip to finish applies the normalisation backward: df = (dq - q (q.dq)) / max(|f|, eps)
+    // Frame t receives dqa from pair t and dqb from pair t-1.  Whichever pair CTA delivers the last contribution of a
+    // frame applies the normalisation backward to it: df = (dq - q (q.dq)) / max(|f|, eps)   (model.py:118)
     __threadfence();
     __syncthreads();
-    if (tid == 0) {
-        const unsigned t = atomicAdd(p.ws_clipcnt + b, 1u);
-        *s_last = (t == (unsigned)(T - 2)) ? 1u : 0u;
-        if (*s_last) p.ws_clipcnt[b] = 0u;
+    if (tid < 2) {
+        const int t = i + tid;
+        const unsigned need = (t < T - 1 ? 1u : 0u) + (t > 0 ? 1u : 0u);
+        const unsigned got = atomicAdd(p.ws_clipcnt + (int64_t)b * T + t, 1u) + 1u;
+        s_last[tid] = got == need ? 1u : 0u;
+        if (got == need) p.ws_clipcnt[(int64_t)b * T + t] = 0u;
     }
     __syncthreads();
-    if (!*s_last) return;
+    if (!s_last[0] && !s_last[1]) return;
     __threadfence();
     float* gb = p.grad + (int64_t)b * N * gs;
-    for (int row = warp; row < N * T; row += NW) {
-        const int n = row / T, t = row - n * T;
+    for (int row = warp; row < 2 * N; row += NW) {
+        const int which = row >= N, n = row - which * N, t = i + which;
+        if (!s_last[which]) continue;
+        const int64_t ro = (int64_t)n * gs + (int64_t)t * D;
         float4 qv[2], gv[2];
         float dot = 0.f;
         int c = 0;
         for (int d = lane * 4; d < D; d += 128, ++c) {
-            qv[c] = ld_cg4(qb + (int64_t)row * D + d);
+            qv[c] = ld_cg4(qb + ro + d);
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t < T - 1) {
                 const float4 a = ld_cg4(p.ws_dqa + (((int64_t)b * (T - 1) + t) * N + n) * D + d);
@@ -691,7 +718,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
             o.y = (gv[c].y - qv[c].y * dot) * in;
             o.z = (gv[c].z - qv[c].z * dot) * in;
             o.w = (gv[c].w - qv[c].w * dot) * in;
-            *reinterpret_cast<float4*>(gb + (int64_t)row * D + d) = o;
+            *reinterpret_cast<float4*>(gb + ro + d) = o;
         }
     }
 }
@@ -708,12 +735,13 @@ int launch_walk_fused(const WalkParams& p, crw_stream_t stream) {
     CRW_LAUNCH(k1, p.B * (T - 1), kFusedThreads, L.pair_bytes, stream, p);
     int e = check_launch("walk_pairs_fwd");
     if (e != CRW_OK) return e;
-    if (p.dev_state && p.rate > 0.f && !p.u12) {     // every pair has read the device-resident Philox state: advance it
-        CRW_LAUNCH(advance_philox_state_kernel, 1, 32, 0, stream, p.dev_state, (uint64_t)p.pinc * 2u * (unsigned)(T - 1));
-        e = check_launch("advance_philox_state");
-        if (e != CRW_OK) return e;
+    if (T < 3) {
+        if (p.dev_state && p.rate > 0.f && !p.u12) {     // no chain kernel to do it: advance the device-resident Philox state here
+            CRW_LAUNCH(advance_philox_state_kernel, 1, 32, 0, stream, p.dev_state, (uint64_t)p.pinc * 2u * (unsigned)(T - 1));
+            e = check_launch("advance_philox_state");
+        }
+        return e;
     }
-    if (T < 3) return CRW_OK;
     auto k2 = walk_chain_kernel;
     cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.chain_bytes);
     CRW_LAUNCH(k2, p.B, kFusedThreads, L.chain_bytes, stream, p);

@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(float* __restrict__ W, f
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ rowloss, const float* __restrict__ rowacc,
                                                           float* __restrict__ xent, float* __restrict__ acc, int B, int J, int N) {
     __shared__ float sl[256], sa[256];
+    float tot = 0.f;
     for (int j = 0; j < J; ++j) {
         float l = 0.f, a = 0.f;
         for (int64_t e = threadIdx.x; e < (int64_t)B * N; e += 256) {
@@ -271,9 +272,10 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
             if ((int)threadIdx.x < s) { sl[threadIdx.x] += sl[threadIdx.x + s]; sa[threadIdx.x] += sa[threadIdx.x + s]; }
             __syncthreads();
         }
-        if (threadIdx.x == 0) { xent[j] = sl[0] / ((float)B * N); acc[j] = sa[0] / ((float)B * N); }
+        if (threadIdx.x == 0) { xent[j] = sl[0] / ((float)B * N); acc[j] = sa[0] / ((float)B * N); tot += xent[j]; }
         __syncthreads();
     }
+    if (threadIdx.x == 0) xent[J] = tot / (float)J;          // the loss itself (model.py:413)
 }
 
 // ---- transition-matrix backward rows: overwrites the raw affinity with its gradient contribution -----------------

@@ -269,8 +269,9 @@ class _Walk(torch.autograd.Function):
         ws = _workspace(("walk", B, N, T, D, flags), nbytes, dev)
         q = torch.empty_like(feats)
         nw = max(T - 2, 0)
-        xent = torch.zeros(max(nw, 1), dtype=torch.float32, device=dev)
-        acc = torch.zeros(max(nw, 1), dtype=torch.float32, device=dev)
+        # xent[0..nw) per-walk cross-entropies, xent[nw] their mean = the loss (written by the kernel)
+        xent = torch.empty(nw + 1, dtype=torch.float32, device=dev) if nw > 0 else torch.zeros(1, dtype=torch.float32, device=dev)
+        acc = torch.empty(max(nw, 1), dtype=torch.float32, device=dev)
         grad = torch.empty_like(feats) if (need_grad and nw > 0) else None
         L.check(L.crw_walk_fwd_bwd(feats.data_ptr(), B, N, T, D, float(tau), float(rate),
                                    u12.data_ptr() if u12 is not None else None,
@@ -279,8 +280,8 @@ class _Walk(torch.autograd.Function):
                                    flags, q.data_ptr(), xent.data_ptr(), acc.data_ptr(),
                                    grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(), _stream()),
                 "walk_fwd_bwd")
+        loss = xent[nw:nw + 1]                                 # model.py:413 (zeros when there is no walk)
         xent, acc = xent[:nw], acc[:nw]
-        loss = (xent.sum() / max(1, nw)).reshape(1)            # model.py:413
         ctx.save_for_backward(grad if grad is not None else torch.empty(0, device=dev), q, feats)
         ctx.has_grad = grad is not None
         ctx.set_materialize_grads(False)

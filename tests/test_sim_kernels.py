@@ -34,12 +34,14 @@ def run_walk(sim, f, tau, p, u12, u21p, flags=0, need_grad=True):
     wsb = sim.crw_walk_workspace_bytes(B, N, T, D, flags)
     ws = torch.zeros(wsb, dtype=torch.uint8)
     q = torch.empty_like(f)
-    xe, ac = torch.zeros(max(T - 2, 1)), torch.zeros(max(T - 2, 1))
+    xe, ac = torch.zeros(max(T - 2, 0) + 1), torch.zeros(max(T - 2, 1))
     g = torch.empty_like(f) if need_grad else None
     for _ in range(2):       # twice: the workspace must be reusable without re-zeroing
         sim.check(sim.crw_walk_fwd_bwd(ptr(f), B, N, T, D, tau, p, ptr(u12) if p > 0 else None,
                                        ptr(u21p) if p > 0 else None, 0, 0, 0, None, flags, ptr(q), ptr(xe), ptr(ac), ptr(g),
                                        ptr(ws), wsb, None), "walk")
+    if T >= 3:
+        assert abs(float(xe[T - 2]) - float(xe[: T - 2].mean())) < 1e-6
     return q, xe[: max(T - 2, 0)], ac[: max(T - 2, 0)], g
 
 
@@ -311,10 +313,10 @@ def test_walk_device_rng_state(sim, flags):
 
     def run(seed, off, state):
         q, g = torch.empty_like(f), torch.empty_like(f)
-        xe, ac = torch.zeros(T - 2), torch.zeros(T - 2)
+        xe, ac = torch.zeros(T - 1), torch.zeros(T - 2)
         sim.check(sim.crw_walk_fwd_bwd(ptr(f), B, N, T, D, 0.07, 0.3, None, None, seed, off, thr, ptr(state), flags, ptr(q),
                                        ptr(xe), ptr(ac), ptr(g), ptr(ws), wsb, None))
-        return xe, g
+        return xe[: T - 2].clone(), g
 
     xe1, g1 = run(42, 8, None)
     state = torch.tensor([42, 8], dtype=torch.int64)
