@@ -34,7 +34,9 @@ constexpr int NW = kFusedThreads / 32;
 template <int TMAX>
 __device__ __forceinline__ void wr_nn(float* C, int ldc, const float* A, const float* B, int N, int NP, bool accumulate,
                                       int w, int nw, int lane) {
-    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    constexpr int TMW = TMAX;              // rows per warp; warps beyond ceil(N / TMAX) idle
+    const int r0 = w * TMW;
+    (void)nw;
     if (r0 >= N) return;
     const int c0 = min(2 * lane, NP - 2);
     float acc[TMAX][2];
@@ -85,7 +87,9 @@ __device__ __forceinline__ void wr_nn(float* C, int ldc, const float* A, const f
 template <int TMAX>
 __device__ __forceinline__ void wr_nt(float* C, int ldc, const float* A, int lda, const float* B, int ldb, int K, int N,
                                       bool accumulate, int w, int nw, int lane) {
-    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    constexpr int TMW = TMAX;              // rows per warp; warps beyond ceil(N / TMAX) idle
+    const int r0 = w * TMW;
+    (void)nw;
     if (r0 >= N) return;
     float acc[TMAX][2];
     const float* arow[TMAX];
@@ -138,7 +142,9 @@ __device__ __forceinline__ void wr_nt(float* C, int ldc, const float* A, int lda
 template <int TMAX>
 __device__ __forceinline__ void wr_tn(float* C, int ldc, const float* A, const float* B, int N, int NP, bool accumulate,
                                       int w, int nw, int lane) {
-    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    constexpr int TMW = TMAX;              // rows per warp; warps beyond ceil(N / TMAX) idle
+    const int r0 = w * TMW;
+    (void)nw;
     if (r0 >= N) return;
     const int c0 = min(2 * lane, NP - 2);
     float acc[TMAX][2];
@@ -146,14 +152,21 @@ __device__ __forceinline__ void wr_tn(float* C, int ldc, const float* A, const f
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = 0.f; ro[i] = min(r0 + i, N - 1); }
     const float* bp = B + c0;
+    const float* ap = A + r0;                      // r0 is a multiple of TMAX (4 or 8): 16-byte aligned row chunks,
+    (void)ro;                                      // the chunk may run into the pad columns (< NP), never past the row
 #pragma unroll 4
     for (int k = 0; k < N; ++k) {
         const float2 b2 = *reinterpret_cast<const float2*>(bp + k * NP);
+        float av[TMAX];
+#pragma unroll
+        for (int i4 = 0; i4 < TMAX / 4; ++i4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(ap + k * NP + i4 * 4);
+            av[i4 * 4 + 0] = a4.x; av[i4 * 4 + 1] = a4.y; av[i4 * 4 + 2] = a4.z; av[i4 * 4 + 3] = a4.w;
+        }
 #pragma unroll
         for (int i = 0; i < TMAX; ++i) {
-            const float a = A[k * NP + ro[i]];
-            acc[i][0] = fmaf(a, b2.x, acc[i][0]);
-            acc[i][1] = fmaf(a, b2.y, acc[i][1]);
+            acc[i][0] = fmaf(av[i], b2.x, acc[i][0]);
+            acc[i][1] = fmaf(av[i], b2.y, acc[i][1]);
         }
     }
 #pragma unroll
@@ -175,7 +188,9 @@ __device__ __forceinline__ void wr_tn(float* C, int ldc, const float* A, const f
 template <int TMAX>
 __device__ __forceinline__ void dq_wr(float* O, const float* Z, int NP, const float* Q, int DP, int N, int D, bool transposed,
                                       int w, int nw, int lane) {
-    const int TMW = (N + nw - 1) / nw, r0 = w * TMW;
+    constexpr int TMW = TMAX;              // rows per warp; warps beyond ceil(N / TMAX) idle
+    const int r0 = w * TMW;
+    (void)nw;
     if (r0 >= N) return;
     for (int d0 = lane * 4; d0 < D; d0 += 128) {
         float4 acc[TMAX];
@@ -184,16 +199,22 @@ __device__ __forceinline__ void dq_wr(float* O, const float* Z, int NP, const fl
         for (int i = 0; i < TMAX; ++i) { acc[i] = make_float4(0.f, 0.f, 0.f, 0.f); ro[i] = min(r0 + i, N - 1); }
         const float* qp = Q + d0;
         if (transposed) {
+            const float* zp = Z + r0;                  // aligned chunk of TMAX (multiple of 4) columns of row k
 #pragma unroll 4
             for (int k = 0; k < N; ++k) {
                 const float4 qv = *reinterpret_cast<const float4*>(qp + k * DP);
+                float zz[TMAX];
+#pragma unroll
+                for (int i4 = 0; i4 < TMAX / 4; ++i4) {
+                    const float4 z4 = *reinterpret_cast<const float4*>(zp + k * NP + i4 * 4);
+                    zz[i4 * 4 + 0] = z4.x; zz[i4 * 4 + 1] = z4.y; zz[i4 * 4 + 2] = z4.z; zz[i4 * 4 + 3] = z4.w;
+                }
 #pragma unroll
                 for (int i = 0; i < TMAX; ++i) {
-                    const float z = Z[k * NP + ro[i]];
-                    acc[i].x = fmaf(z, qv.x, acc[i].x);
-                    acc[i].y = fmaf(z, qv.y, acc[i].y);
-                    acc[i].z = fmaf(z, qv.z, acc[i].z);
-                    acc[i].w = fmaf(z, qv.w, acc[i].w);
+                    acc[i].x = fmaf(zz[i], qv.x, acc[i].x);
+                    acc[i].y = fmaf(zz[i], qv.y, acc[i].y);
+                    acc[i].z = fmaf(zz[i], qv.z, acc[i].z);
+                    acc[i].w = fmaf(zz[i], qv.w, acc[i].w);
                 }
             }
         } else {
@@ -554,23 +575,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_chain_kernel(WalkParams
 
     // cross-clip reduction of the per-clip sums by the last CTA to finish, in clip order (deterministic);
     // xent[T-2] receives the loss itself, sum_j xent_j / (T-2) (model.py:413)
+    unsigned* s_flag = reinterpret_cast<unsigned*>(red + 2 * NW);
     if (tid == 0) {
         __threadfence();
-        const unsigned ticket = atomicAdd(p.ws_counter, 1u);
-        if (ticket == (unsigned)p.B - 1u) {
-            __threadfence();
-            const float inv = 1.0f / ((float)p.B * (float)N);
-            float tot = 0.f;
-            for (int j = 0; j < T - 2; ++j) {
-                float l = 0.f, a = 0.f;
-                for (int bb = 0; bb < p.B; ++bb) {
-                    l += ld_cg(p.ws_partial + ((int64_t)bb * (T - 2) + j) * 2 + 0);
-                    a += ld_cg(p.ws_partial + ((int64_t)bb * (T - 2) + j) * 2 + 1);
+        *s_flag = atomicAdd(p.ws_counter, 1u) == (unsigned)p.B - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*s_flag && warp == 0) {
+        __threadfence();
+        const float inv = 1.0f / ((float)p.B * (float)N);
+        float tot = 0.f;
+        for (int j = 0; j < T - 2; ++j) {
+            float l = 0.f, a = 0.f;
+            for (int b0 = 0; b0 < p.B; b0 += 32) {                     // fixed order: chunks of 32 clips, butterfly inside
+                const int bb = b0 + lane;
+                float lv = 0.f, av = 0.f;
+                if (bb < p.B) {
+                    lv = ld_cg(p.ws_partial + ((int64_t)bb * (T - 2) + j) * 2 + 0);
+                    av = ld_cg(p.ws_partial + ((int64_t)bb * (T - 2) + j) * 2 + 1);
                 }
-                p.xent[j] = l * inv;
-                p.acc[j] = a * inv;
-                tot += l * inv;
+                l += warp_sum(lv);
+                a += warp_sum(av);
             }
+            if (lane == 0) { p.xent[j] = l * inv; p.acc[j] = a * inv; }
+            tot += l * inv;
+        }
+        if (lane == 0) {
             p.xent[T - 2] = tot / (float)(T - 2);
             // every pair CTA of the previous launch has consumed the device-resident Philox state: advance it
             if (p.dev_state && p.rate > 0.f && !p.u12)
