@@ -28,7 +28,8 @@ extern "C" {
 /* walk flags */
 #define CRW_WALK_SOFTMAX 1u   /* F.softmax rows (teacherstudent.py:80) instead of ZeroSoftmax (model.py:90) */
 #define CRW_WALK_FLIP 2u      /* args.flip: reversed product order, model.py:380-382 */
-#define CRW_WALK_FORCE_GENERAL 4u /* skip the single-CTA fused kernel even when the clip fits shared memory */
+#define CRW_WALK_FORCE_GENERAL 4u
+#define CRW_LP_FORCE_SIMT 1u /* skip the single-CTA fused kernel even when the clip fits shared memory */
 
 typedef void* crw_stream_t;
 
@@ -105,11 +106,16 @@ int crw_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, ui
  * restricted slots instead visit every key and add dense_mask[key, query] to the score - the reference's literal
  * semantics for an arbitrary mask, without the window skipping.
  * Ws (Nt,k,hw) fp32 softmax over the k best scores / temperature; Is (Nt,k,hw) int64 = slot*hw + key_pos,
- * sorted by descending score, ties broken by ascending index. */
-size_t crw_lp_topk_workspace_bytes(int Nt, int S, int h, int w, int C, int k);
-int crw_lp_topk(const float* feats, const int64_t* key_frames, const int64_t* query_frames, int Nt, int S,
+ * sorted by descending score, ties broken by ascending index.
+ * Two implementations with identical results: a tcgen05/TMEM/TMA tensor-core kernel (C % 64 == 0, C <= 256, k <= 16,
+ * radius <= 13, no dense mask; fp16 hi/lo split operands, fp32 accumulation, see csrc/lp_tc.cu) and an exact-fp32 SIMT
+ * kernel for everything else (or when flags has CRW_LP_FORCE_SIMT).  feats holds Nf frames.  After the stream has
+ * drained, the first 32-bit word of the workspace is non-zero if the tensor-core kernel hit an internal barrier
+ * timeout (results invalid). */
+size_t crw_lp_topk_workspace_bytes(int Nf, int Nt, int S, int h, int w, int C, int k);
+int crw_lp_topk(const float* feats, int Nf, const int64_t* key_frames, const int64_t* query_frames, int Nt, int S,
                 int n_long, int h, int w, int C, float radius, const float* dense_mask, float temperature, int k,
-                float* Ws, int64_t* Is, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+                unsigned flags, float* Ws, int64_t* Is, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
 /* feats (C, Nf, hw) channel-first (the encoder's layout, test.py:90-93) -> (Nf, hw, C) channel-last with
  * optional L2 normalisation over C (eps 1e-12). */

@@ -22,6 +22,7 @@ CRW_OK = 0
 WALK_SOFTMAX = 1
 WALK_FLIP = 2
 WALK_FORCE_GENERAL = 4
+LP_FORCE_SIMT = 1
 
 _SIGNATURES = {
     "crw_version": (c_int, []),
@@ -39,9 +40,9 @@ _SIGNATURES = {
                                  c_uint64, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
     "crw_philox_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint32, c_void_p]),
-    "crw_lp_topk_workspace_bytes": (c_size_t, [c_int] * 6),
-    "crw_lp_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
-                            c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crw_lp_topk_workspace_bytes": (c_size_t, [c_int] * 7),
+    "crw_lp_topk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                            c_float, c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_lp_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

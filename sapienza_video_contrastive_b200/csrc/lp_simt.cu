@@ -260,19 +260,41 @@ static int launch_lp(const LpArgs& a, crw_stream_t stream) {
     return check_launch("lp_topk");
 }
 
+// tensor-core path (lp_tc.cu)
+struct LpTcArgs {
+    const int64_t* key_frames;
+    const int64_t* query_frames;
+    int Nt, S, n_long, h, w, C, k, R, r2i;
+    int restricted;
+    float tau;
+    float* Ws;
+    int64_t* Is;
+    unsigned* err;
+};
+size_t lp_tc_workspace_bytes(int Nf, int h, int w, int C);
+bool lp_tc_supported(int C, int k, float radius, int R, bool dense);
+int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+
 }  // namespace crw
 
 using namespace crw;
 
-extern "C" size_t crw_lp_topk_workspace_bytes(int Nt, int S, int h, int w, int C, int k) {
-    (void)Nt; (void)S; (void)h; (void)w; (void)C; (void)k;
-    return 256;      // the SIMT path needs no scratch; a non-zero size keeps caller code uniform
+static int radius_R(float radius) {          // largest integer offset R with R*R < radius^2
+    int R = 0;
+    while ((float)((R + 1) * (R + 1)) < radius * radius) ++R;
+    return R;
 }
 
-extern "C" int crw_lp_topk(const float* feats, const int64_t* key_frames, const int64_t* query_frames, int Nt, int S,
+extern "C" size_t crw_lp_topk_workspace_bytes(int Nf, int Nt, int S, int h, int w, int C, int k) {
+    (void)Nt; (void)S;
+    size_t b = 256;                          // word 0: device-side error flag
+    if (lp_tc_supported(C, k, 1.f, 0, false)) b = lp_tc_workspace_bytes(Nf, h, w, C);
+    return b;
+}
+
+extern "C" int crw_lp_topk(const float* feats, int Nf, const int64_t* key_frames, const int64_t* query_frames, int Nt, int S,
                            int n_long, int h, int w, int C, float radius, const float* dense_mask, float temperature, int k,
-                           float* Ws, int64_t* Is, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
+                           unsigned flags, float* Ws, int64_t* Is, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
     if (Nt < 0 || S <= 0 || h <= 0 || w <= 0 || C <= 0 || k <= 0 || n_long < 0 || n_long > S || !(temperature > 0.f)) {
         set_error("lp_topk: bad arguments"); return CRW_ERR_SHAPE;
     }
@@ -280,16 +302,29 @@ extern "C" int crw_lp_topk(const float* feats, const int64_t* key_frames, const 
     if (k > 32) { set_error("lp_topk: k <= 32 supported"); return CRW_ERR_UNSUPPORTED; }
     if ((int64_t)S * h * w >= 0x7fffffff || h >= 32768 || w >= 32768) { set_error("lp_topk: index range"); return CRW_ERR_UNSUPPORTED; }
     if (Nt == 0) return CRW_OK;
+    if (!workspace || workspace_bytes < 256) { set_error("lp_topk: workspace missing"); return CRW_ERR_SHAPE; }
+    const int Rr = radius > 0.f ? radius_R(radius) : 0;
+    if (!(flags & CRW_LP_FORCE_SIMT) && lp_tc_supported(C, k, radius, Rr, dense_mask != nullptr) &&
+        workspace_bytes >= lp_tc_workspace_bytes(Nf, h, w, C)) {
+        LpTcArgs t{};
+        t.key_frames = key_frames; t.query_frames = query_frames;
+        t.Nt = Nt; t.S = S; t.n_long = n_long; t.h = h; t.w = w; t.C = C; t.k = k; t.R = Rr;
+        t.restricted = radius > 0.f ? 1 : 0;
+        // d2 < radius^2 for integer d2  <=>  d2 <= r2i
+        int r2i = 0;
+        while ((float)(r2i + 1) < radius * radius) ++r2i;
+        t.r2i = radius > 0.f ? r2i : 0;
+        t.tau = temperature; t.Ws = Ws; t.Is = Is;
+        return launch_lp_tc(feats, Nf, t, workspace, workspace_bytes, stream);
+    }
+    cudaMemsetAsync(workspace, 0, 4, (cudaStream_t)stream);
     LpArgs a{};
     a.feats = feats; a.key_frames = key_frames; a.query_frames = query_frames;
     a.Nt = Nt; a.S = S; a.n_long = n_long; a.h = h; a.w = w; a.C = C; a.k = k;
     a.restricted = (radius > 0.f && !dense_mask) ? 1 : 0;
     a.dense_mask = dense_mask;
     a.r2 = radius * radius;
-    // largest integer offset R with R*R < radius^2
-    int R = 0;
-    while ((float)((R + 1) * (R + 1)) < a.r2) ++R;
-    a.R = R;
+    a.R = Rr;
     a.tau = temperature;
     a.Ws = Ws; a.Is = Is;
     if (k <= 4) return launch_lp<4>(a, stream);

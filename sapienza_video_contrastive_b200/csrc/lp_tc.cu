@@ -1,0 +1,448 @@
+// lp_tc.cu - label-propagation affinity + streaming top-k on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
+// Reference semantics: code/utils/test_utils.py:148-179 (affinity, mask, /T, topk, softmax) with the radius mask of
+// code/utils/__init__.py:377-391 + code/test.py:118-122 evaluated as an integer test.  Same results as lp_simt.cu.
+//
+// fp32-faithful scores on fp16 tensor cores: every feature is split x = hi + lo * 2^-11 (hi = fp16(x),
+// lo = fp16((x - hi) * 2^11)); a score is  <q,k> = qhi.khi + (qhi.klo + qlo.khi) * 2^-11  with fp32 accumulation in
+// TMEM (two accumulators, three tcgen05.mma per 16-channel step); the dropped lo.lo term is ~2^-22 relative.
+// Dyadic inputs (lo = 0) are reproduced exactly.
+//
+// One CTA = one target frame x one 16x8 block of 128 queries (the M = 128 rows / TMEM lanes of the MMA):
+//   warp 0   TMA producer: the query tile once (hi+lo, 128 x C, 128B-swizzled, resident for the CTA's lifetime),
+//            then a 3-stage ring of 32-key sub-tiles (hi+lo).  Restricted slots only visit the rows of the block's
+//            (16+2R) x (8+2R) window - one 32-key box per window row; long-memory slots sweep the frame linearly.
+//   warp 1   MMA issuer (one elected thread): per sub-tile 3 x C/16 tcgen05.mma (M128 N32 K16, kind::f16) into the main /
+//            correction accumulators; four sub-tiles fill one 128-column accumulator stage, two stages ping-pong
+//            (2 x 2 x 128 = all 512 TMEM columns) so the epilogue of one stage overlaps the MMAs of the next.
+//   warps 2-5  epilogue: thread = query = TMEM lane.  tcgen05.ld pulls the 32 main + 32 correction values of a sub-tile
+//            into registers, applies validity + the radius test, and feeds a register-resident sorted top-k list; no
+//            cross-thread merging, the affinity matrix never leaves the SM.  Final softmax over the k winners.
+#include "common.cuh"
+
+#ifndef CRW_SIM
+#include <cuda.h>
+#include <cuda_fp16.h>
+#endif
+
+namespace crw {
+
+constexpr int TC_M = 128;        // queries per CTA (16 rows x 8 cols)
+constexpr int TC_QH = 16, TC_QW = 8;
+constexpr int TC_NS = 32;        // keys per sub-tile (one TMA box, one MMA N)
+constexpr int TC_SUB = 4;        // sub-tiles per accumulator stage
+constexpr int TC_STAGES = 3;     // key ring depth
+constexpr int TC_THREADS = 192;
+
+struct LpTcArgs {
+    const int64_t* key_frames;   // (Nt, S)
+    const int64_t* query_frames; // (Nt)
+    int Nt, S, n_long, h, w, C, k, R, r2i;   // r2i: largest integer d2 admitted (d2 <= r2i  <=>  d2 < radius^2)
+    int restricted;
+    float tau;
+    float* Ws;
+    int64_t* Is;
+    unsigned* err;               // device error flag (barrier timeout)
+};
+
+#ifndef CRW_SIM
+
+// ---- split kernel: fp32 channel-last features -> fp16 hi / lo planes ----------------------------------------------
+__global__ void __launch_bounds__(256) lp_split_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2half_rn(f[j]);
+            l[j] = __float2half_rn((f[j] - __half2float(h[j])) * 2048.0f);
+        }
+        uint2 ho, lo_;
+        ho.x = (unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16);
+        ho.y = (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16);
+        lo_.x = (unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16);
+        lo_.y = (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16);
+        hi[i] = ho;
+        lo[i] = lo_;
+    }
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a protocol bug becomes an error code instead of a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, unsigned* err) {
+    const unsigned a = smem_u32(bar);
+    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    atomicExch(err, 1u);
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(unsigned d_tmem, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor:
+// start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | SWIZZLE_128B (2) <<61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(unsigned smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1u << 16) | ((uint64_t)(1024u >> 4) << 32) |
+           ((uint64_t)1u << 46) | ((uint64_t)2u << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ unsigned umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+// Enumeration of a CTA's key sub-tiles, shared by producer, issuer and epilogue: slots in order; a long-memory slot
+// sweeps the frame in runs of 32 keys; a restricted slot visits one 32-key run per row of the block's window.
+struct SubIter {
+    int slot, step, nsteps, y0, x0;
+    const LpTcArgs* a;
+    int qy0, qx0;
+    __device__ void init(const LpTcArgs* a_, int qy0_, int qx0_) {
+        a = a_; qy0 = qy0_; qx0 = qx0_; slot = 0; step = 0; setup();
+    }
+    __device__ void setup() {
+        while (slot < a->S) {
+            const bool restricted = a->restricted && slot >= a->n_long;
+            if (restricted) {
+                y0 = max(qy0 - a->R, 0);
+                const int y1 = min(qy0 + TC_QH - 1 + a->R, a->h - 1);
+                nsteps = y1 - y0 + 1;
+                x0 = qx0 - a->R;
+            } else {
+                nsteps = (a->h * a->w + TC_NS - 1) / TC_NS;
+            }
+            if (nsteps > 0) return;
+            ++slot;
+        }
+    }
+    __device__ bool done() const { return slot >= a->S; }
+    // key run of the current sub-tile: first key position in the frame (may be negative / wrap: validity is tested per key)
+    __device__ int kidx0() const {
+        const bool restricted = a->restricted && slot >= a->n_long;
+        return restricted ? (y0 + step) * a->w + x0 : step * TC_NS;
+    }
+    __device__ int row_y() const { return y0 + step; }
+    __device__ void next() {
+        if (++step >= nsteps) { ++slot; step = 0; setup(); }
+    }
+};
+
+template <int K>
+struct RegTopK {
+    float v[K];
+    int idx[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < K; ++i) { v[i] = -INFINITY; idx[i] = 0x7fffffff; }
+    }
+    __device__ __forceinline__ void push(float x, int id) {      // candidates arrive with ascending id
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const bool better = x > v[i];
+            const float tv = better ? v[i] : x;
+            const int ti = better ? idx[i] : id;
+            v[i] = better ? x : v[i];
+            idx[i] = better ? id : idx[i];
+            x = tv;
+            id = ti;
+        }
+    }
+};
+
+template <int K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                  const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo, LpTcArgs a) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int C = a.C, KC = C / 64, hw = a.h * a.w;
+    const unsigned q_plane = (unsigned)TC_M * C * 2;              // bytes of one query plane (hi or lo), all channel chunks
+    const unsigned q_chunk = (unsigned)TC_M * 128;                // one 64-channel chunk: 128 rows x 128 B
+    const unsigned k_plane = (unsigned)TC_NS * C * 2;
+    const unsigned k_chunk = (unsigned)TC_NS * 128;
+    const unsigned k_stage = 2 * k_plane;
+    unsigned char* q_smem = smem;                                 // [hi|lo][chunk][128 rows][128 B]
+    unsigned char* k_smem = smem + 2 * q_plane;                   // [stage][hi|lo][chunk][32 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(k_smem + TC_STAGES * k_stage);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + TC_STAGES;
+    uint64_t* t_full = k_empty + TC_STAGES;
+    uint64_t* t_empty = t_full + 2;
+    unsigned* tmem_base_smem = reinterpret_cast<unsigned*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.y;
+    const int tiles_x = (a.w + TC_QW - 1) / TC_QW;
+    const int qy0 = (blockIdx.x / tiles_x) * TC_QH, qx0 = (blockIdx.x % tiles_x) * TC_QW;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_base_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int64_t qrow0 = a.query_frames[n] * (int64_t)hw;
+            mbar_expect_tx(q_full, 2 * q_plane);
+            for (int yy = 0; yy < TC_QH; ++yy) {
+                const int row = (int)(qrow0 + (int64_t)(qy0 + yy) * a.w + qx0);
+                for (int c = 0; c < KC; ++c) {
+                    tma_load_2d(q_smem + c * q_chunk + yy * 1024, &map_q_hi, c * 64, row, q_full);
+                    tma_load_2d(q_smem + q_plane + c * q_chunk + yy * 1024, &map_q_lo, c * 64, row, q_full);
+                }
+            }
+            SubIter it;
+            it.init(&a, qy0, qx0);
+            bool ok = true;
+            for (unsigned i = 0; ok && !it.done(); ++i, it.next()) {
+                const unsigned st = i % TC_STAGES, ph = (i / TC_STAGES) & 1u;
+                ok = mbar_wait(k_empty + st, ph ^ 1u, a.err);
+                if (!ok) break;
+                const int row = (int)(a.key_frames[(int64_t)n * a.S + it.slot] * (int64_t)hw + it.kidx0());
+                unsigned char* dst = k_smem + st * k_stage;
+                mbar_expect_tx(k_full + st, k_stage);
+                for (int c = 0; c < KC; ++c) {
+                    tma_load_2d(dst + c * k_chunk, &map_k_hi, c * 64, row, k_full + st);
+                    tma_load_2d(dst + k_plane + c * k_chunk, &map_k_lo, c * 64, row, k_full + st);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const unsigned idesc = umma_idesc_f16(TC_M, TC_NS);
+            bool ok = mbar_wait(q_full, 0, a.err);
+            tc_fence_after();
+            SubIter it;
+            it.init(&a, qy0, qx0);
+            const unsigned qa = smem_u32(q_smem);
+            unsigned i = 0;
+            for (unsigned g = 0; ok && !it.done(); ++g) {
+                const unsigned as = g & 1u, aph = (g >> 1) & 1u;
+                ok = mbar_wait(t_empty + as, aph ^ 1u, a.err);
+                if (!ok) break;
+                tc_fence_after();
+                for (int sub = 0; sub < TC_SUB && !it.done(); ++sub, ++i, it.next()) {
+                    const unsigned st = i % TC_STAGES, ph = (i / TC_STAGES) & 1u;
+                    ok = mbar_wait(k_full + st, ph, a.err);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const unsigned ka = smem_u32(k_smem + st * k_stage);
+                    const unsigned d_main = tmem_base + as * 256u + (unsigned)sub * TC_NS;
+                    const unsigned d_corr = d_main + 128u;
+                    for (int j = 0; j < C / 16; ++j) {
+                        const unsigned off_q = (unsigned)(j >> 2) * q_chunk + (unsigned)(j & 3) * 32u;
+                        const unsigned off_k = (unsigned)(j >> 2) * k_chunk + (unsigned)(j & 3) * 32u;
+                        const uint64_t q_hi = umma_desc_sw128(qa + off_q), q_lo = umma_desc_sw128(qa + q_plane + off_q);
+                        const uint64_t k_hi = umma_desc_sw128(ka + off_k), k_lo = umma_desc_sw128(ka + k_plane + off_k);
+                        tc_mma_f16(d_main, q_hi, k_hi, idesc, j > 0);
+                        tc_mma_f16(d_corr, q_hi, k_lo, idesc, j > 0);
+                        tc_mma_f16(d_corr, q_lo, k_hi, idesc, 1u);
+                    }
+                    tc_commit(k_empty + st);          // frees the key stage once these MMAs have read it
+                }
+                if (!ok) break;
+                tc_commit(t_full + as);               // accumulator stage complete
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = query = TMEM lane =====================
+        const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int q = quarter * 32 + lane;                             // query row inside the tile
+        const int qy = qy0 + (q >> 3), qx = qx0 + (q & 7);
+        const bool qvalid = qy < a.h && qx < a.w;
+        RegTopK<K> top;
+        top.init();
+        SubIter it;
+        it.init(&a, qy0, qx0);
+        const unsigned lane_addr = tmem_base + ((unsigned)(quarter * 32) << 16);
+        bool ok = true;
+        for (unsigned g = 0; ok && !it.done(); ++g) {
+            const unsigned as = g & 1u, aph = (g >> 1) & 1u;
+            ok = mbar_wait(t_full + as, aph, a.err);
+            if (!ok) break;
+            tc_fence_after();
+            for (int sub = 0; sub < TC_SUB && !it.done(); ++sub, it.next()) {
+                unsigned m[32], c[32];
+                tc_ld32(lane_addr + as * 256u + (unsigned)sub * TC_NS, m);
+                tc_ld32(lane_addr + as * 256u + 128u + (unsigned)sub * TC_NS, c);
+                tc_wait_ld();
+                const int kidx0 = it.kidx0();
+                const bool restricted = a.restricted && it.slot >= a.n_long;
+                const int base_id = it.slot * hw;
+                if (restricted) {
+                    const int dy = it.row_y() - qy;
+                    const int rem = a.r2i - dy * dy;                   // need dx^2 <= rem
+                    const int dx0 = it.x0 - qx;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int kx = it.x0 + j, dx = dx0 + j;
+                        const float s = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
+                        if (kx >= 0 && kx < a.w && dx * dx <= rem && s > top.v[K - 1]) top.push(s, base_id + kidx0 + j);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
+                        if (kidx0 + j < hw && s > top.v[K - 1]) top.push(s, base_id + kidx0 + j);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(t_empty + as);
+        }
+        if (ok && qvalid) {
+            const int64_t obase = (int64_t)n * a.k * hw + qy * a.w + qx;
+            float vals[K];
+            float mx = 0.f, den = 0.f;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                vals[r] = top.v[r] / a.tau;
+                if (r == 0) mx = vals[0];
+            }
+#pragma unroll
+            for (int r = 0; r < K; ++r) { vals[r] = r < a.k ? expf(vals[r] - mx) : 0.f; den += vals[r]; }
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                if (r < a.k) {
+                    a.Ws[obase + (int64_t)r * hw] = vals[r] / den;
+                    a.Is[obase + (int64_t)r * hw] = top.idx[r] == 0x7fffffff ? 0 : top.idx[r];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* m, const void* base, int C, int64_t rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t lp_tc_workspace_bytes(int Nf, int h, int w, int C) { return 2 * (size_t)Nf * h * w * C * 2 + 256; }
+
+bool lp_tc_supported(int C, int k, float radius, int R, bool dense) {
+    return !dense && C % 64 == 0 && C >= 64 && C <= 256 && k >= 1 && k <= 16 && (radius <= 0.f || TC_QW + 2 * R <= TC_NS);
+}
+
+int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
+    const int hw = a0.h * a0.w, C = a0.C;
+    const size_t plane = (size_t)Nf * hw * C * 2;
+    if (workspace_bytes < 2 * plane + 256) { set_error("lp_topk: workspace too small for the tensor-core path"); return CRW_ERR_SHAPE; }
+    unsigned char* ws = (unsigned char*)workspace;
+    unsigned* err = (unsigned*)ws;
+    void* hi = ws + 256;
+    void* lo = ws + 256 + plane;
+    cudaMemsetAsync(err, 0, 4, (cudaStream_t)stream);
+    const int64_t n4 = (int64_t)Nf * hw * C / 4;
+    const int sgrid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    lp_split_kernel<<<sgrid, 256, 0, (cudaStream_t)stream>>>((const float4*)feats, (uint2*)hi, (uint2*)lo, n4);
+    int e = check_launch("lp_split");
+    if (e != CRW_OK) return e;
+    CUtensorMap mqh, mql, mkh, mkl;
+    const int64_t rows = (int64_t)Nf * hw;
+    if (!make_map(&mqh, hi, C, rows, TC_QW) || !make_map(&mql, lo, C, rows, TC_QW) || !make_map(&mkh, hi, C, rows, TC_NS) ||
+        !make_map(&mkl, lo, C, rows, TC_NS)) {
+        set_error("lp_topk: cuTensorMapEncodeTiled failed");
+        return CRW_ERR_CUDA;
+    }
+    LpTcArgs a = a0;
+    a.err = err;
+    const size_t smem = 1024 + 2 * (size_t)TC_M * C * 2 + TC_STAGES * 2 * (size_t)TC_NS * C * 2 + 256;
+    dim3 grid(((a.w + TC_QW - 1) / TC_QW) * ((a.h + TC_QH - 1) / TC_QH), a.Nt);
+    if (a.k == 10) {
+        auto k = lp_topk_tc_kernel<10>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mqh, mql, mkh, mkl, a);
+    } else {
+        auto k = lp_topk_tc_kernel<16>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mqh, mql, mkh, mkl, a);
+    }
+    return check_launch("lp_topk_tc");
+}
+
+#else   // CRW_SIM: the tensor-core path needs real hardware; the host simulator always takes the SIMT kernel
+
+size_t lp_tc_workspace_bytes(int, int, int, int) { return 256; }
+bool lp_tc_supported(int, int, float, int, bool) { return false; }
+int launch_lp_tc(const float*, int, const LpTcArgs&, void*, size_t, crw_stream_t) { return CRW_ERR_UNSUPPORTED; }
+
+#endif
+
+}  // namespace crw

@@ -401,7 +401,8 @@ def lp_prepare(feats_cf: torch.Tensor, normalize: bool) -> torch.Tensor:
 
 
 def lp_topk(feats_cl: torch.Tensor, key_frames: torch.Tensor, query_frames: torch.Tensor, n_long: int, h: int, w: int,
-            radius: float, temperature: float, k: int, dense_mask: Optional[torch.Tensor] = None):
+            radius: float, temperature: float, k: int, dense_mask: Optional[torch.Tensor] = None, force_simt: bool = False,
+            check: bool = True):
     """feats_cl (Nf,hw,C); key_frames (Nt,S) int64; query_frames (Nt) int64 -> Ws (Nt,k,hw) fp32, Is (Nt,k,hw) int64."""
     _need_cuda(feats_cl, key_frames, query_frames, dense_mask)
     check_device(feats_cl.device)
@@ -420,11 +421,14 @@ def lp_topk(feats_cl: torch.Tensor, key_frames: torch.Tensor, query_frames: torc
     Ws = torch.empty(Nt, k, hw, dtype=torch.float32, device=dev)
     Is = torch.empty(Nt, k, hw, dtype=torch.int64, device=dev)
     L = _lib.lib()
-    nbytes = L.crw_lp_topk_workspace_bytes(Nt, S, h, w, C, k)
-    ws = _workspace(("lp", Nt, S, h, w, C, k), nbytes, dev)
-    L.check(L.crw_lp_topk(feats_cl.data_ptr(), key_frames.data_ptr(), query_frames.data_ptr(), Nt, S, n_long, h, w, C,
+    nbytes = L.crw_lp_topk_workspace_bytes(Nf, Nt, S, h, w, C, k)
+    ws = _workspace(("lp", Nf, h, w, C, k), nbytes, dev)
+    L.check(L.crw_lp_topk(feats_cl.data_ptr(), Nf, key_frames.data_ptr(), query_frames.data_ptr(), Nt, S, n_long, h, w, C,
                           float(radius), dense_mask.data_ptr() if dense_mask is not None else None, float(temperature), k,
-                          Ws.data_ptr(), Is.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "lp_topk")
+                          _lib.LP_FORCE_SIMT if force_simt else 0, Ws.data_ptr(), Is.data_ptr(), ws.data_ptr(), ws.numel(),
+                          _stream()), "lp_topk")
+    if check and int(ws[:4].view(torch.int32)[0]) != 0:          # device-side barrier watchdog of the tensor-core kernel
+        raise _lib.CrwError("lp_topk: tensor-core kernel reported an internal barrier timeout")
     return Ws, Is
 
 

@@ -357,3 +357,49 @@ def test_label_prop_davis_shape_properties(ops):
         mine = torch.gather(sc, 0, Is[n][:, qs].cpu())
         torch.testing.assert_close(mine, v, rtol=1e-5, atol=1e-5)
         assert float((Is[n][:, qs].cpu() == i).float().mean()) > 0.97
+
+
+def _lp_scores(feats, ki, n, n_ctx, h, w, radius, n_long, tau):
+    f = feats[0].flatten(-2).double()
+    add = O.radius_mask_additive(h, w, radius)[0, 0].double()
+    return torch.cat([f[:, ki[n, s]].t() @ f[:, n + n_ctx] + (add if s >= n_long else 0) for s in range(ki.shape[1])], 0) / tau
+
+
+@pytest.mark.parametrize("C,h,w,n_ctx,n_tgt,k,radius,dyadic", [(64, 20, 27, 3, 3, 10, 5, False), (128, 33, 19, 2, 2, 5, 12, False),
+                                                              (256, 17, 40, 4, 2, 10, 12, False), (64, 18, 21, 2, 3, 10, 4, True),
+                                                              (256, 24, 24, 2, 2, 16, 3, True)])
+def test_label_prop_tensor_core_path(ops, C, h, w, n_ctx, n_tgt, k, radius, dyadic):
+    """tcgen05 path (fp16 hi/lo split, fp32 accumulate) vs the exact-fp32 SIMT kernel and the float64 scores:
+    identical index sets up to near-ties (|score difference| < 1e-5 / tau, the documented tolerance), exact on the
+    dyadic grid where every product is exact in both."""
+    from sapienza_video_contrastive_b200 import LabelPropagator, context_index_bank
+    g = torch.Generator().manual_seed(C + h)
+    Nf = n_ctx + n_tgt
+    if dyadic:
+        feats = torch.randint(-64, 65, (1, C, Nf, h, w), generator=g).float() / 64.0
+    else:
+        feats = torch.nn.functional.normalize(torch.randn(1, C, Nf, h, w, generator=g), dim=1)
+    tau = 0.07
+    res = {}
+    for simt in (False, True):
+        lp = LabelPropagator(n_ctx, [0], radius, k, tau, normalize=False, force_simt=simt)
+        ki, Ws, Is = lp.affinity(feats.to(DEV))
+        res[simt] = (Ws.cpu(), Is.cpu())
+    ki = ki.cpu()
+    hw = h * w
+    (Wt, It), (Ws_, Is_) = res[False], res[True]
+    assert int(It.min()) >= 0 and int(It.max()) < ki.shape[1] * hw
+    for n in range(n_tgt):
+        sc = _lp_scores(feats, ki, n, n_ctx, h, w, radius, 1, tau)
+        vt, vs = torch.gather(sc, 0, It[n]), torch.gather(sc, 0, Is_[n])
+        vref, iref = torch.topk(sc, k, dim=0)
+        if dyadic:
+            assert torch.equal(vt, vref) and torch.equal(vs, vref)           # exact arithmetic: identical score multisets
+        else:
+            assert float((vt - vref).abs().max()) < 1e-5 / tau
+            assert float((vs - vref).abs().max()) < 1e-5 / tau
+        srt = It[n].sort(0).values
+        assert bool((srt[1:] != srt[:-1]).all())
+        if n >= 1:
+            assert float((It[n] == iref).float().mean()) > 0.995
+    torch.testing.assert_close(Wt, Ws_, rtol=2e-4, atol=1e-6)

@@ -245,8 +245,8 @@ def run_lp(sim, feats, c, dense=None):
     Ws = torch.empty(Nt, c["k"], hw)
     Is = torch.empty(Nt, c["k"], hw, dtype=torch.int64)
     ws = torch.zeros(256, dtype=torch.uint8)
-    sim.check(sim.crw_lp_topk(ptr(cl), ptr(ki), ptr(qf), Nt, S, len(c["long_mem"]), h, w, C, float(c["radius"]), ptr(dense), c["tau"],
-                              c["k"], ptr(Ws), ptr(Is), ptr(ws), 256, None))
+    sim.check(sim.crw_lp_topk(ptr(cl), Nf, ptr(ki), ptr(qf), Nt, S, len(c["long_mem"]), h, w, C, float(c["radius"]), ptr(dense), c["tau"],
+                              c["k"], 0, ptr(Ws), ptr(Is), ptr(ws), 256, None))
     return cl, ki, Ws, Is
 
 
