@@ -14,9 +14,11 @@
 //   warp 1   MMA issuer (one elected thread): per sub-tile 3 x C/16 tcgen05.mma (M128 N32 K16, kind::f16) into the main /
 //            correction accumulators; four sub-tiles fill one 128-column accumulator stage, two stages ping-pong
 //            (2 x 2 x 128 = all 512 TMEM columns) so the epilogue of one stage overlaps the MMAs of the next.
-//   warps 2-5  epilogue: thread = query = TMEM lane.  tcgen05.ld pulls the 32 main + 32 correction values of a sub-tile
-//            into registers, applies validity + the radius test, and feeds a register-resident sorted top-k list; no
-//            cross-thread merging, the affinity matrix never leaves the SM.  Final softmax over the k winners.
+//   warps 2-9  epilogue: thread = (query = TMEM lane, half of the sub-tile's 32 columns).  tcgen05.ld pulls 16 main + 16
+//            correction values into registers; validity + the radius test are folded into a branch-free running max,
+//            and only when some lane's max beats its k-th best does the warp extract candidates into the register-
+//            resident sorted top-k list.  The two half-lists of a query are merged once at the end through shared
+//            memory; the affinity matrix never leaves the SM.  Final softmax over the k winners.
 #include "common.cuh"
 
 #ifndef CRW_SIM
@@ -31,7 +33,8 @@ constexpr int TC_QH = 16, TC_QW = 8;
 constexpr int TC_NS = 32;        // keys per sub-tile (one TMA box, one MMA N)
 constexpr int TC_SUB = 4;        // sub-tiles per accumulator stage
 constexpr int TC_STAGES = 3;     // key ring depth
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;  // two epilogue warps per TMEM lane quarter, each owning half of a sub-tile's columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct LpTcArgs {
     const int64_t* key_frames;   // (Nt, S)
@@ -112,6 +115,13 @@ __device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -215,7 +225,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -294,8 +304,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             }
         }
     } else {
-        // ===================== epilogue: thread = query = TMEM lane =====================
+        // ===================== epilogue: thread = (query = TMEM lane, column half) =====================
+        const int ew = warp - 2;
         const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                                      // which 16 of a sub-tile's 32 columns
         const int q = quarter * 32 + lane;                             // query row inside the tile
         const int qy = qy0 + (q >> 3), qx = qx0 + (q & 7);
         const bool qvalid = qy < a.h && qx < a.w;
@@ -303,7 +315,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         top.init();
         SubIter it;
         it.init(&a, qy0, qx0);
-        const unsigned lane_addr = tmem_base + ((unsigned)(quarter * 32) << 16);
+        const unsigned lane_addr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)half * 16u;
         bool ok = true;
         for (unsigned g = 0; ok && !it.done(); ++g) {
             const unsigned as = g & 1u, aph = (g >> 1) & 1u;
@@ -311,50 +323,96 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             if (!ok) break;
             tc_fence_after();
             for (int sub = 0; sub < TC_SUB && !it.done(); ++sub, it.next()) {
-                unsigned m[32], c[32];
-                tc_ld32(lane_addr + as * 256u + (unsigned)sub * TC_NS, m);
-                tc_ld32(lane_addr + as * 256u + 128u + (unsigned)sub * TC_NS, c);
+                unsigned m[16], c[16];
+                tc_ld16(lane_addr + as * 256u + (unsigned)sub * TC_NS, m);
+                tc_ld16(lane_addr + as * 256u + 128u + (unsigned)sub * TC_NS, c);
                 tc_wait_ld();
-                const int kidx0 = it.kidx0();
+                const int kidx0 = it.kidx0() + half * 16;
                 const bool restricted = a.restricted && it.slot >= a.n_long;
-                const int base_id = it.slot * hw;
+                const int base_id = it.slot * hw + kidx0;
+                // branch-free: masked scores and their max
+                float sv[16];
+                float mx = -INFINITY;
                 if (restricted) {
                     const int dy = it.row_y() - qy;
-                    const int rem = a.r2i - dy * dy;                   // need dx^2 <= rem
-                    const int dx0 = it.x0 - qx;
+                    const int rem = a.r2i - dy * dy;                   // admissible iff dx^2 <= rem
+                    const int kx0 = it.x0 + half * 16, dx0 = kx0 - qx;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int kx = it.x0 + j, dx = dx0 + j;
-                        const float s = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
-                        if (kx >= 0 && kx < a.w && dx * dx <= rem && s > top.v[K - 1]) top.push(s, base_id + kidx0 + j);
+                    for (int j = 0; j < 16; ++j) {
+                        const int kx = kx0 + j, dx = dx0 + j;
+                        const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
+                        const bool adm = (unsigned)kx < (unsigned)a.w && dx * dx <= rem;
+                        sv[j] = adm ? sc : -INFINITY;
+                        mx = fmaxf(mx, sv[j]);
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
-                        if (kidx0 + j < hw && s > top.v[K - 1]) top.push(s, base_id + kidx0 + j);
+                    for (int j = 0; j < 16; ++j) {
+                        const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
+                        sv[j] = (kidx0 + j < hw) ? sc : -INFINITY;
+                        mx = fmaxf(mx, sv[j]);
+                    }
+                }
+                // rare path: extract candidates in descending value (equal values: ascending column) until none beats the k-th best
+                while (__any_sync(kFull, mx > top.v[K - 1])) {
+                    if (mx > top.v[K - 1]) {
+                        int jm = 0;
+#pragma unroll
+                        for (int j = 15; j >= 0; --j) jm = (sv[j] == mx) ? j : jm;
+                        top.push(mx, base_id + jm);
+                        float nm = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            sv[j] = (j == jm) ? -INFINITY : sv[j];
+                            nm = fmaxf(nm, sv[j]);
+                        }
+                        mx = nm;
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(t_empty + as);
         }
-        if (ok && qvalid) {
+        // merge the two half-lists of each query (sorted by value desc; equal values: lower index first) and write out.
+        // All MMAs are complete (the last t_full was observed), so the query tile's shared memory is free.
+        float* mv = reinterpret_cast<float*>(q_smem);                  // [128 queries][2 halves][K]
+        int* mi = reinterpret_cast<int*>(q_smem + (size_t)TC_M * 2 * K * sizeof(float));
+        asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");
+#pragma unroll
+        for (int r = 0; r < K; ++r) { mv[(q * 2 + half) * K + r] = top.v[r]; mi[(q * 2 + half) * K + r] = top.idx[r]; }
+        asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");
+        if (ok && qvalid && half == 0) {
             const int64_t obase = (int64_t)n * a.k * hw + qy * a.w + qx;
+            const float* v0 = mv + (q * 2 + 0) * K;
+            const float* v1 = mv + (q * 2 + 1) * K;
+            const int* i0 = mi + (q * 2 + 0) * K;
+            const int* i1 = mi + (q * 2 + 1) * K;
+            int h0 = 0, h1 = 0;
             float vals[K];
-            float mx = 0.f, den = 0.f;
+            int ids[K];
 #pragma unroll
             for (int r = 0; r < K; ++r) {
-                vals[r] = top.v[r] / a.tau;
-                if (r == 0) mx = vals[0];
+                const float a0 = h0 < K ? v0[h0] : -INFINITY, a1 = h1 < K ? v1[h1] : -INFINITY;
+                const int b0 = h0 < K ? i0[h0] : 0x7fffffff, b1 = h1 < K ? i1[h1] : 0x7fffffff;
+                const bool first = a0 > a1 || (a0 == a1 && b0 <= b1);
+                vals[r] = first ? a0 : a1;
+                ids[r] = first ? b0 : b1;
+                h0 += first ? 1 : 0;
+                h1 += first ? 0 : 1;
+            }
+            float mxv = 0.f, den = 0.f;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                vals[r] = vals[r] / a.tau;
+                if (r == 0) mxv = vals[0];
             }
 #pragma unroll
-            for (int r = 0; r < K; ++r) { vals[r] = r < a.k ? expf(vals[r] - mx) : 0.f; den += vals[r]; }
+            for (int r = 0; r < K; ++r) { vals[r] = r < a.k ? expf(vals[r] - mxv) : 0.f; den += vals[r]; }
 #pragma unroll
             for (int r = 0; r < K; ++r) {
                 if (r < a.k) {
                     a.Ws[obase + (int64_t)r * hw] = vals[r] / den;
-                    a.Is[obase + (int64_t)r * hw] = top.idx[r] == 0x7fffffff ? 0 : top.idx[r];
+                    a.Is[obase + (int64_t)r * hw] = ids[r] == 0x7fffffff ? 0 : ids[r];
                 }
             }
         }
