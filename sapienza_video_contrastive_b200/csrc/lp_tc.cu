@@ -132,6 +132,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(unsigned smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1u << 16) | ((uint64_t)(1024u >> 4) << 32) |
            ((uint64_t)1u << 46) | ((uint64_t)2u << 61);
 }
+__device__ __forceinline__ unsigned desc_lo(unsigned smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_make(unsigned lo) {
+    constexpr unsigned kHi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO | version 1 | SWIZZLE_128B
+    return ((uint64_t)kHi << 32) | lo;
+}
 // kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, N>>3 at bit 17, M>>4 at bit 24
 __device__ __forceinline__ unsigned umma_idesc_f16(int M, int N) {
     return (1u << 4) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
@@ -285,17 +290,25 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                     ok = mbar_wait(k_full + st, ph, a.err);
                     if (!ok) break;
                     tc_fence_after();
+                    // descriptors: constant upper word; the lower word carries (address >> 4) and advances by 2 per 32-byte
+                    // K step inside a 128-byte swizzled row and by chunk/16 per 64-channel chunk
                     const unsigned ka = smem_u32(k_smem + st * k_stage);
                     const unsigned d_main = tmem_base + as * 256u + (unsigned)sub * TC_NS;
                     const unsigned d_corr = d_main + 128u;
-                    for (int j = 0; j < C / 16; ++j) {
-                        const unsigned off_q = (unsigned)(j >> 2) * q_chunk + (unsigned)(j & 3) * 32u;
-                        const unsigned off_k = (unsigned)(j >> 2) * k_chunk + (unsigned)(j & 3) * 32u;
-                        const uint64_t q_hi = umma_desc_sw128(qa + off_q), q_lo = umma_desc_sw128(qa + q_plane + off_q);
-                        const uint64_t k_hi = umma_desc_sw128(ka + off_k), k_lo = umma_desc_sw128(ka + k_plane + off_k);
-                        tc_mma_f16(d_main, q_hi, k_hi, idesc, j > 0);
-                        tc_mma_f16(d_corr, q_hi, k_lo, idesc, j > 0);
-                        tc_mma_f16(d_corr, q_lo, k_hi, idesc, 1u);
+                    unsigned lq_hi = desc_lo(qa), lq_lo = desc_lo(qa + q_plane);
+                    unsigned lk_hi = desc_lo(ka), lk_lo = desc_lo(ka + k_plane);
+                    for (int cch = 0; cch < KC; ++cch) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t q_hi = desc_make(lq_hi + 2u * kk), q_lo = desc_make(lq_lo + 2u * kk);
+                            const uint64_t k_hi = desc_make(lk_hi + 2u * kk), k_lo = desc_make(lk_lo + 2u * kk);
+                            const unsigned accum = (cch | kk) ? 1u : 0u;
+                            tc_mma_f16(d_main, q_hi, k_hi, idesc, accum);
+                            tc_mma_f16(d_corr, q_hi, k_lo, idesc, accum);
+                            tc_mma_f16(d_corr, q_lo, k_hi, idesc, 1u);
+                        }
+                        lq_hi += q_chunk >> 4; lq_lo += q_chunk >> 4;
+                        lk_hi += k_chunk >> 4; lk_lo += k_chunk >> 4;
                     }
                     tc_commit(k_empty + st);          // frees the key stage once these MMAs have read it
                 }
