@@ -8,17 +8,21 @@
 // Dyadic inputs (lo = 0) are reproduced exactly.
 //
 // One CTA = one target frame x one 16x8 block of 128 queries (the M = 128 rows / TMEM lanes of the MMA):
-//   warp 0   TMA producer: the query tile once (hi+lo, 128 x C, 128B-swizzled, resident for the CTA's lifetime),
-//            then a 3-stage ring of 32-key sub-tiles (hi+lo).  Restricted slots only visit the rows of the block's
-//            (16+2R) x (8+2R) window - one 32-key box per window row; long-memory slots sweep the frame linearly.
-//   warp 1   MMA issuer (one elected thread): per sub-tile 3 x C/16 tcgen05.mma (M128 N32 K16, kind::f16) into the main /
-//            correction accumulators; four sub-tiles fill one 128-column accumulator stage, two stages ping-pong
-//            (2 x 2 x 128 = all 512 TMEM columns) so the epilogue of one stage overlaps the MMAs of the next.
-//   warps 2-9  epilogue: thread = (query = TMEM lane, half of the sub-tile's 32 columns).  tcgen05.ld pulls 16 main + 16
-//            correction values into registers; validity + the radius test are folded into a branch-free running max,
-//            and only when some lane's max beats its k-th best does the warp extract candidates into the register-
-//            resident sorted top-k list.  The two half-lists of a query are merged once at the end through shared
-//            memory; the affinity matrix never leaves the SM.  Final softmax over the k winners.
+//   TMEM     the query tile itself (hi and lo planes, 2 x C/2 columns) lives in tensor memory for the CTA's lifetime
+//            (tcgen05.mma with the A operand in TMEM): it is re-used by every key tile, so it is never re-read from
+//            shared memory, which would otherwise bound small-N MMAs.  The remaining 256 columns hold two accumulator
+//            stages (main + correction, 64 keys each).
+//   warp 0   TMA producer: the query tile once (staged in shared memory, copied to TMEM by the epilogue warps), then a
+//            3-stage ring of 64-key tiles (hi+lo planes, 128B-swizzled).  A tile is two 32-key runs: restricted slots
+//            only visit the rows of the block's (16+2R) x (8+2R) window, one run per window row; long-memory slots
+//            sweep the frame linearly.
+//   warp 1   MMA issuer (one elected thread): per key tile 3 x C/16 tcgen05.mma (M128 N64 K16, kind::f16, A from TMEM,
+//            B from shared memory) into the main / correction accumulators of one of two ping-pong stages.
+//   warps 2-9  epilogue: thread = (query = TMEM lane, one 32-key run of the tile).  tcgen05.ld pulls main + correction
+//            values into registers; validity + the radius test are folded into a branch-free running max, and only
+//            when some lane's max beats its k-th best does the warp extract candidates into the register-resident
+//            sorted top-k list.  The two half-lists of a query are merged once at the end through shared memory; the
+//            affinity matrix never leaves the SM.  Final softmax over the k winners.
 #include "common.cuh"
 
 #ifndef CRW_SIM
@@ -30,8 +34,8 @@ namespace crw {
 
 constexpr int TC_M = 128;        // queries per CTA (16 rows x 8 cols)
 constexpr int TC_QH = 16, TC_QW = 8;
-constexpr int TC_NS = 32;        // keys per sub-tile (one TMA box, one MMA N)
-constexpr int TC_SUB = 4;        // sub-tiles per accumulator stage
+constexpr int TC_NS = 32;        // keys per run (one TMA box)
+constexpr int TC_NT = 64;        // keys per tile = MMA N (two runs)
 constexpr int TC_STAGES = 3;     // key ring depth
 constexpr int TC_EPI_WARPS = 8;  // two epilogue warps per TMEM lane quarter, each owning half of a sub-tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
@@ -124,6 +128,21 @@ __device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tc_st32(unsigned taddr, const unsigned (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void tc_mma_f16_ts(unsigned d_tmem, unsigned a_tmem, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor:
@@ -167,6 +186,12 @@ struct SubIter {
         }
     }
     __device__ bool done() const { return slot >= a->S; }
+    __device__ int total_runs() const {                               // number of runs this CTA will see
+        SubIter c = *this;
+        int n = 0;
+        while (!c.done()) { n += c.nsteps - c.step; ++c.slot; c.step = 0; c.setup(); }
+        return n;
+    }
     // key run of the current sub-tile: first key position in the frame (may be negative / wrap: validity is tested per key)
     __device__ int kidx0() const {
         const bool restricted = a->restricted && slot >= a->n_long;
@@ -207,16 +232,17 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int C = a.C, KC = C / 64, hw = a.h * a.w;
-    const unsigned q_plane = (unsigned)TC_M * C * 2;              // bytes of one query plane (hi or lo), all channel chunks
-    const unsigned q_chunk = (unsigned)TC_M * 128;                // one 64-channel chunk: 128 rows x 128 B
-    const unsigned k_plane = (unsigned)TC_NS * C * 2;
-    const unsigned k_chunk = (unsigned)TC_NS * 128;
+    const unsigned q_chunk = (unsigned)TC_M * 128;                // staged query tile: one 64-channel chunk = 128 rows x 128 B
+    const unsigned q_plane = (unsigned)KC * q_chunk;
+    const unsigned k_chunk = (unsigned)TC_NT * 128;               // key tile: one chunk = 64 rows x 128 B
+    const unsigned k_plane = (unsigned)KC * k_chunk;
     const unsigned k_stage = 2 * k_plane;
-    unsigned char* q_smem = smem;                                 // [hi|lo][chunk][128 rows][128 B]
-    unsigned char* k_smem = smem + 2 * q_plane;                   // [stage][hi|lo][chunk][32 rows][128 B]
+    unsigned char* k_smem = smem;                                 // [stage][hi|lo][chunk][64 rows][128 B]
+    unsigned char* q_smem = smem;                                 // staging of the query tile (aliases the first stages)
     uint64_t* bars = reinterpret_cast<uint64_t*>(k_smem + TC_STAGES * k_stage);
     uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;
+    uint64_t* q_ready = bars + 1;
+    uint64_t* k_full = bars + 2;
     uint64_t* k_empty = k_full + TC_STAGES;
     uint64_t* t_full = k_empty + TC_STAGES;
     uint64_t* t_empty = t_full + 2;
@@ -229,6 +255,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
+        mbar_init(q_ready, 32 * TC_EPI_WARPS);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,6 +268,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_base = *tmem_base_smem;
+    const unsigned tm_qhi = tmem_base, tm_qlo = tmem_base + (unsigned)(C / 2), tm_acc = tmem_base + 256u;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -254,142 +282,164 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                     tma_load_2d(q_smem + q_plane + c * q_chunk + yy * 1024, &map_q_lo, c * 64, row, q_full);
                 }
             }
+            bool ok = mbar_wait(q_ready, 0, a.err);              // the staged query tile has moved to TMEM
             SubIter it;
             it.init(&a, qy0, qx0);
-            bool ok = true;
-            for (unsigned i = 0; ok && !it.done(); ++i, it.next()) {
-                const unsigned st = i % TC_STAGES, ph = (i / TC_STAGES) & 1u;
+            for (unsigned t = 0; ok && !it.done(); ++t) {
+                const unsigned st = t % TC_STAGES, ph = (t / TC_STAGES) & 1u;
                 ok = mbar_wait(k_empty + st, ph ^ 1u, a.err);
                 if (!ok) break;
-                const int row = (int)(a.key_frames[(int64_t)n * a.S + it.slot] * (int64_t)hw + it.kidx0());
                 unsigned char* dst = k_smem + st * k_stage;
-                mbar_expect_tx(k_full + st, k_stage);
-                for (int c = 0; c < KC; ++c) {
-                    tma_load_2d(dst + c * k_chunk, &map_k_hi, c * 64, row, k_full + st);
-                    tma_load_2d(dst + k_plane + c * k_chunk, &map_k_lo, c * 64, row, k_full + st);
-                }
+                int rows[2];
+                int nrun = 0;
+                for (; nrun < 2 && !it.done(); ++nrun, it.next())
+                    rows[nrun] = (int)(a.key_frames[(int64_t)n * a.S + it.slot] * (int64_t)hw + it.kidx0());
+                mbar_expect_tx(k_full + st, (unsigned)nrun * 2u * (unsigned)KC * (TC_NS * 128u));
+                for (int r = 0; r < nrun; ++r)
+                    for (int c = 0; c < KC; ++c) {
+                        tma_load_2d(dst + c * k_chunk + r * (TC_NS * 128), &map_k_hi, c * 64, rows[r], k_full + st);
+                        tma_load_2d(dst + k_plane + c * k_chunk + r * (TC_NS * 128), &map_k_lo, c * 64, rows[r], k_full + st);
+                    }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const unsigned idesc = umma_idesc_f16(TC_M, TC_NS);
-            bool ok = mbar_wait(q_full, 0, a.err);
+            const unsigned idesc = umma_idesc_f16(TC_M, TC_NT);
+            bool ok = mbar_wait(q_ready, 0, a.err);
             tc_fence_after();
             SubIter it;
             it.init(&a, qy0, qx0);
-            const unsigned qa = smem_u32(q_smem);
-            unsigned i = 0;
-            for (unsigned g = 0; ok && !it.done(); ++g) {
-                const unsigned as = g & 1u, aph = (g >> 1) & 1u;
+            for (unsigned t = 0; ok && !it.done(); ++t) {
+                it.next();
+                if (!it.done()) it.next();
+                const unsigned as = t & 1u, aph = (t >> 1) & 1u;
+                const unsigned st = t % TC_STAGES, ph = (t / TC_STAGES) & 1u;
                 ok = mbar_wait(t_empty + as, aph ^ 1u, a.err);
                 if (!ok) break;
-                tc_fence_after();
-                for (int sub = 0; sub < TC_SUB && !it.done(); ++sub, ++i, it.next()) {
-                    const unsigned st = i % TC_STAGES, ph = (i / TC_STAGES) & 1u;
-                    ok = mbar_wait(k_full + st, ph, a.err);
-                    if (!ok) break;
-                    tc_fence_after();
-                    // descriptors: constant upper word; the lower word carries (address >> 4) and advances by 2 per 32-byte
-                    // K step inside a 128-byte swizzled row and by chunk/16 per 64-channel chunk
-                    const unsigned ka = smem_u32(k_smem + st * k_stage);
-                    const unsigned d_main = tmem_base + as * 256u + (unsigned)sub * TC_NS;
-                    const unsigned d_corr = d_main + 128u;
-                    unsigned lq_hi = desc_lo(qa), lq_lo = desc_lo(qa + q_plane);
-                    unsigned lk_hi = desc_lo(ka), lk_lo = desc_lo(ka + k_plane);
-                    for (int cch = 0; cch < KC; ++cch) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t q_hi = desc_make(lq_hi + 2u * kk), q_lo = desc_make(lq_lo + 2u * kk);
-                            const uint64_t k_hi = desc_make(lk_hi + 2u * kk), k_lo = desc_make(lk_lo + 2u * kk);
-                            const unsigned accum = (cch | kk) ? 1u : 0u;
-                            tc_mma_f16(d_main, q_hi, k_hi, idesc, accum);
-                            tc_mma_f16(d_corr, q_hi, k_lo, idesc, accum);
-                            tc_mma_f16(d_corr, q_lo, k_hi, idesc, 1u);
-                        }
-                        lq_hi += q_chunk >> 4; lq_lo += q_chunk >> 4;
-                        lk_hi += k_chunk >> 4; lk_lo += k_chunk >> 4;
-                    }
-                    tc_commit(k_empty + st);          // frees the key stage once these MMAs have read it
-                }
+                ok = mbar_wait(k_full + st, ph, a.err);
                 if (!ok) break;
+                tc_fence_after();
+                const unsigned ka = smem_u32(k_smem + st * k_stage);
+                const unsigned d_main = tm_acc + as * 128u, d_corr = d_main + 64u;
+                unsigned lk_hi = desc_lo(ka), lk_lo = desc_lo(ka + k_plane);
+                unsigned a_hi = tm_qhi, a_lo = tm_qlo;
+                for (int cch = 0; cch < KC; ++cch) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t k_hi = desc_make(lk_hi + 2u * kk), k_lo = desc_make(lk_lo + 2u * kk);
+                        const unsigned accum = (cch | kk) ? 1u : 0u;
+                        tc_mma_f16_ts(d_main, a_hi + 8u * kk, k_hi, idesc, accum);
+                        tc_mma_f16_ts(d_corr, a_hi + 8u * kk, k_lo, idesc, accum);
+                        tc_mma_f16_ts(d_corr, a_lo + 8u * kk, k_hi, idesc, 1u);
+                    }
+                    lk_hi += k_chunk >> 4; lk_lo += k_chunk >> 4;
+                    a_hi += 32u; a_lo += 32u;
+                }
+                tc_commit(k_empty + st);              // frees the key stage once these MMAs have read it
                 tc_commit(t_full + as);               // accumulator stage complete
             }
         }
     } else {
-        // ===================== epilogue: thread = (query = TMEM lane, column half) =====================
+        // ===================== epilogue: thread = (query = TMEM lane, run of the tile) =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                                      // which 16 of a sub-tile's 32 columns
+        const int half = ew >> 2;                                      // which 32-key run of a tile / which query plane
         const int q = quarter * 32 + lane;                             // query row inside the tile
         const int qy = qy0 + (q >> 3), qx = qx0 + (q & 7);
         const bool qvalid = qy < a.h && qx < a.w;
+        const unsigned lane_sel = (unsigned)(quarter * 32) << 16;
+        bool ok = mbar_wait(q_full, 0, a.err);
+        // move this query row's plane (half 0: hi, half 1: lo) from the swizzled staging tile to TMEM: 8 fp16 = 4 columns per 16 B
+        {
+            const unsigned char* src = q_smem + (half ? q_plane : 0u) + (unsigned)q * 128u;
+            const unsigned dstc = (half ? tm_qlo : tm_qhi) + lane_sel;
+            for (int c = 0; c < KC; ++c) {
+                unsigned r[32];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(src + c * q_chunk + ((ch ^ (q & 7)) << 4));
+                    r[ch * 4 + 0] = v.x; r[ch * 4 + 1] = v.y; r[ch * 4 + 2] = v.z; r[ch * 4 + 3] = v.w;
+                }
+                tc_st32(dstc + (unsigned)c * 32u, r);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(q_ready);
+        }
         RegTopK<K> top;
         top.init();
         SubIter it;
         it.init(&a, qy0, qx0);
-        const unsigned lane_addr = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)half * 16u;
-        bool ok = true;
-        for (unsigned g = 0; ok && !it.done(); ++g) {
-            const unsigned as = g & 1u, aph = (g >> 1) & 1u;
+        if (half && !it.done()) it.next();                             // this warp's run of tile 0
+        const unsigned ntiles = (unsigned)((it.total_runs() + 1) / 2);
+        for (unsigned t = 0; ok && t < ntiles; ++t) {
+            const bool mine_exists = !it.done();                       // the last tile may hold a single run
+            const unsigned as = t & 1u, aph = (t >> 1) & 1u;
             ok = mbar_wait(t_full + as, aph, a.err);
             if (!ok) break;
             tc_fence_after();
-            for (int sub = 0; sub < TC_SUB && !it.done(); ++sub, it.next()) {
-                unsigned m[16], c[16];
-                tc_ld16(lane_addr + as * 256u + (unsigned)sub * TC_NS, m);
-                tc_ld16(lane_addr + as * 256u + 128u + (unsigned)sub * TC_NS, c);
-                tc_wait_ld();
-                const int kidx0 = it.kidx0() + half * 16;
+            if (mine_exists) {
                 const bool restricted = a.restricted && it.slot >= a.n_long;
-                const int base_id = it.slot * hw + kidx0;
-                // branch-free: masked scores and their max
-                float sv[16];
-                float mx = -INFINITY;
-                if (restricted) {
-                    const int dy = it.row_y() - qy;
-                    const int rem = a.r2i - dy * dy;                   // admissible iff dx^2 <= rem
-                    const int kx0 = it.x0 + half * 16, dx0 = kx0 - qx;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int kx = kx0 + j, dx = dx0 + j;
-                        const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
-                        const bool adm = (unsigned)kx < (unsigned)a.w && dx * dx <= rem;
-                        sv[j] = adm ? sc : -INFINITY;
-                        mx = fmaxf(mx, sv[j]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
-                        sv[j] = (kidx0 + j < hw) ? sc : -INFINITY;
-                        mx = fmaxf(mx, sv[j]);
-                    }
-                }
-                // rare path: extract candidates in descending value (equal values: ascending column) until none beats the k-th best
-                while (__any_sync(kFull, mx > top.v[K - 1])) {
-                    if (mx > top.v[K - 1]) {
-                        int jm = 0;
-#pragma unroll
-                        for (int j = 15; j >= 0; --j) jm = (sv[j] == mx) ? j : jm;
-                        top.push(mx, base_id + jm);
-                        float nm = -INFINITY;
+                for (int part = 0; part < 2; ++part) {
+                    unsigned m[16], c[16];
+                    const unsigned col = tm_acc + as * 128u + (unsigned)half * 32u + (unsigned)part * 16u + lane_sel;
+                    tc_ld16(col, m);
+                    tc_ld16(col + 64u, c);
+                    tc_wait_ld();
+                    const int kidx0 = it.kidx0() + part * 16;
+                    const int base_id = it.slot * hw + kidx0;
+                    float sv[16];
+                    float mx = -INFINITY;
+                    if (restricted) {
+                        const int dy = it.row_y() - qy;
+                        const int rem = a.r2i - dy * dy;               // admissible iff dx^2 <= rem
+                        const int kx0 = it.x0 + part * 16, dx0 = kx0 - qx;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            sv[j] = (j == jm) ? -INFINITY : sv[j];
-                            nm = fmaxf(nm, sv[j]);
+                            const int kx = kx0 + j, dx = dx0 + j;
+                            const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
+                            const bool adm = (unsigned)kx < (unsigned)a.w && dx * dx <= rem;
+                            sv[j] = adm ? sc : -INFINITY;
+                            mx = fmaxf(mx, sv[j]);
                         }
-                        mx = nm;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
+                            sv[j] = (kidx0 + j < hw) ? sc : -INFINITY;
+                            mx = fmaxf(mx, sv[j]);
+                        }
+                    }
+                    // rare path: extract candidates in descending value (equal values: ascending column) while one beats the k-th best
+                    while (__any_sync(kFull, mx > top.v[K - 1])) {
+                        if (mx > top.v[K - 1]) {
+                            int jm = 0;
+#pragma unroll
+                            for (int j = 15; j >= 0; --j) jm = (sv[j] == mx) ? j : jm;
+                            top.push(mx, base_id + jm);
+                            float nm = -INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                sv[j] = (j == jm) ? -INFINITY : sv[j];
+                                nm = fmaxf(nm, sv[j]);
+                            }
+                            mx = nm;
+                        }
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(t_empty + as);
+            // advance to this warp's run of the next tile
+            if (!it.done()) it.next();
+            if (!it.done()) it.next();
         }
         // merge the two half-lists of each query (sorted by value desc; equal values: lower index first) and write out.
-        // All MMAs are complete (the last t_full was observed), so the query tile's shared memory is free.
-        float* mv = reinterpret_cast<float*>(q_smem);                  // [128 queries][2 halves][K]
-        int* mi = reinterpret_cast<int*>(q_smem + (size_t)TC_M * 2 * K * sizeof(float));
+        // All MMAs are complete (the last t_full was observed), so the key ring's shared memory is free.
+        float* mv = reinterpret_cast<float*>(smem);                    // [128 queries][2 halves][K]
+        int* mi = reinterpret_cast<int*>(smem + (size_t)TC_M * 2 * K * sizeof(float));
         asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");
 #pragma unroll
         for (int r = 0; r < K; ++r) { mv[(q * 2 + half) * K + r] = top.v[r]; mi[(q * 2 + half) * K + r] = top.idx[r]; }
@@ -494,7 +544,8 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
     }
     LpTcArgs a = a0;
     a.err = err;
-    const size_t smem = 1024 + 2 * (size_t)TC_M * C * 2 + TC_STAGES * 2 * (size_t)TC_NS * C * 2 + 256;
+    size_t ring = TC_STAGES * 2 * (size_t)TC_NT * C * 2, stagingq = 2 * (size_t)TC_M * C * 2;
+    const size_t smem = 1024 + (ring > stagingq ? ring : stagingq) + 256;
     dim3 grid(((a.w + TC_QW - 1) / TC_QW) * ((a.h + TC_QH - 1) / TC_QH), a.Nt);
     if (a.k == 10) {
         auto k = lp_topk_tc_kernel<10>;
