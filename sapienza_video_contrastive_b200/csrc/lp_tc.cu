@@ -271,16 +271,15 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     const unsigned tm_qhi = tmem_base, tm_qlo = tmem_base + (unsigned)(C / 2), tm_acc = tmem_base + 256u;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp: one lane per box, so a tile's 16 loads issue in parallel) ==========
+        {
             const int64_t qrow0 = a.query_frames[n] * (int64_t)hw;
-            mbar_expect_tx(q_full, 2 * q_plane);
-            for (int yy = 0; yy < TC_QH; ++yy) {
+            if (lane == 0) mbar_expect_tx(q_full, 2 * q_plane);
+            __syncwarp();
+            for (int op = lane; op < TC_QH * KC * 2; op += 32) {
+                const int yy = op / (KC * 2), rem = op - yy * (KC * 2), c = rem >> 1, pl = rem & 1;
                 const int row = (int)(qrow0 + (int64_t)(qy0 + yy) * a.w + qx0);
-                for (int c = 0; c < KC; ++c) {
-                    tma_load_2d(q_smem + c * q_chunk + yy * 1024, &map_q_hi, c * 64, row, q_full);
-                    tma_load_2d(q_smem + q_plane + c * q_chunk + yy * 1024, &map_q_lo, c * 64, row, q_full);
-                }
+                tma_load_2d(q_smem + (pl ? q_plane : 0u) + c * q_chunk + yy * 1024, pl ? &map_q_lo : &map_q_hi, c * 64, row, q_full);
             }
             bool ok = mbar_wait(q_ready, 0, a.err);              // the staged query tile has moved to TMEM
             SubIter it;
@@ -294,12 +293,13 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 int nrun = 0;
                 for (; nrun < 2 && !it.done(); ++nrun, it.next())
                     rows[nrun] = (int)(a.key_frames[(int64_t)n * a.S + it.slot] * (int64_t)hw + it.kidx0());
-                mbar_expect_tx(k_full + st, (unsigned)nrun * 2u * (unsigned)KC * (TC_NS * 128u));
-                for (int r = 0; r < nrun; ++r)
-                    for (int c = 0; c < KC; ++c) {
-                        tma_load_2d(dst + c * k_chunk + r * (TC_NS * 128), &map_k_hi, c * 64, rows[r], k_full + st);
-                        tma_load_2d(dst + k_plane + c * k_chunk + r * (TC_NS * 128), &map_k_lo, c * 64, rows[r], k_full + st);
-                    }
+                if (lane == 0) mbar_expect_tx(k_full + st, (unsigned)nrun * 2u * (unsigned)KC * (TC_NS * 128u));
+                __syncwarp();
+                if (lane < nrun * KC * 2) {
+                    const int r = lane / (KC * 2), rem = lane - r * (KC * 2), c = rem >> 1, pl = rem & 1;
+                    tma_load_2d(dst + (pl ? k_plane : 0u) + c * k_chunk + r * (TC_NS * 128), pl ? &map_k_lo : &map_k_hi, c * 64,
+                                rows[r], k_full + st);
+                }
             }
         }
     } else if (warp == 1) {
