@@ -102,6 +102,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -304,15 +309,19 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp runs this loop with warp-uniform values (so the descriptors / TMEM addresses live in uniform
+        // registers and every tcgen05.mma is a single UTCHMMA, no divergence waterfall); one elected lane issues.
+        {
             const unsigned idesc = umma_idesc_f16(TC_M, TC_NT);
+            const unsigned tb = __shfl_sync(kFull, tmem_base, 0);
+            const unsigned u_qhi = tb, u_qlo = tb + (unsigned)(C / 2), u_acc = tb + 256u;
             bool ok = mbar_wait(q_ready, 0, a.err);
             tc_fence_after();
             SubIter it;
             it.init(&a, qy0, qx0);
-            for (unsigned t = 0; ok && !it.done(); ++t) {
-                it.next();
-                if (!it.done()) it.next();
+            const unsigned ntiles = (unsigned)((it.total_runs() + 1) / 2);
+            const unsigned k_base = __shfl_sync(kFull, smem_u32(k_smem), 0);
+            for (unsigned t = 0; ok && t < ntiles; ++t) {
                 const unsigned as = t & 1u, aph = (t >> 1) & 1u;
                 const unsigned st = t % TC_STAGES, ph = (t / TC_STAGES) & 1u;
                 ok = mbar_wait(t_empty + as, aph ^ 1u, a.err);
@@ -320,24 +329,27 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 ok = mbar_wait(k_full + st, ph, a.err);
                 if (!ok) break;
                 tc_fence_after();
-                const unsigned ka = smem_u32(k_smem + st * k_stage);
-                const unsigned d_main = tm_acc + as * 128u, d_corr = d_main + 64u;
-                unsigned lk_hi = desc_lo(ka), lk_lo = desc_lo(ka + k_plane);
-                unsigned a_hi = tm_qhi, a_lo = tm_qlo;
-                for (int cch = 0; cch < KC; ++cch) {
+                const unsigned ka = k_base + st * k_stage;
+                const unsigned d_main = u_acc + as * 128u, d_corr = d_main + 64u;
+                if (elect_one()) {
+                    unsigned lk_hi = desc_lo(ka), lk_lo = desc_lo(ka + k_plane);
+                    unsigned a_hi = u_qhi, a_lo = u_qlo;
+                    for (int cch = 0; cch < KC; ++cch) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t k_hi = desc_make(lk_hi + 2u * kk), k_lo = desc_make(lk_lo + 2u * kk);
-                        const unsigned accum = (cch | kk) ? 1u : 0u;
-                        tc_mma_f16_ts(d_main, a_hi + 8u * kk, k_hi, idesc, accum);
-                        tc_mma_f16_ts(d_corr, a_hi + 8u * kk, k_lo, idesc, accum);
-                        tc_mma_f16_ts(d_corr, a_lo + 8u * kk, k_hi, idesc, 1u);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t k_hi = desc_make(lk_hi + 2u * kk), k_lo = desc_make(lk_lo + 2u * kk);
+                            const unsigned accum = (cch | kk) ? 1u : 0u;
+                            tc_mma_f16_ts(d_main, a_hi + 8u * kk, k_hi, idesc, accum);
+                            tc_mma_f16_ts(d_corr, a_hi + 8u * kk, k_lo, idesc, accum);
+                            tc_mma_f16_ts(d_corr, a_lo + 8u * kk, k_hi, idesc, 1u);
+                        }
+                        lk_hi += k_chunk >> 4; lk_lo += k_chunk >> 4;
+                        a_hi += 32u; a_lo += 32u;
                     }
-                    lk_hi += k_chunk >> 4; lk_lo += k_chunk >> 4;
-                    a_hi += 32u; a_lo += 32u;
+                    tc_commit(k_empty + st);              // frees the key stage once these MMAs have read it
+                    tc_commit(t_full + as);               // accumulator stage complete
                 }
-                tc_commit(k_empty + st);              // frees the key stage once these MMAs have read it
-                tc_commit(t_full + as);               // accumulator stage complete
+                __syncwarp();
             }
         }
     } else {
