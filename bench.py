@@ -152,6 +152,7 @@ class HotPath:
         torch.manual_seed(0)
         self.head = torch.nn.Linear(c["Ce"], c["D"], bias=False).to(dev)
         self.rng_state = torch.tensor([123, 0], dtype=torch.int64, device=dev)
+        self.ones = torch.ones(1, device=dev)
         self.maps_in = self.maps.clone().requires_grad_(True)
         self.graph = None
         self.use_graph = use_graph
@@ -164,9 +165,9 @@ class HotPath:
         self.maps_in.grad = None
         self.head.weight.grad = None
         pooled = ops.pool_patch(self.maps_in)                                        # (BN, T, Ce)
-        f = self.head(pooled).view(c["B"], c["N"], c["T"], c["D"])
+        f = ops.head_linear(pooled, self.head.weight).view(c["B"], c["N"], c["T"], c["D"])
         q, loss, xent, acc = ops.walk(f, c["tau"], c["p"], rng="device", rng_state=self.rng_state)
-        loss.sum().backward()
+        loss.backward(self.ones)
         self.loss = loss
         return loss
 
@@ -336,9 +337,9 @@ def run_ours(args, rank, world, local_rank):
             x.grad = None
             hp.head.weight.grad = None
             pooled = ops.pool_patch(x)
-            f = hp.head(pooled).view(c["B"], c["N"], c["T"], c["D"])
+            f = ops.head_linear(pooled, hp.head.weight).view(c["B"], c["N"], c["T"], c["D"])
             q, loss, xent, acc = ops.walk(f, c["tau"], c["p"], rng="device", rng_state=hp.rng_state)
-            loss.sum().backward()
+            loss.backward(hp.ones)
             loss_host.copy_(loss.detach(), non_blocking=True)
             ghead_host.copy_(hp.head.weight.grad, non_blocking=True)
             done[cur].record()
@@ -378,8 +379,9 @@ def run_ours(args, rank, world, local_rank):
            "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "note": "pinned host maps -> device (double-buffered copy stream) -> hot path -> loss + head grad back to host"},
-           "gpu_launches": 3 * args.steps,
-           "gpu_launches_note": "per step: crw pool_fwd_kernel, walk_fused_kernel, pool_bwd_kernel (head GEMMs are cuBLAS)",
+           "gpu_launches": 7 * args.steps,
+           "gpu_launches_note": "per step: crw pool_fwd, walk_pairs_fwd, walk_chain, walk_pairs_bwd, gemm_f32 (split-K head wgrad), "
+                                "splitk_reduce, pool_bwd; head forward / input-gradient GEMMs are cuBLAS",
            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kr[dom]["gbs"], "peak": hbm, "unit": "GB/s",
                         "frac": kr[dom]["gbs"] / hbm, "traffic": traffic, "peak_source": src,
                         "step_hbm_frac": (2 * kr[dom]["algorithmic_bytes"]) / (ms / args.steps * 1e-3) / 1e9 / hbm},

@@ -85,6 +85,13 @@ int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float tempe
                      uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
                      float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
+/* ---- a1: weight gradient of the projection head, model.py:117 (nn.Linear(C_e,128,bias=False)) ---------------------
+ * dW (D,C) = grad_out^T (D,R) x (R,C) with R = B*N*T rows.  The forward and the input gradient stay on cuBLAS; this
+ * product has a tiny 128 x 512 output and a long reduction, so it is split over R (deterministic two-pass reduction). */
+size_t crw_head_wgrad_workspace_bytes(int64_t R, int D, int C);
+int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, void* workspace,
+                   size_t workspace_bytes, crw_stream_t stream);
+
 /* L2 normalisation of rows (F.normalize, eps 1e-12; model.py:118,329): q = f / max(|f|, eps).  inv_norm and norm
  * (rows each) are kept for the backward, which overwrites grad in place: g <- (g - q (q.g)) * inv_norm. */
 int crw_l2norm_fwd(const float* f, float* q, float* inv_norm, float* norm, int64_t rows, int D, crw_stream_t stream);

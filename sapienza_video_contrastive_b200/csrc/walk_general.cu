@@ -26,6 +26,7 @@ struct GemmArgs {
     int64_t csb, csj, ldc;
     int M, N, nj;
     int accumulate;
+    int ktot;                // split-K: if > 0, batch j covers k in [j*K[0], min((j+1)*K[0], ktot))
 };
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
         const float* Ap = g.A[t].p + b * g.A[t].sb + j * g.A[t].sj;
         const float* Bp = g.B[t].p + b * g.B[t].sb + j * g.B[t].sj;
         const int64_t ars = g.A[t].rs, acs = g.A[t].cs, brs = g.B[t].rs, bcs = g.B[t].cs;
-        const int K = g.K[t];
+        int K = g.K[t];
+        if (g.ktot > 0) K = min(K, g.ktot - j * g.K[t]);
         for (int k0 = 0; k0 < K; k0 += BK) {
 #pragma unroll
             for (int pass = 0; pass < 4; ++pass) {
@@ -587,6 +589,47 @@ extern "C" int crw_stoch_mat(float* A, const float* drop_uniform, float rate, fl
     if (s.rows == 0) return CRW_OK;
     CRW_LAUNCH(stoch_rows_kernel, rows_grid(s.rows), 256, 0, stream, s);
     return check_launch("stoch_mat");
+}
+
+// ---- head weight gradient: dW (D,C) = g^T (D,R) x (R,C), split over R so the small output still fills the GPU ----
+namespace crw {
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int j = 0; j < S; ++j) s += part[(int64_t)j * n + e];          // fixed order: deterministic
+        out[e] = s;
+    }
+}
+static int wgrad_splits(int64_t R, int D, int C) {
+    const int tiles = ((D + BM - 1) / BM) * ((C + BN - 1) / BN);
+    int S = (148 * 4 + tiles - 1) / tiles;                                   // ~4 CTAs per SM
+    const int maxS = (int)((R + 63) / 64);
+    if (S > maxS) S = maxS;
+    return S < 1 ? 1 : S;
+}
+}  // namespace crw
+
+extern "C" size_t crw_head_wgrad_workspace_bytes(int64_t R, int D, int C) {
+    if (R <= 0 || D <= 0 || C <= 0) return 0;
+    return sizeof(float) * (size_t)wgrad_splits(R, D, C) * D * C;
+}
+
+extern "C" int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, void* workspace,
+                              size_t workspace_bytes, crw_stream_t stream) {
+    if (R <= 0 || D <= 0 || C <= 0) { set_error("head_wgrad: bad shape"); return CRW_ERR_SHAPE; }
+    const int S = wgrad_splits(R, D, C);
+    if (!workspace || workspace_bytes < sizeof(float) * (size_t)S * D * C) { set_error("head_wgrad: workspace too small"); return CRW_ERR_SHAPE; }
+    const int KS = (int)((R + S - 1) / S);
+    GemmArgs g{};
+    g.nterms = 1; g.K[0] = KS; g.ktot = (int)R; g.M = D; g.N = C; g.nj = S; g.accumulate = 0;
+    g.A[0] = mref(grad_out, 0, (int64_t)KS * D, 1, D);          // A(r = d, k = row): g[row*D + d]
+    g.B[0] = mref(x, 0, (int64_t)KS * C, C, 1);                 // B(k = row, c)
+    g.C = (float*)workspace; g.csb = 0; g.csj = (int64_t)D * C; g.ldc = C;
+    int e = run_gemm(g, 1, stream);
+    if (e != CRW_OK) return e;
+    const int64_t n = (int64_t)D * C;
+    CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256), 256, 0, stream, (const float*)workspace, dW, n, S);
+    return check_launch("head_wgrad_reduce");
 }
 
 extern "C" int crw_l2norm_fwd(const float* f, float* q, float* inv_norm, float* norm, int64_t rows, int D, crw_stream_t stream) {

@@ -144,8 +144,15 @@ class CRW(nn.Module):
             maps = maps.permute(0, 3, 4, 1, 2).contiguous()
             maps = maps.view(-1, *maps.shape[3:])[..., None, None]
             N, H, W = maps.shape[0] // B, 1, 1
-        f = self.selfsim_fc(self._pool_nodes(maps))                              # (BN, T, D), contiguous
+        f = self._head(self._pool_nodes(maps))                                   # (BN, T, D), contiguous
         return f.reshape(B, N, T, f.shape[-1]), maps.view(B, N, *maps.shape[1:]), B, N
+
+    def _head(self, pooled):
+        """selfsim_fc (model.py:117).  The default single bias-free Linear goes through ops.head_linear (same cuBLAS forward,
+        split-K weight gradient); deeper heads (head_depth > 0) run as the stock nn.Sequential."""
+        if len(self.selfsim_fc) == 1 and pooled.is_cuda:
+            return ops.head_linear(pooled, self.selfsim_fc[0].weight)
+        return self.selfsim_fc(pooled)
 
     @staticmethod
     def _pool_nodes(maps):
@@ -166,7 +173,7 @@ class CRW(nn.Module):
             maps = self.featdrop(maps)
         labels = sp_mask[:, :, 0, :, :]                                          # strided view, no copy (model.py:298)
         pooled = ops.segment_mean(maps, labels, int(max_sp_num))                 # (B, SP, T, C')
-        return self.selfsim_fc(pooled), maps                                     # (B, SP, T, D)
+        return self._head(pooled), maps                                          # (B, SP, T, D)
 
     # -- forward (model.py:334-415) ----------------------------------------------------------------------------------
     def forward(self, x, sp_mask=None, max_sp_num=None, just_feats=False, orig_unnorm=None, walk_uniforms=None):

@@ -99,6 +99,41 @@ def pool_patch(maps: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# a1: projection head (model.py:117).  Forward and input gradient are stock cuBLAS GEMMs (torch.matmul); the weight
+# gradient - 128 x 512 outputs reduced over B*N*T rows - uses the split-K kernel.
+# ------------------------------------------------------------------------------------------------------------------
+class _HeadLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        _need_cuda(x, weight)
+        ctx.save_for_backward(x, weight)
+        return x.matmul(weight.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = g.matmul(weight)
+        if ctx.needs_input_grad[1]:
+            D, C = weight.shape
+            g2, x2 = _f32c(g.reshape(-1, D)), _f32c(x.reshape(-1, C))
+            R = g2.shape[0]
+            L = _lib.lib()
+            nbytes = L.crw_head_wgrad_workspace_bytes(R, D, C)
+            ws = _workspace(("wgrad", R, D, C), nbytes, g.device)
+            gw = torch.empty(D, C, dtype=torch.float32, device=g.device)
+            L.check(L.crw_head_wgrad(g2.data_ptr(), x2.data_ptr(), gw.data_ptr(), R, D, C, ws.data_ptr(), ws.numel(), _stream()),
+                    "head_wgrad")
+        return gx, gw
+
+
+def head_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """x (..., C) @ weight (D, C)^T -> (..., D); nn.Linear(bias=False) with a split-K weight gradient."""
+    return _HeadLinear.apply(x, weight)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # a2/a3: superpixel segment-mean pooling (model.py:296-325)
 # ------------------------------------------------------------------------------------------------------------------
 class _SegMean(torch.autograd.Function):

@@ -403,3 +403,20 @@ def test_label_prop_tensor_core_path(ops, C, h, w, n_ctx, n_tgt, k, radius, dyad
         if n >= 1:
             assert float((It[n] == iref).float().mean()) > 0.995
     torch.testing.assert_close(Wt, Ws_, rtol=2e-4, atol=1e-6)
+
+
+def test_head_linear_matches_nn_linear(ops):
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(512, 128, bias=False).to(DEV)
+    x = torch.randn(980, 4, 512, device=DEV, requires_grad=True)
+    g = torch.randn(980, 4, 128, device=DEV)
+    y0 = lin(x)
+    y0.backward(g)
+    gx0, gw0 = x.grad.clone(), lin.weight.grad.clone()
+    x.grad = None
+    lin.weight.grad = None
+    y1 = ops.head_linear(x, lin.weight)
+    y1.backward(g)
+    torch.testing.assert_close(y1, y0, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(x.grad, gx0, rtol=1e-5, atol=1e-5)
+    assert relmax(lin.weight.grad, gw0) < 1e-5

@@ -335,3 +335,14 @@ def test_walk_device_rng_state(sim, flags):
     u21p = u[T - 1:].view(T - 1, B, N, N).contiguous()
     q, xe5, _, g5 = run_walk(sim, f, 0.07, 0.3, u12, u21p, flags)
     assert torch.equal(xe5, xe1) and torch.equal(g5, g1)
+
+
+def test_head_wgrad_splitk(sim):
+    torch.manual_seed(0)
+    R, D, C = 389, 128, 96
+    g, x = torch.randn(R, D), torch.randn(R, C)
+    nb = sim.crw_head_wgrad_workspace_bytes(R, D, C)
+    ws = torch.empty(nb, dtype=torch.uint8)
+    dW = torch.empty(D, C)
+    sim.check(sim.crw_head_wgrad(ptr(g), ptr(x), ptr(dW), R, D, C, ptr(ws), nb, None))
+    torch.testing.assert_close(dW, g.t() @ x, rtol=1e-4, atol=1e-4)
