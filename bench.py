@@ -168,6 +168,7 @@ class HotPath:
         f = ops.head_linear(pooled, self.head.weight).view(c["B"], c["N"], c["T"], c["D"])
         q, loss, xent, acc = ops.walk(f, c["tau"], c["p"], rng="device", rng_state=self.rng_state)
         loss.backward(self.ones)
+        ops.join_side_streams()                       # the head's weight gradient ran beside the pooling backward
         self.loss = loss
         return loss
 
@@ -295,6 +296,7 @@ def run_ours(args, rank, world, local_rank):
     _lib.lib()
     ops.check_device(dev)
     c = CFG
+    ops.set_async_wgrad(True)
     hp = HotPath(dev, rank, use_graph=not args.eager)
     hp.prepare()
     grads = torch.zeros(RESNET18_GRAD_FLOATS, device=dev) if world > 1 else None
@@ -340,6 +342,7 @@ def run_ours(args, rank, world, local_rank):
             f = ops.head_linear(pooled, hp.head.weight).view(c["B"], c["N"], c["T"], c["D"])
             q, loss, xent, acc = ops.walk(f, c["tau"], c["p"], rng="device", rng_state=hp.rng_state)
             loss.backward(hp.ones)
+            ops.join_side_streams()
             loss_host.copy_(loss.detach(), non_blocking=True)
             ghead_host.copy_(hp.head.weight.grad, non_blocking=True)
             done[cur].record()

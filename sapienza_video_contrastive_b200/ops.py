@@ -102,6 +102,34 @@ def pool_patch(maps: torch.Tensor) -> torch.Tensor:
 # a1: projection head (model.py:117).  Forward and input gradient are stock cuBLAS GEMMs (torch.matmul); the weight
 # gradient - 128 x 512 outputs reduced over B*N*T rows - uses the split-K kernel.
 # ------------------------------------------------------------------------------------------------------------------
+_async_wgrad = False
+_side_streams = {}
+_pending_events = []
+
+
+def set_async_wgrad(flag: bool) -> None:
+    """Opt-in: run the head's weight-gradient kernel on a side stream so it overlaps the (HBM-bound) pooling backward.
+    The caller must then call `join_side_streams()` before anything consumes `weight.grad` (optimizer step, all-reduce,
+    a copy to the host, the end of a CUDA-graph capture).  Off by default: the drop-in module needs no extra calls."""
+    global _async_wgrad
+    _async_wgrad = bool(flag)
+
+
+def join_side_streams() -> None:
+    """Make the current stream wait for every side-stream launch issued since the last join."""
+    cur = torch.cuda.current_stream()
+    while _pending_events:
+        cur.wait_event(_pending_events.pop())
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _side_streams:
+        _side_streams[idx] = torch.cuda.Stream(device=idx)
+    return _side_streams[idx]
+
+
 class _HeadLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
@@ -113,6 +141,11 @@ class _HeadLinear(torch.autograd.Function):
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         gx = gw = None
+        cur = torch.cuda.current_stream()
+        fork = None
+        if ctx.needs_input_grad[1] and _async_wgrad:
+            fork = torch.cuda.Event()
+            fork.record(cur)                       # the side stream only needs g and x, not the input gradient below
         if ctx.needs_input_grad[0]:
             gx = g.matmul(weight)
         if ctx.needs_input_grad[1]:
@@ -121,10 +154,23 @@ class _HeadLinear(torch.autograd.Function):
             R = g2.shape[0]
             L = _lib.lib()
             nbytes = L.crw_head_wgrad_workspace_bytes(R, D, C)
-            ws = _workspace(("wgrad", R, D, C), nbytes, g.device)
             gw = torch.empty(D, C, dtype=torch.float32, device=g.device)
-            L.check(L.crw_head_wgrad(g2.data_ptr(), x2.data_ptr(), gw.data_ptr(), R, D, C, ws.data_ptr(), ws.numel(), _stream()),
-                    "head_wgrad")
+            if fork is None:
+                ws = _workspace(("wgrad", R, D, C), nbytes, g.device)
+                L.check(L.crw_head_wgrad(g2.data_ptr(), x2.data_ptr(), gw.data_ptr(), R, D, C, ws.data_ptr(), ws.numel(),
+                                         _stream()), "head_wgrad")
+            else:
+                side = _side_stream(g.device)
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    ws = _workspace(("wgrad", R, D, C), nbytes, g.device)
+                    L.check(L.crw_head_wgrad(g2.data_ptr(), x2.data_ptr(), gw.data_ptr(), R, D, C, ws.data_ptr(), ws.numel(),
+                                             side.cuda_stream), "head_wgrad")
+                    done = torch.cuda.Event()
+                    done.record(side)
+                for t in (g2, x2, gw):
+                    t.record_stream(side)
+                _pending_events.append(done)
         return gx, gw
 
 

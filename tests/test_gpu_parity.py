@@ -420,3 +420,26 @@ def test_head_linear_matches_nn_linear(ops):
     torch.testing.assert_close(y1, y0, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(x.grad, gx0, rtol=1e-5, atol=1e-5)
     assert relmax(lin.weight.grad, gw0) < 1e-5
+
+
+def test_async_wgrad_overlap_gives_identical_gradients(ops):
+    """ops.set_async_wgrad(True) only changes scheduling (side stream + explicit join), never values."""
+    torch.manual_seed(1)
+    w = torch.randn(128, 512, device=DEV, requires_grad=True)
+    maps = torch.randn(98, 4, 512, 8, 8, device=DEV)
+    outs = []
+    for flag in (False, True):
+        ops.set_async_wgrad(flag)
+        try:
+            w.grad = None
+            m = maps.clone().requires_grad_(True)
+            f = ops.head_linear(ops.pool_patch(m), w).view(2, 49, 4, 128)
+            torch.manual_seed(5)
+            q, loss, xent, acc = ops.walk(f, 0.07, 0.1)
+            loss.backward()
+            ops.join_side_streams()
+            torch.cuda.synchronize()
+            outs.append((w.grad.clone(), m.grad.clone()))
+        finally:
+            ops.set_async_wgrad(False)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
