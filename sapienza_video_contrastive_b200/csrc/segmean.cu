@@ -5,11 +5,10 @@
 // straight from the label map:
 //   1. segmean_count: one warp per feature cell turns its sy*sx labels into a short (label,count) list
 //      (<= 64 entries, typically 1-4) and adds the counts to the per-label sizes;
-//   2. segmean_accum: one CTA per (clip, frame, 32-channel tile) streams the feature tile once, coalesced, and
-//      scatter-adds count*feature into a shared-memory accumulator [SP][32+1]; the epilogue divides by the sizes;
+//   2. segmean_accum: one CTA per (clip, frame, 16-channel tile) pulls the feature tile in with TMA bulk copies and
+//      reduces it per label through per-label cell bitmasks (see the kernel); the epilogue divides by the sizes;
 //   3. segmean_bwd mirrors 2 as a gather (deterministic).
-// Neither the one-hot nor the broadcast product is ever materialised.  The forward uses shared-memory fp32 atomics,
-// so the summation order inside a segment is not fixed (differences ~1e-7 relative).
+// Neither the one-hot nor the broadcast product is ever materialised; forward and backward are deterministic.
 #include "common.cuh"
 
 namespace crw {
@@ -88,43 +87,100 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
     }
 }
 
-__device__ __forceinline__ void smem_red_add(float* p, float v) {
-#ifdef CRW_SIM
-    *p += v;
-#else
-    atomicAdd(p, v);
-#endif
-}
+// Forward accumulation, one CTA per (clip, frame, 16-channel tile):
+//   * the feature tile [16 channels][cells] arrives by TMA bulk copies (each channel row is contiguous in HBM);
+//   * a per-label bitmask of the cells that contain the label is built in shared memory from the per-cell lists;
+//   * a warp owns a label at a time: for every 32-cell word of its mask, lane l takes cell 32w+l, looks its pixel count up
+//     once and feeds 16 per-channel register accumulators from conflict-free shared-memory rows; 16 butterfly sums finish
+//     the label.  No floating-point atomics: the result is deterministic and every feature is read from HBM exactly once.
+constexpr int kSegCTF = 16;          // channels per CTA in the forward
+constexpr int kSegSlots = 4;         // per-cell list entries cached in shared memory (rest read from the workspace)
 
 __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restrict__ maps, SegWs ws, int C, int T, int cells,
                                                             int SP, float* __restrict__ out) {
     CRW_DYN_SMEM(smem_raw);
-    float* acc = reinterpret_cast<float*>(smem_raw);            // [SP][kSegCT + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bt = blockIdx.y, b = bt / T, t = bt - b * T;
-    const int c0 = blockIdx.x * kSegCT;
-    constexpr int LD = kSegCT + 1;
-    for (int e = tid; e < SP * LD; e += 256) acc[e] = 0.f;
+    const int c0 = blockIdx.x * kSegCTF;
+    const int nwords = (cells + 31) / 32;
+    float* tile = reinterpret_cast<float*>(smem_raw);                              // [16][cells]
+    unsigned* mask = reinterpret_cast<unsigned*>(tile + kSegCTF * cells);           // [SP][nwords]
+    unsigned* ents = mask + (size_t)SP * nwords;                                    // [kSegSlots][cells]
+    unsigned char* nes = reinterpret_cast<unsigned char*>(ents + kSegSlots * cells);  // [cells]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(nes + ((cells + 15) & ~15));
+
+    const int nch = min(kSegCTF, C - c0);
+#ifndef CRW_SIM
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const unsigned char* nent = ws.nent + (int64_t)bt * cells;
-    const unsigned* ent = ws.ent + (int64_t)bt * ws.cap * cells;
-    for (int cell = lane; cell < cells; cell += 32) {
-        const int ne = nent[cell];
-        for (int cl = warp; cl < kSegCT; cl += 8) {
-            const int c = c0 + cl;
-            if (c >= C) break;
-            const float f = __ldg(maps + (((int64_t)b * C + c) * T + t) * cells + cell);
-            for (int s = 0; s < ne; ++s) {
-                const unsigned e = __ldg(ent + (int64_t)s * cells + cell);
-                smem_red_add(acc + (e >> 8) * LD + cl, (float)(e & 255u) * f);
-            }
+    if (tid == 0) {
+        const unsigned rowb = (unsigned)cells * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(rowb * (unsigned)nch) : "memory");
+        for (int c = 0; c < nch; ++c)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((unsigned)__cvta_generic_to_shared(tile + c * cells)),
+                            "l"(maps + (((int64_t)b * C + c0 + c) * T + t) * cells), "r"(rowb),
+                            "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+    }
+#else
+    for (int e = tid; e < nch * cells; e += 256) tile[e] = maps[(((int64_t)b * C + c0 + e / cells) * T + t) * cells + e % cells];
+#endif
+    // label masks + cached per-cell lists (overlaps the bulk copies)
+    for (int e = tid; e < SP * nwords; e += 256) mask[e] = 0u;
+    __syncthreads();
+    const unsigned char* gnent = ws.nent + (int64_t)bt * cells;
+    const unsigned* gent = ws.ent + (int64_t)bt * ws.cap * cells;
+    for (int cell = tid; cell < cells; cell += 256) {
+        const int ne = gnent[cell];
+        nes[cell] = (unsigned char)ne;
+        for (int sl = 0; sl < ne; ++sl) {
+            const unsigned e = gent[(int64_t)sl * cells + cell];
+            if (sl < kSegSlots) ents[sl * cells + cell] = e;
+            atomicOr(mask + (size_t)(e >> 8) * nwords + (cell >> 5), 1u << (cell & 31));
         }
     }
     __syncthreads();
+#ifndef CRW_SIM
+    {
+        const unsigned bb = (unsigned)__cvta_generic_to_shared(bar);
+        asm volatile("{\n\t.reg .pred p;\n\tSEG_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SEG_DONE_%=;\n\t"
+                     "bra SEG_WAIT_%=;\n\tSEG_DONE_%=:\n\t}" :: "r"(bb), "r"(0u) : "memory");
+    }
+#endif
     const int* size = ws.size + (int64_t)bt * SP;
-    for (int e = tid; e < SP * kSegCT; e += 256) {
-        const int s = e / kSegCT, cl = e - s * kSegCT;
-        if (c0 + cl < C) out[(((int64_t)b * SP + s) * T + t) * C + c0 + cl] = acc[s * LD + cl] / ((float)size[s] + kEpsLog);
+    for (int s = warp; s < SP; s += 8) {
+        float acc[kSegCTF];
+#pragma unroll
+        for (int c = 0; c < kSegCTF; ++c) acc[c] = 0.f;
+        for (int w = 0; w < nwords; ++w) {
+            const unsigned bits = mask[(size_t)s * nwords + w];
+            if (!bits) continue;                                        // warp-uniform
+            const int cell = w * 32 + lane;
+            float cnt = 0.f;
+            if ((bits >> lane) & 1u) {
+                const int ne = nes[cell];
+                for (int sl = 0; sl < ne; ++sl) {
+                    const unsigned e = sl < kSegSlots ? ents[sl * cells + cell] : gent[(int64_t)sl * cells + cell];
+                    if ((int)(e >> 8) == s) { cnt = (float)(e & 255u); break; }
+                }
+            }
+            if (cell < cells) {
+#pragma unroll
+                for (int c = 0; c < kSegCTF; ++c) acc[c] = fmaf(cnt, tile[c * cells + cell], acc[c]);
+            }
+        }
+        const float den = (float)size[s] + kEpsLog;
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < kSegCTF; ++c) {
+            const float v = warp_sum(acc[c]);
+            if (lane == c) mine = v;
+        }
+        if (lane < nch) out[(((int64_t)b * SP + s) * T + t) * C + c0 + lane] = mine / den;
     }
 }
 
@@ -198,10 +254,16 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     CRW_LAUNCH(segmean_count_kernel, grid1, 256, 0, stream, labels, ls_b, ls_t, ls_y, ls_x, T, Hm, Wm, h / Hm, w / Wm, SP, ws, total);
     e = check_launch("segmean_count");
     if (e != CRW_OK) return e;
-    const size_t smem = (size_t)SP * (kSegCT + 1) * sizeof(float);
+    const int nwords = (cells + 31) / 32;
+    const size_t smem = sizeof(float) * (size_t)kSegCTF * cells + sizeof(unsigned) * ((size_t)SP * nwords + (size_t)kSegSlots * cells) +
+                        (size_t)((cells + 15) & ~15) + 16;
+    if (smem > 227 * 1024 || (cells * 4) % 16 != 0 || (((uintptr_t)maps) & 15) != 0) {
+        set_error("segmean_fwd: unsupported size (cells=%d, SP=%d) or unaligned maps", cells, SP);
+        return CRW_ERR_UNSUPPORTED;
+    }
     auto k = segmean_accum_kernel;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((C + kSegCT - 1) / kSegCT, B * T);
+    dim3 grid((C + kSegCTF - 1) / kSegCTF, B * T);
     CRW_LAUNCH(k, grid, 256, smem, stream, maps, ws, C, T, cells, SP, out);
     return check_launch("segmean_accum");
 }

@@ -166,6 +166,7 @@ static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mas
 
 // atomics: fibers are cooperatively scheduled on one OS thread, so plain RMW is atomic
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; *p = o > v ? o : v; return o; }
 static inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *p = (o >= lim) ? 0 : o + 1; return o; }
 static inline unsigned atomicExch(unsigned* p, unsigned v) { unsigned o = *p; *p = v; return o; }
