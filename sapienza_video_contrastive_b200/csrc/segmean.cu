@@ -5,7 +5,7 @@
 // straight from the label map:
 //   1. segmean_count: one warp per feature cell turns its sy*sx labels into a short (label,count) list
 //      (<= 64 entries, typically 1-4) and adds the counts to the per-label sizes;
-//   2. segmean_accum: one CTA per (clip, frame, 16-channel tile) pulls the feature tile in with TMA bulk copies and
+//   2. segmean_accum: one CTA per (clip, frame, 32-channel tile) stages the feature tile transposed in shared memory and
 //      reduces it per label through per-label cell bitmasks (see the kernel); the epilogue divides by the sizes;
 //   3. segmean_bwd mirrors 2 as a gather (deterministic).
 // Neither the one-hot nor the broadcast product is ever materialised; forward and backward are deterministic.
@@ -87,13 +87,14 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
     }
 }
 
-// Forward accumulation, one CTA per (clip, frame, 16-channel tile):
-//   * the feature tile [16 channels][cells] arrives by TMA bulk copies (each channel row is contiguous in HBM);
-//   * a per-label bitmask of the cells that contain the label is built in shared memory from the per-cell lists;
-//   * a warp owns a label at a time: for every 32-cell word of its mask, lane l takes cell 32w+l, looks its pixel count up
-//     once and feeds 16 per-channel register accumulators from conflict-free shared-memory rows; 16 butterfly sums finish
-//     the label.  No floating-point atomics: the result is deterministic and every feature is read from HBM exactly once.
-constexpr int kSegCTF = 16;          // channels per CTA in the forward
+// Forward accumulation, one CTA per (clip, frame, 32-channel tile):
+//   * the feature tile is read once, coalesced along the cells, and stored TRANSPOSED in shared memory ([cell][32+1]) so
+//     that the 32 lanes of a warp = 32 channels read one cell's features without bank conflicts;
+//   * a per-label bitmask of the cells containing the label (plus a 32-bit summary of its non-empty words) is built in
+//     shared memory from the per-cell lists;
+//   * a warp owns one label at a time and walks the set bits of its mask in increasing cell order: every lane does one
+//     useful FMA per (cell, label) entry.  No floating-point atomics: deterministic, each feature read from HBM once.
+constexpr int kSegCTF = 32;          // channels per CTA in the forward
 constexpr int kSegSlots = 4;         // per-cell list entries cached in shared memory (rest read from the workspace)
 
 __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restrict__ maps, SegWs ws, int C, int T, int cells,
@@ -103,34 +104,21 @@ __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restr
     const int bt = blockIdx.y, b = bt / T, t = bt - b * T;
     const int c0 = blockIdx.x * kSegCTF;
     const int nwords = (cells + 31) / 32;
-    float* tile = reinterpret_cast<float*>(smem_raw);                              // [16][cells]
-    unsigned* mask = reinterpret_cast<unsigned*>(tile + kSegCTF * cells);           // [SP][nwords]
-    unsigned* ents = mask + (size_t)SP * nwords;                                    // [kSegSlots][cells]
+    constexpr int LD = kSegCTF + 1;
+    float* tile = reinterpret_cast<float*>(smem_raw);                              // [cells][33]
+    unsigned* mask = reinterpret_cast<unsigned*>(tile + (size_t)cells * LD);        // [SP][nwords]
+    unsigned* occ = mask + (size_t)SP * nwords;                                     // [SP] non-empty words (nwords <= 32)
+    unsigned* ents = occ + SP;                                                      // [kSegSlots][cells]
     unsigned char* nes = reinterpret_cast<unsigned char*>(ents + kSegSlots * cells);  // [cells]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(nes + ((cells + 15) & ~15));
 
-    const int nch = min(kSegCTF, C - c0);
-#ifndef CRW_SIM
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(1) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned rowb = (unsigned)cells * 4u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                     :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(rowb * (unsigned)nch) : "memory");
-        for (int c = 0; c < nch; ++c)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"((unsigned)__cvta_generic_to_shared(tile + c * cells)),
-                            "l"(maps + (((int64_t)b * C + c0 + c) * T + t) * cells), "r"(rowb),
-                            "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-    }
-#else
-    for (int e = tid; e < nch * cells; e += 256) tile[e] = maps[(((int64_t)b * C + c0 + e / cells) * T + t) * cells + e % cells];
-#endif
-    // label masks + cached per-cell lists (overlaps the bulk copies)
     for (int e = tid; e < SP * nwords; e += 256) mask[e] = 0u;
+    for (int e = tid; e < SP; e += 256) occ[e] = 0u;
+    // transposing tile load: warp w streams channels w, w+8, ... (coalesced along the cells)
+    for (int cl = warp; cl < kSegCTF; cl += 8) {
+        const int c = c0 + cl;
+        const float* src = maps + (((int64_t)b * C + min(c, C - 1)) * T + t) * cells;
+        for (int cell = lane; cell < cells; cell += 32) tile[cell * LD + cl] = c < C ? __ldg(src + cell) : 0.f;
+    }
     __syncthreads();
     const unsigned char* gnent = ws.nent + (int64_t)bt * cells;
     const unsigned* gent = ws.ent + (int64_t)bt * ws.cap * cells;
@@ -141,46 +129,31 @@ __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restr
             const unsigned e = gent[(int64_t)sl * cells + cell];
             if (sl < kSegSlots) ents[sl * cells + cell] = e;
             atomicOr(mask + (size_t)(e >> 8) * nwords + (cell >> 5), 1u << (cell & 31));
+            atomicOr(occ + (e >> 8), 1u << (cell >> 5));
         }
     }
     __syncthreads();
-#ifndef CRW_SIM
-    {
-        const unsigned bb = (unsigned)__cvta_generic_to_shared(bar);
-        asm volatile("{\n\t.reg .pred p;\n\tSEG_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SEG_DONE_%=;\n\t"
-                     "bra SEG_WAIT_%=;\n\tSEG_DONE_%=:\n\t}" :: "r"(bb), "r"(0u) : "memory");
-    }
-#endif
     const int* size = ws.size + (int64_t)bt * SP;
     for (int s = warp; s < SP; s += 8) {
-        float acc[kSegCTF];
-#pragma unroll
-        for (int c = 0; c < kSegCTF; ++c) acc[c] = 0.f;
-        for (int w = 0; w < nwords; ++w) {
-            const unsigned bits = mask[(size_t)s * nwords + w];
-            if (!bits) continue;                                        // warp-uniform
-            const int cell = w * 32 + lane;
-            float cnt = 0.f;
-            if ((bits >> lane) & 1u) {
+        float acc = 0.f;
+        unsigned ow = occ[s];
+        while (ow) {                                                    // warp-uniform control flow throughout
+            const int w = __ffs((int)ow) - 1;
+            ow &= ow - 1;
+            unsigned bits = mask[(size_t)s * nwords + w];
+            while (bits) {
+                const int cell = w * 32 + __ffs((int)bits) - 1;
+                bits &= bits - 1;
                 const int ne = nes[cell];
+                float cnt = 0.f;
                 for (int sl = 0; sl < ne; ++sl) {
                     const unsigned e = sl < kSegSlots ? ents[sl * cells + cell] : gent[(int64_t)sl * cells + cell];
                     if ((int)(e >> 8) == s) { cnt = (float)(e & 255u); break; }
                 }
-            }
-            if (cell < cells) {
-#pragma unroll
-                for (int c = 0; c < kSegCTF; ++c) acc[c] = fmaf(cnt, tile[c * cells + cell], acc[c]);
+                acc = fmaf(cnt, tile[cell * LD + lane], acc);
             }
         }
-        const float den = (float)size[s] + kEpsLog;
-        float mine = 0.f;
-#pragma unroll
-        for (int c = 0; c < kSegCTF; ++c) {
-            const float v = warp_sum(acc[c]);
-            if (lane == c) mine = v;
-        }
-        if (lane < nch) out[(((int64_t)b * SP + s) * T + t) * C + c0 + lane] = mine / den;
+        if (c0 + lane < C) out[(((int64_t)b * SP + s) * T + t) * C + c0 + lane] = acc / ((float)size[s] + kEpsLog);
     }
 }
 
@@ -255,10 +228,10 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     e = check_launch("segmean_count");
     if (e != CRW_OK) return e;
     const int nwords = (cells + 31) / 32;
-    const size_t smem = sizeof(float) * (size_t)kSegCTF * cells + sizeof(unsigned) * ((size_t)SP * nwords + (size_t)kSegSlots * cells) +
+    const size_t smem = sizeof(float) * (size_t)cells * (kSegCTF + 1) + sizeof(unsigned) * ((size_t)SP * nwords + SP + (size_t)kSegSlots * cells) +
                         (size_t)((cells + 15) & ~15) + 16;
-    if (smem > 227 * 1024 || (cells * 4) % 16 != 0 || (((uintptr_t)maps) & 15) != 0) {
-        set_error("segmean_fwd: unsupported size (cells=%d, SP=%d) or unaligned maps", cells, SP);
+    if (smem > 227 * 1024 || nwords > 32) {
+        set_error("segmean_fwd: unsupported size (cells=%d, SP=%d)", cells, SP);
         return CRW_ERR_UNSUPPORTED;
     }
     auto k = segmean_accum_kernel;
