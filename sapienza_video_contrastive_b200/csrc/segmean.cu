@@ -113,11 +113,34 @@ __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restr
 
     for (int e = tid; e < SP * nwords; e += 256) mask[e] = 0u;
     for (int e = tid; e < SP; e += 256) occ[e] = 0u;
-    // transposing tile load: warp w streams channels w, w+8, ... (coalesced along the cells)
+    // transposing tile load: warp w streams channels w, w+8, ... (coalesced along the cells, 8 x 128-bit loads in flight per lane)
+    const bool vec = (cells & 127) == 0 && ((reinterpret_cast<uintptr_t>(maps) & 15) == 0);
     for (int cl = warp; cl < kSegCTF; cl += 8) {
         const int c = c0 + cl;
         const float* src = maps + (((int64_t)b * C + min(c, C - 1)) * T + t) * cells;
-        for (int cell = lane; cell < cells; cell += 32) tile[cell * LD + cl] = c < C ? __ldg(src + cell) : 0.f;
+        if (vec) {
+            for (int base = 0; base < cells; base += 1024) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int cell = base + (u * 32 + lane) * 4;
+                    v[u] = cell < cells ? __ldg(reinterpret_cast<const float4*>(src + cell)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int cell = base + (u * 32 + lane) * 4;
+                    if (cell < cells) {
+                        const float m = c < C ? 1.f : 0.f;
+                        tile[(cell + 0) * LD + cl] = v[u].x * m;
+                        tile[(cell + 1) * LD + cl] = v[u].y * m;
+                        tile[(cell + 2) * LD + cl] = v[u].z * m;
+                        tile[(cell + 3) * LD + cl] = v[u].w * m;
+                    }
+                }
+            }
+        } else {
+            for (int cell = lane; cell < cells; cell += 32) tile[cell * LD + cl] = c < C ? __ldg(src + cell) : 0.f;
+        }
     }
     __syncthreads();
     const unsigned char* gnent = ws.nent + (int64_t)bt * cells;
