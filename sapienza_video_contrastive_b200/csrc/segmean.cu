@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
 //     useful FMA per (cell, label) entry.  No floating-point atomics: deterministic, each feature read from HBM once.
 constexpr int kSegCTF = 32;          // channels per CTA in the forward
 constexpr int kSegSlots = 4;         // per-cell list entries cached in shared memory (rest read from the workspace)
+constexpr int kSegFwdThreads = 1024; // one CTA per SM (the transposed tile fills shared memory): many warps hide the label walks' latency
 
-__global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restrict__ maps, SegWs ws, int C, int T, int cells,
+__global__ void __launch_bounds__(kSegFwdThreads, 1) segmean_accum_kernel(const float* __restrict__ maps, SegWs ws, int C, int T, int cells,
                                                             int SP, float* __restrict__ out) {
     CRW_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,11 +112,11 @@ __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restr
     unsigned* ents = occ + SP;                                                      // [kSegSlots][cells]
     unsigned char* nes = reinterpret_cast<unsigned char*>(ents + kSegSlots * cells);  // [cells]
 
-    for (int e = tid; e < SP * nwords; e += 256) mask[e] = 0u;
-    for (int e = tid; e < SP; e += 256) occ[e] = 0u;
+    for (int e = tid; e < SP * nwords; e += kSegFwdThreads) mask[e] = 0u;
+    for (int e = tid; e < SP; e += kSegFwdThreads) occ[e] = 0u;
     // transposing tile load: warp w streams channels w, w+8, ... (coalesced along the cells, 8 x 128-bit loads in flight per lane)
     const bool vec = (cells & 127) == 0 && ((reinterpret_cast<uintptr_t>(maps) & 15) == 0);
-    for (int cl = warp; cl < kSegCTF; cl += 8) {
+    for (int cl = warp; cl < kSegCTF; cl += kSegFwdThreads / 32) {
         const int c = c0 + cl;
         const float* src = maps + (((int64_t)b * C + min(c, C - 1)) * T + t) * cells;
         if (vec) {
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restr
     __syncthreads();
     const unsigned char* gnent = ws.nent + (int64_t)bt * cells;
     const unsigned* gent = ws.ent + (int64_t)bt * ws.cap * cells;
-    for (int cell = tid; cell < cells; cell += 256) {
+    for (int cell = tid; cell < cells; cell += kSegFwdThreads) {
         const int ne = gnent[cell];
         nes[cell] = (unsigned char)ne;
         for (int sl = 0; sl < ne; ++sl) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) segmean_accum_kernel(const float* __restr
     }
     __syncthreads();
     const int* size = ws.size + (int64_t)bt * SP;
-    for (int s = warp; s < SP; s += 8) {
+    for (int s = warp; s < SP; s += kSegFwdThreads / 32) {
         float acc = 0.f;
         unsigned ow = occ[s];
         while (ow) {                                                    // warp-uniform control flow throughout
@@ -260,7 +261,7 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     auto k = segmean_accum_kernel;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((C + kSegCTF - 1) / kSegCTF, B * T);
-    CRW_LAUNCH(k, grid, 256, smem, stream, maps, ws, C, T, cells, SP, out);
+    CRW_LAUNCH(k, grid, kSegFwdThreads, smem, stream, maps, ws, C, T, cells, SP, out);
     return check_launch("segmean_accum");
 }
 
