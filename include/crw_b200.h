@@ -28,8 +28,9 @@ extern "C" {
 /* walk flags */
 #define CRW_WALK_SOFTMAX 1u   /* F.softmax rows (teacherstudent.py:80) instead of ZeroSoftmax (model.py:90) */
 #define CRW_WALK_FLIP 2u      /* args.flip: reversed product order, model.py:380-382 */
-#define CRW_WALK_FORCE_GENERAL 4u
-#define CRW_LP_FORCE_SIMT 1u /* skip the single-CTA fused kernel even when the clip fits shared memory */
+#define CRW_WALK_FORCE_GENERAL 4u /* skip the fused small-graph kernels even when the clip fits shared memory */
+#define CRW_WALK_FORCE_SIMT 8u    /* large-graph path: exact-fp32 SIMT GEMMs instead of the tcgen05 hi/lo-split GEMM */
+#define CRW_LP_FORCE_SIMT 1u      /* label propagation: exact-fp32 SIMT scores instead of the tcgen05 kernel */
 
 typedef void* crw_stream_t;
 
@@ -97,6 +98,15 @@ int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, 
 int crw_l2norm_fwd(const float* f, float* q, float* inv_norm, float* norm, int64_t rows, int D, crw_stream_t stream);
 int crw_l2norm_bwd(const float* q, float* grad_inout, const float* inv_norm, const float* norm, int64_t rows, int D,
                    crw_stream_t stream);
+
+/* Batched fp32-faithful GEMM on the tensor cores (the contraction engine of the large-graph walk, exported for
+ * tests and for callers of CRW.affinity at large N): C[z] (M,N) (+)= op(A[z]) (M,K) op(B[z]) (K,N), all fp32 row-major
+ * contiguous; trans_a: A stored (Z,K,M); trans_b: B stored (Z,N,K).  Operands are split into per-row-scaled fp16
+ * hi/lo planes and multiplied with three tcgen05 MMAs per k-step (error ~2^-22 |a||b|).  Needs M >= 128, N >= 64,
+ * K >= 64 (CRW_ERR_UNSUPPORTED otherwise).  Workspace: zero-filled once, crw_bmm_tc_workspace_bytes. */
+size_t crw_bmm_tc_workspace_bytes(int Z, int M, int N, int K);
+int crw_bmm_tc(const float* A, const float* B, float* C, int Z, int M, int N, int K, int trans_a, int trans_b,
+               int accumulate, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
 /* torch-compatible uniform draw (same Philox stream as torch.rand on CUDA); used by tests to pin the
  * in-kernel replay.  out (n). */

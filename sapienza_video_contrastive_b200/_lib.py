@@ -22,6 +22,7 @@ CRW_OK = 0
 WALK_SOFTMAX = 1
 WALK_FLIP = 2
 WALK_FORCE_GENERAL = 4
+WALK_FORCE_SIMT = 8
 LP_FORCE_SIMT = 1
 
 _SIGNATURES = {
@@ -40,6 +41,8 @@ _SIGNATURES = {
                                  c_uint64, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
     "crw_philox_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint32, c_void_p]),
+    "crw_bmm_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "crw_bmm_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "crw_lp_topk_workspace_bytes": (c_size_t, [c_int] * 7),
     "crw_lp_topk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                             c_float, c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -100,7 +103,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in sources():
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + ARCH_FLAGS + ["-c", s, "-o", o]
+        cmd = ([NVCC, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + ARCH_FLAGS
+               + os.environ.get("CRW_NVCC_EXTRA", "").split() + ["-c", s, "-o", o])
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

@@ -25,6 +25,8 @@ struct WalkParams {
     unsigned* ws_counter;      // 1 ticket counter (zero between launches)
     float* ws_mats;            // general path: transition / chain / gradient matrices
     float* ws_stat;            // general path: row denominators, norms
+    void* ws_tc;               // general path: tensor-core GEMM operand planes (nullptr = SIMT GEMM only)
+    size_t ws_tc_bytes;
     // fused (small-N) path exchange buffers, all compact (stride N)
     float *ws_F, *ws_G, *ws_dF, *ws_dG;        // (B,T-1,N,N)
     float *ws_s12, *ws_s21;                    // (B,T-1,N) row denominators

@@ -1,6 +1,7 @@
 // walk_api.cu - C ABI of the walk (include/crw_b200.h): workspace carve-up and dispatch between the single-CTA
 // fused kernel (walk_fused.cu) and the batched multi-kernel path (walk_general.cu).
 #include "walk.cuh"
+#include "gemm_tc.cuh"
 
 using namespace crw;
 
@@ -8,7 +9,7 @@ namespace {
 
 struct WsLayout {
     size_t o_counter, o_clipcnt, o_partial, o_araw, o_codes, o_mats, o_stat;
-    size_t o_F, o_G, o_dF, o_dG, o_s12, o_s21, o_invn, o_nrm, o_dqa, o_dqb, total;
+    size_t o_F, o_G, o_dF, o_dG, o_s12, o_s21, o_invn, o_nrm, o_dqa, o_dqb, o_tc, tc_bytes, total;
     bool fused;
 };
 
@@ -34,6 +35,13 @@ WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
         w.o_invn = take(sizeof(float) * B * T * N); w.o_nrm = take(sizeof(float) * B * T * N);
         w.o_dqa = take(sizeof(float) * B * t1 * N * D); w.o_dqb = take(sizeof(float) * B * t1 * N * D);
     }
+    // general path on large graphs: operand planes of the tensor-core GEMM (gemm_tc.cu)
+    const int NK = N > D ? N : D;
+    // measured crossover against the SIMT GEMM (tools/bench_tc_gemm.py): 0.83x at N = 128, 1.1x at 196, 1.9x at 512, 4.1x at 1024
+    const bool tc = !w.fused && !(flags & CRW_WALK_FORCE_SIMT) && t1 > 0 && N >= 192 &&
+                    gemm_tc_eligible(N, N < D ? N : D, N < D ? N : D, NK);
+    w.tc_bytes = tc ? gemm_tc_workspace_bytes(N, NK, NK, (int)(B * t1)) : 0;
+    w.o_tc = take(w.tc_bytes);
     w.total = o;
     return w;
 }
@@ -78,6 +86,8 @@ extern "C" int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, 
     p.ws_mats = (float*)(ws + w.o_mats);
     p.ws_stat = (float*)(ws + w.o_stat);
     p.ws_clipcnt = (unsigned*)(ws + w.o_clipcnt);
+    p.ws_tc = w.tc_bytes ? (void*)(ws + w.o_tc) : nullptr;
+    p.ws_tc_bytes = w.tc_bytes;
     if (w.fused) {
         p.ws_F = (float*)(ws + w.o_F); p.ws_G = (float*)(ws + w.o_G);
         p.ws_dF = (float*)(ws + w.o_dF); p.ws_dG = (float*)(ws + w.o_dG);

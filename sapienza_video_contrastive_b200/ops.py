@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import WALK_FLIP, WALK_FORCE_GENERAL, WALK_SOFTMAX  # noqa: F401
+from ._lib import WALK_FLIP, WALK_FORCE_GENERAL, WALK_FORCE_SIMT, WALK_SOFTMAX  # noqa: F401
 
 
 def _stream() -> int:
@@ -395,7 +395,7 @@ class _Walk(torch.autograd.Function):
 
 def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = False, softmax: bool = False,
          rng: str = "philox", u12: Optional[torch.Tensor] = None, u21p: Optional[torch.Tensor] = None,
-         force_general: bool = False, rng_state: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+         force_general: bool = False, rng_state: Optional[torch.Tensor] = None, force_simt: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """feats (B,N,T,D) pre-normalisation node vectors -> (q (B,N,T,D) unit-norm, loss [1], xent (T-2), acc (T-2)).
 
     One launch computes the forward AND d loss / d feats; backward() only scales it by the incoming gradient.
@@ -405,6 +405,7 @@ def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = Fals
     safe: every replay draws fresh masks); explicit (u12, u21p) override all of these.
     """
     flags = (WALK_FLIP if flip else 0) | (WALK_SOFTMAX if softmax else 0) | (WALK_FORCE_GENERAL if force_general else 0)
+    flags |= WALK_FORCE_SIMT if force_simt else 0
     if u12 is not None:
         rng = "torch"
     return _Walk.apply(feats, float(temperature), float(rate), flags, rng, u12, u21p, rng_state)
@@ -445,6 +446,38 @@ class _Affinity(torch.autograd.Function):
 def affinity_nodes(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     """node-major affinity: x1 (R,N1,D), x2 (R,N2,D) -> (R,N1,N2) = x1 x2^T (differentiable)."""
     return _Affinity.apply(x1, x2)
+
+
+_bmm_ws = {}
+
+
+def bmm_tc(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
+           out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """Batched fp32 GEMM on the tensor cores (the large-graph walk's contraction engine, gemm_tc.cu):
+    A (Z,M,K) [or (Z,K,M) if trans_a], B (Z,K,N) [or (Z,N,K) if trans_b] -> (Z,M,N).  Needs M >= 128, N, K >= 64."""
+    _need_cuda(A, B)
+    check_device(A.device)
+    A, B = _f32c(A), _f32c(B)
+    Z = A.shape[0]
+    M, K = (A.shape[2], A.shape[1]) if trans_a else (A.shape[1], A.shape[2])
+    N = B.shape[1] if trans_b else B.shape[2]
+    if (B.shape[2] if trans_b else B.shape[1]) != K or B.shape[0] != Z:
+        raise ValueError("bmm_tc: shape mismatch %s x %s" % (tuple(A.shape), tuple(B.shape)))
+    if out is None:
+        if accumulate:
+            raise ValueError("bmm_tc: accumulate needs `out`")
+        out = torch.empty(Z, M, N, device=A.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = L.crw_bmm_tc_workspace_bytes(Z, M, N, K)
+    key = (A.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _bmm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _bmm_ws[key] = torch.zeros(nbytes, dtype=torch.uint8, device=A.device)
+    L.check(L.crw_bmm_tc(A.data_ptr(), B.data_ptr(), out.data_ptr(), Z, M, N, K, int(trans_a), int(trans_b), int(accumulate),
+                         ws.data_ptr(), ws.numel(), _stream()), "bmm_tc")
+    if int(ws[:4].view(torch.int32)[0]) != 0:
+        raise RuntimeError("bmm_tc: tensor-core pipeline timed out (error flag %d)" % int(ws[:4].view(torch.int32)[0]))
+    return out
 
 
 def stoch_mat_(A: torch.Tensor, temperature: float, rate: float = 0.0, softmax: bool = False,

@@ -143,6 +143,50 @@ def test_walk_matches_oracle(ops, B, N, T, D, p, flip, softmax):
             assert float(loss) == 0.0
 
 
+@pytest.mark.parametrize("Z,M,N,K,ta,tb", [(3, 128, 128, 128, False, False), (2, 256, 128, 256, False, True), (2, 200, 72, 100, True, False),
+                                            (1, 1024, 1024, 1024, True, True), (5, 130, 129, 67, False, False),
+                                            (2, 512, 128, 512, True, False)])
+def test_bmm_tc_is_fp32_faithful(ops, Z, M, N, K, ta, tb):
+    """The tensor-core GEMM of the large-graph walk against an fp64 product: its error must be of the order of an fp32
+    sgemm's, for plain operands, for rows of wildly different magnitude (per-row scaling), and when accumulating."""
+    torch.manual_seed(Z * 1000 + M + N + K)
+    A = torch.randn(Z, M, K, device=DEV)
+    B = torch.randn(Z, K, N, device=DEV)
+    A *= torch.exp(6 * torch.randn(Z, M, 1, device=DEV))              # per-row magnitudes over ~10 decades
+    B *= torch.exp(6 * torch.randn(Z, 1, N, device=DEV))
+    ref = A.double() @ B.double()
+    bound = (A.double().abs() @ B.double().abs())                      # elementwise error scale |a|.|b|
+    As = A.transpose(1, 2).contiguous() if ta else A
+    Bs = B.transpose(1, 2).contiguous() if tb else B
+    C = ops.bmm_tc(As, Bs, trans_a=ta, trans_b=tb)
+    err_tc = ((C.double() - ref).abs() / bound).max().item()
+    err_f32 = (((A @ B).double() - ref).abs() / bound).max().item()
+    assert err_tc < 2e-6, (err_tc, err_f32)
+    C2 = ops.bmm_tc(As, Bs, trans_a=ta, trans_b=tb, out=C.clone(), accumulate=True)
+    assert ((C2.double() - 2 * ref).abs() / bound).max().item() < 4e-6
+    # exactness on small integers (every partial product is representable)
+    Ai = torch.randint(-8, 9, (Z, M, K), device=DEV).float()
+    Bi = torch.randint(-8, 9, (Z, K, N), device=DEV).float()
+    Ci = ops.bmm_tc(Ai.transpose(1, 2).contiguous() if ta else Ai, Bi.transpose(1, 2).contiguous() if tb else Bi, trans_a=ta, trans_b=tb)
+    assert torch.equal(Ci, Ai @ Bi)
+
+
+@pytest.mark.parametrize("B,N,T,flip", [(2, 192, 4, False), (1, 320, 5, True), (2, 200, 3, False), (1, 515, 4, False)])
+def test_walk_large_graph_tensor_core_vs_simt(ops, B, N, T, flip):
+    """Large graphs: the tcgen05 GEMM path and the exact-fp32 SIMT path of the same walk agree to fp32 noise."""
+    torch.manual_seed(N)
+    f = torch.randn(B, N, T, 128, device=DEV)
+    u12, u21p = O.draw_uniforms(B, N, T)
+    res = []
+    for simt in (True, False):
+        fd = f.clone().requires_grad_(True)
+        q, loss, xent, acc = ops.walk(fd, 0.07, 0.1, flip=flip, u12=u12.to(DEV), u21p=u21p.to(DEV), force_simt=simt)
+        loss.sum().backward()
+        res.append((loss.detach(), xent.detach(), fd.grad))
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-5, atol=0)
+    assert relmax(res[0][2], res[1][2]) < 5e-5
+
+
 def test_walk_in_kernel_dropout_equals_torch_draws(ops):
     """rng='philox' (drawn inside the kernel) must give exactly the run that rng='torch' (torch.rand draws handed to
     the kernel) gives from the same generator state, and leave the generator in the same state."""
