@@ -23,6 +23,7 @@ WALK_SOFTMAX = 1
 WALK_FLIP = 2
 WALK_FORCE_GENERAL = 4
 WALK_FORCE_SIMT = 8
+WALK_FORCE_TC = 16
 LP_FORCE_SIMT = 1
 
 _SIGNATURES = {

@@ -321,7 +321,7 @@ bool gemm_tc_eligible(int M, int N, int Kmin, int Kmax) {
     (void)M; (void)N; (void)Kmin; (void)Kmax;
     return false;
 #else
-    return M >= 128 && N >= 64 && Kmin >= 64 && Kmax <= kSplitMaxK;
+    return M >= 64 && N >= 64 && Kmin >= 64 && Kmax <= kSplitMaxK;
 #endif
 }
 
@@ -420,7 +420,7 @@ extern "C" int crw_bmm_tc(const float* A, const float* B, float* C, int Z, int M
                           int accumulate, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
     if (Z < 0 || M <= 0 || N <= 0 || K <= 0) { set_error("bmm_tc: bad shape Z=%d M=%d N=%d K=%d", Z, M, N, K); return CRW_ERR_SHAPE; }
     if (Z == 0) return CRW_OK;
-    if (!gemm_tc_eligible(M, N, K, K)) { set_error("bmm_tc: needs M >= 128, N >= 64, 64 <= K <= 4096 (got %d, %d, %d)", M, N, K); return CRW_ERR_UNSUPPORTED; }
+    if (!gemm_tc_eligible(M, N, K, K)) { set_error("bmm_tc: needs M >= 64, N >= 64, 64 <= K <= 4096 (got %d, %d, %d)", M, N, K); return CRW_ERR_UNSUPPORTED; }
     TcGemmCall c{};
     c.nterms = 1; c.K[0] = K; c.M = M; c.N = N; c.nb = Z; c.nj = 1; c.accumulate = accumulate;
     c.A[0] = TcOperand{A, (int64_t)M * K, 0, trans_a ? 1 : K, trans_a ? M : 1};

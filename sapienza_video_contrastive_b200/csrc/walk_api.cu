@@ -38,7 +38,7 @@ WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
     // general path on large graphs: operand planes of the tensor-core GEMM (gemm_tc.cu)
     const int NK = N > D ? N : D;
     // measured crossover against the SIMT GEMM (tools/bench_tc_gemm.py): 0.83x at N = 128, 1.1x at 196, 1.9x at 512, 4.1x at 1024
-    const bool tc = !w.fused && !(flags & CRW_WALK_FORCE_SIMT) && t1 > 0 && N >= 192 &&
+    const bool tc = !w.fused && !(flags & CRW_WALK_FORCE_SIMT) && t1 > 0 && (N >= 192 || (flags & CRW_WALK_FORCE_TC)) &&
                     gemm_tc_eligible(N, N < D ? N : D, N < D ? N : D, NK);
     w.tc_bytes = tc ? gemm_tc_workspace_bytes(N, NK, NK, (int)(B * t1)) : 0;
     w.o_tc = take(w.tc_bytes);
