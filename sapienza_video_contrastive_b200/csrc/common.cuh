@@ -112,4 +112,49 @@ __host__ __forceinline__ uint32_t torch_rand_threads(int64_t numel, int sm_count
     return (uint32_t)(grid * 256);
 }
 
+// global -> shared TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: thread 0 announces the total
+// byte count, issues the copies, and the whole CTA waits on the barrier.  Sizes are multiples of 16, both sides aligned.
+__device__ __forceinline__ void bulk_bar_init(uint64_t* bar, int tid) {
+#ifndef CRW_SIM
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#else
+    (void)bar; (void)tid;
+#endif
+    __syncthreads();
+}
+__device__ __forceinline__ void bulk_expect(uint64_t* bar, unsigned total_bytes, int tid) {
+#ifndef CRW_SIM
+    if (tid == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(total_bytes) : "memory");
+#else
+    (void)bar; (void)total_bytes; (void)tid;
+#endif
+}
+__device__ __forceinline__ void bulk_copy(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar, int tid) {
+#ifdef CRW_SIM
+    for (unsigned o = tid * 16; o < bytes; o += blockDim.x * 16)
+        *reinterpret_cast<float4*>((char*)dst_smem + o) = *reinterpret_cast<const float4*>((const char*)src_gmem + o);
+    (void)bar;
+#else
+    if (tid == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem), "r"(bytes),
+                        "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_wait(uint64_t* bar, unsigned phase) {
+#ifdef CRW_SIM
+    (void)bar; (void)phase;
+    __syncthreads();
+#else
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tCRW_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra CRW_DONE_%=;\n\t"
+                 "bra CRW_WAIT_%=;\n\tCRW_DONE_%=:\n\t}" :: "r"(b), "r"(phase) : "memory");
+#endif
+}
+
 }  // namespace crw

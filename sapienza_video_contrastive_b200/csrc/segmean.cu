@@ -5,22 +5,38 @@
 // straight from the label map:
 //   1. segmean_count: one warp per feature cell turns its sy*sx labels into a short (label,count) list
 //      (<= 64 entries, typically 1-4) and adds the counts to the per-label sizes;
-//   2. segmean_accum: one CTA per (clip, frame, 32-channel tile) stages the feature tile transposed in shared memory and
-//      reduces it per label through per-label cell bitmasks (see the kernel); the epilogue divides by the sizes;
-//   3. segmean_bwd mirrors 2 as a gather (deterministic).
+//   2. segmean_csr: one CTA per (clip, frame) turns the per-cell lists into a CSR sorted by (256-cell chunk, label, cell)
+//      with one offset per (chunk, label);
+//   3. segmean_accum: one CTA per (clip, frame, 32-channel tile) streams the feature tile through a double-buffered
+//      cp.async pipeline and reduces it per label with the accumulators in registers; the epilogue divides by the sizes;
+//   4. segmean_bwd mirrors 3 as a gather over the per-cell lists (deterministic).
 // Neither the one-hot nor the broadcast product is ever materialised; forward and backward are deterministic.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace crw {
 
+#ifdef CRW_SIM
+struct SegMap { int unused; };
+#define CRW_GRID_CONSTANT
+#else
+typedef CUtensorMap SegMap;
+#define CRW_GRID_CONSTANT __grid_constant__
+#endif
+
 constexpr int kSegCT = 32;       // channels per CTA
 constexpr int kSegMaxEnt = 64;   // max distinct labels per feature cell (= max sy*sx)
+
+constexpr int kSegChunk = 256;   // cells per pipeline stage of the forward
+constexpr int kSegCTF = 64;      // channels per CTA in the forward (two per lane)
+constexpr int kSegLDC = kSegChunk + 1;  // staged tile is [channel][cell], row stride 257 floats: 32 channels of one cell sit in 32 banks
 
 struct SegWs {
     int* size;               // (B*T, SP)
     unsigned char* nent;     // (B*T, cells)
     unsigned* ent;           // (B*T, cap, cells): label << 8 | count
-    int cap;
+    uint2* csr;              // (B*T, cap*cells): {count as float bits, cell % kSegChunk}, sorted by (chunk, label, cell)
+    int* cstart;             // (B*T, nchunks*SP + 1): CSR offset of (chunk k, label s) at [k*SP + s]; the last entry is the total
+    int cap, nchunks;
     size_t bytes;
 };
 
@@ -32,7 +48,12 @@ __host__ __device__ inline SegWs seg_ws(void* base, int B, int T, int cells, int
     w.nent = (unsigned char*)base + o;
     o += ((size_t)B * T * cells + 255) / 256 * 256;
     w.ent = (unsigned*)((char*)base + o);
-    o += (size_t)B * T * cap * cells * sizeof(unsigned);
+    o += ((size_t)B * T * cap * cells * sizeof(unsigned) + 255) / 256 * 256;
+    w.csr = (uint2*)((char*)base + o);
+    o += ((size_t)B * T * cap * cells * sizeof(uint2) + 255) / 256 * 256;
+    w.nchunks = (cells + kSegChunk - 1) / kSegChunk;
+    w.cstart = (int*)((char*)base + o);
+    o += ((size_t)B * T * ((size_t)w.nchunks * SP + 1) * sizeof(int) + 255) / 256 * 256;
     w.cap = cap;
     w.bytes = o;
     return w;
@@ -87,105 +108,371 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
     }
 }
 
-// Forward accumulation, one CTA per (clip, frame, 32-channel tile):
-//   * the feature tile is read once, coalesced along the cells, and stored TRANSPOSED in shared memory ([cell][32+1]) so
-//     that the 32 lanes of a warp = 32 channels read one cell's features without bank conflicts;
-//   * a per-label bitmask of the cells containing the label (plus a 32-bit summary of its non-empty words) is built in
-//     shared memory from the per-cell lists;
-//   * a warp owns one label at a time and walks the set bits of its mask in increasing cell order: every lane does one
-//     useful FMA per (cell, label) entry.  No floating-point atomics: deterministic, each feature read from HBM once.
-constexpr int kSegCTF = 32;          // channels per CTA in the forward
-constexpr int kSegSlots = 4;         // per-cell list entries cached in shared memory (rest read from the workspace)
-constexpr int kSegFwdThreads = 1024; // one CTA per SM (the transposed tile fills shared memory): many warps hide the label walks' latency
-
-__global__ void __launch_bounds__(kSegFwdThreads, 1) segmean_accum_kernel(const float* __restrict__ maps, SegWs ws, int C, int T, int cells,
-                                                            int SP, float* __restrict__ out) {
+// CSR of one (clip, frame), one CTA: entries ordered by (chunk of kSegChunk cells, label, cell).  A per-label bitmask over
+// the cells (shared memory) gives every (cell, label) entry its rank inside its (chunk, label) group by popcount, so the
+// order needs no sort and no atomics on the positions: deterministic.  Needs cells <= 1024 (32 mask words per label).
+__global__ void __launch_bounds__(1024) segmean_csr_kernel(SegWs ws, int cells, int SP) {
     CRW_DYN_SMEM(smem_raw);
+    constexpr int wpc = kSegChunk / 32;                               // mask words per chunk
+    unsigned* mask = reinterpret_cast<unsigned*>(smem_raw);          // [SP][32]
+    int* P = reinterpret_cast<int*>(mask + (size_t)SP * 32);         // [nchunks * SP + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bt = blockIdx.y, b = bt / T, t = bt - b * T;
-    const int c0 = blockIdx.x * kSegCTF;
-    const int nwords = (cells + 31) / 32;
-    constexpr int LD = kSegCTF + 1;
-    float* tile = reinterpret_cast<float*>(smem_raw);                              // [cells][33]
-    unsigned* mask = reinterpret_cast<unsigned*>(tile + (size_t)cells * LD);        // [SP][nwords]
-    unsigned* occ = mask + (size_t)SP * nwords;                                     // [SP] non-empty words (nwords <= 32)
-    unsigned* ents = occ + SP;                                                      // [kSegSlots][cells]
-    unsigned char* nes = reinterpret_cast<unsigned char*>(ents + kSegSlots * cells);  // [cells]
-
-    for (int e = tid; e < SP * nwords; e += kSegFwdThreads) mask[e] = 0u;
-    for (int e = tid; e < SP; e += kSegFwdThreads) occ[e] = 0u;
-    // transposing tile load: warp w streams channels w, w+8, ... (coalesced along the cells, 8 x 128-bit loads in flight per lane)
-    const bool vec = (cells & 127) == 0 && ((reinterpret_cast<uintptr_t>(maps) & 15) == 0);
-    for (int cl = warp; cl < kSegCTF; cl += kSegFwdThreads / 32) {
-        const int c = c0 + cl;
-        const float* src = maps + (((int64_t)b * C + min(c, C - 1)) * T + t) * cells;
-        if (vec) {
-            for (int base = 0; base < cells; base += 1024) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int cell = base + (u * 32 + lane) * 4;
-                    v[u] = cell < cells ? __ldg(reinterpret_cast<const float4*>(src + cell)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int cell = base + (u * 32 + lane) * 4;
-                    if (cell < cells) {
-                        const float m = c < C ? 1.f : 0.f;
-                        tile[(cell + 0) * LD + cl] = v[u].x * m;
-                        tile[(cell + 1) * LD + cl] = v[u].y * m;
-                        tile[(cell + 2) * LD + cl] = v[u].z * m;
-                        tile[(cell + 3) * LD + cl] = v[u].w * m;
-                    }
-                }
-            }
-        } else {
-            for (int cell = lane; cell < cells; cell += 32) tile[cell * LD + cl] = c < C ? __ldg(src + cell) : 0.f;
-        }
-    }
-    __syncthreads();
+    const int bt = blockIdx.x;
+    const int L = ws.nchunks * SP;
     const unsigned char* gnent = ws.nent + (int64_t)bt * cells;
     const unsigned* gent = ws.ent + (int64_t)bt * ws.cap * cells;
-    for (int cell = tid; cell < cells; cell += kSegFwdThreads) {
+    for (int e = tid; e < SP * 32; e += 1024) mask[e] = 0u;
+    __syncthreads();
+    for (int cell = tid; cell < cells; cell += 1024) {
         const int ne = gnent[cell];
-        nes[cell] = (unsigned char)ne;
         for (int sl = 0; sl < ne; ++sl) {
             const unsigned e = gent[(int64_t)sl * cells + cell];
-            if (sl < kSegSlots) ents[sl * cells + cell] = e;
-            atomicOr(mask + (size_t)(e >> 8) * nwords + (cell >> 5), 1u << (cell & 31));
-            atomicOr(occ + (e >> 8), 1u << (cell >> 5));
+            atomicOr(mask + (size_t)(e >> 8) * 32 + (cell >> 5), 1u << (cell & 31));
         }
     }
     __syncthreads();
-    const int* size = ws.size + (int64_t)bt * SP;
-    for (int s = warp; s < SP; s += kSegFwdThreads / 32) {
-        float acc = 0.f;
-        unsigned ow = occ[s];
-        while (ow) {                                                    // warp-uniform control flow throughout
-            const int w = __ffs((int)ow) - 1;
-            ow &= ow - 1;
-            unsigned bits = mask[(size_t)s * nwords + w];
-            while (bits) {
-                const int cell = w * 32 + __ffs((int)bits) - 1;
-                bits &= bits - 1;
-                const int ne = nes[cell];
-                float cnt = 0.f;
-                for (int sl = 0; sl < ne; ++sl) {
-                    const unsigned e = sl < kSegSlots ? ents[sl * cells + cell] : gent[(int64_t)sl * cells + cell];
-                    if ((int)(e >> 8) == s) { cnt = (float)(e & 255u); break; }
-                }
-                acc = fmaf(cnt, tile[cell * LD + lane], acc);
+    // group sizes
+    for (int g = tid; g < L; g += 1024) {
+        const int k = g / SP, sidx = g - k * SP;
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < wpc; ++i) n += __popc(mask[(size_t)sidx * 32 + k * wpc + i]);
+        P[g + 1] = n;
+    }
+    if (tid == 0) P[0] = 0;
+    __syncthreads();
+    if (warp == 0) {                                                   // inclusive scan, 32 groups at a time
+        int carry = 0;
+        for (int g0 = 0; g0 < L; g0 += 32) {
+            int v = g0 + lane < L ? P[g0 + lane + 1] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(kFull, v, d);
+                if (lane >= d) v += u;
             }
+            if (g0 + lane < L) P[g0 + lane + 1] = v + carry;
+            carry += __shfl_sync(kFull, v, 31);
         }
-        if (c0 + lane < C) out[(((int64_t)b * SP + s) * T + t) * C + c0 + lane] = acc / ((float)size[s] + kEpsLog);
+    }
+    __syncthreads();
+    int* gP = ws.cstart + (int64_t)bt * (L + 1);
+    for (int g = tid; g <= L; g += 1024) gP[g] = P[g];
+    // scatter the entries to their ranks
+    uint2* csr = ws.csr + (int64_t)bt * ws.cap * cells;
+    for (int cell = tid; cell < cells; cell += 1024) {
+        const int ne = gnent[cell];
+        const int w = cell >> 5, k = cell / kSegChunk;
+        for (int sl = 0; sl < ne; ++sl) {
+            const unsigned e = gent[(int64_t)sl * cells + cell];
+            const unsigned* m = mask + (size_t)(e >> 8) * 32;
+            int pos = P[k * SP + (int)(e >> 8)] + __popc(m[w] & ((1u << (cell & 31)) - 1u));
+            for (int i = k * wpc; i < w; ++i) pos += __popc(m[i]);
+            csr[pos] = make_uint2(__float_as_uint((float)(e & 255u)), (unsigned)(cell - k * kSegChunk));
+        }
     }
 }
 
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+#ifdef CRW_SIM
+    *dst = *src;
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef CRW_SIM
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef CRW_SIM
+    asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+#endif
+}
+
+__device__ __forceinline__ float2 ffma2(float a, float2 x, float2 acc) {
+#ifdef CRW_SIM
+    return make_float2(fmaf(a, x.x, acc.x), fmaf(a, x.y, acc.y));
+#else
+    return __ffma2_rn(make_float2(a, a), x, acc);
+#endif
+}
+
+// Forward accumulation: persistent CTAs (one per SM, 32 warps) walk contiguous runs of (clip, frame, 64-channel tile) items.
+//   * a lane owns channels l and l + 32 of the tile; warp w owns labels w, w + 32, ... and keeps their running sums in
+//     registers (LMAX float2 per lane), so nothing is accumulated in shared memory and there are no atomics: deterministic;
+//   * the features stream in 256-cell chunks: TMA bulk copies (one 1 KB row per channel, two chunks = 128 KB in flight per
+//     SM, completing on mbarriers) land in dense staging buffers; the CTA re-lays a landed chunk out as [channel][257]
+//     (128-bit reads, transposing 4-byte stores, both conflict-free) so that the 32 channels of one cell sit in 32
+//     different banks; every feature is read from HBM exactly once;
+//   * per chunk a warp walks, for each of its labels, the label's CSR entries (cell order): one broadcast 8-byte load of
+//     the entry, two conflict-free loads of the features and one packed FMA per (cell, label) pair and 64 channels.
+// Shapes the bulk copies cannot take (cells % 256, C % 64, unaligned base) use 4-byte cp.async copies instead.
+constexpr int kSegEntCap = 1024;     // CSR entries of a chunk staged in shared memory (a fuller chunk is read from L2)
+constexpr int kSegTileWords = (kSegCTF * kSegLDC + 3) & ~3;
+
+__host__ __device__ inline size_t seg_meta_words(int SP) { return 2 * kSegEntCap + (size_t)((SP + 1 + 3) & ~3); }
+
+// (chunk, tile, frame, clip) cursor advanced incrementally: no integer division inside the pipeline
+struct SegCursor {
+    int k, tile, b, t;
+};
+__device__ __forceinline__ void seg_advance(SegCursor& c, int nchunks, int ntiles, int T) {
+    if (++c.k == nchunks) {
+        c.k = 0;
+        if (++c.tile == ntiles) {
+            c.tile = 0;
+            if (++c.t == T) { c.t = 0; ++c.b; }
+        }
+    }
+}
+
+// CSR entries + per-label offsets of one chunk -> shared memory (4-byte cp.async, one commit group)
+__device__ __forceinline__ int2 seg_entry_range(const SegWs& ws, const SegCursor& q, int T, int SP) {      // (first entry, count) of a chunk
+    const int* pk = ws.cstart + (int64_t)(q.b * T + q.t) * ((int64_t)ws.nchunks * SP + 1) + (int64_t)q.k * SP;
+    const int eb = __ldg(pk);
+    return make_int2(eb, __ldg(pk + SP) - eb);
+}
+template <int NT>
+__device__ __forceinline__ void seg_issue_meta(const SegWs& ws, const SegCursor& q, int2 range, int T, int cells, int SP, uint2* est, int* pst, int tid) {
+    const int bt = q.b * T + q.t;
+    const int* pk = ws.cstart + (int64_t)bt * ((int64_t)ws.nchunks * SP + 1) + (int64_t)q.k * SP;
+    for (int i = tid; i <= SP; i += NT) cp_async4(reinterpret_cast<float*>(pst + i), reinterpret_cast<const float*>(pk + i));
+    const int eb = range.x, ne = range.y;
+    if (ne <= kSegEntCap) {
+        const float* esrc = reinterpret_cast<const float*>(ws.csr + (int64_t)bt * ws.cap * cells + eb);
+        for (int i = tid; i < 2 * ne; i += NT) cp_async4(reinterpret_cast<float*>(est) + i, esrc + i);
+    }
+    cp_async_commit();
+}
+
+template <int LMAX>
+__device__ __forceinline__ void seg_reduce_chunk(float2 (&acc)[LMAX], const float* tile, const uint2* est, const int* pst,
+                                                 const uint2* csr_bt, int SP, int warp, int lane) {
+    const float* tl0 = tile + lane * kSegLDC;
+    const float* tl1 = tl0 + 32 * kSegLDC;
+    const int eb = pst[0];
+    const uint2* ents = (pst[SP] - eb <= kSegEntCap) ? est - eb : csr_bt;          // indexed by the CSR position
+#pragma unroll
+    for (int i = 0; i < LMAX; ++i) {
+        const int s = warp + 32 * i;
+        if (s < SP) {
+            const int e0 = pst[s], e1 = pst[s + 1];
+            float2 a = acc[i];
+#pragma unroll 8
+            for (int e = e0; e < e1; ++e) {
+                const uint2 en = ents[e];
+                a = ffma2(__uint_as_float(en.x), make_float2(tl0[en.y], tl1[en.y]), a);
+            }
+            acc[i] = a;
+        }
+    }
+}
+
+template <int LMAX>
+__device__ __forceinline__ void seg_load_den(float (&den)[LMAX], const SegWs& ws, const SegCursor& q, int T, int SP, int warp) {
+    const int* size = ws.size + (int64_t)(q.b * T + q.t) * SP;
+#pragma unroll
+    for (int i = 0; i < LMAX; ++i) den[i] = warp + 32 * i < SP ? (float)__ldg(size + warp + 32 * i) + kEpsLog : 1.f;
+}
+
+// x / d for a positive normal d through one reciprocal per label and one FMA correction per value: the quotient the
+// division operator gives (its fast path is the same sequence) at a fraction of the instructions - the epilogue of
+// 32 warps is issue-bound otherwise
+__device__ __forceinline__ float seg_div(float x, float d, float r) {
+    const float q = x * r;
+    return fmaf(fmaf(-q, d, x), r, q);
+}
+
+template <int LMAX>
+__device__ __forceinline__ void seg_write_out(const float2 (&acc)[LMAX], const float (&den)[LMAX], const SegCursor& q, int C, int T, int SP,
+                                              float* __restrict__ out, int warp, int lane) {
+    const int c = q.tile * kSegCTF + lane;
+#pragma unroll
+    for (int i = 0; i < LMAX; ++i) {
+        const int s = warp + 32 * i;
+        if (s < SP) {
+            const float d = den[i];
+            float r = 1.0f / d;                                    // d >= 1, or d = 1e-20 for an empty label whose sums are 0
+            r = fmaf(fmaf(-d, r, 1.0f), r, r);
+            float* o = out + (((int64_t)q.b * SP + s) * T + q.t) * C + c;
+            if (c < C) o[0] = seg_div(acc[i].x, d, r);
+            if (c + 32 < C) o[32] = seg_div(acc[i].y, d, r);
+        }
+    }
+}
+
+template <int LMAX>
+__device__ __forceinline__ void seg_first_cursor(SegCursor& cur, int& total, int BT, int C, int T, int nchunks) {
+    const int ntiles = (C + kSegCTF - 1) / kSegCTF;
+    const int nitems = BT * ntiles;                              // item = bt * ntiles + tile: neighbours share their CSR in L2
+    const int item_lo = (int)(((int64_t)nitems * blockIdx.x) / gridDim.x), item_hi = (int)(((int64_t)nitems * (blockIdx.x + 1)) / gridDim.x);
+    total = (item_hi - item_lo) * nchunks;                      // this CTA's contiguous run of items, chunk by chunk
+    const int bt0 = item_lo / ntiles;
+    cur.k = 0; cur.tile = item_lo - bt0 * ntiles; cur.b = bt0 / T; cur.t = bt0 - cur.b * T;
+}
+
+// ---- TMA path: cells % 256 == 0, C % 64 == 0, 16-byte aligned maps ---------------------------------------------------
+// shared memory: staging[2][64][256] | tile[64][257] | meta[2] (entries, offsets) | 2 mbarriers
+template <int LMAX>
+__global__ void __launch_bounds__(1024, 1) segmean_accum_tma_kernel(const CRW_GRID_CONSTANT SegMap fmap, const float* __restrict__ maps, SegWs ws,
+                                                                    int C, int T, int BT, int cells, int SP, float* __restrict__ out) {
+    CRW_DYN_SMEM(smem_raw);
+    constexpr int NT = 1024, kStageWords = kSegCTF * kSegChunk;
+    float* staging = reinterpret_cast<float*>(smem_raw);
+    float* tile = staging + 2 * kStageWords;
+    float* meta = tile + kSegTileWords;
+    const size_t meta_words = seg_meta_words(SP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * meta_words);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = ws.nchunks, ntiles = C / kSegCTF;
+    const int64_t cstride = (int64_t)T * cells;
+    SegCursor cur;
+    int total;
+    seg_first_cursor<LMAX>(cur, total, BT, C, T, nchunks);
+    SegCursor nxt = cur;            // next chunk whose features get issued
+    SegCursor mnx = cur;            // next chunk whose entries / offsets get issued
+
+    bulk_bar_init(bars, tid);
+    bulk_bar_init(bars + 1, tid);
+
+    // one TMA tensor copy per chunk: box (256 cells, 1 frame, 64 channels) of the (cells, T, B*C) view of the maps, issued by
+    // one thread (every thread copies in the host simulator)
+    auto issue_rows = [&](const SegCursor& q, int s) {
+        float* dst = staging + (size_t)s * kStageWords;
+#ifdef CRW_SIM
+        const float* src = maps + (((int64_t)q.b * C + q.tile * kSegCTF) * T + q.t) * cells + q.k * kSegChunk;
+        for (int i = tid; i < kStageWords; i += NT) dst[i] = src[(int64_t)(i / kSegChunk) * cstride + (i % kSegChunk)];
+#else
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer was just read through the generic proxy
+            mbar_expect_tx(bars + s, (unsigned)(kStageWords * 4));
+            tma_load_3d(dst, &fmap, q.k * kSegChunk, q.t, q.b * C + q.tile * kSegCTF, bars + s);
+        }
+#endif
+    };
+    auto meta_est = [&](int s) { return reinterpret_cast<uint2*>(meta + (size_t)s * meta_words); };
+    auto meta_pst = [&](int s) { return reinterpret_cast<int*>(meta_est(s) + kSegEntCap); };
+
+    float2 acc[LMAX];
+    float den[LMAX];
+    int issued = 0;
+    if (total > 0) {
+        issue_rows(nxt, 0);
+        issued = 1;
+        seg_issue_meta<NT>(ws, mnx, seg_entry_range(ws, mnx, T, SP), T, cells, SP, meta_est(0), meta_pst(0), tid);
+        if (total > 1) {
+            seg_advance(nxt, nchunks, ntiles, T);
+            issue_rows(nxt, 1);
+            issued = 2;
+        }
+    }
+    int2 range1 = make_int2(0, 0);                                   // entry range of chunk g + 1, fetched one iteration early
+    if (total > 1) { seg_advance(mnx, nchunks, ntiles, T); range1 = seg_entry_range(ws, mnx, T, SP); }
+    for (int g = 0; g < total; ++g, seg_advance(cur, nchunks, ntiles, T)) {
+        const int s = g & 1;
+        // entries / offsets of chunk g + 1 (their buffer was last read in iteration g - 1)
+        if (g + 1 < total) {
+            seg_issue_meta<NT>(ws, mnx, range1, T, cells, SP, meta_est(s ^ 1), meta_pst(s ^ 1), tid);
+            if (g + 2 < total) { seg_advance(mnx, nchunks, ntiles, T); range1 = seg_entry_range(ws, mnx, T, SP); }
+            cp_async_wait<1>();
+        } else cp_async_wait<0>();
+        bulk_wait(bars + s, (unsigned)((g >> 1) & 1));
+        // dense [64][256] -> padded [64][257]: a warp instruction covers 4 channels x 32 cells
+        {
+            const float* src = staging + (size_t)s * kStageWords;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int p = warp + 32 * u, ch = (p >> 3) * 4 + (lane >> 3), j = (p & 7) * 32 + 4 * (lane & 7);
+                const float4 v = *reinterpret_cast<const float4*>(src + ch * kSegChunk + j);
+                float* d = tile + ch * kSegLDC + j;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+        __syncthreads();
+        if (issued < total) {                                        // staging[s] is free again: fetch chunk g + 2 into it
+            seg_advance(nxt, nchunks, ntiles, T);
+            issue_rows(nxt, s);
+            ++issued;
+        }
+        if (cur.k == 0) {
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) acc[i] = make_float2(0.f, 0.f);
+            seg_load_den<LMAX>(den, ws, cur, T, SP, warp);           // the divisors arrive while the item is reduced
+        }
+        seg_reduce_chunk<LMAX>(acc, tile, meta_est(s), meta_pst(s), ws.csr + (int64_t)(cur.b * T + cur.t) * ws.cap * cells, SP, warp, lane);
+        if (cur.k == nchunks - 1) seg_write_out<LMAX>(acc, den, cur, C, T, SP, out, warp, lane);
+        __syncthreads();
+    }
+}
+
+// ---- generic path: two-stage pipeline of 4-byte cp.async copies -----------------------------------------------------
+// shared memory: 2 x (tile[64][257] | meta)
+template <int LMAX>
+__global__ void __launch_bounds__(1024, 1) segmean_accum_kernel(const float* __restrict__ maps, SegWs ws, int C, int T, int BT, int cells,
+                                                                int SP, float* __restrict__ out) {
+    CRW_DYN_SMEM(smem_raw);
+    constexpr int NT = 1024, CSTEP = NT / kSegChunk;
+    float* stage0 = reinterpret_cast<float*>(smem_raw);
+    const size_t stage_words = kSegTileWords + seg_meta_words(SP);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = ws.nchunks, ntiles = (C + kSegCTF - 1) / kSegCTF;
+    const int64_t cstride = (int64_t)T * cells;
+    SegCursor cur;
+    int total;
+    seg_first_cursor<LMAX>(cur, total, BT, C, T, nchunks);
+    SegCursor nxt = cur;
+
+    auto issue = [&](const SegCursor& q, int buf) {
+        float* tile = stage0 + (size_t)buf * stage_words;
+        uint2* est = reinterpret_cast<uint2*>(tile + kSegTileWords);
+        const int c0 = q.tile * kSegCTF;
+        {   // thread = one cell of the chunk, stepping over the channels: coalesced 128-byte reads along the cells
+            const int j = tid & (kSegChunk - 1), cell = q.k * kSegChunk + j, cl0 = tid / kSegChunk;
+            float* d = tile + cl0 * kSegLDC + j;
+            const float* gsrc = maps + (((int64_t)q.b * C + c0 + cl0) * T + q.t) * cells + cell;
+            for (int cl = cl0; cl < kSegCTF; cl += CSTEP, d += CSTEP * kSegLDC, gsrc += CSTEP * cstride) {
+                if (cell < cells && c0 + cl < C) cp_async4(d, gsrc);
+                else *d = 0.f;
+            }
+        }
+        seg_issue_meta<NT>(ws, q, seg_entry_range(ws, q, T, SP), T, cells, SP, est, reinterpret_cast<int*>(est + kSegEntCap), tid);     // commits the group
+    };
+
+    float2 acc[LMAX];
+    float den[LMAX];
+    if (total > 0) issue(cur, 0);
+    for (int g = 0; g < total; ++g, seg_advance(cur, nchunks, ntiles, T)) {
+        if (g + 1 < total) {
+            seg_advance(nxt, nchunks, ntiles, T);
+            issue(nxt, (g + 1) & 1);
+            cp_async_wait<1>();
+        } else cp_async_wait<0>();
+        __syncthreads();
+        if (cur.k == 0) {
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) acc[i] = make_float2(0.f, 0.f);
+            seg_load_den<LMAX>(den, ws, cur, T, SP, warp);
+        }
+        const float* tile = stage0 + (size_t)(g & 1) * stage_words;
+        const uint2* est = reinterpret_cast<const uint2*>(tile + kSegTileWords);
+        seg_reduce_chunk<LMAX>(acc, tile, est, reinterpret_cast<const int*>(est + kSegEntCap),
+                               ws.csr + (int64_t)(cur.b * T + cur.t) * ws.cap * cells, SP, warp, lane);
+        if (cur.k == nchunks - 1) seg_write_out<LMAX>(acc, den, cur, C, T, SP, out, warp, lane);
+        __syncthreads();
+    }
+}
+
+// Backward, one CTA per (clip, frame, 32-channel tile): gout / size staged in shared memory as [label][33]; a thread owns
+// a cell, keeps the cell's first four (label, count) entries in registers and produces the cell's 32 channels, so a warp
+// writes 128 contiguous bytes per channel and reads shared memory without conflicts (distinct labels -> distinct banks,
+// equal labels -> broadcast).  A gather: deterministic.
 __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restrict__ gout, SegWs ws, int C, int T, int cells,
                                                           int SP, float* __restrict__ gmaps) {
     CRW_DYN_SMEM(smem_raw);
     float* wg = reinterpret_cast<float*>(smem_raw);             // [SP][kSegCT + 1] = gout / size
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int bt = blockIdx.y, b = bt / T, t = bt - b * T;
     const int c0 = blockIdx.x * kSegCT;
     constexpr int LD = kSegCT + 1;
@@ -197,17 +484,37 @@ __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restric
     __syncthreads();
     const unsigned char* nent = ws.nent + (int64_t)bt * cells;
     const unsigned* ent = ws.ent + (int64_t)bt * ws.cap * cells;
-    for (int cell = lane; cell < cells; cell += 32) {
+    const int nc = min(kSegCT, C - c0);
+    float* dst0 = gmaps + (((int64_t)b * C + c0) * T + t) * cells;
+    const int64_t cstride = (int64_t)T * cells;
+    for (int cell = tid; cell < cells; cell += 256) {
         const int ne = nent[cell];
-        for (int cl = warp; cl < kSegCT; cl += 8) {
-            const int c = c0 + cl;
-            if (c >= C) break;
-            float g = 0.f;
-            for (int s = 0; s < ne; ++s) {
-                const unsigned e = __ldg(ent + (int64_t)s * cells + cell);
-                g = fmaf((float)(e & 255u), wg[(e >> 8) * LD + cl], g);
+        float cnt[4];
+        const float* row[4];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            const unsigned e = sl < ne ? __ldg(ent + (int64_t)sl * cells + cell) : 0u;
+            cnt[sl] = (float)(e & 255u);                          // 0 for the unused slots: they add wg[0][c] * 0
+            row[sl] = wg + (e >> 8) * LD;
+        }
+        if (ne <= 4) {
+#pragma unroll 8
+            for (int cl = 0; cl < nc; ++cl) {
+                float g = cnt[0] * row[0][cl];
+                g = fmaf(cnt[1], row[1][cl], g);
+                g = fmaf(cnt[2], row[2][cl], g);
+                g = fmaf(cnt[3], row[3][cl], g);
+                dst0[cl * cstride + cell] = g;
             }
-            gmaps[(((int64_t)b * C + c) * T + t) * cells + cell] = g;
+        } else {
+            for (int cl = 0; cl < nc; ++cl) {
+                float g = 0.f;
+                for (int sl = 0; sl < ne; ++sl) {
+                    const unsigned e = __ldg(ent + (int64_t)sl * cells + cell);
+                    g = fmaf((float)(e & 255u), wg[(e >> 8) * LD + cl], g);
+                }
+                dst0[cl * cstride + cell] = g;
+            }
         }
     }
 }
@@ -251,17 +558,56 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     CRW_LAUNCH(segmean_count_kernel, grid1, 256, 0, stream, labels, ls_b, ls_t, ls_y, ls_x, T, Hm, Wm, h / Hm, w / Wm, SP, ws, total);
     e = check_launch("segmean_count");
     if (e != CRW_OK) return e;
-    const int nwords = (cells + 31) / 32;
-    const size_t smem = sizeof(float) * (size_t)cells * (kSegCTF + 1) + sizeof(unsigned) * ((size_t)SP * nwords + SP + (size_t)kSegSlots * cells) +
-                        (size_t)((cells + 15) & ~15) + 16;
-    if (smem > 227 * 1024 || nwords > 32) {
+    if (cells > 1024 || SP > 1024 || (size_t)SP * 33 * 4 > 200 * 1024) {
         set_error("segmean_fwd: unsupported size (cells=%d, SP=%d)", cells, SP);
         return CRW_ERR_UNSUPPORTED;
     }
-    auto k = segmean_accum_kernel;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((C + kSegCTF - 1) / kSegCTF, B * T);
-    CRW_LAUNCH(k, grid, kSegFwdThreads, smem, stream, maps, ws, C, T, cells, SP, out);
+    {
+        const size_t smem = sizeof(unsigned) * (size_t)SP * 32 + sizeof(int) * ((size_t)ws.nchunks * SP + 1);
+        auto k = segmean_csr_kernel;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CRW_LAUNCH(k, B * T, 1024, smem, stream, ws, cells, SP);
+        e = check_launch("segmean_csr");
+        if (e != CRW_OK) return e;
+    }
+    const bool tma = cells % kSegChunk == 0 && C % kSegCTF == 0 && (reinterpret_cast<uintptr_t>(maps) & 15) == 0;
+    const size_t smem = tma ? sizeof(float) * (2 * (size_t)kSegCTF * kSegChunk + kSegTileWords + 2 * seg_meta_words(SP)) + 16
+                            : sizeof(float) * 2 * (kSegTileWords + seg_meta_words(SP));
+    SegMap fmap{};
+#ifndef CRW_SIM
+    if (tma) {   // the maps as a (cells, T, B*C) tensor; one box = 256 cells of one frame of 64 consecutive channels
+        EncodeTiledFn enc = get_encode();
+        cuuint64_t dims[3] = {(cuuint64_t)cells, (cuuint64_t)T, (cuuint64_t)B * C};
+        cuuint64_t strides[2] = {(cuuint64_t)cells * 4, (cuuint64_t)T * cells * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kSegChunk, 1, (cuuint32_t)kSegCTF};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (!enc || enc(&fmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(maps), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            set_error("segmean_fwd: cuTensorMapEncodeTiled failed");
+            return CRW_ERR_CUDA;
+        }
+    }
+#endif
+    const int nitems = B * T * ((C + kSegCTF - 1) / kSegCTF);
+    const int grid = nitems < 148 ? nitems : 148;                 // persistent: one CTA per SM
+#define CRW_SEG_LAUNCH(LMAX)                                                                              \
+    do {                                                                                                  \
+        if (tma) {                                                                                        \
+            auto k = segmean_accum_tma_kernel<LMAX>;                                                      \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+            CRW_LAUNCH(k, grid, 1024, smem, stream, fmap, maps, ws, C, T, B * T, cells, SP, out);         \
+        } else {                                                                                          \
+            auto k = segmean_accum_kernel<LMAX>;                                                          \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+            CRW_LAUNCH(k, grid, 1024, smem, stream, maps, ws, C, T, B * T, cells, SP, out);               \
+        }                                                                                                 \
+    } while (0)
+    if (SP <= 4 * 32) CRW_SEG_LAUNCH(4);
+    else if (SP <= 7 * 32) CRW_SEG_LAUNCH(7);
+    else if (SP <= 8 * 32) CRW_SEG_LAUNCH(8);
+    else if (SP <= 16 * 32) CRW_SEG_LAUNCH(16);
+    else CRW_SEG_LAUNCH(32);
+#undef CRW_SEG_LAUNCH
     return check_launch("segmean_accum");
 }
 

@@ -198,6 +198,33 @@ def test_segmean_vs_reference_golden(sim, name):
     torch.testing.assert_close(gm, m2.grad, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("B,T,C,Hm,scale,SP", [(1, 2, 64, 16, 4, 20), (2, 1, 128, 32, 2, 70), (1, 1, 64, 16, 8, 300)])
+def test_segmean_bulk_copy_path_vs_oracle(sim, B, T, C, Hm, scale, SP):
+    """Shapes the TMA kernel takes (cells % 256 == 0, C % 64 == 0): several chunks, several tiles, several items per CTA,
+    labels out of range, more labels than cells; forward against the oracle, backward against autograd."""
+    g = torch.Generator().manual_seed(B * 100 + SP)
+    maps = torch.randn(B, C, T, Hm, Hm, generator=g)
+    lab = cases.voronoi_labels(B, T, SP, Hm * scale, g, one_based=False)
+    lab[:, :, :3, :5] = SP + 2                                  # ignored labels
+    lab[:, :, -2:, :] = -1
+    wsb = sim.crw_segmean_workspace_bytes(B, T, Hm, Hm, Hm * scale, Hm * scale, SP)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    out = torch.empty(B, SP, T, C)
+    sb, st, sy, sx = lab.stride()
+    sim.check(sim.crw_segmean_fwd(ptr(maps), ptr(lab), sb, st, sy, sx, B, C, T, Hm, Hm, Hm * scale, Hm * scale, SP, ptr(out), ptr(ws), wsb, None))
+    torch.testing.assert_close(out.transpose(1, 2), O.segment_mean(maps, lab, SP), rtol=1e-5, atol=1e-6)
+    gout = torch.randn(B, SP, T, C, generator=g)
+    gm = torch.empty_like(maps)
+    sim.check(sim.crw_segmean_bwd(ptr(gout), ptr(ws), wsb, B, C, T, Hm, Hm, Hm * scale, Hm * scale, SP, ptr(gm), None))
+    m2 = maps.clone().requires_grad_(True)
+    up = m2.repeat_interleave(scale, -1).repeat_interleave(scale, -2)
+    ok = (lab >= 0) & (lab < SP)
+    oh = torch.nn.functional.one_hot(lab.clamp(0, SP - 1), SP).float() * ok[..., None]
+    ref = torch.einsum("bcthw,bthws->btsc", up, oh) / (oh.sum((2, 3))[..., None] + 1e-20)
+    ref.backward(gout.transpose(1, 2))
+    torch.testing.assert_close(gm, m2.grad, rtol=1e-4, atol=1e-6)
+
+
 def check_topk_indices(feats, ki, Is, Is_ref, c):
     """Top-k indices must be bit-exact apart from DOCUMENTED EXACT TIES.  torch.topk's order among equal scores is
     unspecified (ours: lowest flat index first), and equal scores are systematic here: target 0's long-memory frame 0
