@@ -464,22 +464,43 @@ __global__ void __launch_bounds__(1024, 1) segmean_accum_kernel(const float* __r
     }
 }
 
-// Backward, one CTA per (clip, frame, 32-channel tile): gout / size staged in shared memory as [label][33]; a thread owns
-// a cell, keeps the cell's first four (label, count) entries in registers and produces the cell's 32 channels, so a warp
-// writes 128 contiguous bytes per channel and reads shared memory without conflicts (distinct labels -> distinct banks,
-// equal labels -> broadcast).  A gather: deterministic.
+// Backward, one CTA per (clip, frame, 32-channel tile): gout / size staged in shared memory as [label][36]; a thread owns
+// a cell, keeps the cell's first four (label, count) entries in registers and produces the cell's 32 channels with 128-bit
+// shared-memory reads (equal labels broadcast, different labels mostly sit in different bank groups), so a warp writes 128
+// contiguous bytes per channel.  A gather: deterministic.
+constexpr int kSegLDB = kSegCT + 4;
+
 __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restrict__ gout, SegWs ws, int C, int T, int cells,
                                                           int SP, float* __restrict__ gmaps) {
     CRW_DYN_SMEM(smem_raw);
-    float* wg = reinterpret_cast<float*>(smem_raw);             // [SP][kSegCT + 1] = gout / size
+    float* wg = reinterpret_cast<float*>(smem_raw);             // [SP][kSegLDB] = gout / size
+    float* dn = wg + (size_t)SP * kSegLDB;                      // [SP] size + eps
+    float* rc = dn + SP;                                        // [SP] its reciprocal
     const int tid = threadIdx.x;
     const int bt = blockIdx.y, b = bt / T, t = bt - b * T;
     const int c0 = blockIdx.x * kSegCT;
-    constexpr int LD = kSegCT + 1;
     const int* size = ws.size + (int64_t)bt * SP;
-    for (int e = tid; e < SP * kSegCT; e += 256) {
-        const int s = e / kSegCT, cl = e - s * kSegCT;
-        wg[s * LD + cl] = (c0 + cl < C) ? __ldg(gout + (((int64_t)b * SP + s) * T + t) * C + c0 + cl) / ((float)size[s] + kEpsLog) : 0.f;
+    for (int s = tid; s < SP; s += 256) {
+        const float d = (float)size[s] + kEpsLog;
+        float r = 1.0f / d;
+        r = fmaf(fmaf(-d, r, 1.0f), r, r);
+        dn[s] = d;
+        rc[s] = r;
+    }
+    __syncthreads();
+    const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(gout) & 15) == 0 && c0 + kSegCT <= C;
+    if (vec) {      // 8 threads x 16 bytes cover one label's 32 channels
+        for (int e = tid; e < SP * (kSegCT / 4); e += 256) {
+            const int s = e >> 3, c4 = e & 7;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gout + (((int64_t)b * SP + s) * T + t) * C + c0) + c4);
+            const float d = dn[s], r = rc[s];
+            *reinterpret_cast<float4*>(wg + s * kSegLDB + 4 * c4) = make_float4(seg_div(g.x, d, r), seg_div(g.y, d, r), seg_div(g.z, d, r), seg_div(g.w, d, r));
+        }
+    } else {
+        for (int e = tid; e < SP * kSegCT; e += 256) {
+            const int s = e / kSegCT, cl = e - s * kSegCT;
+            wg[s * kSegLDB + cl] = (c0 + cl < C) ? seg_div(__ldg(gout + (((int64_t)b * SP + s) * T + t) * C + c0 + cl), dn[s], rc[s]) : 0.f;
+        }
     }
     __syncthreads();
     const unsigned char* nent = ws.nent + (int64_t)bt * cells;
@@ -487,33 +508,38 @@ __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restric
     const int nc = min(kSegCT, C - c0);
     float* dst0 = gmaps + (((int64_t)b * C + c0) * T + t) * cells;
     const int64_t cstride = (int64_t)T * cells;
-    for (int cell = tid; cell < cells; cell += 256) {
-        const int ne = nent[cell];
-        float cnt[4];
-        const float* row[4];
+    for (int cell0 = 0; cell0 < cells; cell0 += 256) {                        // warp-uniform trip count
+        const int cell = cell0 + tid;
+        const bool live = cell < cells;
+        const int ne = live ? nent[cell] : 0;
+        int nmax = ne;                                                        // slots are taken four at a time, for as long as any lane of the warp has some
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-            const unsigned e = sl < ne ? __ldg(ent + (int64_t)sl * cells + cell) : 0u;
-            cnt[sl] = (float)(e & 255u);                          // 0 for the unused slots: they add wg[0][c] * 0
-            row[sl] = wg + (e >> 8) * LD;
-        }
-        if (ne <= 4) {
-#pragma unroll 8
-            for (int cl = 0; cl < nc; ++cl) {
-                float g = cnt[0] * row[0][cl];
-                g = fmaf(cnt[1], row[1][cl], g);
-                g = fmaf(cnt[2], row[2][cl], g);
-                g = fmaf(cnt[3], row[3][cl], g);
-                dst0[cl * cstride + cell] = g;
+        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, o));
+        for (int base = 0; base < nmax || base == 0; base += 4) {
+            float cnt[4];
+            const float4* row[4];
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+                const unsigned e = base + sl < ne ? __ldg(ent + (int64_t)(base + sl) * cells + cell) : 0u;
+                cnt[sl] = (float)(e & 255u);                      // 0 for the unused slots: they add wg[0][c] * 0
+                row[sl] = reinterpret_cast<const float4*>(wg + (e >> 8) * kSegLDB);
             }
-        } else {
-            for (int cl = 0; cl < nc; ++cl) {
-                float g = 0.f;
-                for (int sl = 0; sl < ne; ++sl) {
-                    const unsigned e = __ldg(ent + (int64_t)sl * cells + cell);
-                    g = fmaf((float)(e & 255u), wg[(e >> 8) * LD + cl], g);
+            if (!live || (base > 0 && base >= ne)) continue;
+            float* d = dst0 + cell;
+#pragma unroll
+            for (int c4 = 0; c4 < kSegCT / 4; ++c4) {
+                const float4 v0 = row[0][c4], v1 = row[1][c4], v2 = row[2][c4], v3 = row[3][c4];
+                float g[4] = {fmaf(cnt[3], v3.x, fmaf(cnt[2], v2.x, fmaf(cnt[1], v1.x, cnt[0] * v0.x))),
+                              fmaf(cnt[3], v3.y, fmaf(cnt[2], v2.y, fmaf(cnt[1], v1.y, cnt[0] * v0.y))),
+                              fmaf(cnt[3], v3.z, fmaf(cnt[2], v2.z, fmaf(cnt[1], v1.z, cnt[0] * v0.z))),
+                              fmaf(cnt[3], v3.w, fmaf(cnt[2], v2.w, fmaf(cnt[1], v1.w, cnt[0] * v0.w)))};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (4 * c4 + u < nc) {
+                        float* o = d + (4 * c4 + u) * cstride;
+                        *o = base == 0 ? g[u] : *o + g[u];        // cells with more than four labels (rare) take another round
+                    }
                 }
-                dst0[cl * cstride + cell] = g;
             }
         }
     }
@@ -525,7 +551,7 @@ static int seg_check(int B, int C, int T, int Hm, int Wm, int h, int w, int SP, 
         return CRW_ERR_SHAPE;
     }
     const int npix = (h / Hm) * (w / Wm);
-    if (npix > kSegMaxEnt || SP >= (1 << 24) || (size_t)SP * (kSegCT + 1) * 4 > 227 * 1024) {
+    if (npix > kSegMaxEnt || SP >= (1 << 24) || (size_t)SP * (kSegCT + 6) * 4 > 227 * 1024) {
         set_error("segmean: unsupported scale %dx%d or SP=%d", h / Hm, w / Wm, SP);
         return CRW_ERR_UNSUPPORTED;
     }
@@ -620,7 +646,7 @@ extern "C" int crw_segmean_bwd(const float* grad_out, const void* workspace, siz
     const int cells = Hm * Wm;
     SegWs ws = seg_ws(const_cast<void*>(workspace), B, T, cells, SP, cap);
     if (!workspace || workspace_bytes < ws.bytes) { set_error("segmean_bwd: workspace too small"); return CRW_ERR_SHAPE; }
-    const size_t smem = (size_t)SP * (kSegCT + 1) * sizeof(float);
+    const size_t smem = ((size_t)SP * kSegLDB + 2 * (size_t)SP) * sizeof(float);
     auto k = segmean_bwd_kernel;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((C + kSegCT - 1) / kSegCT, B * T);
