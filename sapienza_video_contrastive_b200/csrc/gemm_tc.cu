@@ -35,7 +35,7 @@ __device__ __forceinline__ int tc_exponent_of(int maxbits) {
 __device__ __forceinline__ float tc_pow2(int e) { return __int_as_float((127 + e) << 23); }
 
 struct SplitSide {
-    TcOperand x;
+    TcOperand x[2][2];           // [group][term], as a (rows x K_t) operand
     int R;                       // rows of this operand's K-major plane (M for A, N for B)
     int* expo;                   // [Z][R] row exponents e: the plane holds x 2^-e
     __half* hi;
@@ -43,7 +43,8 @@ struct SplitSide {
 };
 struct SplitArgs {
     SplitSide s[2];
-    int K, Kp, nj, Z;
+    int K[2], Kp[2];             // per term: K and K rounded up to 8; a plane row is [term 0 | term 1], Kcat = Kp[0] + Kp[1] wide
+    int Kcat, nj, Z, zpg;        // Z = matrices over all groups, zpg = matrices per group
 };
 
 __device__ __forceinline__ void tc_split_store(__half* hi, __half* lo, int64_t o, float v0, float v1) {
@@ -53,75 +54,93 @@ __device__ __forceinline__ void tc_split_store(__half* hi, __half* lo, int64_t o
     *reinterpret_cast<__half2*>(lo + o) = __halves2half2(l0, l1);
 }
 
-// One launch converts both operands.  grid (ceil(Rmax / 8), 2 Z), 256 threads: a block owns 8 plane rows over the whole K
-// range, one row per warp, so the row maxima never leave the warp and the source is read exactly once.  A row of up to 2048
-// floats stays in registers between the max and the split.  Transposed operands (rows are the source's fast dimension) are
-// first staged through shared memory with 32-byte-sector reads (8 rows x 4 k per warp instruction).
+// One launch converts both operands of every group.  grid (ceil(Rmax / 8), 2 Z), 256 threads: a block owns 8 plane rows
+// over the whole K range of all terms, one row per warp, so the row maxima never leave the warp and the source is read
+// exactly once.  A term's row of up to 64 kRegs floats stays in registers between the max and the split.  Transposed
+// operands (rows are the source's fast dimension) are first staged through shared memory with 32-byte-sector reads
+// (8 rows x 4 k per warp instruction).
 __device__ __forceinline__ int tc_split_stride(int K) { return ((K + 31) & ~31) + 4; }      // = 4 mod 32: conflict-free staging
 
-template <int kRegs>                                      // 2 floats per lane per step: rows of up to 64 kRegs floats stay in registers
+template <int kRegs, int NTERMS>
 __global__ void __launch_bounds__(256) tc_split_kernel(SplitArgs a) {
-    extern __shared__ float stage[];                          // row-fast sources only: [8][tc_split_stride(K)]
+    extern __shared__ float stage[];                          // row-fast sources only: [term][8][tc_split_stride(K_t)]
     const int side = blockIdx.y >= a.Z, z = blockIdx.y - side * a.Z;
     const SplitSide& S = a.s[side];
     const int r0 = blockIdx.x * 8;
     if (r0 >= S.R) return;
-    const float* base = S.x.p + (int64_t)(z / a.nj) * S.x.sb + (int64_t)(z % a.nj) * S.x.sj;
+    const int grp = z / a.zpg, zl = z - grp * a.zpg;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const bool rfast = S.x.rs == 1 && S.x.cs != 1;
-    const float* row;
-    int64_t cs;
-    if (rfast) {
-        const int stride = tc_split_stride(a.K);
-        const int rr = threadIdx.x & 7, kk = threadIdx.x >> 3;
-        if (r0 + rr < S.R)
-            for (int k = kk; k < a.K; k += 32) stage[rr * stride + k] = __ldg(base + r0 + rr + (int64_t)k * S.x.cs);
-        __syncthreads();
-        row = stage + ty * stride;
-        cs = 1;
-    } else {
-        row = base + (int64_t)(r0 + ty) * S.x.rs;
-        cs = S.x.cs;
+    const float* row[NTERMS];
+    int64_t cs[NTERMS];
+    bool staged = false;
+    int soff = 0;
+#pragma unroll
+    for (int t = 0; t < NTERMS; ++t) {
+        const TcOperand& x = S.x[grp][t];
+        const float* base = x.p + (int64_t)(zl / a.nj) * x.sb + (int64_t)(zl % a.nj) * x.sj;
+        if (x.rs == 1 && x.cs != 1) {
+            const int stride = tc_split_stride(a.K[t]);
+            const int rr = threadIdx.x & 7, kk = threadIdx.x >> 3;
+            if (r0 + rr < S.R)
+                for (int k = kk; k < a.K[t]; k += 32) stage[soff + rr * stride + k] = __ldg(base + r0 + rr + (int64_t)k * x.cs);
+            row[t] = stage + soff + ty * stride;
+            cs[t] = 1;
+            soff += 8 * stride;
+            staged = true;
+        } else {
+            row[t] = base + (int64_t)(r0 + ty) * x.rs;
+            cs[t] = x.cs;
+        }
     }
+    if (staged) __syncthreads();
     const int r = r0 + ty;
     if (r >= S.R) return;
-    float2 v[kRegs];
+    float2 v[NTERMS][kRegs];
     float m = 0.f;
-    const bool inreg = a.Kp <= 64 * kRegs;
-    if (inreg) {
+    bool inreg[NTERMS];
 #pragma unroll
-        for (int q = 0; q < kRegs; ++q) {
-            const int k = q * 64 + 2 * tx;
-            v[q].x = k < a.K ? row[(int64_t)k * cs] : 0.f;
-            v[q].y = k + 1 < a.K ? row[(int64_t)(k + 1) * cs] : 0.f;
-            m = fmaxf(m, fmaxf(fabsf(v[q].x), fabsf(v[q].y)));
+    for (int t = 0; t < NTERMS; ++t) {
+        inreg[t] = a.Kp[t] <= 64 * kRegs;
+        if (inreg[t]) {
+#pragma unroll
+            for (int q = 0; q < kRegs; ++q) {
+                const int k = q * 64 + 2 * tx;
+                v[t][q].x = k < a.K[t] ? row[t][(int64_t)k * cs[t]] : 0.f;
+                v[t][q].y = k + 1 < a.K[t] ? row[t][(int64_t)(k + 1) * cs[t]] : 0.f;
+                m = fmaxf(m, fmaxf(fabsf(v[t][q].x), fabsf(v[t][q].y)));
+            }
+        } else {
+            for (int k = tx; k < a.K[t]; k += 32) m = fmaxf(m, fabsf(row[t][(int64_t)k * cs[t]]));
         }
-    } else {
-        for (int k = tx; k < a.K; k += 32) m = fmaxf(m, fabsf(row[(int64_t)k * cs]));
     }
     m = warp_max(m);
     const int e = tc_exponent_of(__float_as_int(m));
     const float sc = tc_pow2(-e);
     if (tx == 0) S.expo[(int64_t)z * S.R + r] = e;
-    const int64_t o = ((int64_t)z * S.R + r) * a.Kp;
-    if (inreg) {
+    int64_t o = ((int64_t)z * S.R + r) * a.Kcat;
 #pragma unroll
-        for (int q = 0; q < kRegs; ++q) {
-            const int k = q * 64 + 2 * tx;
-            if (k < a.Kp) tc_split_store(S.hi, S.lo, o + k, v[q].x * sc, v[q].y * sc);       // Kp is even: the pair is inside the plane
+    for (int t = 0; t < NTERMS; ++t) {
+        if (inreg[t]) {
+#pragma unroll
+            for (int q = 0; q < kRegs; ++q) {
+                const int k = q * 64 + 2 * tx;
+                if (k < a.Kp[t]) tc_split_store(S.hi, S.lo, o + k, v[t][q].x * sc, v[t][q].y * sc);   // Kp is even: the pair is inside the plane
+            }
+        } else {
+            for (int k = 2 * tx; k < a.Kp[t]; k += 64) {
+                const float v0 = k < a.K[t] ? row[t][(int64_t)k * cs[t]] : 0.f, v1 = k + 1 < a.K[t] ? row[t][(int64_t)(k + 1) * cs[t]] : 0.f;
+                tc_split_store(S.hi, S.lo, o + k, v0 * sc, v1 * sc);
+            }
         }
-    } else {
-        for (int k = 2 * tx; k < a.Kp; k += 64) {
-            const float v0 = k < a.K ? row[(int64_t)k * cs] : 0.f, v1 = k + 1 < a.K ? row[(int64_t)(k + 1) * cs] : 0.f;
-            tc_split_store(S.hi, S.lo, o + k, v0 * sc, v1 * sc);
-        }
+        o += a.Kp[t];
     }
 }
 
 struct GtArgs {
-    float* C;
-    int64_t csb, csj, ldc;
-    int M, N, nj, accumulate, K;
+    float* C[2];                 // per group
+    int64_t csb[2], csj[2], ldc[2];
+    int accumulate[2];
+    int M, N, nj, zpg, K;        // K = concatenated width of the operand planes
     const int* aexp;             // per-row exponents of the operands, [z][M] and [z][N]
     const int* bexp;
     unsigned* err;
@@ -224,9 +243,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi0, const __grid_constant_
         tc_fence_after();
         if (warp == 2) GT_MARK(4);
         const float ua = row < g.M ? tc_pow2(__ldg(g.aexp + (int64_t)z * g.M + row)) : 1.f;      // powers of two: exact
-        float* crow = g.C + (int64_t)(z / g.nj) * g.csb + (int64_t)(z % g.nj) * g.csj + (int64_t)row * g.ldc;
+        const int grp = z / g.zpg, zl = z - grp * g.zpg;
+        const int64_t ldc = g.ldc[grp];
+        const int accumulate = g.accumulate[grp];
+        float* cbase = g.C[grp] + (int64_t)(zl / g.nj) * g.csb[grp] + (int64_t)(zl % g.nj) * g.csj[grp];
+        float* crow = cbase + (int64_t)row * ldc;
         const unsigned lane_addr = tmem_base + ((unsigned)(quarter * 32) << 16);
-        const bool vec = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && ((g.csb | g.csj) & 3) == 0;
+        const bool vec = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(cbase) & 15) == 0;
         if (ok) {
             for (int c0 = 0; c0 < GT_N; c0 += 32) {
                 unsigned m[32], c[32];
@@ -241,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi0, const __grid_constant_
                     const int col = n0 + c0;
                     if (vec && col + 32 <= g.N) {
                         float4* o = reinterpret_cast<float4*>(crow + col);
-                        if (g.accumulate) {                  // all eight loads in flight before the first add
+                        if (accumulate) {                    // all eight loads in flight before the first add
                             float4 old[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) old[j] = o[j];
@@ -253,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi0, const __grid_constant_
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (col + j < g.N) crow[col + j] = g.accumulate ? crow[col + j] + v[j] : v[j];
+                            if (col + j < g.N) crow[col + j] = accumulate ? crow[col + j] + v[j] : v[j];
                     }
                 }
             }
@@ -310,10 +333,9 @@ static bool make_map3_uncached(CUtensorMap* m, const void* base, int K, int Kp, 
 // ---- host entry used by walk_general.cu ------------------------------------------------------------------------------
 static inline size_t gt_align(size_t x) { return (x + 255) / 256 * 256; }
 
-size_t gemm_tc_workspace_bytes(int M, int N, int Kmax, int Z) {
-    const size_t Kp = (size_t)((Kmax + 7) & ~7);
-    // A planes 2 * Z*M*Kp halves, B planes 2 * Z*N*Kp halves, row exponents Z*(M+N) words; + error word
-    return 256 + gt_align(2 * (size_t)Z * M * Kp * 2) + gt_align(2 * (size_t)Z * N * Kp * 2) + gt_align((size_t)Z * (M + N) * 4);
+size_t gemm_tc_workspace_bytes(int M, int N, int Kcat, int Z) {
+    // A planes 2 * Z*M*Kcat halves, B planes 2 * Z*N*Kcat halves, row exponents Z*(M+N) words; + error word
+    return 256 + gt_align(2 * (size_t)Z * M * Kcat * 2) + gt_align(2 * (size_t)Z * N * Kcat * 2) + gt_align((size_t)Z * (M + N) * 4);
 }
 
 bool gemm_tc_eligible(int M, int N, int Kmin, int Kmax) {
@@ -325,21 +347,30 @@ bool gemm_tc_eligible(int M, int N, int Kmin, int Kmax) {
 #endif
 }
 
+#ifndef CRW_SIM
+template <int kRegs>
+static void launch_split(const SplitArgs& sa, int nterms, dim3 grid, size_t smem, cudaStream_t st) {
+    if (nterms == 1) tc_split_kernel<kRegs, 1><<<grid, 256, smem, st>>>(sa);
+    else tc_split_kernel<kRegs, 2><<<grid, 256, smem, st>>>(sa);
+}
+#endif
+
 int gemm_tc_run(const TcGemmCall& c, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
 #ifdef CRW_SIM
     (void)c; (void)workspace; (void)workspace_bytes; (void)stream;
     return CRW_ERR_UNSUPPORTED;
 #else
-    const int Z = c.nb * c.nj;
-    int Kmax = 0;
-    for (int t = 0; t < c.nterms; ++t) Kmax = c.K[t] > Kmax ? c.K[t] : Kmax;
-    if (workspace_bytes < gemm_tc_workspace_bytes(c.M, c.N, Kmax, Z)) { set_error("gemm_tc: workspace too small"); return CRW_ERR_SHAPE; }
+    if (c.ngroups < 1 || c.ngroups > 2 || c.nterms < 1 || c.nterms > 2) { set_error("gemm_tc: bad call"); return CRW_ERR_SHAPE; }
+    const int zpg = c.nb * c.nj, Z = c.ngroups * zpg;
+    int Kmax = 0, Kcat = 0;
+    for (int t = 0; t < c.nterms; ++t) { Kmax = c.K[t] > Kmax ? c.K[t] : Kmax; Kcat += (c.K[t] + 7) & ~7; }
+    if (Kmax > kSplitMaxK) { set_error("gemm_tc: K = %d exceeds %d", Kmax, kSplitMaxK); return CRW_ERR_UNSUPPORTED; }
+    if (workspace_bytes < gemm_tc_workspace_bytes(c.M, c.N, Kcat, Z)) { set_error("gemm_tc: workspace too small"); return CRW_ERR_SHAPE; }
     unsigned char* ws = (unsigned char*)workspace;
     unsigned* err = (unsigned*)ws;
     size_t o = 256;
-    const size_t Kpm = (size_t)((Kmax + 7) & ~7);
-    __half* a_hi = (__half*)(ws + o); __half* a_lo = a_hi + (size_t)Z * c.M * Kpm; o += gt_align(2 * (size_t)Z * c.M * Kpm * 2);
-    __half* b_hi = (__half*)(ws + o); __half* b_lo = b_hi + (size_t)Z * c.N * Kpm; o += gt_align(2 * (size_t)Z * c.N * Kpm * 2);
+    __half* a_hi = (__half*)(ws + o); __half* a_lo = a_hi + (size_t)Z * c.M * Kcat; o += gt_align(2 * (size_t)Z * c.M * Kcat * 2);
+    __half* b_hi = (__half*)(ws + o); __half* b_lo = b_hi + (size_t)Z * c.N * Kcat; o += gt_align(2 * (size_t)Z * c.N * Kcat * 2);
     int* aexp = (int*)(ws + o); int* bexp = aexp + (size_t)Z * c.M;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = 1024 + GT_STAGES * 4 * (size_t)GT_M * 128 + 256 + 512;
@@ -347,50 +378,63 @@ int gemm_tc_run(const TcGemmCall& c, void* workspace, size_t workspace_bytes, cr
     static thread_local int attr_device = -1;                // once per (thread, device)
     int device = 0;
     cudaGetDevice(&device);
-    if (Kmax > kSplitMaxK) { set_error("gemm_tc: K = %d exceeds %d", Kmax, kSplitMaxK); return CRW_ERR_UNSUPPORTED; }
     if (attr_device != device) {
+        const int split_smem_max = 2 * 8 * (kSplitMaxK + 4) * 4;
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(tc_split_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (kSplitMaxK + 4) * 4) != cudaSuccess) {
+            cudaFuncSetAttribute(tc_split_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem_max / 2) != cudaSuccess ||
+            cudaFuncSetAttribute(tc_split_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(tc_split_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (1024 + 4) * 4) != cudaSuccess) {
             set_error("gemm_tc: %s", cudaGetErrorString(cudaGetLastError()));
             return CRW_ERR_CUDA;
         }
         attr_device = device;
     }
-    // two-term products run as two accumulating launches: each term has its own per-row operand exponents
+    // every term's operands -> one pair of K-concatenated planes per operand, one launch
+    SplitArgs sa{};
+    sa.s[0].R = c.M; sa.s[0].expo = aexp; sa.s[0].hi = a_hi; sa.s[0].lo = a_lo;
+    sa.s[1].R = c.N; sa.s[1].expo = bexp; sa.s[1].hi = b_hi; sa.s[1].lo = b_lo;
+    size_t split_smem_a = 0, split_smem_b = 0;
     for (int t = 0; t < c.nterms; ++t) {
-        const int K = c.K[t], Kp = (K + 7) & ~7;
-        TcOperand Bt = c.B[t];                       // as an (N x K) row operand: element (c, k) = p[c * cs + k * rs]
-        const int64_t tmp = Bt.rs; Bt.rs = Bt.cs; Bt.cs = tmp;
-        SplitArgs sa{};
-        sa.s[0] = SplitSide{c.A[t], c.M, aexp, a_hi, a_lo};
-        sa.s[1] = SplitSide{Bt, c.N, bexp, b_hi, b_lo};
-        sa.K = K; sa.Kp = Kp; sa.nj = c.nj; sa.Z = Z;
-        const int rb = ((c.M > c.N ? c.M : c.N) + 7) / 8;
-        const bool rfast = (c.A[t].rs == 1 && c.A[t].cs != 1) || (Bt.rs == 1 && Bt.cs != 1);
-        const size_t split_smem = rfast ? 8 * (size_t)(((K + 31) & ~31) + 4) * sizeof(float) : 0;
-        const dim3 sg(rb, 2 * Z);
-        if (Kp <= 256) tc_split_kernel<4><<<sg, 256, split_smem, st>>>(sa);
-        else if (Kp <= 512) tc_split_kernel<8><<<sg, 256, split_smem, st>>>(sa);
-        else if (Kp <= 1024) tc_split_kernel<16><<<sg, 256, split_smem, st>>>(sa);
-        else tc_split_kernel<32><<<sg, 256, split_smem, st>>>(sa);
-        int e = check_launch("gemm_tc_split");
-        if (e != CRW_OK) return e;
-        CUtensorMap maps[4];
-        if (!make_map3(&maps[0], a_hi, K, Kp, c.M, Z) || !make_map3(&maps[1], a_lo, K, Kp, c.M, Z) ||
-            !make_map3(&maps[2], b_hi, K, Kp, c.N, Z) || !make_map3(&maps[3], b_lo, K, Kp, c.N, Z)) {
-            set_error("gemm_tc: cuTensorMapEncodeTiled failed");
-            return CRW_ERR_CUDA;
+        sa.K[t] = c.K[t]; sa.Kp[t] = (c.K[t] + 7) & ~7;
+        bool ra = false, rb = false;
+        for (int gi = 0; gi < c.ngroups; ++gi) {
+            sa.s[0].x[gi][t] = c.grp[gi].A[t];
+            TcOperand Bt = c.grp[gi].B[t];                   // as an (N x K) row operand: element (c, k) = p[c * cs + k * rs]
+            const int64_t tmp = Bt.rs; Bt.rs = Bt.cs; Bt.cs = tmp;
+            sa.s[1].x[gi][t] = Bt;
+            ra |= c.grp[gi].A[t].rs == 1 && c.grp[gi].A[t].cs != 1;
+            rb |= Bt.rs == 1 && Bt.cs != 1;
         }
-        GtArgs g{};
-        g.C = c.C; g.csb = c.csb; g.csj = c.csj; g.ldc = c.ldc; g.M = c.M; g.N = c.N; g.nj = c.nj;
-        g.accumulate = (c.accumulate || t > 0) ? 1 : 0;
-        g.K = K; g.aexp = aexp; g.bexp = bexp; g.err = err;
-        dim3 grid((c.N + GT_N - 1) / GT_N, (c.M + GT_M - 1) / GT_M, Z);
-        k<<<grid, GT_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
-        e = check_launch("gemm_tc");
-        if (e != CRW_OK) return e;
+        const size_t one = 8 * (size_t)(((c.K[t] + 31) & ~31) + 4) * sizeof(float);
+        if (ra) split_smem_a += one;
+        if (rb) split_smem_b += one;
     }
-    return CRW_OK;
+    sa.Kcat = Kcat; sa.nj = c.nj; sa.Z = Z; sa.zpg = zpg;
+    const size_t split_smem = split_smem_a > split_smem_b ? split_smem_a : split_smem_b;
+    if (split_smem > 200 * 1024) { set_error("gemm_tc: transposed operands too wide to stage (K = %d)", Kmax); return CRW_ERR_UNSUPPORTED; }
+    const dim3 sg(((c.M > c.N ? c.M : c.N) + 7) / 8, 2 * Z);
+    const int Kpm = (Kmax + 7) & ~7;
+    if (Kpm <= 256) launch_split<4>(sa, c.nterms, sg, split_smem, st);
+    else if (Kpm <= 512) launch_split<8>(sa, c.nterms, sg, split_smem, st);
+    else if (Kpm <= 1024) launch_split<16>(sa, c.nterms, sg, split_smem, st);
+    else launch_split<32>(sa, c.nterms, sg, split_smem, st);
+    int e = check_launch("gemm_tc_split");
+    if (e != CRW_OK) return e;
+    CUtensorMap maps[4];
+    if (!make_map3(&maps[0], a_hi, Kcat, Kcat, c.M, Z) || !make_map3(&maps[1], a_lo, Kcat, Kcat, c.M, Z) ||
+        !make_map3(&maps[2], b_hi, Kcat, Kcat, c.N, Z) || !make_map3(&maps[3], b_lo, Kcat, Kcat, c.N, Z)) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled failed");
+        return CRW_ERR_CUDA;
+    }
+    GtArgs g{};
+    for (int gi = 0; gi < c.ngroups; ++gi) {
+        g.C[gi] = c.grp[gi].C; g.csb[gi] = c.grp[gi].csb; g.csj[gi] = c.grp[gi].csj; g.ldc[gi] = c.grp[gi].ldc;
+        g.accumulate[gi] = c.grp[gi].accumulate;
+    }
+    g.M = c.M; g.N = c.N; g.nj = c.nj; g.zpg = zpg; g.K = Kcat; g.aexp = aexp; g.bexp = bexp; g.err = err;
+    dim3 grid((c.N + GT_N - 1) / GT_N, (c.M + GT_M - 1) / GT_M, Z);
+    k<<<grid, GT_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+    return check_launch("gemm_tc");
 #endif
 }
 
@@ -414,7 +458,7 @@ int gemm_tc_check(void* workspace, crw_stream_t stream) {
 
 using namespace crw;
 
-extern "C" size_t crw_bmm_tc_workspace_bytes(int Z, int M, int N, int K) { return gemm_tc_workspace_bytes(M, N, K, Z); }
+extern "C" size_t crw_bmm_tc_workspace_bytes(int Z, int M, int N, int K) { return gemm_tc_workspace_bytes(M, N, (K + 7) & ~7, Z); }
 
 extern "C" int crw_bmm_tc(const float* A, const float* B, float* C, int Z, int M, int N, int K, int trans_a, int trans_b,
                           int accumulate, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
@@ -422,10 +466,11 @@ extern "C" int crw_bmm_tc(const float* A, const float* B, float* C, int Z, int M
     if (Z == 0) return CRW_OK;
     if (!gemm_tc_eligible(M, N, K, K)) { set_error("bmm_tc: needs M >= 64, N >= 64, 64 <= K <= 4096 (got %d, %d, %d)", M, N, K); return CRW_ERR_UNSUPPORTED; }
     TcGemmCall c{};
-    c.nterms = 1; c.K[0] = K; c.M = M; c.N = N; c.nb = Z; c.nj = 1; c.accumulate = accumulate;
-    c.A[0] = TcOperand{A, (int64_t)M * K, 0, trans_a ? 1 : K, trans_a ? M : 1};
-    c.B[0] = TcOperand{B, (int64_t)K * N, 0, trans_b ? 1 : N, trans_b ? K : 1};
-    c.C = C; c.csb = (int64_t)M * N; c.csj = 0; c.ldc = N;
+    c.ngroups = 1; c.nterms = 1; c.K[0] = K; c.M = M; c.N = N; c.nb = Z; c.nj = 1;
+    c.grp[0].accumulate = accumulate;
+    c.grp[0].A[0] = TcOperand{A, (int64_t)M * K, 0, trans_a ? 1 : K, trans_a ? M : 1};
+    c.grp[0].B[0] = TcOperand{B, (int64_t)K * N, 0, trans_b ? 1 : N, trans_b ? K : 1};
+    c.grp[0].C = C; c.grp[0].csb = (int64_t)M * N; c.grp[0].csj = 0; c.grp[0].ldc = N;
     int e = gemm_tc_run(c, workspace, workspace_bytes, stream);
     return e;
 }

@@ -9,17 +9,27 @@ struct TcOperand {           // element (r, k) of matrix z: p[(z / nj) * sb + (z
     int64_t sb, sj, rs, cs;
 };
 
-// C[z] (M x N, fp32, row stride ldc, matrix z at C + (z / nj) * csb + (z % nj) * csj)  (+)=  sum_t A_t[z] (M x K_t) B_t[z] (K_t x N)
-struct TcGemmCall {
+// One launch computes up to two independent batched products of identical shape ("groups", e.g. P_j = P_{j-1} X_j and
+// S_j = Y_j S_{j-1}), each the sum of up to two terms:
+//   C_g[z] (M x N, fp32, row stride ldc, matrix z at C + (z / nj) * csb + (z % nj) * csj)  (+)=  sum_t A_gt[z] (M x K_t) B_gt[z] (K_t x N)
+// The terms of a product are concatenated along K into one pair of operand planes (common per-row exponents), so a
+// two-term product is still a single pass of the tensor-core pipeline.
+struct TcGroup {
     TcOperand A[2], B[2];        // B given as (k, c): element (k, c) of B_t = p[... + k * rs + c * cs]
-    int K[2];
-    int nterms;
     float* C;
     int64_t csb, csj, ldc;
-    int M, N, nb, nj, accumulate;
+    int accumulate;
+};
+struct TcGemmCall {
+    TcGroup grp[2];
+    int ngroups;
+    int K[2];
+    int nterms;
+    int M, N, nb, nj;
 };
 
-size_t gemm_tc_workspace_bytes(int M, int N, int Kmax, int Z);
+// Kcat = sum over terms of K_t rounded up to 8; Z = ngroups * nb * nj
+size_t gemm_tc_workspace_bytes(int M, int N, int Kcat, int Z);
 bool gemm_tc_eligible(int M, int N, int Kmin, int Kmax);
 int gemm_tc_run(const TcGemmCall& c, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 int gemm_tc_check(void* workspace, crw_stream_t stream);          // reads the error word back (synchronises the stream)

@@ -37,10 +37,21 @@ WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
     }
     // general path on large graphs: operand planes of the tensor-core GEMM (gemm_tc.cu)
     const int NK = N > D ? N : D;
-    // measured crossover against the SIMT GEMM (tools/bench_tc_gemm.py): 0.83x at N = 128, 1.1x at 196, 1.9x at 512, 4.1x at 1024
-    const bool tc = !w.fused && !(flags & CRW_WALK_FORCE_SIMT) && t1 > 0 && (N >= 192 || (flags & CRW_WALK_FORCE_TC)) &&
+    w.tc_bytes = 0;
+    // measured against the SIMT GEMM (tools/bench_tc_gemm.py): 0.8-1.2x at N = 64 (SIMT kept: its 64x64 tiles fit exactly),
+    // 1.1-1.2x at 72..80, 1.15-1.45x at 100..160, 1.75x at 196, 2.45x at 512, 4.4x at 1024
+    const bool tc = !w.fused && !(flags & CRW_WALK_FORCE_SIMT) && t1 > 0 && (N >= 72 || (flags & CRW_WALK_FORCE_TC)) &&
                     gemm_tc_eligible(N, N < D ? N : D, N < D ? N : D, NK);
-    w.tc_bytes = tc ? gemm_tc_workspace_bytes(N, NK, NK, (int)(B * t1)) : 0;
+    if (tc) {    // the largest of the calls launch_walk_general makes (groups x batch, K-concatenated terms)
+        const int Np = (N + 7) & ~7, Dp = (D + 7) & ~7, b = B, m1 = (int)t1, m2 = (int)t2;
+        const size_t calls[6] = {gemm_tc_workspace_bytes(N, N, Dp, 2 * b * m1),          // affinities, both orientations
+                                 gemm_tc_workspace_bytes(N, N, Np, 2 * b),               // one chain level
+                                 gemm_tc_workspace_bytes(N, N, Np, b * m2),              // W_j
+                                 gemm_tc_workspace_bytes(N, N, 2 * Np, 2 * b),           // one reverse-sweep level, two terms
+                                 gemm_tc_workspace_bytes(N, N, Np, 2 * b * (m2 > 1 ? m2 - 1 : 1)),   // dX_j, dY_j
+                                 gemm_tc_workspace_bytes(N, D, 2 * Np, b * m1)};         // dQ
+        for (size_t c : calls) w.tc_bytes = c > w.tc_bytes ? c : w.tc_bytes;
+    } else w.tc_bytes = 0;
     w.o_tc = take(w.tc_bytes);
     w.total = o;
     return w;

@@ -105,27 +105,50 @@ struct TcCtx {
     size_t bytes;
 };
 
-static int run_gemm(const GemmArgs& g, int nb, crw_stream_t stream, const TcCtx* tc = nullptr) {
+static int run_gemm_simt(const GemmArgs& g, int nb, crw_stream_t stream) {
     if (g.M <= 0 || g.N <= 0 || nb * g.nj <= 0) return CRW_OK;
-    if (tc && tc->ws && g.ktot == 0 && g.nterms >= 1) {
-        int kmin = g.K[0], kmax = g.K[0];
-        for (int t = 1; t < g.nterms; ++t) { kmin = g.K[t] < kmin ? g.K[t] : kmin; kmax = g.K[t] > kmax ? g.K[t] : kmax; }
-        if (gemm_tc_eligible(g.M, g.N, kmin, kmax) && gemm_tc_workspace_bytes(g.M, g.N, kmax, nb * g.nj) <= tc->bytes) {
-            TcGemmCall c{};
-            for (int t = 0; t < g.nterms; ++t) {
-                c.A[t] = TcOperand{g.A[t].p, g.A[t].sb, g.A[t].sj, g.A[t].rs, g.A[t].cs};
-                c.B[t] = TcOperand{g.B[t].p, g.B[t].sb, g.B[t].sj, g.B[t].rs, g.B[t].cs};
-                c.K[t] = g.K[t];
-            }
-            c.nterms = g.nterms; c.C = g.C; c.csb = g.csb; c.csj = g.csj; c.ldc = g.ldc;
-            c.M = g.M; c.N = g.N; c.nb = nb; c.nj = g.nj; c.accumulate = g.accumulate;
-            return gemm_tc_run(c, tc->ws, tc->bytes, stream);
-        }
-    }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nb * g.nj);
     CRW_LAUNCH(gemm_f32_kernel, grid, 256, 0, stream, g);
     return check_launch("gemm_f32");
 }
+
+static void tc_group_of(TcGroup& o, const GemmArgs& g) {
+    for (int t = 0; t < g.nterms; ++t) {
+        o.A[t] = TcOperand{g.A[t].p, g.A[t].sb, g.A[t].sj, g.A[t].rs, g.A[t].cs};
+        o.B[t] = TcOperand{g.B[t].p, g.B[t].sb, g.B[t].sj, g.B[t].rs, g.B[t].cs};
+    }
+    o.C = g.C; o.csb = g.csb; o.csj = g.csj; o.ldc = g.ldc; o.accumulate = g.accumulate;
+}
+
+// One or two independent products of identical shape (same M, N, K's, term count and batch): a single tensor-core launch
+// when the walk has a tensor-core workspace and the shape is worth it, the SIMT kernel otherwise.
+static int run_gemms(const GemmArgs* gs, int ng, int nb, crw_stream_t stream, const TcCtx* tc) {
+    const GemmArgs& g = gs[0];
+    if (g.M <= 0 || g.N <= 0 || nb * g.nj <= 0) return CRW_OK;
+    if (tc && tc->ws && g.ktot == 0 && g.nterms >= 1) {
+        int kmin = g.K[0], kmax = g.K[0], kcat = 0;
+        for (int t = 0; t < g.nterms; ++t) {
+            kmin = g.K[t] < kmin ? g.K[t] : kmin;
+            kmax = g.K[t] > kmax ? g.K[t] : kmax;
+            kcat += (g.K[t] + 7) & ~7;
+        }
+        if (gemm_tc_eligible(g.M, g.N, kmin, kmax) && gemm_tc_workspace_bytes(g.M, g.N, kcat, ng * nb * g.nj) <= tc->bytes) {
+            TcGemmCall c{};
+            for (int i = 0; i < ng; ++i) tc_group_of(c.grp[i], gs[i]);
+            c.ngroups = ng; c.nterms = g.nterms; c.K[0] = g.K[0]; c.K[1] = g.K[1];
+            c.M = g.M; c.N = g.N; c.nb = nb; c.nj = g.nj;
+            const int e = gemm_tc_run(c, tc->ws, tc->bytes, stream);
+            if (e != CRW_ERR_UNSUPPORTED) return e;
+        }
+    }
+    for (int i = 0; i < ng; ++i) {
+        const int e = run_gemm_simt(gs[i], nb, stream);
+        if (e != CRW_OK) return e;
+    }
+    return CRW_OK;
+}
+
+static int run_gemm(const GemmArgs& g, int nb, crw_stream_t stream, const TcCtx* tc = nullptr) { return run_gemms(&g, 1, nb, stream, tc); }
 
 static MatRef mref(const float* p, int64_t sb, int64_t sj, int64_t rs, int64_t cs) { return MatRef{p, sb, sj, rs, cs}; }
 
@@ -427,16 +450,16 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
 
     // 2. raw affinities in both orientations (model.py:68): A_i = Q_i Q_{i+1}^T, AT_i = Q_{i+1} Q_i^T
     {
-        GemmArgs g{};
-        g.nterms = 1; g.K[0] = D; g.M = N; g.N = N; g.nj = t1; g.accumulate = 0;
-        g.A[0] = mref(p.q, cs, D, gs, 1);
-        g.B[0] = mref(p.q + D, cs, D, 1, gs);
-        g.C = A; g.csb = s1; g.csj = MS; g.ldc = N;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
-        g.A[0] = mref(p.q + D, cs, D, gs, 1);
-        g.B[0] = mref(p.q, cs, D, 1, gs);
-        g.C = AT;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
+        GemmArgs g[2] = {};
+        g[0].nterms = 1; g[0].K[0] = D; g[0].M = N; g[0].N = N; g[0].nj = t1; g[0].accumulate = 0;
+        g[0].A[0] = mref(p.q, cs, D, gs, 1);
+        g[0].B[0] = mref(p.q + D, cs, D, 1, gs);
+        g[0].C = A; g[0].csb = s1; g[0].csj = MS; g[0].ldc = N;
+        g[1] = g[0];
+        g[1].A[0] = mref(p.q + D, cs, D, gs, 1);
+        g[1].B[0] = mref(p.q, cs, D, 1, gs);
+        g[1].C = AT;
+        CRW_TRY(run_gemms(g, 2, B, stream, &tc));
     }
     // 3. transition rows (model.py:74-90) in both directions
     for (int dir = 1; dir <= 2; ++dir) {
@@ -462,16 +485,16 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
 
     // 4. chains (model.py:376-380 re-associated): P_j = P_{j-1} X_j, S_j = Y_j S_{j-1}
     for (int j = 1; j <= T - 2; ++j) {
-        GemmArgs g{};
-        g.nterms = 1; g.K[0] = N; g.M = N; g.N = N; g.nj = 1; g.accumulate = 0; g.csb = s2; g.csj = 0; g.ldc = N;
-        g.A[0] = j == 1 ? mref(X, s1, 0, N, 1) : mref(P + (j - 2) * MS, s2, 0, N, 1);
-        g.B[0] = mref(X + j * MS, s1, 0, N, 1);
-        g.C = P + (j - 1) * MS;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
-        g.A[0] = mref(Y + j * MS, s1, 0, N, 1);
-        g.B[0] = j == 1 ? mref(Y, s1, 0, N, 1) : mref(S + (j - 2) * MS, s2, 0, N, 1);
-        g.C = S + (j - 1) * MS;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
+        GemmArgs g[2] = {};                              // the two chains of a level are independent: one launch
+        g[0].nterms = 1; g[0].K[0] = N; g[0].M = N; g[0].N = N; g[0].nj = 1; g[0].accumulate = 0; g[0].csb = s2; g[0].csj = 0; g[0].ldc = N;
+        g[0].A[0] = j == 1 ? mref(X, s1, 0, N, 1) : mref(P + (j - 2) * MS, s2, 0, N, 1);
+        g[0].B[0] = mref(X + j * MS, s1, 0, N, 1);
+        g[0].C = P + (j - 1) * MS;
+        g[1] = g[0];
+        g[1].A[0] = mref(Y + j * MS, s1, 0, N, 1);
+        g[1].B[0] = j == 1 ? mref(Y, s1, 0, N, 1) : mref(S + (j - 2) * MS, s2, 0, N, 1);
+        g[1].C = S + (j - 1) * MS;
+        CRW_TRY(run_gemms(g, 2, B, stream, &tc));
     }
     {   // W_j = P_j S_j, all walks in one launch
         GemmArgs g{};
@@ -493,36 +516,29 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
 
     // 6. reverse sweep: gP_j = dW_j S_j^T + gP_{j+1} X_{j+1}^T ; gS_j = P_j^T dW_j + Y_{j+1}^T gS_{j+1}
     for (int j = T - 2; j >= 0; --j) {
-        GemmArgs g{};
-        g.M = N; g.N = N; g.nj = 1; g.accumulate = 0; g.csb = s1; g.csj = 0; g.ldc = N;
+        GemmArgs g[2] = {};                                  // gP_j and gS_j have the same shape and term count: one launch
+        for (int i = 0; i < 2; ++i) { g[i].M = N; g[i].N = N; g[i].nj = 1; g[i].accumulate = 0; g[i].csb = s1; g[i].csj = 0; g[i].ldc = N; }
         int t = 0;
         if (j >= 1) {
-            g.A[t] = mref(W + (j - 1) * MS, s2, 0, N, 1);
-            g.B[t] = mref(S + (j - 1) * MS, s2, 0, 1, N);
-            g.K[t++] = N;
+            g[0].A[t] = mref(W + (j - 1) * MS, s2, 0, N, 1);
+            g[0].B[t] = mref(S + (j - 1) * MS, s2, 0, 1, N);
+            g[1].A[t] = mref(P + (j - 1) * MS, s2, 0, 1, N);
+            g[1].B[t] = mref(W + (j - 1) * MS, s2, 0, N, 1);
+            g[0].K[t] = g[1].K[t] = N;
+            ++t;
         }
         if (j + 1 <= T - 2) {
-            g.A[t] = mref(gP + (j + 1) * MS, s1, 0, N, 1);
-            g.B[t] = mref(X + (j + 1) * MS, s1, 0, 1, N);
-            g.K[t++] = N;
+            g[0].A[t] = mref(gP + (j + 1) * MS, s1, 0, N, 1);
+            g[0].B[t] = mref(X + (j + 1) * MS, s1, 0, 1, N);
+            g[1].A[t] = mref(Y + (j + 1) * MS, s1, 0, 1, N);
+            g[1].B[t] = mref(gS + (j + 1) * MS, s1, 0, N, 1);
+            g[0].K[t] = g[1].K[t] = N;
+            ++t;
         }
-        g.nterms = t;
-        g.C = gP + j * MS;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
-        t = 0;
-        if (j >= 1) {
-            g.A[t] = mref(P + (j - 1) * MS, s2, 0, 1, N);
-            g.B[t] = mref(W + (j - 1) * MS, s2, 0, N, 1);
-            g.K[t++] = N;
-        }
-        if (j + 1 <= T - 2) {
-            g.A[t] = mref(Y + (j + 1) * MS, s1, 0, 1, N);
-            g.B[t] = mref(gS + (j + 1) * MS, s1, 0, N, 1);
-            g.K[t++] = N;
-        }
-        g.nterms = t;
-        g.C = gS + j * MS;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
+        g[0].nterms = g[1].nterms = t;
+        g[0].C = gP + j * MS;
+        g[1].C = gS + j * MS;
+        CRW_TRY(run_gemms(g, 2, B, stream, &tc));
     }
     // 7. dX_j = P_{j-1}^T gP_j, dY_j = gS_j S_{j-1}^T (j >= 1); dX_0 = gP_0, dY_0 = gS_0
     {
@@ -530,20 +546,19 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
         CRW_LAUNCH(copy_mats_kernel, cg, 256, 0, stream, dX, gP, s1, s1, MS, B);
         CRW_LAUNCH(copy_mats_kernel, cg, 256, 0, stream, dY, gS, s1, s1, MS, B);
         CRW_TRY(check_launch("copy_mats"));
-        GemmArgs g{};
-        g.nterms = 1; g.K[0] = N; g.M = N; g.N = N; g.accumulate = 0; g.csb = s1; g.ldc = N;
+        GemmArgs g[2] = {};
+        g[0].nterms = 1; g[0].K[0] = N; g[0].M = N; g[0].N = N; g[0].accumulate = 0; g[0].csb = s1; g[0].ldc = N;
         // j = 1 (P_0 = X_0, S_0 = Y_0 live in the transition stacks)
-        g.nj = 1; g.csj = 0;
-        g.A[0] = mref(X, s1, 0, 1, N); g.B[0] = mref(gP + MS, s1, 0, N, 1); g.C = dX + MS;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
-        g.A[0] = mref(gS + MS, s1, 0, N, 1); g.B[0] = mref(Y, s1, 0, 1, N); g.C = dY + MS;
-        CRW_TRY(run_gemm(g, B, stream, &tc));
+        g[0].nj = 1; g[0].csj = 0;
+        g[1] = g[0];
+        g[0].A[0] = mref(X, s1, 0, 1, N); g[0].B[0] = mref(gP + MS, s1, 0, N, 1); g[0].C = dX + MS;
+        g[1].A[0] = mref(gS + MS, s1, 0, N, 1); g[1].B[0] = mref(Y, s1, 0, 1, N); g[1].C = dY + MS;
+        CRW_TRY(run_gemms(g, 2, B, stream, &tc));
         if (T - 2 >= 2) {
-            g.nj = T - 3; g.csj = MS;
-            g.A[0] = mref(P, s2, MS, 1, N); g.B[0] = mref(gP + 2 * MS, s1, MS, N, 1); g.C = dX + 2 * MS;
-            CRW_TRY(run_gemm(g, B, stream, &tc));
-            g.A[0] = mref(gS + 2 * MS, s1, MS, N, 1); g.B[0] = mref(S, s2, MS, 1, N); g.C = dY + 2 * MS;
-            CRW_TRY(run_gemm(g, B, stream, &tc));
+            g[0].nj = g[1].nj = T - 3; g[0].csj = g[1].csj = MS;
+            g[0].A[0] = mref(P, s2, MS, 1, N); g[0].B[0] = mref(gP + 2 * MS, s1, MS, N, 1); g[0].C = dX + 2 * MS;
+            g[1].A[0] = mref(gS + 2 * MS, s1, MS, N, 1); g[1].B[0] = mref(S, s2, MS, 1, N); g[1].C = dY + 2 * MS;
+            CRW_TRY(run_gemms(g, 2, B, stream, &tc));
         }
     }
     // 8. transition-matrix backward, in place over the raw affinities: A <- Z (rows of F), AT <- Z2 (rows of G)
@@ -560,6 +575,8 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
     // 9. dQ_i += Z_i Q_{i+1} + Z2_i^T Q_{i+1} ; dQ_{i+1} += Z_i^T Q_i + Z2_i Q_i
     cudaMemsetAsync(p.grad, 0, sizeof(float) * (size_t)B * N * T * D, (cudaStream_t)stream);
     {
+        // the two products write interleaved frames of dQ (i and i + 1): they stay two launches, the second accumulating
+        // onto the first's rows
         GemmArgs g{};
         g.nterms = 2; g.K[0] = g.K[1] = N; g.M = N; g.N = D; g.nj = t1; g.accumulate = 1; g.csb = cs; g.csj = D; g.ldc = gs;
         g.A[0] = mref(A, s1, MS, N, 1);  g.B[0] = mref(p.q + D, cs, D, gs, 1);
