@@ -112,6 +112,22 @@ __host__ __forceinline__ uint32_t torch_rand_threads(int64_t numel, int sm_count
     return (uint32_t)(grid * 256);
 }
 
+// packed fp32 FMA (Blackwell FFMA2): two independent IEEE fused multiply-adds per instruction, scalar x vector or vector x vector
+__device__ __forceinline__ float2 ffma2(float a, float2 x, float2 acc) {
+#ifdef CRW_SIM
+    return make_float2(fmaf(a, x.x, acc.x), fmaf(a, x.y, acc.y));
+#else
+    return __ffma2_rn(make_float2(a, a), x, acc);
+#endif
+}
+__device__ __forceinline__ float2 ffma2v(float2 a, float2 x, float2 acc) {
+#ifdef CRW_SIM
+    return make_float2(fmaf(a.x, x.x, acc.x), fmaf(a.y, x.y, acc.y));
+#else
+    return __ffma2_rn(a, x, acc);
+#endif
+}
+
 // global -> shared TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: thread 0 announces the total
 // byte count, issues the copies, and the whole CTA waits on the barrier.  Sizes are multiples of 16, both sides aligned.
 __device__ __forceinline__ void bulk_bar_init(uint64_t* bar, int tid) {

@@ -191,14 +191,6 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
-__device__ __forceinline__ float2 ffma2(float a, float2 x, float2 acc) {
-#ifdef CRW_SIM
-    return make_float2(fmaf(a, x.x, acc.x), fmaf(a, x.y, acc.y));
-#else
-    return __ffma2_rn(make_float2(a, a), x, acc);
-#endif
-}
-
 // Forward accumulation: persistent CTAs (one per SM, 32 warps) walk contiguous runs of (clip, frame, 64-channel tile) items.
 //   * a lane owns channels l and l + 32 of the tile; warp w owns labels w, w + 32, ... and keeps their running sums in
 //     registers (LMAX float2 per lane), so nothing is accumulated in shared memory and there are no atomics: deterministic;

@@ -39,10 +39,10 @@ __device__ __forceinline__ void wr_nn(float* C, int ldc, const float* A, const f
     (void)nw;
     if (r0 >= N) return;
     const int c0 = min(2 * lane, NP - 2);
-    float acc[TMAX][2];
+    float2 acc[TMAX];                      // the lane's two adjacent columns ride in one packed FMA
     const float* arow[TMAX];
 #pragma unroll
-    for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = 0.f; arow[i] = A + min(r0 + i, N - 1) * NP; }
+    for (int i = 0; i < TMAX; ++i) { acc[i] = make_float2(0.f, 0.f); arow[i] = A + min(r0 + i, N - 1) * NP; }
     const float* bp = B + c0;
     const int K4 = N >> 2;
     for (int k4 = 0; k4 < K4; ++k4) {
@@ -53,21 +53,13 @@ __device__ __forceinline__ void wr_nn(float* C, int ldc, const float* A, const f
         for (int kk = 0; kk < 4; ++kk) {
             const float2 b2 = *reinterpret_cast<const float2*>(bp + (k4 * 4 + kk) * NP);
 #pragma unroll
-            for (int i = 0; i < TMAX; ++i) {
-                const float a = CRW_COMP4(a4[i], kk);
-                acc[i][0] = fmaf(a, b2.x, acc[i][0]);
-                acc[i][1] = fmaf(a, b2.y, acc[i][1]);
-            }
+            for (int i = 0; i < TMAX; ++i) acc[i] = ffma2(CRW_COMP4(a4[i], kk), b2, acc[i]);
         }
     }
     for (int k = K4 * 4; k < N; ++k) {
         const float2 b2 = *reinterpret_cast<const float2*>(bp + k * NP);
 #pragma unroll
-        for (int i = 0; i < TMAX; ++i) {
-            const float a = arow[i][k];
-            acc[i][0] = fmaf(a, b2.x, acc[i][0]);
-            acc[i][1] = fmaf(a, b2.y, acc[i][1]);
-        }
+        for (int i = 0; i < TMAX; ++i) acc[i] = ffma2(arow[i][k], b2, acc[i]);
     }
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) {
@@ -78,7 +70,8 @@ __device__ __forceinline__ void wr_nn(float* C, int ldc, const float* A, const f
             const int c = 2 * lane + j;
             if (c >= N) continue;
             float* o = C + r * ldc + c;
-            *o = accumulate ? (*o + acc[i][j]) : acc[i][j];
+            const float v = j ? acc[i].y : acc[i].x;
+            *o = accumulate ? (*o + v) : v;
         }
     }
 }
@@ -91,10 +84,10 @@ __device__ __forceinline__ void wr_nt(float* C, int ldc, const float* A, int lda
     const int r0 = w * TMW;
     (void)nw;
     if (r0 >= N) return;
-    float acc[TMAX][2];
+    float2 acc[TMAX][2];                   // (even k, odd k) partial sums: both operands of the packed FMA are adjacent pairs
     const float* arow[TMAX];
 #pragma unroll
-    for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = 0.f; arow[i] = A + min(r0 + i, N - 1) * lda; }
+    for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = make_float2(0.f, 0.f); arow[i] = A + min(r0 + i, N - 1) * lda; }
     const float* brow[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) brow[j] = B + min(lane + 32 * j, N - 1) * ldb;
@@ -109,11 +102,9 @@ __device__ __forceinline__ void wr_nt(float* C, int ldc, const float* A, int lda
             const float4 a4 = *reinterpret_cast<const float4*>(arow[i] + k4 * 4);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                float s = acc[i][j];
-                s = fmaf(a4.x, b4[j].x, s);
-                s = fmaf(a4.y, b4[j].y, s);
-                s = fmaf(a4.z, b4[j].z, s);
-                s = fmaf(a4.w, b4[j].w, s);
+                float2 s = acc[i][j];
+                s = ffma2v(make_float2(a4.x, a4.y), make_float2(b4[j].x, b4[j].y), s);
+                s = ffma2v(make_float2(a4.z, a4.w), make_float2(b4[j].z, b4[j].w), s);
                 acc[i][j] = s;
             }
         }
@@ -122,7 +113,7 @@ __device__ __forceinline__ void wr_nt(float* C, int ldc, const float* A, int lda
 #pragma unroll
         for (int i = 0; i < TMAX; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) acc[i][j] = fmaf(arow[i][k], brow[j][k], acc[i][j]);
+            for (int j = 0; j < 2; ++j) acc[i][j].x = fmaf(arow[i][k], brow[j][k], acc[i][j].x);
     }
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) {
@@ -133,7 +124,8 @@ __device__ __forceinline__ void wr_nt(float* C, int ldc, const float* A, int lda
             const int c = lane + 32 * j;
             if (c >= N) continue;
             float* o = C + r * ldc + c;
-            *o = accumulate ? (*o + acc[i][j]) : acc[i][j];
+            const float v = acc[i][j].x + acc[i][j].y;
+            *o = accumulate ? (*o + v) : v;
         }
     }
 }
@@ -147,10 +139,10 @@ __device__ __forceinline__ void wr_tn(float* C, int ldc, const float* A, const f
     (void)nw;
     if (r0 >= N) return;
     const int c0 = min(2 * lane, NP - 2);
-    float acc[TMAX][2];
+    float2 acc[TMAX];
     int ro[TMAX];
 #pragma unroll
-    for (int i = 0; i < TMAX; ++i) { acc[i][0] = acc[i][1] = 0.f; ro[i] = min(r0 + i, N - 1); }
+    for (int i = 0; i < TMAX; ++i) { acc[i] = make_float2(0.f, 0.f); ro[i] = min(r0 + i, N - 1); }
     const float* bp = B + c0;
     const float* ap = A + r0;                      // r0 is a multiple of TMAX (4 or 8): 16-byte aligned row chunks,
     (void)ro;                                      // the chunk may run into the pad columns (< NP), never past the row
@@ -164,10 +156,7 @@ __device__ __forceinline__ void wr_tn(float* C, int ldc, const float* A, const f
             av[i4 * 4 + 0] = a4.x; av[i4 * 4 + 1] = a4.y; av[i4 * 4 + 2] = a4.z; av[i4 * 4 + 3] = a4.w;
         }
 #pragma unroll
-        for (int i = 0; i < TMAX; ++i) {
-            acc[i][0] = fmaf(av[i], b2.x, acc[i][0]);
-            acc[i][1] = fmaf(av[i], b2.y, acc[i][1]);
-        }
+        for (int i = 0; i < TMAX; ++i) acc[i] = ffma2(av[i], b2, acc[i]);
     }
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) {
@@ -178,7 +167,8 @@ __device__ __forceinline__ void wr_tn(float* C, int ldc, const float* A, const f
             const int c = 2 * lane + j;
             if (c >= N) continue;
             float* o = C + r * ldc + c;
-            *o = accumulate ? (*o + acc[i][j]) : acc[i][j];
+            const float v = j ? acc[i].y : acc[i].x;
+            *o = accumulate ? (*o + v) : v;
         }
     }
 }

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--lp", action="store_true")
 ap.add_argument("--walk-general", action="store_true")
+ap.add_argument("--kineto", action="store_true", help="per-kernel device times in situ from torch.profiler")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
@@ -24,4 +25,11 @@ else:
     for _ in range(a.steps):
         hp.step()
     torch.cuda.synchronize()
+    if a.kineto:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(10):
+                hp.step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
 print("ok")
