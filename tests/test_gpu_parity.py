@@ -325,6 +325,31 @@ def test_segmean_config3_shape_properties(ops):
     torch.testing.assert_close(out[:1, :, :, :64].cpu().transpose(1, 2), ref, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("B,T,C,Hm,scale,SP", [(2, 3, 128, 32, 8, 100), (1, 2, 64, 32, 4, 256), (1, 2, 64, 16, 8, 300), (1, 1, 64, 32, 2, 600),
+                                               (2, 2, 96, 32, 8, 196), (1, 2, 64, 24, 4, 50)])
+def test_segmean_forward_backward_vs_oracle(ops, B, T, C, Hm, scale, SP):
+    """Every accumulator tier of the forward (SP up to 128 / 224 / 256 / 512 / 1024 labels), the TMA path (cells % 256 == 0,
+    C % 64 == 0) and the generic cp.async path (C = 96, 24x24 maps), labels out of range, more labels than cells: forward
+    against the oracle, backward against autograd through a one-hot restatement."""
+    g = torch.Generator().manual_seed(B * 100 + SP)
+    maps = torch.randn(B, C, T, Hm, Hm, generator=g)
+    lab = cases.voronoi_labels(B, T, SP, Hm * scale, g, one_based=False)
+    lab[:, :, :3, :5] = SP + 2
+    lab[:, :, -2:, :] = -1
+    md = maps.to(DEV).requires_grad_(True)
+    out = ops.segment_mean(md, lab.to(DEV), SP)                                   # (B, SP, T, C)
+    torch.testing.assert_close(out.detach().cpu().transpose(1, 2), O.segment_mean(maps, lab, SP), rtol=1e-5, atol=1e-6)
+    gout = torch.randn(B, SP, T, C, generator=g)
+    out.backward(gout.to(DEV))
+    m2 = maps.clone().requires_grad_(True)
+    up = m2.repeat_interleave(scale, -1).repeat_interleave(scale, -2)
+    ok = (lab >= 0) & (lab < SP)
+    oh = torch.nn.functional.one_hot(lab.clamp(0, SP - 1), SP).float() * ok[..., None]
+    ref = torch.einsum("bcthw,bthws->btsc", up, oh) / (oh.sum((2, 3))[..., None] + 1e-20)
+    ref.backward(gout.transpose(1, 2))
+    torch.testing.assert_close(md.grad.cpu(), m2.grad, rtol=1e-4, atol=1e-6)
+
+
 @pytest.mark.parametrize("name", list(cases.LP_CASES))
 def test_label_prop_matches_reference_golden(ops, name):
     from sapienza_video_contrastive_b200 import LabelPropagator, context_index_bank
