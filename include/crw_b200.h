@@ -31,6 +31,7 @@ extern "C" {
 #define CRW_WALK_FORCE_GENERAL 4u /* skip the fused small-graph kernels even when the clip fits shared memory */
 #define CRW_WALK_FORCE_SIMT 8u    /* large-graph path: exact-fp32 SIMT GEMMs instead of the tcgen05 hi/lo-split GEMM */
 #define CRW_WALK_FORCE_TC 16u     /* large-graph path: tcgen05 GEMM wherever the shapes allow it (N, D >= 64), not only above the measured crossover */
+#define CRW_WALK_NO_CLUSTER 32u   /* small-graph path: one CTA per clip for the chain instead of a 4-CTA cluster */
 #define CRW_LP_FORCE_SIMT 1u      /* label propagation: exact-fp32 SIMT scores instead of the tcgen05 kernel */
 
 typedef void* crw_stream_t;

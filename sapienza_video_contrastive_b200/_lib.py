@@ -24,6 +24,7 @@ WALK_FLIP = 2
 WALK_FORCE_GENERAL = 4
 WALK_FORCE_SIMT = 8
 WALK_FORCE_TC = 16
+WALK_NO_CLUSTER = 32
 LP_FORCE_SIMT = 1
 
 _SIGNATURES = {

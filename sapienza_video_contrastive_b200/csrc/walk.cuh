@@ -66,6 +66,9 @@ inline bool fused_fits(int N, int T, int D) {
     return L.pair_bytes <= kMaxDynSmem && L.chain_bytes <= kMaxDynSmem && L.pairb_bytes <= kMaxDynSmem;
 }
 
+constexpr int kChainCluster = 4;                   // CTAs (SMs) per clip in the clustered chain kernel
+bool chain_cluster_fits(int N, int T);
+int launch_walk_chain_cluster(const WalkParams& p, size_t smem_bytes, crw_stream_t stream);
 int launch_walk_fused(const WalkParams& p, crw_stream_t stream);
 int launch_walk_general(const WalkParams& p, crw_stream_t stream);
 size_t walk_general_mats_floats(int B, int N, int T);

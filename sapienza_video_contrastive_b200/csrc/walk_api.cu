@@ -24,7 +24,7 @@ WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     w.o_counter = take(256);
     w.o_clipcnt = take(sizeof(unsigned) * B * T);                  // zero-initialised region ends here (see crw_b200.h)
-    w.o_partial = take(sizeof(float) * B * t2 * 2);
+    w.o_partial = take(sizeof(float) * B * t2 * 2 * kChainCluster);       // per-clip (per-CTA in the clustered chain) loss sums
     w.o_araw = take(w.fused ? mat : 0);
     w.o_codes = take((size_t)B * t1 * N * N * (w.fused ? 1 : 2));
     w.o_mats = take(w.fused ? 0 : sizeof(float) * walk_general_mats_floats(B, N, T));

@@ -717,10 +717,14 @@ int launch_walk_fused(const WalkParams& p, crw_stream_t stream) {
         }
         return e;
     }
-    auto k2 = walk_chain_kernel;
-    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.chain_bytes);
-    CRW_LAUNCH(k2, p.B, kFusedThreads, L.chain_bytes, stream, p);
-    e = check_launch("walk_chain");
+    if (p.grad && !(p.flags & CRW_WALK_NO_CLUSTER) && chain_cluster_fits(p.N, T)) {
+        e = launch_walk_chain_cluster(p, L.chain_bytes, stream);          // one clip = a cluster of 4 CTAs (walk_chain_cluster.cu)
+    } else {
+        auto k2 = walk_chain_kernel;
+        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.chain_bytes);
+        CRW_LAUNCH(k2, p.B, kFusedThreads, L.chain_bytes, stream, p);
+        e = check_launch("walk_chain");
+    }
     if (e != CRW_OK || !p.grad) return e;
     auto k3 = walk_pairs_bwd_kernel;
     cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.pairb_bytes);

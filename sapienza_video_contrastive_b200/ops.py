@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import WALK_FLIP, WALK_FORCE_GENERAL, WALK_FORCE_SIMT, WALK_FORCE_TC, WALK_SOFTMAX  # noqa: F401
+from ._lib import WALK_FLIP, WALK_FORCE_GENERAL, WALK_FORCE_SIMT, WALK_FORCE_TC, WALK_NO_CLUSTER, WALK_SOFTMAX  # noqa: F401
 
 
 def _stream() -> int:
@@ -395,7 +395,7 @@ class _Walk(torch.autograd.Function):
 
 def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = False, softmax: bool = False,
          rng: str = "philox", u12: Optional[torch.Tensor] = None, u21p: Optional[torch.Tensor] = None,
-         force_general: bool = False, rng_state: Optional[torch.Tensor] = None, force_simt: bool = False, force_tc: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+         force_general: bool = False, rng_state: Optional[torch.Tensor] = None, force_simt: bool = False, force_tc: bool = False, no_cluster: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """feats (B,N,T,D) pre-normalisation node vectors -> (q (B,N,T,D) unit-norm, loss [1], xent (T-2), acc (T-2)).
 
     One launch computes the forward AND d loss / d feats; backward() only scales it by the incoming gradient.
@@ -407,6 +407,7 @@ def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = Fals
     flags = (WALK_FLIP if flip else 0) | (WALK_SOFTMAX if softmax else 0) | (WALK_FORCE_GENERAL if force_general else 0)
     flags |= WALK_FORCE_SIMT if force_simt else 0
     flags |= WALK_FORCE_TC if force_tc else 0
+    flags |= WALK_NO_CLUSTER if no_cluster else 0
     if u12 is not None:
         rng = "torch"
     return _Walk.apply(feats, float(temperature), float(rate), flags, rng, u12, u21p, rng_state)

@@ -187,6 +187,23 @@ def test_walk_large_graph_tensor_core_vs_simt(ops, B, N, T, flip):
     assert relmax(res[0][2], res[1][2]) < 5e-5
 
 
+@pytest.mark.parametrize("B,N,T,flip", [(20, 49, 4, False), (3, 64, 4, True), (5, 33, 6, False), (2, 8, 3, False), (7, 49, 5, True)])
+def test_walk_chain_cluster_vs_single_cta(ops, B, N, T, flip):
+    """Small graphs: the chain split over a 4-CTA cluster (distributed shared memory) against the one-CTA-per-clip chain."""
+    torch.manual_seed(N + T)
+    f = torch.randn(B, N, T, 128, device=DEV)
+    u12, u21p = O.draw_uniforms(B, N, T)
+    res = []
+    for no_cluster in (True, False):
+        fd = f.clone().requires_grad_(True)
+        q, loss, xent, acc = ops.walk(fd, 0.07, 0.1, flip=flip, u12=u12.to(DEV), u21p=u21p.to(DEV), no_cluster=no_cluster)
+        loss.sum().backward()
+        res.append((loss.detach(), xent.detach(), acc.detach(), fd.grad))
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=2e-6, atol=0)
+    torch.testing.assert_close(res[0][2], res[1][2], rtol=0, atol=1e-6)
+    assert relmax(res[0][3], res[1][3]) < 2e-6
+
+
 def test_walk_in_kernel_dropout_equals_torch_draws(ops):
     """rng='philox' (drawn inside the kernel) must give exactly the run that rng='torch' (torch.rand draws handed to
     the kernel) gives from the same generator state, and leave the generator in the same state."""
