@@ -9,6 +9,7 @@
 // goes through shared memory to a streaming per-query top-k kept in registers (4 partial lists per query,
 // merged at the end), followed by the softmax over the k winners.  The affinity matrix never reaches HBM.
 #include "common.cuh"
+#include "lp_tc.cuh"
 
 namespace crw {
 
@@ -259,21 +260,6 @@ static int launch_lp(const LpArgs& a, crw_stream_t stream) {
     CRW_LAUNCH(k, grid, 256, smem, stream, a);
     return check_launch("lp_topk");
 }
-
-// tensor-core path (lp_tc.cu)
-struct LpTcArgs {
-    const int64_t* key_frames;
-    const int64_t* query_frames;
-    int Nt, S, n_long, h, w, C, k, R, r2i;
-    int restricted;
-    float tau;
-    float* Ws;
-    int64_t* Is;
-    unsigned* err;
-};
-size_t lp_tc_workspace_bytes(int Nf, int h, int w, int C);
-bool lp_tc_supported(int C, int k, float radius, int R, bool dense);
-int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
 }  // namespace crw
 

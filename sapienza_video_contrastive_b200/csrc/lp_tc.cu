@@ -26,6 +26,7 @@
 #include "common.cuh"
 
 #include "tc_common.cuh"
+#include "lp_tc.cuh"
 
 namespace crw {
 
@@ -36,17 +37,6 @@ constexpr int TC_NT = 64;        // keys per tile = MMA N (two runs)
 constexpr int TC_STAGES = 3;     // key ring depth
 constexpr int TC_EPI_WARPS = 8;  // two epilogue warps per TMEM lane quarter, each owning half of a sub-tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-
-struct LpTcArgs {
-    const int64_t* key_frames;   // (Nt, S)
-    const int64_t* query_frames; // (Nt)
-    int Nt, S, n_long, h, w, C, k, R, r2i;   // r2i: largest integer d2 admitted (d2 <= r2i  <=>  d2 < radius^2)
-    int restricted;
-    float tau;
-    float* Ws;
-    int64_t* Is;
-    unsigned* err;               // device error flag (barrier timeout)
-};
 
 #ifndef CRW_SIM
 

@@ -66,22 +66,28 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int cells = Hm * Wm, npix = sy * sx;
+    const bool pow2 = (sx & (sx - 1)) == 0;
+    const int sxs = 31 - __clz(sx);
     for (int64_t gc = warp; gc < total_cells; gc += nw) {
         const int64_t bt = gc / cells;
         const int cell = (int)(gc - bt * cells);
         const int b = (int)(bt / T), t = (int)(bt - (int64_t)b * T);
         const int cy = cell / Wm, cx = cell - cy * Wm;
-        int64_t lab[2];
+        const int64_t* base = labels + b * ls_b + t * ls_t + (int64_t)(cy * sy) * ls_y + (int64_t)(cx * sx) * ls_x;
+        // labels outside [0,SP) never match a one-hot plane (model.py:299-301): they are dropped here, and everything
+        // below works on 32-bit labels
+        int lab[2];
         bool pend[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int pix = lane + 32 * h;
-            pend[h] = pix < npix;
             lab[h] = -1;
-            if (pend[h]) {
-                const int py = pix / sx, px = pix - py * sx;
-                lab[h] = labels[b * ls_b + t * ls_t + (int64_t)(cy * sy + py) * ls_y + (int64_t)(cx * sx + px) * ls_x];
+            if (pix < npix) {
+                const int py = pow2 ? pix >> sxs : pix / sx, px = pix - py * sx;
+                const int64_t L = base[(int64_t)py * ls_y + (int64_t)px * ls_x];
+                if (L >= 0 && L < SP) lab[h] = (int)L;
             }
+            pend[h] = lab[h] >= 0;
         }
         int n = 0;
         for (;;) {
@@ -89,20 +95,16 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
             const unsigned m1 = __ballot_sync(kFull, pend[1]);
             if (!(m0 | m1)) break;
             // leader: lowest pending pixel
-            int64_t L;
-            if (m0) L = __shfl_sync(kFull, lab[0], __ffs((int)m0) - 1);
-            else    L = __shfl_sync(kFull, lab[1], __ffs((int)m1) - 1);
-            const bool h0 = pend[0] && lab[0] == L, h1 = pend[1] && lab[1] == L;
+            const int L = m0 ? __shfl_sync(kFull, lab[0], __ffs((int)m0) - 1) : __shfl_sync(kFull, lab[1], __ffs((int)m1) - 1);
+            const bool h0 = lab[0] == L, h1 = lab[1] == L;         // pending by construction: equal labels retire together
             const int cnt = __popc(__ballot_sync(kFull, h0)) + __popc(__ballot_sync(kFull, h1));
             if (h0) pend[0] = false;
             if (h1) pend[1] = false;
-            if (L >= 0 && L < SP) {              // labels outside [0,SP) never match a one-hot plane (model.py:299-301)
-                if (lane == 0) {
-                    ws.ent[((int64_t)bt * ws.cap + n) * cells + cell] = ((unsigned)L << 8) | (unsigned)cnt;
-                    atomicAdd(ws.size + bt * SP + (int)L, cnt);
-                }
-                ++n;
+            if (lane == 0) {
+                ws.ent[((int64_t)bt * ws.cap + n) * cells + cell] = ((unsigned)L << 8) | (unsigned)cnt;
+                atomicAdd(ws.size + bt * SP + L, cnt);
             }
+            ++n;
         }
         if (lane == 0) ws.nent[bt * cells + cell] = (unsigned char)n;
     }

@@ -300,31 +300,42 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(float* __restrict__ W, f
     }
 }
 
-// sums rowloss / rowacc laid out as (B, J, N) into xent[j], acc[j]; one CTA, fixed order -> deterministic
+// sums rowloss / rowacc laid out as (B, J, N) into xent[j], acc[j]: one CTA per walk j with a fixed summation tree, and
+// the last CTA to finish (ticket) adds the J results in order -> deterministic
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ rowloss, const float* __restrict__ rowacc,
                                                           float* __restrict__ xent, float* __restrict__ acc, int B, int J, int N,
-                                                          const unsigned* __restrict__ tc_err) {
+                                                          const unsigned* __restrict__ tc_err, unsigned* __restrict__ ticket) {
     __shared__ float sl[256], sa[256];
-    float tot = 0.f;
-    for (int j = 0; j < J; ++j) {
-        float l = 0.f, a = 0.f;
-        for (int64_t e = threadIdx.x; e < (int64_t)B * N; e += 256) {
-            const int64_t b = e / N, n = e - b * N;
-            l += rowloss[(b * J + j) * N + n];
-            a += rowacc[(b * J + j) * N + n];
-        }
-        sl[threadIdx.x] = l;
-        sa[threadIdx.x] = a;
-        __syncthreads();
-        for (int s = 128; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) { sl[threadIdx.x] += sl[threadIdx.x + s]; sa[threadIdx.x] += sa[threadIdx.x + s]; }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) { xent[j] = sl[0] / ((float)B * N); acc[j] = sa[0] / ((float)B * N); tot += xent[j]; }
+    __shared__ unsigned last;
+    const int j = blockIdx.x;
+    float l = 0.f, a = 0.f;
+    for (int64_t e = threadIdx.x; e < (int64_t)B * N; e += 256) {
+        const int64_t b = e / N, n = e - b * N;
+        l += rowloss[(b * J + j) * N + n];
+        a += rowacc[(b * J + j) * N + n];
+    }
+    sl[threadIdx.x] = l;
+    sa[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { sl[threadIdx.x] += sl[threadIdx.x + s]; sa[threadIdx.x] += sa[threadIdx.x + s]; }
         __syncthreads();
     }
-    // a tensor-core pipeline that timed out (gemm_tc.cu) left garbage behind: poison the loss instead of returning it
-    if (threadIdx.x == 0) xent[J] = (tc_err && *tc_err) ? __int_as_float(0x7fc00000) : tot / (float)J;          // the loss itself (model.py:413)
+    if (threadIdx.x == 0) {
+        xent[j] = sl[0] / ((float)B * N);
+        acc[j] = sa[0] / ((float)B * N);
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == (unsigned)J - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        float tot = 0.f;
+        for (int jj = 0; jj < J; ++jj) tot += ld_cg(xent + jj);
+        // a tensor-core pipeline that timed out (gemm_tc.cu) left garbage behind: poison the loss instead of returning it
+        xent[J] = (tc_err && *tc_err) ? __int_as_float(0x7fc00000) : tot / (float)J;          // the loss itself (model.py:413)
+        *ticket = 0u;
+    }
 }
 
 // ---- transition-matrix backward rows: overwrites the raw affinity with its gradient contribution -----------------
@@ -510,7 +521,7 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
     const int64_t lrows = (int64_t)B * t2 * N;
     CRW_LAUNCH(loss_rows_kernel, rows_grid(lrows), 256, 0, stream, W, rowloss, rowacc, lrows, N, cgrad, need_grad);
     CRW_TRY(check_launch("loss_rows"));
-    CRW_LAUNCH(loss_reduce_kernel, 1, 256, 0, stream, rowloss, rowacc, p.xent, p.acc, B, t2, N, (const unsigned*)p.ws_tc);
+    CRW_LAUNCH(loss_reduce_kernel, t2, 256, 0, stream, rowloss, rowacc, p.xent, p.acc, B, t2, N, (const unsigned*)p.ws_tc, p.ws_counter);
     CRW_TRY(check_launch("loss_reduce"));
     if (!need_grad) return CRW_OK;
 
