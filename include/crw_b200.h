@@ -31,6 +31,7 @@ extern "C" {
 #define CRW_WALK_FORCE_GENERAL 4u /* skip the fused small-graph kernels even when the clip fits shared memory */
 #define CRW_WALK_FORCE_SIMT 8u    /* large-graph path: exact-fp32 SIMT GEMMs instead of the tcgen05 hi/lo-split GEMM */
 #define CRW_WALK_FORCE_TC 16u     /* large-graph path: tcgen05 GEMM wherever the shapes allow it (N, D >= 64), not only above the measured crossover */
+#define CRW_WALK_NO_TF32 64u      /* large-graph path: always the fp16 hi/lo-split GEMM, never the fused kind::tf32 one */
 #define CRW_WALK_NO_CLUSTER 32u   /* small-graph path: one CTA per clip for the chain instead of a 4-CTA cluster */
 #define CRW_LP_FORCE_SIMT 1u      /* label propagation: exact-fp32 SIMT scores instead of the tcgen05 kernel */
 
@@ -109,6 +110,13 @@ int crw_l2norm_bwd(const float* q, float* grad_inout, const float* inv_norm, con
 size_t crw_bmm_tc_workspace_bytes(int Z, int M, int N, int K);
 int crw_bmm_tc(const float* A, const float* B, float* C, int Z, int M, int N, int K, int trans_a, int trans_b,
                int accumulate, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+
+/* Same product on tcgen05 kind::tf32: TMA reads A and B in place (16-byte aligned bases, M/N/K strides multiples of 4
+ * floats) and the kernel splits them into tf32 big + small parts itself; no workspace.  err_word: one zero-initialised
+ * device word that receives a non-zero value if the pipeline times out.  CRW_ERR_UNSUPPORTED if a shape is not
+ * addressable. */
+int crw_bmm_tf32(const float* A, const float* B, float* C, int Z, int M, int N, int K, int trans_a, int trans_b,
+                 int accumulate, unsigned* err_word, crw_stream_t stream);
 
 /* torch-compatible uniform draw (same Philox stream as torch.rand on CUDA); used by tests to pin the
  * in-kernel replay.  out (n). */

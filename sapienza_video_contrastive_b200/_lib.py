@@ -25,6 +25,7 @@ WALK_FORCE_GENERAL = 4
 WALK_FORCE_SIMT = 8
 WALK_FORCE_TC = 16
 WALK_NO_CLUSTER = 32
+WALK_NO_TF32 = 64
 LP_FORCE_SIMT = 1
 
 _SIGNATURES = {
@@ -45,6 +46,7 @@ _SIGNATURES = {
     "crw_philox_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint32, c_void_p]),
     "crw_bmm_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "crw_bmm_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "crw_bmm_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "crw_lp_topk_workspace_bytes": (c_size_t, [c_int] * 7),
     "crw_lp_topk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                             c_float, c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
 struct TcCtx {
     void* ws;
     size_t bytes;
+    bool no_tf32;
 };
+constexpr int kTf32MaxDim = 512;
 
 static int run_gemm_simt(const GemmArgs& g, int nb, crw_stream_t stream) {
     if (g.M <= 0 || g.N <= 0 || nb * g.nj <= 0) return CRW_OK;
@@ -137,6 +139,10 @@ static int run_gemms(const GemmArgs* gs, int ng, int nb, crw_stream_t stream, co
             for (int i = 0; i < ng; ++i) tc_group_of(c.grp[i], gs[i]);
             c.ngroups = ng; c.nterms = g.nterms; c.K[0] = g.K[0]; c.K[1] = g.K[1];
             c.M = g.M; c.N = g.N; c.nb = nb; c.nj = g.nj;
+            // mid-size products: operands read in place and split inside the kernel (gemm_tf32.cu); large ones amortise the
+            // separate fp16 operand pass and run the faster kind::f16 pipeline (gemm_tc.cu)
+            if (g.M < kTf32MaxDim && g.N < kTf32MaxDim && !tc->no_tf32 && gemm_tf32_eligible(c))
+                return gemm_tf32_run(c, (unsigned*)tc->ws, stream);
             const int e = gemm_tc_run(c, tc->ws, tc->bytes, stream);
             if (e != CRW_ERR_UNSUPPORTED) return e;
         }
@@ -433,7 +439,7 @@ size_t walk_general_stat_floats(int B, int N, int T) {
 int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
     const int B = p.B, N = p.N, T = p.T, D = p.D;
     const GenLayout L = gen_layout(B, N, T);
-    const TcCtx tc{p.ws_tc, p.ws_tc_bytes};
+    const TcCtx tc{p.ws_tc, p.ws_tc_bytes, (p.flags & CRW_WALK_NO_TF32) != 0};
     const int64_t MS = L.MS, s1 = L.s1, s2 = L.s2;
     const int t1 = T > 1 ? T - 1 : 0, t2 = T >= 3 ? T - 2 : 0;
     float* M0 = p.ws_mats;

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import WALK_FLIP, WALK_FORCE_GENERAL, WALK_FORCE_SIMT, WALK_FORCE_TC, WALK_NO_CLUSTER, WALK_SOFTMAX  # noqa: F401
+from ._lib import WALK_FLIP, WALK_FORCE_GENERAL, WALK_FORCE_SIMT, WALK_FORCE_TC, WALK_NO_CLUSTER, WALK_NO_TF32, WALK_SOFTMAX  # noqa: F401
 
 
 def _stream() -> int:
@@ -395,7 +395,7 @@ class _Walk(torch.autograd.Function):
 
 def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = False, softmax: bool = False,
          rng: str = "philox", u12: Optional[torch.Tensor] = None, u21p: Optional[torch.Tensor] = None,
-         force_general: bool = False, rng_state: Optional[torch.Tensor] = None, force_simt: bool = False, force_tc: bool = False, no_cluster: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+         force_general: bool = False, rng_state: Optional[torch.Tensor] = None, force_simt: bool = False, force_tc: bool = False, no_cluster: bool = False, no_tf32: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """feats (B,N,T,D) pre-normalisation node vectors -> (q (B,N,T,D) unit-norm, loss [1], xent (T-2), acc (T-2)).
 
     One launch computes the forward AND d loss / d feats; backward() only scales it by the incoming gradient.
@@ -408,6 +408,7 @@ def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = Fals
     flags |= WALK_FORCE_SIMT if force_simt else 0
     flags |= WALK_FORCE_TC if force_tc else 0
     flags |= WALK_NO_CLUSTER if no_cluster else 0
+    flags |= WALK_NO_TF32 if no_tf32 else 0
     if u12 is not None:
         rng = "torch"
     return _Walk.apply(feats, float(temperature), float(rate), flags, rng, u12, u21p, rng_state)
@@ -479,6 +480,31 @@ def bmm_tc(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: boo
                          ws.data_ptr(), ws.numel(), _stream()), "bmm_tc")
     if int(ws[:4].view(torch.int32)[0]) != 0:
         raise RuntimeError("bmm_tc: tensor-core pipeline timed out (error flag %d)" % int(ws[:4].view(torch.int32)[0]))
+    return out
+
+
+def bmm_tf32(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
+             out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """Batched fp32 GEMM on tcgen05 kind::tf32 with in-kernel operand splitting (gemm_tf32.cu); same conventions as bmm_tc.
+    Needs M, N >= 64, K >= 32 and dimensions that are multiples of 4 (TMA reads the operands in place)."""
+    _need_cuda(A, B)
+    check_device(A.device)
+    A, B = _f32c(A), _f32c(B)
+    Z = A.shape[0]
+    M, K = (A.shape[2], A.shape[1]) if trans_a else (A.shape[1], A.shape[2])
+    N = B.shape[1] if trans_b else B.shape[2]
+    if (B.shape[2] if trans_b else B.shape[1]) != K or B.shape[0] != Z:
+        raise ValueError("bmm_tf32: shape mismatch %s x %s" % (tuple(A.shape), tuple(B.shape)))
+    if out is None:
+        if accumulate:
+            raise ValueError("bmm_tf32: accumulate needs `out`")
+        out = torch.empty(Z, M, N, device=A.device, dtype=torch.float32)
+    err = torch.zeros(1, dtype=torch.int32, device=A.device)
+    L = _lib.lib()
+    L.check(L.crw_bmm_tf32(A.data_ptr(), B.data_ptr(), out.data_ptr(), Z, M, N, K, int(trans_a), int(trans_b), int(accumulate),
+                           err.data_ptr(), _stream()), "bmm_tf32")
+    if int(err[0]) != 0:
+        raise RuntimeError("bmm_tf32: tensor-core pipeline timed out (error flag %d)" % int(err[0]))
     return out
 
 

@@ -171,6 +171,31 @@ def test_bmm_tc_is_fp32_faithful(ops, Z, M, N, K, ta, tb):
     assert torch.equal(Ci, Ai @ Bi)
 
 
+@pytest.mark.parametrize("Z,M,N,K,ta,tb", [(3, 128, 128, 128, False, False), (2, 256, 128, 256, False, True), (2, 200, 72, 100, True, False),
+                                            (1, 384, 256, 196, True, True), (5, 132, 128, 68, False, False), (2, 196, 196, 196, True, False),
+                                            (2, 196, 128, 392, False, False)])
+def test_bmm_tf32_is_fp32_faithful(ops, Z, M, N, K, ta, tb):
+    """The fused kind::tf32 GEMM (operands read in place, K-major or MN-major, split inside the kernel) against an fp64 product."""
+    torch.manual_seed(Z * 1000 + M + N + K)
+    A = torch.randn(Z, M, K, device=DEV)
+    B = torch.randn(Z, K, N, device=DEV)
+    A *= torch.exp(6 * torch.randn(Z, M, 1, device=DEV))
+    B *= torch.exp(6 * torch.randn(Z, 1, N, device=DEV))
+    ref = A.double() @ B.double()
+    bound = (A.double().abs() @ B.double().abs())
+    As = A.transpose(1, 2).contiguous() if ta else A
+    Bs = B.transpose(1, 2).contiguous() if tb else B
+    C = ops.bmm_tf32(As, Bs, trans_a=ta, trans_b=tb)
+    err = ((C.double() - ref).abs() / bound).max().item()
+    assert err < 2e-6, err
+    C2 = ops.bmm_tf32(As, Bs, trans_a=ta, trans_b=tb, out=C.clone(), accumulate=True)
+    assert ((C2.double() - 2 * ref).abs() / bound).max().item() < 4e-6
+    Ai = torch.randint(-8, 9, (Z, M, K), device=DEV).float()
+    Bi = torch.randint(-8, 9, (Z, K, N), device=DEV).float()
+    Ci = ops.bmm_tf32(Ai.transpose(1, 2).contiguous() if ta else Ai, Bi.transpose(1, 2).contiguous() if tb else Bi, trans_a=ta, trans_b=tb)
+    assert torch.equal(Ci, Ai @ Bi)
+
+
 @pytest.mark.parametrize("B,N,T,flip", [(2, 192, 4, False), (1, 320, 5, True), (2, 200, 3, False), (1, 515, 4, False)])
 def test_walk_large_graph_tensor_core_vs_simt(ops, B, N, T, flip):
     """Large graphs: the tcgen05 GEMM path and the exact-fp32 SIMT path of the same walk agree to fp32 noise."""

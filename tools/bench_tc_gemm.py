@@ -20,20 +20,21 @@ def main():
         B = torch.randn(Z, K, N, device=dev)
         out = torch.empty(Z, M, N, device=dev)
         t_tc = timeit(lambda: ops.bmm_tc(A, B, out=out))
+        t_tf32 = timeit(lambda: ops.bmm_tf32(A, B, out=out))
         t_cublas = timeit(lambda: torch.bmm(A, B, out=out))
         fl = 2.0 * Z * M * N * K
-        print(json.dumps({"kind": "bmm", "Z": Z, "M": M, "N": N, "K": K, "tc_ms": t_tc, "cublas_sgemm_ms": t_cublas,
-                          "tc_tflops": fl / t_tc / 1e9, "cublas_tflops": fl / t_cublas / 1e9}), flush=True)
+        print(json.dumps({"kind": "bmm", "Z": Z, "M": M, "N": N, "K": K, "tc_ms": t_tc, "tf32_fused_ms": t_tf32, "cublas_sgemm_ms": t_cublas,
+                          "tc_tflops": fl / t_tc / 1e9, "tf32_fused_tflops": fl / t_tf32 / 1e9, "cublas_tflops": fl / t_cublas / 1e9}), flush=True)
     ones = torch.ones(1, device=dev)
     for (B, N, T) in [(8, 128, 4), (8, 196, 8), (8, 256, 4), (4, 512, 4), (2, 1024, 4), (4, 256, 8), (1, 1024, 8)]:
         f = torch.randn(B, N, T, 128, device=dev, requires_grad=True)
         row = {"kind": "walk_fwd_bwd", "B": B, "N": N, "T": T}
-        for simt in (True, False):
+        for name, kw in (("simt_ms", dict(force_simt=True)), ("f16split_ms", dict(no_tf32=True)), ("tc_ms", dict())):
             def step():
                 f.grad = None
-                q, loss, xent, acc = ops.walk(f, 0.07, 0.1, rng="philox", force_simt=simt)
+                q, loss, xent, acc = ops.walk(f, 0.07, 0.1, rng="philox", **kw)
                 loss.backward(ones)
-            row["simt_ms" if simt else "tc_ms"] = timeit(step)
+            row[name] = timeit(step)
         flops = 3 * (2 * (T - 1) * N * N * 128 + 2 * N ** 3 * 3 * (T - 2)) * B
         row["tc_algorithmic_tflops"] = flops / row["tc_ms"] / 1e9
         row["speedup"] = row["simt_ms"] / row["tc_ms"]
