@@ -89,9 +89,17 @@ int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float tempe
                      uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
                      float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
-/* ---- a1: weight gradient of the projection head, model.py:117 (nn.Linear(C_e,128,bias=False)) ---------------------
- * dW (D,C) = grad_out^T (D,R) x (R,C) with R = B*N*T rows.  The forward and the input gradient stay on cuBLAS; this
- * product has a tiny 128 x 512 output and a long reduction, so it is split over R (deterministic two-pass reduction). */
+/* ---- a1: the projection head, model.py:117 (nn.Linear(C_e,128,bias=False)) ------------------------------------------
+ * out (R,D) = x (R,C) weight^T, grad_x (R,C) = grad_out (R,D) weight, with R = B*N*T rows, on the fused tcgen05 kind::tf32
+ * GEMM (fp32-faithful: tf32 big + small operand parts, error ~2^-22 |a||b|).  err_word: one zero-initialised device word
+ * that turns non-zero if the pipeline times out.  CRW_ERR_UNSUPPORTED when the shape is not TMA-addressable (C, D multiples
+ * of 4, >= 64 / 32; 16-byte aligned pointers): use a library GEMM then.
+ * dW (D,C) = grad_out^T (D,R) x (R,C): a tiny 128 x 512 output with a long reduction, split over R into equal slices on the
+ * same tensor-core kernel (or ragged slices on the exact-fp32 SIMT kernel) and folded in a fixed order: deterministic.  The
+ * workspace (crw_head_wgrad_workspace_bytes) must be zero-filled once. */
+int crw_head_fwd(const float* x, const float* weight, float* out, int64_t R, int D, int C, unsigned* err_word, crw_stream_t stream);
+int crw_head_dgrad(const float* grad_out, const float* weight, float* grad_x, int64_t R, int D, int C, unsigned* err_word,
+                   crw_stream_t stream);
 size_t crw_head_wgrad_workspace_bytes(int64_t R, int D, int C);
 int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, void* workspace,
                    size_t workspace_bytes, crw_stream_t stream);

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "crw_lp_topk_workspace_bytes": (c_size_t, [c_int] * 7),
     "crw_lp_topk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                             c_float, c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crw_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "crw_head_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "crw_head_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "crw_head_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "crw_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),

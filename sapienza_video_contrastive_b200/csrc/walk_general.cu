@@ -668,16 +668,51 @@ static int wgrad_splits(int64_t R, int D, int C) {
 }
 }  // namespace crw
 
+namespace crw {
+// split-K factor for the tensor-core weight gradient: equal slices (TMA needs one slice extent), about one wave of CTAs;
+// 0 when no divisor of R fits or the shape is not TMA-addressable
+static int wgrad_tc_splits(int64_t R, int D, int C) {
+    if (D < 64 || C < 64 || (D & 3) || (C & 3) || R < 256) return 0;
+    const int tiles = ((D + 127) / 128) * ((C + 127) / 128);
+    const int target = 148 / tiles > 1 ? 148 / tiles : 1;
+    int best = 0;
+    for (int S = 1; S <= 4 * target && S <= 512; ++S) {
+        if (R % S != 0 || R / S < 32) continue;
+        if (best == 0 || abs(S - target) < abs(best - target)) best = S;
+    }
+    return (best >= target / 4 && best >= 1) ? best : 0;
+}
+}  // namespace crw
+
 extern "C" size_t crw_head_wgrad_workspace_bytes(int64_t R, int D, int C) {
     if (R <= 0 || D <= 0 || C <= 0) return 0;
-    return sizeof(float) * (size_t)wgrad_splits(R, D, C) * D * C;
+    const int S = wgrad_splits(R, D, C), St = wgrad_tc_splits(R, D, C);
+    return sizeof(float) * (size_t)(S > St ? S : St) * D * C + 256;          // + one error word for the tensor-core pipeline
 }
 
 extern "C" int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, void* workspace,
                               size_t workspace_bytes, crw_stream_t stream) {
     if (R <= 0 || D <= 0 || C <= 0) { set_error("head_wgrad: bad shape"); return CRW_ERR_SHAPE; }
+    if (!workspace || workspace_bytes < crw_head_wgrad_workspace_bytes(R, D, C)) { set_error("head_wgrad: workspace too small"); return CRW_ERR_SHAPE; }
+    const int64_t n = (int64_t)D * C;
+    // tensor cores: dW = sum over S equal row slices of g_s^T x_s, both operands read in place as MN-major tf32 tiles
+    const int St = wgrad_tc_splits(R, D, C);
+    if (St > 0) {
+        const int64_t Ks = R / St;
+        TcGemmCall c{};
+        c.ngroups = 1; c.nterms = 1; c.K[0] = (int)Ks; c.M = D; c.N = C; c.nb = St; c.nj = 1;
+        c.grp[0].A[0] = TcOperand{grad_out, Ks * D, 0, 1, D};         // A(r = d, k = row) = g[row * D + d]
+        c.grp[0].B[0] = TcOperand{x, Ks * C, 0, C, 1};                // B(k = row, c) = x[row * C + c]
+        c.grp[0].C = (float*)workspace; c.grp[0].csb = n; c.grp[0].csj = 0; c.grp[0].ldc = C; c.grp[0].accumulate = 0;
+        if (gemm_tf32_eligible(c)) {
+            unsigned* err = (unsigned*)((char*)workspace + sizeof(float) * (size_t)St * n);
+            int e = gemm_tf32_run(c, err, stream);
+            if (e != CRW_OK) return e;
+            CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256), 256, 0, stream, (const float*)workspace, dW, n, St);
+            return check_launch("head_wgrad_reduce");
+        }
+    }
     const int S = wgrad_splits(R, D, C);
-    if (!workspace || workspace_bytes < sizeof(float) * (size_t)S * D * C) { set_error("head_wgrad: workspace too small"); return CRW_ERR_SHAPE; }
     const int KS = (int)((R + S - 1) / S);
     GemmArgs g{};
     g.nterms = 1; g.K[0] = KS; g.ktot = (int)R; g.M = D; g.N = C; g.nj = S; g.accumulate = 0;
@@ -686,9 +721,33 @@ extern "C" int crw_head_wgrad(const float* grad_out, const float* x, float* dW, 
     g.C = (float*)workspace; g.csb = 0; g.csj = (int64_t)D * C; g.ldc = C;
     int e = run_gemm(g, 1, stream);
     if (e != CRW_OK) return e;
-    const int64_t n = (int64_t)D * C;
     CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256), 256, 0, stream, (const float*)workspace, dW, n, S);
     return check_launch("head_wgrad_reduce");
+}
+
+// head forward / input gradient (model.py:117, nn.Linear(bias=False)) on the fused tf32 GEMM.  CRW_ERR_UNSUPPORTED when the
+// shape is not TMA-addressable (the caller then uses a library GEMM).
+extern "C" int crw_head_fwd(const float* x, const float* weight, float* out, int64_t R, int D, int C, unsigned* err_word, crw_stream_t stream) {
+    if (R <= 0 || D <= 0 || C <= 0 || R > 0x7fffffff) { set_error("head_fwd: bad shape"); return CRW_ERR_SHAPE; }
+    TcGemmCall c{};
+    c.ngroups = 1; c.nterms = 1; c.K[0] = C; c.M = (int)R; c.N = D; c.nb = 1; c.nj = 1;
+    c.grp[0].A[0] = TcOperand{x, 0, 0, C, 1};                        // x (R, C)
+    c.grp[0].B[0] = TcOperand{weight, 0, 0, 1, C};                   // B(k, d) = weight[d * C + k]
+    c.grp[0].C = out; c.grp[0].csb = 0; c.grp[0].csj = 0; c.grp[0].ldc = D; c.grp[0].accumulate = 0;
+    if (!gemm_tf32_eligible(c)) { set_error("head_fwd: shape not addressable by the tensor-core path"); return CRW_ERR_UNSUPPORTED; }
+    return gemm_tf32_run(c, err_word, stream);
+}
+
+extern "C" int crw_head_dgrad(const float* grad_out, const float* weight, float* grad_x, int64_t R, int D, int C, unsigned* err_word,
+                              crw_stream_t stream) {
+    if (R <= 0 || D <= 0 || C <= 0 || R > 0x7fffffff) { set_error("head_dgrad: bad shape"); return CRW_ERR_SHAPE; }
+    TcGemmCall c{};
+    c.ngroups = 1; c.nterms = 1; c.K[0] = D; c.M = (int)R; c.N = C; c.nb = 1; c.nj = 1;
+    c.grp[0].A[0] = TcOperand{grad_out, 0, 0, D, 1};                 // g (R, D)
+    c.grp[0].B[0] = TcOperand{weight, 0, 0, C, 1};                   // B(k = d, c) = weight[d * C + c]
+    c.grp[0].C = grad_x; c.grp[0].csb = 0; c.grp[0].csj = 0; c.grp[0].ldc = C; c.grp[0].accumulate = 0;
+    if (!gemm_tf32_eligible(c)) { set_error("head_dgrad: shape not addressable by the tensor-core path"); return CRW_ERR_UNSUPPORTED; }
+    return gemm_tf32_run(c, err_word, stream);
 }
 
 extern "C" int crw_l2norm_fwd(const float* f, float* q, float* inv_norm, float* norm, int64_t rows, int D, crw_stream_t stream) {

@@ -130,12 +130,47 @@ def _side_stream(device) -> torch.cuda.Stream:
     return _side_streams[idx]
 
 
+_ERR_UNSUPPORTED = -2
+_tc_head = True
+
+
+def set_tensor_core_head(enabled: bool) -> None:
+    """Head forward / input gradient on the fused tcgen05 tf32 GEMM (default) or on the library fp32 GEMM.  The tensor-core
+    path feeds full-precision operands (tf32 big + small) but accumulates with the tensor core's truncating fp32 adder:
+    ~5e-6 of the largest output at K = 512 against ~5e-7 for an fp32 sgemm."""
+    global _tc_head
+    _tc_head = bool(enabled)
+
+
+def tc_error_word(device) -> torch.Tensor:
+    """The device word the tensor-core head GEMMs raise on a pipeline timeout (never read on the hot path; tests check it)."""
+    return _workspace("tc_err", 256, device)[:4].view(torch.int32)
+
+
+def _head_gemm(fn_name: str, a: torch.Tensor, weight: torch.Tensor, out_cols: int) -> Optional[torch.Tensor]:
+    """a (R, K) and weight (D, C) through crw_head_fwd / crw_head_dgrad; None when the shape is not TMA-addressable."""
+    L = _lib.lib()
+    R = a.shape[0]
+    D, C = weight.shape
+    out = torch.empty(R, out_cols, dtype=torch.float32, device=a.device)
+    rc = getattr(L, fn_name)(a.data_ptr(), weight.data_ptr(), out.data_ptr(), R, D, C, tc_error_word(a.device).data_ptr(), _stream())
+    if rc == _ERR_UNSUPPORTED:
+        return None
+    L.check(rc, fn_name)
+    return out
+
+
 class _HeadLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
         _need_cuda(x, weight)
         ctx.save_for_backward(x, weight)
-        return x.matmul(weight.t())
+        D, C = weight.shape
+        if _tc_head and x.dtype == torch.float32 and weight.dtype == torch.float32:
+            out = _head_gemm("crw_head_fwd", _f32c(x.reshape(-1, C)), _f32c(weight), D)
+            if out is not None:
+                return out.view(*x.shape[:-1], D)
+        return x.matmul(weight.t())               # shapes TMA cannot address (tiny or unaligned): library GEMM
 
     @staticmethod
     def backward(ctx, g):
@@ -147,7 +182,11 @@ class _HeadLinear(torch.autograd.Function):
             fork = torch.cuda.Event()
             fork.record(cur)                       # the side stream only needs g and x, not the input gradient below
         if ctx.needs_input_grad[0]:
-            gx = g.matmul(weight)
+            D, C = weight.shape
+            gx = None
+            if _tc_head and g.dtype == torch.float32 and weight.dtype == torch.float32:
+                gx = _head_gemm("crw_head_dgrad", _f32c(g.reshape(-1, D)), _f32c(weight), C)
+            gx = g.matmul(weight) if gx is None else gx.view(*g.shape[:-1], C)
         if ctx.needs_input_grad[1]:
             D, C = weight.shape
             g2, x2 = _f32c(g.reshape(-1, D)), _f32c(x.reshape(-1, C))

@@ -531,6 +531,19 @@ def test_head_linear_matches_nn_linear(ops):
     torch.testing.assert_close(y1, y0, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(x.grad, gx0, rtol=1e-5, atol=1e-5)
     assert relmax(lin.weight.grad, gw0) < 1e-5
+    assert int(ops.tc_error_word(DEV)[0]) == 0
+    # against fp64: operands enter at full fp32 precision (tf32 big + small parts); what remains is the tensor core's own
+    # fp32 accumulation, which truncates (measured 5e-6 of the largest output at K = 512; an fp32 sgemm gives ~5e-7)
+    y64 = x.detach().double() @ lin.weight.detach().double().t()
+    assert relmax(y1.detach().double(), y64) < 2e-5
+    gw64 = g.double().reshape(-1, 128).t() @ x.detach().double().reshape(-1, 512)
+    assert relmax(lin.weight.grad.double(), gw64) < 2e-5
+    # a shape TMA cannot address (C not a multiple of 4) falls back to the library GEMM
+    w2 = torch.randn(128, 510, device=DEV, requires_grad=True)
+    x2 = torch.randn(77, 510, device=DEV, requires_grad=True)
+    y2 = ops.head_linear(x2, w2)
+    y2.sum().backward()
+    torch.testing.assert_close(y2, x2 @ w2.t(), rtol=1e-5, atol=1e-5)
 
 
 def test_async_wgrad_overlap_gives_identical_gradients(ops):
