@@ -394,9 +394,10 @@ def run_ours(args, rank, world, local_rank):
            "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "note": "pinned host maps -> device (double-buffered copy stream) -> hot path -> loss + head grad back to host"},
-           "gpu_launches": 7 * args.steps,
-           "gpu_launches_note": "per step: crw pool_fwd, walk_pairs_fwd, walk_chain, walk_pairs_bwd, gemm_f32 (split-K head wgrad), "
-                                "splitk_reduce, pool_bwd; head forward / input-gradient GEMMs are cuBLAS",
+           "gpu_launches": 9 * args.steps,
+           "gpu_launches_note": "per step: crw pool_fwd, gemm_tf32 (head fwd), walk_pairs_fwd, walk_chain_cluster, walk_pairs_bwd, "
+                                "gemm_tf32 (head dgrad), gemm_tf32 (split-K head wgrad), splitk_reduce, pool_bwd; "
+                                "plus one torch elementwise scale of the walk gradient",
            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kr[dom]["gbs"], "peak": hbm, "unit": "GB/s",
                         "frac": kr[dom]["gbs"] / hbm, "traffic": traffic, "peak_source": src,
                         "step_hbm_frac": (2 * kr[dom]["algorithmic_bytes"]) / (ms / args.steps * 1e-3) / 1e9 / hbm},
