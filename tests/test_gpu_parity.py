@@ -119,7 +119,8 @@ def test_walk_matches_reference_golden(ops, name, force_general):
 @pytest.mark.parametrize("B,N,T,D,p,flip,softmax", [(20, 49, 4, 128, 0.1, False, False), (4, 49, 8, 128, 0.1, False, False),
                                                     (3, 64, 4, 128, 0.1, True, False), (2, 128, 4, 128, 0.1, False, False),
                                                     (2, 100, 6, 128, 0.2, False, True), (1, 256, 5, 128, 0.1, False, False),
-                                                    (2, 31, 3, 64, 0.5, False, False), (2, 17, 2, 32, 0.1, False, False)])
+                                                    (2, 31, 3, 64, 0.5, False, False), (2, 17, 2, 32, 0.1, False, False),
+                                                    (2, 131, 3, 128, 0.1, False, False), (1, 90, 4, 96, 0.1, True, False)])
 def test_walk_matches_oracle(ops, B, N, T, D, p, flip, softmax):
     torch.manual_seed(B * 100 + N)
     f = torch.randn(B, N, T, D)
@@ -538,6 +539,13 @@ def test_head_linear_matches_nn_linear(ops):
     assert relmax(y1.detach().double(), y64) < 2e-5
     gw64 = g.double().reshape(-1, 128).t() @ x.detach().double().reshape(-1, 512)
     assert relmax(lin.weight.grad.double(), gw64) < 2e-5
+    # a row count with no usable divisor takes the exact-fp32 SIMT split-K weight gradient
+    x3 = torch.randn(977, 512, device=DEV, requires_grad=True)
+    w3 = torch.randn(128, 512, device=DEV, requires_grad=True)
+    g3 = torch.randn(977, 128, device=DEV)
+    ops.head_linear(x3, w3).backward(g3)
+    assert relmax(w3.grad.double(), g3.double().t() @ x3.detach().double()) < 2e-5
+    assert relmax(x3.grad.double(), g3.double() @ w3.detach().double()) < 2e-5
     # a shape TMA cannot address (C not a multiple of 4) falls back to the library GEMM
     w2 = torch.randn(128, 510, device=DEV, requires_grad=True)
     x2 = torch.randn(77, 510, device=DEV, requires_grad=True)
