@@ -38,9 +38,9 @@ WsLayout ws_layout(int B, int N, int T, int D, unsigned flags) {
     // general path on large graphs: operand planes of the tensor-core GEMM (gemm_tc.cu)
     const int NK = N > D ? N : D;
     w.tc_bytes = 0;
-    // measured against the SIMT GEMM (tools/bench_tc_gemm.py): 0.8-1.2x at N = 64 (SIMT kept: its 64x64 tiles fit exactly),
-    // 1.1-1.2x at 72..80, 1.15-1.45x at 100..160, 1.75x at 196, 2.45x at 512, 4.4x at 1024
-    const bool tc = !w.fused && !(flags & CRW_WALK_FORCE_SIMT) && t1 > 0 && (N >= 72 || (flags & CRW_WALK_FORCE_TC)) &&
+    // measured against the SIMT GEMM (tools/bench_tc_gemm.py): 1.3-1.7x at N = 64..68 (T > 4, where the fused kernels do not
+    // fit), 1.45x at 128, 2.1x at 196, 2.5x at 512, 4.4x at 1024
+    const bool tc = !w.fused && !(flags & CRW_WALK_FORCE_SIMT) && t1 > 0 && (N >= 64 || (flags & CRW_WALK_FORCE_TC)) &&
                     gemm_tc_eligible(N, N < D ? N : D, N < D ? N : D, NK);
     if (tc) {    // the largest of the calls launch_walk_general makes (groups x batch, K-concatenated terms)
         const int Np = (N + 7) & ~7, Dp = (D + 7) & ~7, b = B, m1 = (int)t1, m2 = (int)t2;

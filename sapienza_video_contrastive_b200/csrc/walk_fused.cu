@@ -717,7 +717,15 @@ int launch_walk_fused(const WalkParams& p, crw_stream_t stream) {
         }
         return e;
     }
-    if (p.grad && !(p.flags & CRW_WALK_NO_CLUSTER) && chain_cluster_fits(p.N, T)) {
+    // a clip on 4 SMs only pays while the clusters of the whole batch are resident at once (B = 64: two waves of clusters
+    // measured 8 % slower than one CTA per clip)
+    static thread_local int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+    }
+    if (p.grad && !(p.flags & CRW_WALK_NO_CLUSTER) && chain_cluster_fits(p.N, T) && p.B * kChainCluster <= sm_count) {
         e = launch_walk_chain_cluster(p, L.chain_bytes, stream);          // one clip = a cluster of 4 CTAs (walk_chain_cluster.cu)
     } else {
         auto k2 = walk_chain_kernel;

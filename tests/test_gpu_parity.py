@@ -213,7 +213,8 @@ def test_walk_large_graph_tensor_core_vs_simt(ops, B, N, T, flip):
     assert relmax(res[0][2], res[1][2]) < 5e-5
 
 
-@pytest.mark.parametrize("B,N,T,flip", [(20, 49, 4, False), (3, 64, 4, True), (5, 33, 6, False), (2, 8, 3, False), (7, 49, 5, True)])
+@pytest.mark.parametrize("B,N,T,flip", [(20, 49, 4, False), (3, 64, 4, True), (5, 33, 6, False), (2, 8, 3, False), (7, 49, 5, True),
+                                        (37, 49, 4, False), (40, 49, 4, False)])
 def test_walk_chain_cluster_vs_single_cta(ops, B, N, T, flip):
     """Small graphs: the chain split over a 4-CTA cluster (distributed shared memory) against the one-CTA-per-clip chain."""
     torch.manual_seed(N + T)
