@@ -41,7 +41,8 @@ def walk_point(B, N, T, D=128):
     ms = timeit(step)
     flops = 3 * (2 * (T - 1) * N * N * D + 2 * N ** 3 * 3 * (T - 2)) * B            # fwd + 2x bwd, minimal chain count
     return {"kind": "walk_fwd_bwd", "B": B, "N": N, "T": T, "D": D, "ms": ms, "clips_per_s": B / ms * 1e3,
-            "algorithmic_tflops": flops / ms / 1e9, "path": "fused" if N <= 60 and T <= 4 else "general"}
+            "algorithmic_tflops": flops / ms / 1e9,
+            "path": "fused" if N <= 64 and T <= 4 else ("tcgen05 tf32" if 64 <= N < 512 and N % 4 == 0 else ("tcgen05 f16 split" if N >= 512 else "simt"))}
 
 
 def superpixel_point(B=8, T=8, SP=196, C=512):
