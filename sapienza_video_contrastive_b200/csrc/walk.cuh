@@ -39,7 +39,7 @@ struct FusedLayout {
     int NP, MS, DP;
     size_t pair_bytes;     // walk_pairs_fwd: two staged frames + raw affinity + codes
     size_t chain_bytes;    // walk_chain: F, G, P, S stacks + 3 scratch matrices + reduction scratch
-    size_t pairb_bytes;    // walk_pairs_bwd: two staged frames + dA + raw affinity + codes + flag
+    size_t pairb_bytes;    // walk_pairs_bwd: two staged frames + dA + raw affinity + F, dF, G, dG + codes + flag
 };
 
 __host__ __device__ __forceinline__ FusedLayout fused_layout(int N, int T, int D) {
@@ -53,7 +53,7 @@ __host__ __device__ __forceinline__ FusedLayout fused_layout(int N, int T, int D
     L.pair_bytes = sizeof(float) * ((size_t)2 * N * L.DP + L.MS) + codes;
     const int nm = 2 * (T - 1) + (T >= 3 ? 2 * (T - 2) + 3 : 0);
     L.chain_bytes = sizeof(float) * ((size_t)nm * L.MS + 64);     // + reduction scratch (32) + mbarrier
-    L.pairb_bytes = sizeof(float) * ((size_t)2 * N * L.DP + 2 * L.MS) + codes + 16;
+    L.pairb_bytes = sizeof(float) * ((size_t)2 * N * L.DP + 6 * L.MS) + codes + 16;
     return L;
 }
 

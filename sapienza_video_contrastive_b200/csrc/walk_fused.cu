@@ -297,31 +297,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_fwd_kernel(WalkPa
     const float* fb = p.feats + (int64_t)b * N * gs;
     float* qb = p.q + (int64_t)b * N * gs;
 
-    // stage + normalise frames i and i+1; the pair owns frame i (and the last pair also frame T-1)
-    for (int row = warp; row < 2 * N; row += NW) {
-        const int which = row >= N, n = row - which * N, t = i + which;
-        const float* src = fb + (int64_t)n * gs + (int64_t)t * D;
-        float4 v[2];
-        float ss = 0.f;
-        int c = 0;
-        for (int d = lane * 4; d < D; d += 128, ++c) {
-            v[c] = *reinterpret_cast<const float4*>(src + d);
-            ss += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
+    // stage + normalise frames i and i+1; the pair owns frame i (and the last pair also frame T-1).  A warp owns rows
+    // warp, warp + 16, ...: all of their global loads are issued before the first use (one memory round trip, not seven)
+    {
+        constexpr int RP = (2 * 64 + NW - 1) / NW;          // row passes for N <= 64
+        float4 v[RP][2];
+#pragma unroll
+        for (int rp = 0; rp < RP; ++rp) {
+            const int row = warp + NW * rp;
+            const int which = row >= N, n = row - which * N, t = i + which;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int d = lane * 4 + 128 * c;
+                v[rp][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < 2 * N && d < D) v[rp][c] = *reinterpret_cast<const float4*>(fb + (int64_t)n * gs + (int64_t)t * D + d);
+            }
         }
-        ss = warp_sum(ss);
-        const float nr = sqrtf(ss), den = fmaxf(nr, kEpsNorm);
-        const bool owner = !which || i == T - 2;
-        float* dst = (which ? Qb : Qa) + n * DP;
-        c = 0;
-        for (int d = lane * 4; d < D; d += 128, ++c) {
-            float4 o = v[c];
-            o.x /= den; o.y /= den; o.z /= den; o.w /= den;
-            *reinterpret_cast<float4*>(dst + d) = o;
-            if (owner) *reinterpret_cast<float4*>(qb + (int64_t)n * gs + (int64_t)t * D + d) = o;
-        }
-        if (owner && lane == 0) {
-            p.ws_invn[((int64_t)b * T + t) * N + n] = 1.0f / den;
-            p.ws_nrm[((int64_t)b * T + t) * N + n] = nr;
+#pragma unroll
+        for (int rp = 0; rp < RP; ++rp) {
+            const int row = warp + NW * rp;
+            if (row >= 2 * N) break;
+            const int which = row >= N, n = row - which * N, t = i + which;
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) ss += v[rp][c].x * v[rp][c].x + v[rp][c].y * v[rp][c].y + v[rp][c].z * v[rp][c].z + v[rp][c].w * v[rp][c].w;
+            ss = warp_sum(ss);
+            const float nr = sqrtf(ss), den = fmaxf(nr, kEpsNorm);
+            const bool owner = !which || i == T - 2;
+            float* dst = (which ? Qb : Qa) + n * DP;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int d = lane * 4 + 128 * c;
+                if (d < D) {
+                    float4 o = v[rp][c];
+                    o.x /= den; o.y /= den; o.z /= den; o.w /= den;
+                    *reinterpret_cast<float4*>(dst + d) = o;
+                    if (owner) *reinterpret_cast<float4*>(qb + (int64_t)n * gs + (int64_t)t * D + d) = o;
+                }
+            }
+            if (owner && lane == 0) {
+                p.ws_invn[((int64_t)b * T + t) * N + n] = 1.0f / den;
+                p.ws_nrm[((int64_t)b * T + t) * N + n] = nr;
+            }
         }
     }
     __syncthreads();
@@ -568,7 +585,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
     float* Qb = Qa + N * DP;
     float* Z = Qb + N * DP;                   // N x NP: dA
     float* Ar = Z + MS;                       // N x NP: raw affinity
-    unsigned char* codes = reinterpret_cast<unsigned char*>(Ar + MS);
+    float* Fs = Ar + MS;                      // F, dF, G, dG of the pair: staged with the other inputs, one memory round trip
+    float* dFs = Fs + MS;
+    float* Gs = dFs + MS;
+    float* dGs = Gs + MS;
+    unsigned char* codes = reinterpret_cast<unsigned char*>(dGs + MS);
     unsigned* s_last = reinterpret_cast<unsigned*>(codes + ((N * N + 15) & ~15));   // 2 flags
     const bool softmax = (p.flags & CRW_WALK_SOFTMAX) != 0;
     const float tau = p.tau;
@@ -583,14 +604,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
         *reinterpret_cast<float4*>((which ? Qb : Qa) + n * DP + d4 * 4) =
             ld_cg4(qb + (int64_t)n * gs + (int64_t)(i + which) * D + d4 * 4);
     }
-    for (int e = tid; e < MS / 4; e += kFusedThreads)
+    for (int e = tid; e < MS / 4; e += kFusedThreads) {
         *reinterpret_cast<float4*>(Ar + e * 4) = ld_cg4(p.ws_araw + pm + e * 4);
+        *reinterpret_cast<float4*>(Fs + e * 4) = ld_cg4(p.ws_F + pm + e * 4);
+        *reinterpret_cast<float4*>(dFs + e * 4) = ld_cg4(p.ws_dF + pm + e * 4);
+        *reinterpret_cast<float4*>(Gs + e * 4) = ld_cg4(p.ws_G + pm + e * 4);
+        *reinterpret_cast<float4*>(dGs + e * 4) = ld_cg4(p.ws_dG + pm + e * 4);
+    }
     for (int e = tid; e < N * N; e += kFusedThreads) codes[e] = p.ws_codes[pc + e];
     __syncthreads();
-    const float* Fg = p.ws_F + pm;
-    const float* Gg = p.ws_G + pm;
-    const float* dF = p.ws_dF + pm;
-    const float* dG = p.ws_dG + pm;
     // rows of F: Z[n][m] = d loss / d A[n][m] through the forward matrix
     for (int n = warp; n < N; n += NW) {
         float y[2], dy[2];
@@ -599,7 +621,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
         for (int h = 0; h < 2; ++h) {
             const int m = lane + 32 * h;
             y[h] = dy[h] = 0.f;
-            if (m < N) { y[h] = ld_cg(Fg + n * NP + m); dy[h] = ld_cg(dF + n * NP + m); dot += y[h] * dy[h]; }
+            if (m < N) { y[h] = Fs[n * NP + m]; dy[h] = dFs[n * NP + m]; dot += y[h] * dy[h]; }
         }
         dot = warp_sum(dot);
         const float den = ld_cg(p.ws_s12 + ((int64_t)b * (T - 1) + i) * N + n);
@@ -625,7 +647,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
         for (int h = 0; h < 2; ++h) {
             const int n = lane + 32 * h;
             y[h] = dy[h] = 0.f;
-            if (n < N) { y[h] = ld_cg(Gg + m * NP + n); dy[h] = ld_cg(dG + m * NP + n); dot += y[h] * dy[h]; }
+            if (n < N) { y[h] = Gs[m * NP + n]; dy[h] = dGs[m * NP + n]; dot += y[h] * dy[h]; }
         }
         dot = warp_sum(dot);
         const float den = ld_cg(p.ws_s21 + ((int64_t)b * (T - 1) + i) * N + m);
@@ -662,38 +684,59 @@ __global__ void __launch_bounds__(kFusedThreads, 1) walk_pairs_bwd_kernel(WalkPa
     if (!s_last[0] && !s_last[1]) return;
     __threadfence();
     float* gb = p.grad + (int64_t)b * N * gs;
-    for (int row = warp; row < 2 * N; row += NW) {
-        const int which = row >= N, n = row - which * N, t = i + which;
-        if (!s_last[which]) continue;
-        const int64_t ro = (int64_t)n * gs + (int64_t)t * D;
-        float4 qv[2], gv[2];
-        float dot = 0.f;
-        int c = 0;
-        for (int d = lane * 4; d < D; d += 128, ++c) {
-            qv[c] = ld_cg4(qb + ro + d);
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t < T - 1) {
-                const float4 a = ld_cg4(p.ws_dqa + (((int64_t)b * (T - 1) + t) * N + n) * D + d);
-                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+    // a warp owns rows warp, warp + 16, ...; two rows at a time, all their loads in flight before the first use
+    for (int row0 = warp; row0 < 2 * N; row0 += 2 * NW) {
+        float4 qv[2][2], ga[2][2], gbv[2][2];
+        float in[2], nrm[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int row = row0 + NW * u;
+            const int which = row >= N, n = row - which * N, t = i + which;
+            live[u] = row < 2 * N && s_last[which] != 0;
+            in[u] = nrm[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int d = lane * 4 + 128 * c;
+                qv[u][c] = ga[u][c] = gbv[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[u] && d < D) {
+                    qv[u][c] = ld_cg4(qb + (int64_t)n * gs + (int64_t)t * D + d);
+                    if (t < T - 1) ga[u][c] = ld_cg4(p.ws_dqa + (((int64_t)b * (T - 1) + t) * N + n) * D + d);
+                    if (t > 0) gbv[u][c] = ld_cg4(p.ws_dqb + (((int64_t)b * (T - 1) + t - 1) * N + n) * D + d);
+                }
             }
-            if (t > 0) {
-                const float4 a = ld_cg4(p.ws_dqb + (((int64_t)b * (T - 1) + t - 1) * N + n) * D + d);
-                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            if (live[u]) {
+                in[u] = ld_cg(p.ws_invn + ((int64_t)b * T + t) * N + n);
+                nrm[u] = ld_cg(p.ws_nrm + ((int64_t)b * T + t) * N + n);
             }
-            gv[c] = g;
-            dot += qv[c].x * g.x + qv[c].y * g.y + qv[c].z * g.z + qv[c].w * g.w;
         }
-        dot = warp_sum(dot);
-        const float in = ld_cg(p.ws_invn + ((int64_t)b * T + t) * N + n);
-        if (!(ld_cg(p.ws_nrm + ((int64_t)b * T + t) * N + n) > kEpsNorm)) dot = 0.f;      // clamp active: q = f / eps
-        c = 0;
-        for (int d = lane * 4; d < D; d += 128, ++c) {
-            float4 o;
-            o.x = (gv[c].x - qv[c].x * dot) * in;
-            o.y = (gv[c].y - qv[c].y * dot) * in;
-            o.z = (gv[c].z - qv[c].z * dot) * in;
-            o.w = (gv[c].w - qv[c].w * dot) * in;
-            *reinterpret_cast<float4*>(gb + ro + d) = o;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;                         // warp-uniform
+            const int row = row0 + NW * u;
+            const int which = row >= N, n = row - which * N, t = i + which;
+            const int64_t ro = (int64_t)n * gs + (int64_t)t * D;
+            float4 gv[2];
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                gv[c] = make_float4(ga[u][c].x + gbv[u][c].x, ga[u][c].y + gbv[u][c].y, ga[u][c].z + gbv[u][c].z, ga[u][c].w + gbv[u][c].w);
+                dot += qv[u][c].x * gv[c].x + qv[u][c].y * gv[c].y + qv[u][c].z * gv[c].z + qv[u][c].w * gv[c].w;
+            }
+            dot = warp_sum(dot);
+            if (!(nrm[u] > kEpsNorm)) dot = 0.f;            // clamp active: q = f / eps
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int d = lane * 4 + 128 * c;
+                if (d < D) {
+                    float4 o;
+                    o.x = (gv[c].x - qv[u][c].x * dot) * in[u];
+                    o.y = (gv[c].y - qv[u][c].y * dot) * in[u];
+                    o.z = (gv[c].z - qv[u][c].z * dot) * in[u];
+                    o.w = (gv[c].w - qv[u][c].w * dot) * in[u];
+                    *reinterpret_cast<float4*>(gb + ro + d) = o;
+                }
+            }
         }
     }
 }
