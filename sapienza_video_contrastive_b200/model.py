@@ -148,8 +148,9 @@ class CRW(nn.Module):
         return f.reshape(B, N, T, f.shape[-1]), maps.view(B, N, *maps.shape[1:]), B, N
 
     def _head(self, pooled):
-        """selfsim_fc (model.py:117).  The default single bias-free Linear goes through ops.head_linear (same cuBLAS forward,
-        split-K weight gradient); deeper heads (head_depth > 0) run as the stock nn.Sequential."""
+        """selfsim_fc (model.py:117).  The default single bias-free Linear goes through ops.head_linear (forward, input and
+        split-K weight gradient on the fused tcgen05 tf32 GEMM; library GEMM for shapes TMA cannot address); deeper heads
+        (head_depth > 0) run as the stock nn.Sequential."""
         if len(self.selfsim_fc) == 1 and pooled.is_cuda:
             return ops.head_linear(pooled, self.selfsim_fc[0].weight)
         return self.selfsim_fc(pooled)

@@ -214,7 +214,8 @@ class _HeadLinear(torch.autograd.Function):
 
 
 def head_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """x (..., C) @ weight (D, C)^T -> (..., D); nn.Linear(bias=False) with a split-K weight gradient."""
+    """x (..., C) @ weight (D, C)^T -> (..., D); nn.Linear(bias=False) on the fused tensor-core GEMM (gemm_tf32.cu) with a
+    split-K weight gradient; see set_tensor_core_head / set_async_wgrad."""
     return _HeadLinear.apply(x, weight)
 
 
