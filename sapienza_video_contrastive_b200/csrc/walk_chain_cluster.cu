@@ -239,12 +239,16 @@ __global__ void __launch_bounds__(kCcThreads, 1) walk_chain_cluster_kernel(WalkP
     float* gP = nullptr;
     float* gS = nullptr;
     const float cgrad = 1.0f / ((float)(T - 2) * (float)p.B * (float)N);
-    for (int j = T - 2; j >= 0; --j) {
-        float* dW = nullptr;
-        if (j >= 1) {
-            dW = freeb[--nfree];
-            cc_nn<1>(dW, Pj(j), Sj(j), kNone, kNone, N, NP, r1, rhi, lane);            // own rows of W_j
-            __syncwarp();
+    float* dWpre = nullptr;                          // W_j rows already computed in the tail of the previous round
+    for (int j = T - 2; j >= 1; --j) {
+        float* dW;
+        {
+            if (dWpre) dW = dWpre;
+            else {
+                dW = freeb[--nfree];
+                cc_nn<1>(dW, Pj(j), Sj(j), kNone, kNone, N, NP, r1, rhi, lane);        // own rows of W_j
+                __syncwarp();
+            }
             // loss of the warp's row (model.py:395-397) and dW in place
             float lsum = 0.f, asum = 0.f;
             const int n = r1;
@@ -292,30 +296,39 @@ __global__ void __launch_bounds__(kCcThreads, 1) walk_chain_cluster_kernel(WalkP
                 part[1] = a;
             }
         }
-        // gP_j = dW_j S_j^T + gP_{j+1} X_{j+1}^T ;  gS_j = P_j^T dW_j + Y_{j+1}^T gS_{j+1}.  For j = 0 these ARE dX_0 / dY_0.
-        float* nP = j == 0 ? dXg : freeb[--nfree];
-        float* nS = j == 0 ? dYg : freeb[--nfree];
+        // gP_j = dW_j S_j^T + gP_{j+1} X_{j+1}^T ;  gS_j = P_j^T dW_j + Y_{j+1}^T gS_{j+1}
+        float* nP = freeb[--nfree];
+        float* nS = freeb[--nfree];
         if (grp == 0)
-            cc_nt<2>(nP, dW ? dW : gP, dW ? Sj(j) : Xm + (j + 1) * MS,
-                     (dW && gP) ? gP : kNone, (dW && gP) ? Xm + (j + 1) * MS : kNone, N, NP, r2, rhi, lane);
+            cc_nt<2>(nP, dW, Sj(j), gP ? gP : kNone, gP ? Xm + (j + 1) * MS : kNone, N, NP, r2, rhi, lane);
         else
-            cc_tn<2>(nS, dW ? Pj(j) : Ym + (j + 1) * MS, dW ? dW : gS,
-                     (dW && gS) ? Ym + (j + 1) * MS : kNone, (dW && gS) ? gS : kNone, N, NP, r2, rhi, lane);
-        if (j == 0) break;
+            cc_tn<2>(nS, Pj(j), dW, gS ? Ym + (j + 1) * MS : kNone, gS ? gS : kNone, N, NP, r2, rhi, lane);
         cluster.sync();                                     // every CTA's rows of gP_j, gS_j are final
         pull(nP, nS);
-        if (dW) freeb[nfree++] = dW;
+        freeb[nfree++] = dW;
         if (gP) freeb[nfree++] = gP;
         if (gS) freeb[nfree++] = gS;
         freeb[nfree++] = Pj(j);
         freeb[nfree++] = Sj(j);
         gP = nP;
         gS = nS;
-        // dX_j = P_{j-1}^T gP_j ; dY_j = gS_j S_{j-1}^T  -> own rows straight to the workspace
-        if (grp == 0) cc_tn<2>(dXg + (int64_t)j * MS, Pj(j - 1), gP, kNone, kNone, N, NP, r2, rhi, lane);
-        else          cc_nt<2>(dYg + (int64_t)j * MS, gS, Sj(j - 1), kNone, kNone, N, NP, r2, rhi, lane);
-        // no barrier: the buffers just freed are read by nobody any more (peers finished pulling them before the barrier
-        // above), and the ones read here are not written in the next round
+        // Tail of the round, four independent products on four warp groups at once (a product's latency, not its
+        // throughput, is what a round costs):  dX_j = P_{j-1}^T gP_j  and  dY_j = gS_j S_{j-1}^T  go straight to the
+        // workspace; next to them either the next round's W_{j-1} = P_{j-1} S_{j-1} or, after the last round, the walk's
+        // first-frame gradients gP_0 = gP_1 X_1^T and gS_0 = Y_1^T gS_1 (= dX_0, dY_0).
+        // No barrier before it: the buffers just freed are read by nobody any more (peers finished pulling them before the
+        // barrier above), and the ones read here are not written in the next round.
+        const bool last = j == 1;
+        float* dWn = last ? nullptr : freeb[--nfree];
+        const int q4 = warp & 3, r4 = rlo + 4 * q4;
+        if (warp < 4)       cc_tn<4>(dXg + (int64_t)j * MS, Pj(j - 1), gP, kNone, kNone, N, NP, r4, rhi, lane);
+        else if (warp < 8)  cc_nt<4>(dYg + (int64_t)j * MS, gS, Sj(j - 1), kNone, kNone, N, NP, r4, rhi, lane);
+        else if (!last)     cc_nn<2>(dWn, Pj(j - 1), Sj(j - 1), kNone, kNone, N, NP, rlo + 2 * (warp - 8), rhi, lane);
+        else if (warp < 12) cc_nt<4>(dXg, gP, Xm + MS, kNone, kNone, N, NP, r4, rhi, lane);
+        else                cc_tn<4>(dYg, Ym + MS, gS, kNone, kNone, N, NP, r4, rhi, lane);
+        if (last) break;
+        __syncthreads();                                    // W_{j-1} rows (two per warp of the upper half) -> the row-owning warps
+        dWpre = dWn;
     }
 
     // cross-clip reduction of the per-CTA sums by the last CTA to finish, in (clip, rank) order (deterministic);
