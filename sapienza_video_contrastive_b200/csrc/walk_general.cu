@@ -199,6 +199,7 @@ struct StochArgs {
     float* out;
     float* denom;              // per row, may be null
     unsigned char* codes;      // per element, may be null
+    const unsigned char* codes_in;   // mode 2: the codes the mode-1 pass drew, in the forward orientation (no second Philox pass)
     const float* u1;
     const float* u2;
     uint64_t seed, offset;
@@ -234,15 +235,21 @@ __global__ void __launch_bounds__(256) stoch_rows_kernel(StochArgs s) {
                 if (d) a[m] = kNegDrop;
                 return d;
             }
-            // element of the (n_src, m_src) affinity this entry derives from
-            const int64_t e = s.mode == 1 ? ((int64_t)b * s.N + n) * s.N + m : ((int64_t)b * s.N + m) * s.N + n;
-            float u1, u2;
-            if (s.u1) { u1 = s.u1[(int64_t)i * numel + e]; u2 = s.u2[(int64_t)i * numel + e]; }
-            else {
-                u1 = torch_uniform(s.seed, s.offset + (uint64_t)s.pinc * i, s.pthreads, (uint64_t)e);
-                u2 = torch_uniform(s.seed, s.offset + (uint64_t)s.pinc * (s.T - 1 + i), s.pthreads, (uint64_t)e);
+            unsigned code;
+            if (s.mode == 2 && s.codes_in) {
+                // entry m of row n of G is A[m][n]: its draws were made (and stored) by the forward-orientation pass
+                code = s.codes_in[((int64_t)(b * (s.T - 1) + i) * s.N + m) * s.N + n];
+            } else {
+                // element of the (n_src, m_src) affinity this entry derives from
+                const int64_t e = s.mode == 1 ? ((int64_t)b * s.N + n) * s.N + m : ((int64_t)b * s.N + m) * s.N + n;
+                float u1, u2;
+                if (s.u1) { u1 = s.u1[(int64_t)i * numel + e]; u2 = s.u2[(int64_t)i * numel + e]; }
+                else {
+                    u1 = torch_uniform(s.seed, s.offset + (uint64_t)s.pinc * i, s.pthreads, (uint64_t)e);
+                    u2 = torch_uniform(s.seed, s.offset + (uint64_t)s.pinc * (s.T - 1 + i), s.pthreads, (uint64_t)e);
+                }
+                code = (u1 < s.rate ? 1u : 0u) | (u2 < s.rate ? 2u : 0u);
             }
-            const unsigned code = (u1 < s.rate ? 1u : 0u) | (u2 < s.rate ? 2u : 0u);
             if (s.codes) s.codes[row * M + m] = (unsigned char)code;
             return s.mode == 1 ? (code & 1u) != 0 : code != 0;
         };
@@ -485,6 +492,7 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
         s.out = dir == 1 ? F : G;
         s.denom = dir == 1 ? s12 : s21;
         s.codes = dir == 1 ? codesF : codesG;
+        s.codes_in = dir == 2 ? codesF : nullptr;      // each element's two draws are made once, by the forward pass
         s.u1 = p.u12; s.u2 = p.u21p;
         s.seed = p.seed; s.offset = p.offset; s.pthreads = p.pthreads; s.pinc = p.pinc;
         s.dev_state = p.dev_state;
