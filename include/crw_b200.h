@@ -162,6 +162,14 @@ int crw_lp_prepare(const float* feats_cf, int C, int Nf, int hw, int normalize, 
 int crw_lp_gather(float* lbls, const int64_t* key_frames_n, const float* Ws_n, const int64_t* Is_n,
                   int hw, int L, int k, int64_t out_frame, crw_stream_t stream);
 
+/* ---- f1 (SURVEY 8f "next"): label-map post-processing, utils/test_utils.py:85-123 (dump_predictions) + test.py:162-164 ----
+ * pred (n, h, w, L) fp32 soft label maps of n target frames -> cv2.resize(pred, (W, H)) (bilinear, OpenCV's float path and
+ * border rule) -> arg-max over L (first maximum wins) -> cls (n, H, W) uint8 class index and / or rgb (n, H, W, 3) uint8 =
+ * palette[cls] (palette (L, 3) uint8 = np.uint8(lbl_set); NULL: rgb repeats the index).  norm_mask != 0 first applies
+ * pred -= min_L; pred /= max_L per source pixel.  The upsampled (H, W, L) tensor is never materialised.  L <= 255. */
+int crw_lp_upsample_argmax(const float* pred, int n, int h, int w, int L, int H, int W, int norm_mask,
+                           const unsigned char* palette, unsigned char* cls, unsigned char* rgb, crw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,3 +238,22 @@ def lp_propagate(lbls, key_indices, Ws, Is, n_context):
         lbls[t + n_context] = pred
         preds.append(pred.clone())
     return torch.stack(preds)
+
+
+def upsample_argmax(pred: torch.Tensor, lbl_set: torch.Tensor, size, norm_mask: bool = False):
+    """Label-map post-processing: test.py:162-164 (--norm_mask) then utils/test_utils.py:96-103
+    (dump_predictions): cv2.resize of the (h,w,L) soft label map to the image size (bilinear), numpy arg-max over L, colour
+    table look-up.  -> (cls (H,W) int64, pred_lbl (H,W,3) int32, pred_dist (H,W,L) float32).  Needs OpenCV (test infra only)."""
+    import cv2
+    import numpy as np
+    p = pred.clone().float()
+    if norm_mask:
+        p -= p.min(-1)[0][:, :, None]
+        p /= p.max(-1)[0][:, :, None]
+    H, W = int(size[0]), int(size[1])
+    dist = cv2.resize(p.numpy(), (W, H))
+    if dist.ndim == 2:
+        dist = dist[..., None]
+    cls = np.argmax(dist, axis=-1)
+    lbl = np.array(lbl_set.cpu(), dtype=np.int32)[cls]
+    return torch.from_numpy(cls), torch.from_numpy(lbl), torch.from_numpy(dist)

@@ -178,6 +178,31 @@ def gen_lp(ref_model, ref_utils, ref_tu):
         print(name, tuple(fx["Ws"].shape), tuple(fx["preds"].shape))
 
 
+def gen_post(ref_model, ref_utils, ref_tu):
+    """The reference's own dump_predictions (utils/test_utils.py:85-123) on seeded soft label maps; only its file writes and
+    the matplotlib colour map (both outside the path) are replaced.  --norm_mask is applied as test.py:162-164 does."""
+    import types
+    import numpy as np
+    orig_io, orig_cm = ref_tu.imageio, ref_tu.cm
+    ref_tu.imageio = types.SimpleNamespace(imwrite=lambda *a, **k: None)
+    ref_tu.cm = types.SimpleNamespace(jet=lambda x: np.zeros(x.shape + (4,), dtype=np.float32))
+    try:
+        for name, c in cases.POST_CASES.items():
+            pred, lbl_set, img = cases.post_inputs(c)
+            pred = pred.clone()
+            if c["norm_mask"]:
+                pred[:, :, :] -= pred.min(-1)[0][:, :, None]
+                pred[:, :, :] /= pred.max(-1)[0][:, :, None]
+            blend, lbl, _ = ref_tu.dump_predictions(pred.cpu().numpy(), lbl_set, img.numpy(), os.path.join(tempfile.gettempdir(), "x.jpg"))
+            fx = {"pred_lbl": torch.from_numpy(np.asarray(lbl)).to(torch.uint8)}        # colours are 0..255: bytes keep the fixture small
+            if name == "post_shrink":
+                fx["blend"] = torch.from_numpy(np.asarray(blend))
+            torch.save(fx, os.path.join(OUT, name + ".pt"))
+            print("golden", name, tuple(fx["pred_lbl"].shape))
+    finally:
+        ref_tu.imageio, ref_tu.cm = orig_io, orig_cm
+
+
 def gen_misc(ref_model, ref_utils, ref_tu):
     """Small known-answer vectors: ZeroSoftmax, radius mask, context_index_bank, affinity, stoch_mat."""
     g = torch.Generator().manual_seed(5)
@@ -200,7 +225,11 @@ def gen_misc(ref_model, ref_utils, ref_tu):
 def main():
     ref_model, ref_utils, ref_tu = ref_import.load()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "post":           # only the post-processing fixtures (added later)
+        gen_post(ref_model, ref_utils, ref_tu)
+        return
     gen_misc(ref_model, ref_utils, ref_tu)
+    gen_post(ref_model, ref_utils, ref_tu)
     gen_walk(ref_model, ref_utils)
     gen_sp(ref_model, ref_utils)
     gen_lp(ref_model, ref_utils, ref_tu)

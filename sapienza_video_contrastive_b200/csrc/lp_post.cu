@@ -1,0 +1,136 @@
+// lp_post.cu - label-map post-processing of the evaluator (reference: code/utils/test_utils.py:85-123 dump_predictions,
+// code/test.py:162-164 --norm_mask): the propagated soft label maps (h, w, L) of every target frame are upsampled to the
+// image size with OpenCV's bilinear resize (cv2.resize default, the float path of resizeGeneric), the hard label is the
+// arg-max over L (first maximum wins, numpy.argmax) and is mapped through the colour table lbl_set (L, 3).
+//
+// A thread produces four consecutive output pixels: the four source neighbours x L channels are read straight from the low-resolution
+// map (L contiguous, the whole map of a frame sits in L1/L2), interpolated horizontally then vertically with the same
+// float weights OpenCV computes ((dx + 0.5) * scale - 0.5 in double, rounded to float, clamped at the borders), and only
+// the class index (1 byte) and the palette colour (3 bytes) are written: the (H, W, L) float tensor is never materialised.
+// HBM: 4 bytes written per output pixel against 4 L read + 4 L written + 4 read by the reference's resize + argmax.
+#include "common.cuh"
+
+namespace crw {
+
+struct LpPostArgs {
+    const float* pred;          // (n, h, w, L)
+    const unsigned char* pal;   // (L, 3) or null
+    unsigned char* cls;         // (n, H, W) or null
+    unsigned char* rgb;         // (n, H, W, 3) or null
+    int n, h, w, L, H, W, norm_mask;
+    double scale_x, scale_y;    // source / destination extent
+};
+
+// OpenCV's source coordinate and weight for destination index d (imgproc/resize.cpp, INTER_LINEAR, float images)
+__device__ __forceinline__ void cv_linear_coord(int d, double scale, int ssize, int& s0, int& s1, float& w0, float& w1) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    s0 = s;
+    s1 = s + 1 < ssize ? s + 1 : ssize - 1;
+    w0 = 1.f - f;
+    w1 = f;
+}
+
+// arg-max class of output pixel e (flat index over (frame, Y, X))
+__device__ __forceinline__ int lp_post_pixel(const LpPostArgs& a, int64_t e) {
+    const int X = (int)(e % a.W);
+    const int64_t r = e / a.W;
+    const int Y = (int)(r % a.H), f = (int)(r / a.H);
+    int x0, x1, y0, y1;
+    float ax0, ax1, by0, by1;
+    cv_linear_coord(X, a.scale_x, a.w, x0, x1, ax0, ax1);
+    cv_linear_coord(Y, a.scale_y, a.h, y0, y1, by0, by1);
+    const float* base = a.pred + (int64_t)f * a.h * a.w * a.L;
+    const float* p00 = base + ((int64_t)y0 * a.w + x0) * a.L;
+    const float* p01 = base + ((int64_t)y0 * a.w + x1) * a.L;
+    const float* p10 = base + ((int64_t)y1 * a.w + x0) * a.L;
+    const float* p11 = base + ((int64_t)y1 * a.w + x1) * a.L;
+    // --norm_mask (test.py:162-164): per source pixel, subtract the min over L, then divide by the (new) max
+    float mn[4] = {0.f, 0.f, 0.f, 0.f}, mx[4] = {1.f, 1.f, 1.f, 1.f};
+    if (a.norm_mask) {
+        const float* ps[4] = {p00, p01, p10, p11};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float lo = ps[q][0], hi = ps[q][0];
+            for (int l = 1; l < a.L; ++l) { lo = fminf(lo, ps[q][l]); hi = fmaxf(hi, ps[q][l]); }
+            mn[q] = lo;
+            mx[q] = hi - lo;
+        }
+    }
+    float best = -INFINITY;
+    int bi = 0;
+    for (int l = 0; l < a.L; ++l) {
+        float v00 = p00[l], v01 = p01[l], v10 = p10[l], v11 = p11[l];
+        if (a.norm_mask) {
+            v00 = (v00 - mn[0]) / mx[0]; v01 = (v01 - mn[1]) / mx[1];
+            v10 = (v10 - mn[2]) / mx[2]; v11 = (v11 - mn[3]) / mx[3];
+        }
+        // horizontal pass, then vertical pass (separate multiplies and adds, as the scalar OpenCV code)
+        const float r0 = __fadd_rn(__fmul_rn(v00, ax0), __fmul_rn(v01, ax1));
+        const float r1 = __fadd_rn(__fmul_rn(v10, ax0), __fmul_rn(v11, ax1));
+        const float v = __fadd_rn(__fmul_rn(r0, by0), __fmul_rn(r1, by1));
+        if (v > best || (l == 0 && !(v <= best))) { best = v; bi = l; }      // first maximum wins; a NaN at l = 0 stays (numpy)
+    }
+    return bi;
+}
+
+// a thread owns four consecutive output pixels (flat), so the class bytes leave as one 32-bit store and the colours as three
+__global__ void __launch_bounds__(256) lp_post_kernel(LpPostArgs a) {
+    const int64_t total = (int64_t)a.n * a.H * a.W, groups = (total + 3) / 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e0 = g * 4;
+        unsigned char c[4];
+        unsigned char px[12];
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            c[u] = 0;
+            px[3 * u] = px[3 * u + 1] = px[3 * u + 2] = 0;
+            if (e0 + u < total) {
+                const int bi = lp_post_pixel(a, e0 + u);
+                c[u] = (unsigned char)bi;
+                if (a.pal) { px[3 * u] = a.pal[bi * 3]; px[3 * u + 1] = a.pal[bi * 3 + 1]; px[3 * u + 2] = a.pal[bi * 3 + 2]; }
+                else px[3 * u] = px[3 * u + 1] = px[3 * u + 2] = (unsigned char)bi;
+                ++cnt;
+            }
+        }
+        const bool aligned = ((reinterpret_cast<uintptr_t>(a.cls) | reinterpret_cast<uintptr_t>(a.rgb)) & 3) == 0;
+        if (cnt == 4 && aligned) {
+            if (a.cls) *reinterpret_cast<unsigned*>(a.cls + e0) = c[0] | (c[1] << 8) | (c[2] << 16) | ((unsigned)c[3] << 24);
+            if (a.rgb) {
+                unsigned* o = reinterpret_cast<unsigned*>(a.rgb + e0 * 3);
+                o[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((unsigned)px[3] << 24);
+                o[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((unsigned)px[7] << 24);
+                o[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((unsigned)px[11] << 24);
+            }
+        } else {
+            for (int u = 0; u < cnt; ++u) {
+                if (a.cls) a.cls[e0 + u] = c[u];
+                if (a.rgb) { a.rgb[(e0 + u) * 3] = px[3 * u]; a.rgb[(e0 + u) * 3 + 1] = px[3 * u + 1]; a.rgb[(e0 + u) * 3 + 2] = px[3 * u + 2]; }
+            }
+        }
+    }
+}
+
+}  // namespace crw
+
+using namespace crw;
+
+extern "C" int crw_lp_upsample_argmax(const float* pred, int n, int h, int w, int L, int H, int W, int norm_mask,
+                                      const unsigned char* palette, unsigned char* cls, unsigned char* rgb, crw_stream_t stream) {
+    if (n < 0 || h <= 0 || w <= 0 || L <= 0 || H <= 0 || W <= 0) { set_error("lp_upsample_argmax: bad shape"); return CRW_ERR_SHAPE; }
+    if (L > 255) { set_error("lp_upsample_argmax: at most 255 labels (byte class map), got %d", L); return CRW_ERR_UNSUPPORTED; }
+    if (n == 0 || (!cls && !rgb)) return CRW_OK;
+    LpPostArgs a{};
+    a.pred = pred; a.pal = palette; a.cls = cls; a.rgb = rgb;
+    a.n = n; a.h = h; a.w = w; a.L = L; a.H = H; a.W = W; a.norm_mask = norm_mask;
+    a.scale_x = 1.0 / ((double)W / (double)w);          // OpenCV: inv_scale = dsize / ssize, scale = 1 / inv_scale
+    a.scale_y = 1.0 / ((double)H / (double)h);
+    const int64_t groups = ((int64_t)n * H * W + 3) / 4;
+    const int grid = (int)((groups + 255) / 256 < 148 * 16 ? (groups + 255) / 256 : 148 * 16);
+    CRW_LAUNCH(lp_post_kernel, grid, 256, 0, stream, a);
+    return check_launch("lp_upsample_argmax");
+}

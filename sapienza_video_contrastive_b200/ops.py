@@ -624,3 +624,28 @@ def lp_gather_(lbls: torch.Tensor, key_frames_n: torch.Tensor, Ws_n: torch.Tenso
     L = _lib.lib()
     L.check(L.crw_lp_gather(lbls.data_ptr(), key_frames_n.contiguous().data_ptr(), _f32c(Ws_n).data_ptr(),
                             Is_n.contiguous().data_ptr(), hw, Lc, k, int(out_frame), _stream()), "lp_gather")
+
+
+def lp_upsample_argmax(preds: torch.Tensor, size: Tuple[int, int], palette: Optional[torch.Tensor] = None,
+                       norm_mask: bool = False, want_rgb: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """test_utils.py:85-123 on the device: preds (n,h,w,L) or (h,w,L) soft label maps -> (cls (n,H,W) uint8, rgb (n,H,W,3)
+    uint8 = palette[cls]) with OpenCV's bilinear resize rule and numpy's first-maximum arg-max; palette (L,3) integer (any
+    device: it is a few bytes)."""
+    _need_cuda(preds)
+    check_device(preds.device)
+    if preds.dim() == 3:
+        preds = preds[None]
+    preds = _f32c(preds)
+    n, h, w, Lb = preds.shape
+    H, W = int(size[0]), int(size[1])
+    cls = torch.empty(n, H, W, dtype=torch.uint8, device=preds.device)
+    rgb = torch.empty(n, H, W, 3, dtype=torch.uint8, device=preds.device) if want_rgb else None
+    pal = None
+    if palette is not None:
+        if palette.shape != (Lb, 3):
+            raise ValueError("palette must be (L,3), got %s" % (tuple(palette.shape),))
+        pal = palette.to(device=preds.device).to(torch.int64).to(torch.uint8).contiguous()      # np.uint8(lbl_set): wraps modulo 256
+    L = _lib.lib()
+    L.check(L.crw_lp_upsample_argmax(preds.data_ptr(), n, h, w, Lb, H, W, int(norm_mask), pal.data_ptr() if pal is not None else None,
+                                     cls.data_ptr(), rgb.data_ptr() if rgb is not None else None, _stream()), "lp_upsample_argmax")
+    return cls, rgb

@@ -168,6 +168,29 @@ def propagate_labels(lbls: torch.Tensor, key_indices: torch.Tensor, Ws, Is, n_co
     return torch.stack(preds).view(-1, h, w, L)
 
 
+def dump_predictions(pred, lbl_set, img, prefix: Optional[str] = None, norm_mask: bool = False):
+    """test_utils.py:85-123 with the reference's argument order: pred (h,w,L) soft label map of one frame (tensor or numpy),
+    lbl_set (L,3) colour table, img (H,W,3) image in 0..255.  The upsample + arg-max + palette run in one kernel on the
+    device.  Returns (img_with_label (H,W,3) float32, pred_lbl (H,W,3) int32, None); the third element of the reference's
+    tuple is a matplotlib `jet` heat map for visual debugging, which is outside this path.  With `prefix`, the label image
+    is written next to it as the reference does (`<prefix>_mask.png` / `.png`) when OpenCV is importable."""
+    p = torch.as_tensor(pred, dtype=torch.float32)
+    dev = p.device if p.is_cuda else torch.device("cuda")
+    im = torch.as_tensor(img, dtype=torch.float32)
+    H, W = int(im.shape[0]), int(im.shape[1])
+    _, rgb = ops.lp_upsample_argmax(p.to(dev), (H, W), torch.as_tensor(lbl_set), norm_mask=norm_mask)
+    pred_lbl = rgb[0].to(torch.int32)
+    img_with_label = im.to(dev) * 0.5 + pred_lbl.float() * 0.5
+    if prefix is not None:
+        try:
+            import cv2
+            name = prefix + "_mask.png" if prefix[-4] != "." else prefix.replace("jpg", "png")
+            cv2.imwrite(name, rgb[0].cpu().numpy()[..., ::-1])
+        except ImportError:
+            pass
+    return img_with_label, pred_lbl, None
+
+
 class LabelPropagator:
     """Native evaluator: encoder features in, propagated soft label maps out, everything on the device.
 
@@ -197,3 +220,8 @@ class LabelPropagator:
         ki, Ws, Is = self.affinity(feats)
         preds = propagate_labels(lbls, ki, Ws, Is, self.n_context, device=feats.device)
         return preds, (Ws, Is)
+
+    def label_images(self, preds: torch.Tensor, lbl_set: torch.Tensor, size, norm_mask: bool = False):
+        """Full-resolution hard label maps of every target frame (test.py:162-188 + dump_predictions): preds (Nt,h,w,L) ->
+        (cls (Nt,H,W) uint8, rgb (Nt,H,W,3) uint8), one launch for the whole video."""
+        return ops.lp_upsample_argmax(preds, size, lbl_set, norm_mask=norm_mask)

@@ -38,6 +38,27 @@ LP_CASES = {
 }
 
 
+# label-map post-processing cases (utils/test_utils.py:85-123): integer and non-integer scale factors, down-scaling, norm_mask
+POST_CASES = {
+    "post_x8":      dict(h=12, w=17, L=3, H=96, W=136, norm_mask=False, seed=41),
+    "post_davis":   dict(h=30, w=54, L=4, H=240, W=427, norm_mask=False, seed=42),
+    "post_norm":    dict(h=15, w=9, L=5, H=100, W=71, norm_mask=True, seed=43),
+    "post_shrink":  dict(h=40, w=33, L=2, H=17, W=20, norm_mask=False, seed=44),
+}
+
+
+def post_inputs(c):
+    """-> pred (h,w,L) soft label map (smooth blobs + noise, rows sum to 1), lbl_set (L,3) int64 colours, img (H,W,3)."""
+    g = torch.Generator().manual_seed(c["seed"])
+    ys, xs = torch.meshgrid(torch.arange(c["h"]).float(), torch.arange(c["w"]).float(), indexing="ij")
+    logits = torch.stack([-((ys - torch.rand(1, generator=g) * c["h"]) ** 2 + (xs - torch.rand(1, generator=g) * c["w"]) ** 2)
+                          / (0.1 * c["h"] * c["w"]) for _ in range(c["L"])], -1)
+    pred = torch.softmax(logits + 0.3 * torch.randn(c["h"], c["w"], c["L"], generator=g), -1)
+    lbl_set = torch.randint(0, 256, (c["L"], 3), generator=g)
+    img = torch.rand(c["H"], c["W"], 3, generator=g) * 255
+    return pred, lbl_set, img
+
+
 def walk_inputs(c):
     """-> maps (B*N, Ce, T, 8, 8), head_w (128, Ce).  The walk RNG seed is c['seed'] + 1000."""
     g = torch.Generator().manual_seed(c["seed"])

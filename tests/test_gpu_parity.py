@@ -13,7 +13,7 @@ import torch
 
 from oracle import crw_oracle as O
 from tests.golden import cases
-from tests.test_sim_kernels import check_topk_indices, load
+from tests.test_sim_kernels import check_label_images, check_topk_indices, load
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -576,3 +576,43 @@ def test_async_wgrad_overlap_gives_identical_gradients(ops):
         finally:
             ops.set_async_wgrad(False)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("name", list(cases.POST_CASES))
+def test_label_postprocessing_matches_reference_golden(ops, name):
+    """dump_predictions' resize + arg-max + colour table in one kernel, against the reference's own output."""
+    pytest.importorskip("cv2")
+    from sapienza_video_contrastive_b200 import test_utils as TU
+    c = cases.POST_CASES[name]
+    fx = load(name)
+    pred, lbl_set, img = cases.post_inputs(c)
+    cls, rgb = ops.lp_upsample_argmax(pred.to(DEV), (c["H"], c["W"]), lbl_set, norm_mask=c["norm_mask"])
+    check_label_images(cls[0].cpu(), rgb[0].cpu(), pred, lbl_set, c, fx)
+    blend, lbl, _ = TU.dump_predictions(pred.numpy(), lbl_set, img.numpy(), None, norm_mask=c["norm_mask"])        # the reference's signature
+    assert lbl.shape == (c["H"], c["W"], 3) and lbl.dtype == torch.int32 and torch.equal(lbl.cpu().to(torch.uint8), rgb[0].cpu())
+    torch.testing.assert_close(blend.cpu(), img * 0.5 + lbl.cpu().float() * 0.5, rtol=0, atol=1e-4)
+
+
+def test_label_postprocessing_davis_shape_properties(ops):
+    """DAVIS 480p shape (60x107 -> 480x854, 37 frames): one-hot maps reproduce nearest labels away from boundaries, the
+    result is invariant to a positive rescaling of the maps, frames are independent."""
+    torch.manual_seed(3)
+    n, h, w, Lb, H, W = 37, 60, 107, 4, 480, 854
+    hard = torch.randint(0, Lb, (n, h // 6, w // 6 + 1), device=DEV).repeat_interleave(6, 1).repeat_interleave(6, 2)[:, :h, :w]
+    pred = torch.nn.functional.one_hot(hard, Lb).float()
+    pal = torch.tensor([[0, 0, 0], [255, 0, 0], [0, 255, 0], [0, 0, 255]], device=DEV)
+    cls, rgb = ops.lp_upsample_argmax(pred, (H, W), pal)
+    assert cls.shape == (n, H, W) and rgb.shape == (n, H, W, 3)
+    assert torch.equal(rgb, pal.to(torch.uint8)[cls.long()])
+    # inside a 6x6 block of constant label (more than one source pixel from its border) the upsampled label is that label
+    ys = ((torch.arange(H, device=DEV) + 0.5) * h / H - 0.5).round().clamp(0, h - 1).long()
+    xs = ((torch.arange(W, device=DEV) + 0.5) * w / W - 0.5).round().clamp(0, w - 1).long()
+    inner_y = ((ys % 6) >= 2) & ((ys % 6) <= 3)
+    inner_x = ((xs % 6) >= 2) & ((xs % 6) <= 3)
+    near = hard[:, ys][:, :, xs]
+    m = inner_y[:, None] & inner_x[None, :]
+    assert torch.equal(cls[:, m].long(), near[:, m])
+    cls2, _ = ops.lp_upsample_argmax(pred * 3.0, (H, W), pal, want_rgb=False)
+    assert torch.equal(cls2, cls)
+    cls3, _ = ops.lp_upsample_argmax(pred[5:6], (H, W), pal, want_rgb=False)
+    assert torch.equal(cls3[0], cls[5])

@@ -87,6 +87,20 @@ def test_label_prop_matches_reference(name):
     torch.testing.assert_close(preds, fx["preds"], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", list(cases.POST_CASES))
+def test_label_postprocessing_matches_reference(name):
+    """oracle.upsample_argmax == the reference's dump_predictions (utils/test_utils.py:85-123), label image bit for bit."""
+    cv2 = pytest.importorskip("cv2")  # noqa: F841
+    c = cases.POST_CASES[name]
+    fx = load(name)
+    pred, lbl_set, img = cases.post_inputs(c)
+    cls, lbl, dist = O.upsample_argmax(pred, lbl_set, (c["H"], c["W"]), c["norm_mask"])
+    assert torch.equal(lbl.to(torch.uint8), fx["pred_lbl"])
+    assert cls.shape == (c["H"], c["W"]) and int(cls.max()) < c["L"]
+    if "blend" in fx:
+        torch.testing.assert_close(img * 0.5 + lbl.float() * 0.5, fx["blend"], rtol=0, atol=1e-4)
+
+
 def test_misc_known_answers():
     fx = load("misc")
     torch.testing.assert_close(O.zero_softmax(fx["zs_in"]), fx["zs_out"], rtol=1e-6, atol=0)
