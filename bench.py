@@ -281,9 +281,23 @@ def label_prop_bench(dev):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fps = c["n_tgt"] / ms * 1e3
+    # the step right after it in test.py: full-resolution hard label images of every target frame
+    preds, _ = lp(feats, lbls)
+    pal = torch.randint(0, 256, (c["L"], 3), generator=g)
+    lp.label_images(preds, pal, (c["h"] * 8, c["w"] * 8))
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(10):
+        lp.label_images(preds, pal, (c["h"] * 8, c["w"] * 8))
+    p1.record()
+    torch.cuda.synchronize()
+    post_ms = p0.elapsed_time(p1) / 10
     useful_flops = 2 * c["C"] * 90_214_480           # in-radius + long-memory score pairs per target frame
     _, tf, _ = peaks()
     return {"metric": "label_prop_frames_per_s", "value": fps, "unit": "frames/s", "ms_per_frame": ms / c["n_tgt"],
+            "postprocess": {"what": "upsample x8 (cv2 bilinear rule) + arg-max + colour table for the %d frames, one launch" % c["n_tgt"],
+                            "ms": post_ms, "frames_per_s": c["n_tgt"] / post_ms * 1e3},
             "config": "C=%d %dx%d, %d context + long-mem [0], radius %d, top-k %d, %d target frames per call (layout + hi/lo split + tcgen05 top-k + gathers)"
                       % (c["C"], c["h"], c["w"], c["n_ctx"], c["radius"], c["k"], c["n_tgt"]),
             "roofline": {"bound": "tensor", "achieved": useful_flops * fps / 1e12, "peak": tf, "unit": "TFLOP/s",
