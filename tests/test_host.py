@@ -32,6 +32,25 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert lib.crw_segmean_workspace_bytes(2, 3, 32, 32, 256, 256, 100) > 0
 
 
+def test_flag_constants_match_the_header():
+    """The Python copies of the CRW_WALK_* / CRW_LP_* flag bits are the header's; workspace queries honour them."""
+    from sapienza_video_contrastive_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "crw_b200.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+CRW_(WALK_[A-Z0-9_]+)\s+(\d+)u", src)}
+    assert set(flags) >= {"WALK_SOFTMAX", "WALK_FLIP", "WALK_FORCE_GENERAL", "WALK_FORCE_SIMT", "WALK_FORCE_TC", "WALK_NO_CLUSTER", "WALK_NO_TF32"}
+    for name, val in flags.items():
+        assert getattr(_lib, name) == val, name
+    assert len(set(flags.values())) == len(flags)                       # distinct bits
+    lib = _lib.CrwLib(_lib.build())
+    # the general path reserves tensor-core operand planes from N = 64 on, unless the SIMT GEMM is forced
+    big = lib.crw_walk_workspace_bytes(2, 128, 4, 128, 0)
+    simt = lib.crw_walk_workspace_bytes(2, 128, 4, 128, _lib.WALK_FORCE_SIMT)
+    assert big > simt > 0
+    assert lib.crw_walk_workspace_bytes(2, 60, 16, 128, 0) == lib.crw_walk_workspace_bytes(2, 60, 16, 128, _lib.WALK_FORCE_SIMT)
+    assert lib.crw_head_wgrad_workspace_bytes(3920, 128, 512) >= 4 * 35 * 128 * 512
+    assert lib.crw_bmm_tc_workspace_bytes(2, 128, 128, 128) > 0
+
+
 def test_product_never_imports_the_oracle_or_a_cpu_path():
     for dirpath, _, files in os.walk(PKG):
         for f in files:
