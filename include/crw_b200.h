@@ -58,6 +58,23 @@ int crw_segmean_bwd(const float* grad_out, const void* workspace, size_t workspa
                     int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
                     float* grad_maps, crw_stream_t stream);
 
+/* ---- f2: the same pooling with dilated superpixel masks, model.py:303-309 + utils/__init__.py:590-608 ----
+ * Every label's mask is dilated by a ksize x ksize structuring element before the window counts (the reference's
+ * depthwise conv2d(onehot, kernel, padding=ksize/2) > 0): a pixel then belongs to every label that has a pixel inside the
+ * element centred on it, masks overlap, and sizes / window counts are those of the dilated masks.  `shape` picks the
+ * element: diamond ("L1"), disc ("circle") or one row + one column ("cross").  ksize odd, <= 127; SP <= 255.
+ * Same layouts as crw_segmean_*; the backward reads the workspace the forward filled. */
+#define CRW_DILATE_L1 0
+#define CRW_DILATE_CIRCLE 1
+#define CRW_DILATE_CROSS 2
+size_t crw_segmean_dilated_workspace_bytes(int B, int T, int Hm, int Wm, int h, int w, int SP);
+int crw_segmean_dilated_fwd(const float* maps, const int64_t* labels, int64_t ls_b, int64_t ls_t, int64_t ls_y, int64_t ls_x,
+                            int B, int C, int T, int Hm, int Wm, int h, int w, int SP, int ksize, int shape,
+                            float* out, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+int crw_segmean_dilated_bwd(const float* grad_out, const void* workspace, size_t workspace_bytes,
+                            int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
+                            float* grad_maps, crw_stream_t stream);
+
 /* ---- a4: affinity, model.py:63-72  (einsum 'bctn,bctm->btnm') ----------------------------------------
  * x1, x2 node-major: x1[(b*T + t)*N1*D + n*D + d] (unit-norm or not), out (B*T, N1, N2). */
 int crw_affinity(const float* x1, const float* x2, int BT, int N1, int N2, int D, float* out, crw_stream_t stream);

@@ -257,3 +257,60 @@ def upsample_argmax(pred: torch.Tensor, lbl_set: torch.Tensor, size, norm_mask: 
     cls = np.argmax(dist, axis=-1)
     lbl = np.array(lbl_set.cpu(), dtype=np.int32)[cls]
     return torch.from_numpy(cls), torch.from_numpy(lbl), torch.from_numpy(dist)
+
+
+def dilation_halfwidths(ksize: int, shape: str):
+    """Half-width w(dy) of the structuring element of utils/__init__.py:590-608 at vertical offset dy = -R..R (R = ksize//2):
+    the element contains (dy, dx) iff |dx| <= w(dy).  'L1': diamond, 'circle': disc, 'cross': one row and one column."""
+    R = ksize // 2
+    out = []
+    for dy in range(-R, R + 1):
+        if shape == "L1":
+            out.append(R - abs(dy))
+        elif shape == "circle":
+            w = 0
+            while (w + 1) ** 2 + dy * dy <= R * R:
+                w += 1
+            out.append(w)
+        elif shape == "cross":
+            out.append(R if dy == 0 else 0)
+        else:
+            raise ValueError(shape)
+    return out
+
+
+def segment_mean_dilated(maps: torch.Tensor, labels: torch.Tensor, SP: int, ksize: int, shape: str = "L1") -> torch.Tensor:
+    """Superpixel pooling with dilated masks (model.py:303-309 + utils/__init__.py:590-608): every label's
+    binary mask is dilated by the structuring element (a pixel belongs to label s iff some pixel of s lies inside the element
+    centred on it - the reference's depthwise conv2d(...) > 0), masks may overlap, then the same window counts / size
+    normalisation / weighted sum as the plain path (model.py:311-325).  maps (B,C,T,Hm,Wm), labels (B,T,h,w) -> (B,T,SP,C)."""
+    B, C, T, Hm, Wm = maps.shape
+    h, w = labels.shape[-2:]
+    sy, sx = h // Hm, w // Wm
+    R = ksize // 2
+    hw_ = dilation_halfwidths(ksize, shape)
+    out = torch.zeros(B, T, SP, C, dtype=torch.float64)
+    for b in range(B):
+        for t in range(T):
+            lab = labels[b, t].long()
+            onehot = torch.zeros(SP, h, w, dtype=torch.bool)
+            ok = (lab >= 0) & (lab < SP)
+            ys, xs = torch.nonzero(ok, as_tuple=True)
+            onehot[lab[ys, xs], ys, xs] = True
+            dil = torch.zeros_like(onehot)
+            for i, dy in enumerate(range(-R, R + 1)):
+                # rows shifted by dy, dilated horizontally by hw_[i]
+                src = torch.zeros_like(onehot)
+                if dy >= 0:
+                    src[:, : h - dy if dy else h] = onehot[:, dy:]
+                else:
+                    src[:, -dy:] = onehot[:, : h + dy]
+                wv = hw_[i]
+                if wv > 0:
+                    src = torch.nn.functional.max_pool2d(src[None].float(), (1, 2 * wv + 1), stride=1, padding=(0, wv))[0] > 0
+                dil |= src
+            cnt = dil.view(SP, Hm, sy, Wm, sx).sum((2, 4)).double()                       # (SP, Hm, Wm) window counts
+            size = dil.sum((1, 2)).double()
+            wgt = cnt / (size + EPS_LOG)[:, None, None]
+            out[b, t] = torch.einsum("sij,cij->sc", wgt, maps[b, :, t].double())
+    return out.float()

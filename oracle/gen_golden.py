@@ -126,6 +126,24 @@ def gen_sp(ref_model, ref_utils):
         print(name, float(loss), tuple(sp_feats.shape))
 
 
+def gen_spd(ref_model, ref_utils):
+    """CRW.image_to_nodes with --dilate-superpixels (model.py:303-309), all three kernel shapes, plus the gradient of a
+    fixed linear functional of the node embeddings with respect to the maps and the head."""
+    for name, c in cases.SPD_CASES.items():
+        maps, lab3, head_w = cases.sp_inputs(c)
+        crw, enc = make_crw(ref_model, ref_utils, c["Ce"], head_w, dropout=0.0, temp=0.07, dilate_superpixels=True,
+                            dilation_kernel_size=c["ksize"], dilation_kernel_shape=c["shape"])
+        enc.maps = maps.clone().requires_grad_(True)
+        x = torch.zeros(c["B"], c["T"], 3, 256, 256)
+        sp_feats, _ = crw.image_to_nodes(x, lab3, c["SP"])
+        g = torch.Generator().manual_seed(c["seed"] + 7)
+        proj = torch.randn(sp_feats.shape, generator=g)
+        (sp_feats * proj).sum().backward()
+        fx = dict(sp_feats=sp_feats.detach().clone(), grad_maps=enc.maps.grad.clone(), grad_head=crw.selfsim_fc[0].weight.grad.clone())
+        torch.save(fx, os.path.join(OUT, name + ".pt"))
+        print("golden", name, tuple(sp_feats.shape))
+
+
 def gen_lp(ref_model, ref_utils, ref_tu):
     """Runs the reference's own evaluator loop (test.py:67-160) on a fake loader / fake encoder and
     captures (Ws, Is) from mem_efficient_batched_affinity and each `pred` handed to dump_predictions."""
@@ -228,10 +246,14 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "post":           # only the post-processing fixtures (added later)
         gen_post(ref_model, ref_utils, ref_tu)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "spd":            # only the dilated-superpixel fixtures (added later)
+        gen_spd(ref_model, ref_utils)
+        return
     gen_misc(ref_model, ref_utils, ref_tu)
     gen_post(ref_model, ref_utils, ref_tu)
     gen_walk(ref_model, ref_utils)
     gen_sp(ref_model, ref_utils)
+    gen_spd(ref_model, ref_utils)
     gen_lp(ref_model, ref_utils, ref_tu)
     gen_cfg1(ref_model, ref_utils)
 

@@ -27,6 +27,7 @@ WALK_FORCE_TC = 16
 WALK_NO_CLUSTER = 32
 WALK_NO_TF32 = 64
 LP_FORCE_SIMT = 1
+DILATE_SHAPES = {"L1": 0, "circle": 1, "cross": 2}                # CRW_DILATE_* (utils/__init__.py:590-608 kernel names)
 
 _SIGNATURES = {
     "crw_version": (c_int, []),
@@ -37,6 +38,10 @@ _SIGNATURES = {
     "crw_segmean_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64] + [c_int] * 8
                         + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_segmean_bwd": (c_int, [c_void_p, c_void_p, c_size_t] + [c_int] * 8 + [c_void_p, c_void_p]),
+    "crw_segmean_dilated_workspace_bytes": (c_size_t, [c_int] * 7),
+    "crw_segmean_dilated_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64] + [c_int] * 10
+                                + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crw_segmean_dilated_bwd": (c_int, [c_void_p, c_void_p, c_size_t] + [c_int] * 8 + [c_void_p, c_void_p]),
     "crw_affinity": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "crw_stoch_mat": (c_int, [c_void_p, c_void_p, c_float, c_float, c_uint32, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "crw_walk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_uint32]),

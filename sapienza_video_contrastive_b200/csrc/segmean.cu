@@ -110,6 +110,134 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
     }
 }
 
+// ---- dilated superpixel masks (model.py:303-309, utils/__init__.py:590-608) -------------------------------
+// The reference dilates every label's one-hot mask with a 51..55-pixel structuring element (a depthwise 55 x 55 convolution
+// over T*SP channels, thresholded at > 0), so masks overlap and a pixel carries a SET of labels.  Here the element is
+// described by its half-width per vertical offset, w(dy) (diamond: R - |dy|, disc: floor(sqrt(R^2 - dy^2)), cross: R at
+// dy = 0 and 0 elsewhere), and a label s reaches pixel (y, x) iff some row y' = y + dy holds a run of s whose x-range,
+// widened by w(dy), covers x.  Pass 1 turns every label row into its runs; pass 2 (a warp per feature cell) sweeps the rows
+// the cell's pixels can see, builds the pixels' label sets as bitsets in shared memory and emits the cell's (label, count)
+// list - the same lists the undilated path produces, so the CSR / accumulate / backward kernels are shared.
+constexpr int kDilMaxR = 63;            // structuring element up to 127 x 127
+constexpr int kDilWords = 8;            // label bitset: SP <= 255 in the dilated path
+constexpr unsigned kDilBadLabel = 0x3ffu;
+
+struct DilArgs {
+    const int64_t* labels;
+    int64_t ls_b, ls_t, ls_y, ls_x;
+    int T, Hm, Wm, sy, sx, h, w, SP, R;
+    unsigned* runs;              // (B*T, h, w): label << 16 | x0 of every run, in x order (x1 = next x0 - 1)
+    int* nruns;                  // (B*T, h)
+    unsigned char hw[kDilMaxR + 1];
+};
+
+// pass 1: one warp per label row
+__global__ void __launch_bounds__(256) segdil_runs_kernel(DilArgs a, int64_t total_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < total_rows; row += nw) {
+        const int64_t bt = row / a.h;
+        const int y = (int)(row - bt * a.h);
+        const int b = (int)(bt / a.T), t = (int)(bt - (int64_t)b * a.T);
+        const int64_t* src = a.labels + b * a.ls_b + t * a.ls_t + (int64_t)y * a.ls_y;
+        unsigned* out = a.runs + row * a.w;
+        int n = 0;
+        unsigned prev_last = 0xffffffffu;                   // label of the last pixel of the previous 32-pixel chunk
+        for (int x0 = 0; x0 < a.w; x0 += 32) {
+            const int x = x0 + lane;
+            unsigned lab = 0xfffffffeu;
+            if (x < a.w) {
+                const int64_t L = src[(int64_t)x * a.ls_x];
+                lab = (L >= 0 && L < a.SP) ? (unsigned)L : kDilBadLabel;
+            }
+            unsigned prev = __shfl_up_sync(kFull, lab, 1);
+            if (lane == 0) prev = prev_last;
+            const bool start = x < a.w && lab != prev;
+            const unsigned m = __ballot_sync(kFull, start);
+            if (start) out[n + __popc(m & ((1u << lane) - 1u))] = (lab << 16) | (unsigned)x;
+            n += __popc(m);
+            prev_last = __shfl_sync(kFull, lab, 31);
+        }
+        if (lane == 0) a.nruns[row] = n;
+    }
+}
+
+// pass 2: one warp per feature cell; lanes own the cell's pixels (two each), their label sets live in shared memory
+__global__ void __launch_bounds__(256) segdil_count_kernel(DilArgs a, SegWs ws, int64_t total_cells) {
+    __shared__ unsigned sbits[8][64][kDilWords + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int cells = a.Hm * a.Wm, npix = a.sy * a.sx;
+    unsigned (*bits)[kDilWords + 1] = sbits[wib];
+    for (int64_t gc = warp; gc < total_cells; gc += nw) {
+        const int64_t bt = gc / cells;
+        const int cell = (int)(gc - bt * cells);
+        const int cy = cell / a.Wm, cx = cell - cy * a.Wm;
+        int py[2], px[2];
+        bool live[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int pix = lane + 32 * h2;
+            live[h2] = pix < npix;
+            const int ly = live[h2] ? pix / a.sx : 0;
+            py[h2] = cy * a.sy + ly;
+            px[h2] = cx * a.sx + (live[h2] ? pix - ly * a.sx : 0);
+#pragma unroll
+            for (int k = 0; k < kDilWords; ++k) bits[pix][k] = 0u;
+        }
+        __syncwarp();
+        const int ylo = max(0, cy * a.sy - a.R), yhi = min(a.h - 1, cy * a.sy + a.sy - 1 + a.R);
+        for (int yy = ylo; yy <= yhi; ++yy) {
+            const int64_t row = bt * a.h + yy;
+            const unsigned* rr = a.runs + row * a.w;
+            const int nr = __ldg(a.nruns + row);
+            int wv[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int dy = abs(yy - py[h2]);
+                wv[h2] = (live[h2] && dy <= a.R) ? (int)a.hw[dy] : -1;         // -1: this row cannot reach the pixel
+            }
+            unsigned rec = nr > 0 ? __ldg(rr) : 0u;
+            for (int i = 0; i < nr; ++i) {
+                const unsigned nxt = i + 1 < nr ? __ldg(rr + i + 1) : 0u;
+                const unsigned lab = rec >> 16;
+                const int x0 = (int)(rec & 0xffffu), x1 = i + 1 < nr ? (int)(nxt & 0xffffu) - 1 : a.w - 1;
+                if (lab != kDilBadLabel) {
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2)
+                        if (wv[h2] >= 0 && px[h2] >= x0 - wv[h2] && px[h2] <= x1 + wv[h2])
+                            bits[lane + 32 * h2][lab >> 5] |= 1u << (lab & 31u);
+                }
+                rec = nxt;
+            }
+        }
+        __syncwarp();
+        // the cell's (label, count) list, labels ascending
+        int n = 0;
+        for (int k = 0; k < kDilWords; ++k) {
+            const unsigned b0 = bits[lane][k], b1 = bits[lane + 32][k];
+            unsigned u = b0 | b1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) u |= __shfl_xor_sync(kFull, u, o);
+            while (u) {
+                const int bit = __ffs((int)u) - 1;
+                u &= u - 1;
+                const int cnt = __popc(__ballot_sync(kFull, (b0 >> bit) & 1u)) + __popc(__ballot_sync(kFull, (b1 >> bit) & 1u));
+                const int lab = k * 32 + bit;
+                if (lane == 0) {
+                    ws.ent[((int64_t)bt * ws.cap + n) * cells + cell] = ((unsigned)lab << 8) | (unsigned)cnt;
+                    atomicAdd(ws.size + bt * a.SP + lab, cnt);
+                }
+                ++n;
+            }
+        }
+        if (lane == 0) ws.nent[bt * cells + cell] = (unsigned char)n;
+        __syncwarp();
+    }
+}
+
 // CSR of one (clip, frame), one CTA: entries ordered by (chunk of kSegChunk cells, label, cell).  A per-label bitmask over
 // the cells (shared memory) gives every (cell, label) entry its rank inside its (chunk, label) group by popcount, so the
 // order needs no sort and no atomics on the positions: deterministic.  Needs cells <= 1024 (32 mask words per label).
@@ -563,6 +691,9 @@ extern "C" size_t crw_segmean_workspace_bytes(int B, int T, int Hm, int Wm, int 
     return seg_ws(nullptr, B, T, Hm * Wm, SP, cap).bytes;
 }
 
+// everything after the per-cell (label, count) lists: CSR, then the accumulation
+static int seg_fwd_tail(const float* maps, const SegWs& ws, int B, int C, int T, int cells, int SP, float* out, crw_stream_t stream);
+
 extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t ls_b, int64_t ls_t, int64_t ls_y, int64_t ls_x,
                                int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
                                float* out, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
@@ -578,6 +709,11 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     CRW_LAUNCH(segmean_count_kernel, grid1, 256, 0, stream, labels, ls_b, ls_t, ls_y, ls_x, T, Hm, Wm, h / Hm, w / Wm, SP, ws, total);
     e = check_launch("segmean_count");
     if (e != CRW_OK) return e;
+    return seg_fwd_tail(maps, ws, B, C, T, cells, SP, out, stream);
+}
+
+static int seg_fwd_tail(const float* maps, const SegWs& ws, int B, int C, int T, int cells, int SP, float* out, crw_stream_t stream) {
+    int e;
     if (cells > 1024 || SP > 1024 || (size_t)SP * 33 * 4 > 200 * 1024) {
         set_error("segmean_fwd: unsupported size (cells=%d, SP=%d)", cells, SP);
         return CRW_ERR_UNSUPPORTED;
@@ -631,6 +767,8 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     return check_launch("segmean_accum");
 }
 
+static int seg_bwd_run(const float* grad_out, const SegWs& ws, int B, int C, int T, int cells, int SP, float* grad_maps, crw_stream_t stream);
+
 extern "C" int crw_segmean_bwd(const float* grad_out, const void* workspace, size_t workspace_bytes,
                                int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
                                float* grad_maps, crw_stream_t stream) {
@@ -640,10 +778,90 @@ extern "C" int crw_segmean_bwd(const float* grad_out, const void* workspace, siz
     const int cells = Hm * Wm;
     SegWs ws = seg_ws(const_cast<void*>(workspace), B, T, cells, SP, cap);
     if (!workspace || workspace_bytes < ws.bytes) { set_error("segmean_bwd: workspace too small"); return CRW_ERR_SHAPE; }
+    return seg_bwd_run(grad_out, ws, B, C, T, cells, SP, grad_maps, stream);
+}
+
+static int seg_bwd_run(const float* grad_out, const SegWs& ws, int B, int C, int T, int cells, int SP, float* grad_maps, crw_stream_t stream) {
     const size_t smem = ((size_t)SP * kSegLDB + 2 * (size_t)SP) * sizeof(float);
     auto k = segmean_bwd_kernel;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((C + kSegCT - 1) / kSegCT, B * T);
     CRW_LAUNCH(k, grid, 256, smem, stream, grad_out, ws, C, T, cells, SP, grad_maps);
     return check_launch("segmean_bwd");
+}
+
+// ---- dilated masks: C ABI ----------------------------------------------------------------------------------------------
+// workspace = the plain layout with cap = SP (a cell can see every label), then the run records and per-row run counts
+static int segdil_check(int B, int C, int T, int Hm, int Wm, int h, int w, int SP, int ksize, int shape) {
+    int cap = 0;
+    int e = seg_check(B, C, T, Hm, Wm, h, w, SP, &cap);
+    if (e != CRW_OK) return e;
+    if (ksize < 1 || !(ksize & 1) || shape < CRW_DILATE_L1 || shape > CRW_DILATE_CROSS) {
+        set_error("segmean_dilated: kernel size %d must be odd and positive, shape %d one of CRW_DILATE_*", ksize, shape);
+        return CRW_ERR_SHAPE;
+    }
+    if (SP > 255 || w > 65535 || ksize / 2 > kDilMaxR) {
+        set_error("segmean_dilated: unsupported SP=%d (<= 255), width=%d or kernel size %d (<= %d)", SP, w, ksize, 2 * kDilMaxR + 1);
+        return CRW_ERR_UNSUPPORTED;
+    }
+    return CRW_OK;
+}
+
+static SegWs segdil_ws(void* base, int B, int T, int cells, int h, int w, int SP, unsigned** runs, int** nruns) {
+    SegWs ws = seg_ws(base, B, T, cells, SP, SP);
+    *runs = (unsigned*)((char*)base + ws.bytes);
+    ws.bytes += ((size_t)B * T * h * w * sizeof(unsigned) + 255) / 256 * 256;
+    *nruns = (int*)((char*)base + ws.bytes);
+    ws.bytes += ((size_t)B * T * h * sizeof(int) + 255) / 256 * 256;
+    return ws;
+}
+
+extern "C" size_t crw_segmean_dilated_workspace_bytes(int B, int T, int Hm, int Wm, int h, int w, int SP) {
+    if (segdil_check(B, 1, T, Hm, Wm, h, w, SP, 1, CRW_DILATE_L1) != CRW_OK) return 0;
+    unsigned* runs;
+    int* nruns;
+    return segdil_ws(nullptr, B, T, Hm * Wm, h, w, SP, &runs, &nruns).bytes;
+}
+
+extern "C" int crw_segmean_dilated_fwd(const float* maps, const int64_t* labels, int64_t ls_b, int64_t ls_t, int64_t ls_y, int64_t ls_x,
+                                       int B, int C, int T, int Hm, int Wm, int h, int w, int SP, int ksize, int shape,
+                                       float* out, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
+    int e = segdil_check(B, C, T, Hm, Wm, h, w, SP, ksize, shape);
+    if (e != CRW_OK) return e;
+    const int cells = Hm * Wm;
+    DilArgs a{};
+    SegWs ws = segdil_ws(workspace, B, T, cells, h, w, SP, &a.runs, &a.nruns);
+    if (!workspace || workspace_bytes < ws.bytes) { set_error("segmean_dilated_fwd: workspace too small"); return CRW_ERR_SHAPE; }
+    a.labels = labels; a.ls_b = ls_b; a.ls_t = ls_t; a.ls_y = ls_y; a.ls_x = ls_x;
+    a.T = T; a.Hm = Hm; a.Wm = Wm; a.sy = h / Hm; a.sx = w / Wm; a.h = h; a.w = w; a.SP = SP; a.R = ksize / 2;
+    for (int dy = 0; dy <= a.R; ++dy) {                                 // the structuring elements of utils/__init__.py:590-608
+        int wv;
+        if (shape == CRW_DILATE_L1) wv = a.R - dy;
+        else if (shape == CRW_DILATE_CROSS) wv = dy == 0 ? a.R : 0;
+        else for (wv = 0; (wv + 1) * (wv + 1) + dy * dy <= a.R * a.R; ++wv) {}
+        a.hw[dy] = (unsigned char)wv;
+    }
+    cudaMemsetAsync(ws.size, 0, sizeof(int) * (size_t)B * T * SP, (cudaStream_t)stream);
+    const int64_t rows = (int64_t)B * T * h, total = (int64_t)B * T * cells;
+    const int grid0 = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
+    CRW_LAUNCH(segdil_runs_kernel, grid0, 256, 0, stream, a, rows);
+    e = check_launch("segdil_runs");
+    if (e != CRW_OK) return e;
+    const int grid1 = (int)((total + 7) / 8 < 148 * 8 ? (total + 7) / 8 : 148 * 8);
+    CRW_LAUNCH(segdil_count_kernel, grid1, 256, 0, stream, a, ws, total);
+    e = check_launch("segdil_count");
+    if (e != CRW_OK) return e;
+    return seg_fwd_tail(maps, ws, B, C, T, cells, SP, out, stream);
+}
+
+extern "C" int crw_segmean_dilated_bwd(const float* grad_out, const void* workspace, size_t workspace_bytes,
+                                       int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
+                                       float* grad_maps, crw_stream_t stream) {
+    int e = segdil_check(B, C, T, Hm, Wm, h, w, SP, 1, CRW_DILATE_L1);
+    if (e != CRW_OK) return e;
+    unsigned* runs;
+    int* nruns;
+    SegWs ws = segdil_ws(const_cast<void*>(workspace), B, T, Hm * Wm, h, w, SP, &runs, &nruns);
+    if (!workspace || workspace_bytes < ws.bytes) { set_error("segmean_dilated_bwd: workspace too small"); return CRW_ERR_SHAPE; }
+    return seg_bwd_run(grad_out, ws, B, C, T, Hm * Wm, SP, grad_maps, stream);
 }

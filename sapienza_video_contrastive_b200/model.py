@@ -56,9 +56,17 @@ class CRW(nn.Module):
         self.flip = getattr(args, "flip", False)
         self.sk_targets = getattr(args, "sk_targets", False)
         self.vis = vis
+        # superpixel mask dilation (model.py:38, 303-309): the reference materialises a fp16 structuring element and runs a
+        # depthwise convolution over the one-hot masks; here the element is only its (size, shape) and the pooling kernels
+        # dilate label runs directly (ops.segment_mean_dilated)
+        self.dilation = None
         if getattr(args, "dilate_superpixels", False):
-            raise NotImplementedError("superpixel mask dilation (model.py:303-309) is not part of this build (DESIGN.md, next)")
-        self.dilation_kernel = None
+            ksize = int(getattr(args, "dilation_kernel_size", 51))               # utils/arguments.py:209-210 defaults
+            shape = getattr(args, "dilation_kernel_shape", "L1")
+            assert ksize % 2 != 0, "Use an odd kernel size"                      # utils/__init__.py:591
+            if shape not in ("L1", "circle", "cross"):
+                raise ValueError("dilation_kernel_shape must be L1 | circle | cross, got %r" % (shape,))
+            self.dilation = (ksize, shape)
         # 'philox': edge dropout is drawn inside the walk kernel from torch's CUDA generator stream (same numbers,
         # same generator advance as the reference's rand_like calls); 'torch': drawn by torch.rand and passed in.
         self.rng = getattr(args, "crw_rng", "auto")
@@ -173,7 +181,10 @@ class CRW(nn.Module):
         if self.featdrop_rate > 0:
             maps = self.featdrop(maps)
         labels = sp_mask[:, :, 0, :, :]                                          # strided view, no copy (model.py:298)
-        pooled = ops.segment_mean(maps, labels, int(max_sp_num))                 # (B, SP, T, C')
+        if self.dilation is None:
+            pooled = ops.segment_mean(maps, labels, int(max_sp_num))             # (B, SP, T, C')
+        else:
+            pooled = ops.segment_mean_dilated(maps, labels, int(max_sp_num), *self.dilation)
         return self._head(pooled), maps                                          # (B, SP, T, D)
 
     # -- forward (model.py:334-415) ----------------------------------------------------------------------------------

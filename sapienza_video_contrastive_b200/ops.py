@@ -224,7 +224,7 @@ def head_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------------------------
 class _SegMean(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, maps, labels, SP):
+    def forward(ctx, maps, labels, SP, dilation):
         _need_cuda(maps, labels)
         check_device(maps.device)
         maps = _f32c(maps)
@@ -235,16 +235,24 @@ class _SegMean(torch.autograd.Function):
             raise ValueError("labels must be (B,T,h,w), got %s" % (tuple(labels.shape),))
         h, w = labels.shape[-2:]
         L = _lib.lib()
-        nbytes = L.crw_segmean_workspace_bytes(B, T, Hm, Wm, h, w, SP)
+        size_fn = L.crw_segmean_workspace_bytes if dilation is None else L.crw_segmean_dilated_workspace_bytes
+        nbytes = size_fn(B, T, Hm, Wm, h, w, SP)
         if nbytes == 0:
             raise _lib.CrwError("segmean: %s" % L.crw_last_error().decode())
         ws = torch.empty(nbytes, dtype=torch.uint8, device=maps.device)     # kept for the backward
         out = torch.empty(B, SP, T, C, dtype=torch.float32, device=maps.device)
         sb, st, sy, sx = labels.stride()
-        L.check(L.crw_segmean_fwd(maps.data_ptr(), labels.data_ptr(), sb, st, sy, sx, B, C, T, Hm, Wm, h, w, SP,
-                                  out.data_ptr(), ws.data_ptr(), nbytes, _stream()), "segmean_fwd")
+        if dilation is None:
+            L.check(L.crw_segmean_fwd(maps.data_ptr(), labels.data_ptr(), sb, st, sy, sx, B, C, T, Hm, Wm, h, w, SP,
+                                      out.data_ptr(), ws.data_ptr(), nbytes, _stream()), "segmean_fwd")
+        else:
+            ksize, shape = dilation
+            L.check(L.crw_segmean_dilated_fwd(maps.data_ptr(), labels.data_ptr(), sb, st, sy, sx, B, C, T, Hm, Wm, h, w, SP,
+                                              int(ksize), _lib.DILATE_SHAPES[shape], out.data_ptr(), ws.data_ptr(), nbytes,
+                                              _stream()), "segmean_dilated_fwd")
         ctx.ws = ws
         ctx.dims = (B, C, T, Hm, Wm, h, w, SP)
+        ctx.dilated = dilation is not None
         return out
 
     @staticmethod
@@ -253,14 +261,23 @@ class _SegMean(torch.autograd.Function):
         B, C, T, Hm, Wm, h, w, SP = ctx.dims
         gm = torch.empty(B, C, T, Hm, Wm, dtype=torch.float32, device=g.device)
         L = _lib.lib()
-        L.check(L.crw_segmean_bwd(g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), B, C, T, Hm, Wm, h, w, SP,
-                                  gm.data_ptr(), _stream()), "segmean_bwd")
-        return gm, None, None
+        fn = L.crw_segmean_dilated_bwd if ctx.dilated else L.crw_segmean_bwd
+        L.check(fn(g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), B, C, T, Hm, Wm, h, w, SP, gm.data_ptr(), _stream()),
+                "segmean_bwd")
+        return gm, None, None, None
 
 
 def segment_mean(maps: torch.Tensor, labels: torch.Tensor, SP: int) -> torch.Tensor:
     """maps (B,C,T,Hm,Wm), labels (B,T,h,w) integer (any strides) -> (B,SP,T,C) per-superpixel feature means."""
-    return _SegMean.apply(maps, labels, int(SP))
+    return _SegMean.apply(maps, labels, int(SP), None)
+
+
+def segment_mean_dilated(maps: torch.Tensor, labels: torch.Tensor, SP: int, ksize: int, shape: str = "L1") -> torch.Tensor:
+    """segment_mean over masks dilated by a ksize x ksize 'L1' | 'circle' | 'cross' structuring element
+    (model.py:303-309, utils/__init__.py:590-608): overlapping masks, sizes and window counts of the dilated masks."""
+    if shape not in _lib.DILATE_SHAPES:
+        raise ValueError("dilation kernel shape must be one of %s, got %r" % (sorted(_lib.DILATE_SHAPES), shape))
+    return _SegMean.apply(maps, labels, int(SP), (int(ksize), shape))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -25,6 +25,13 @@ SP_CASES = {
     "sp_40_empty": dict(B=2, T=3, SP=40, Ce=16, one_based=True, p=0.1, tau=0.07, seed=22),
 }
 
+# dilated superpixel cases (model.py:303-309, utils/__init__.py:590-608): all three structuring elements, an empty node
+SPD_CASES = {
+    "spd_l1":     dict(B=1, T=2, SP=14, Ce=16, one_based=False, ksize=11, shape="L1", seed=51),
+    "spd_circle": dict(B=1, T=2, SP=12, Ce=16, one_based=True, ksize=15, shape="circle", seed=52),
+    "spd_cross":  dict(B=2, T=1, SP=20, Ce=8, one_based=False, ksize=21, shape="cross", seed=53),
+}
+
 # label-propagation cases (test_utils.py:148-179, test.py:141-160)
 LP_CASES = {
     "lp_small":   dict(C=16, h=12, w=17, n_ctx=4, n_tgt=6, long_mem=[0], radius=3, k=5, tau=0.07, L=3,

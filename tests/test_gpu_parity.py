@@ -354,6 +354,49 @@ def test_superpixel_nodes_and_walk_match_reference(ops, name):
     assert relmax(md.grad.cpu(), fx["grad_maps"]) < 1e-4
 
 
+@pytest.mark.parametrize("name", list(cases.SPD_CASES))
+def test_dilated_superpixel_nodes_match_reference(ops, name):
+    """--dilate-superpixels (model.py:303-309): pooled features against the oracle, node embeddings and the gradients of
+    the maps and the head against the reference's fixtures (its fp16 depthwise-convolution dilation)."""
+    c = cases.SPD_CASES[name]
+    fx = load(name)
+    maps, lab3, head_w = cases.sp_inputs(c)
+    md = maps.to(DEV).requires_grad_(True)
+    hd = head_w.to(DEV).requires_grad_(True)
+    lab = lab3.to(DEV)[:, :, 0]
+    pooled = ops.segment_mean_dilated(md, lab, c["SP"], c["ksize"], c["shape"])          # (B,SP,T,Ce)
+    ref = O.segment_mean_dilated(maps, lab3[:, :, 0], c["SP"], c["ksize"], c["shape"])
+    torch.testing.assert_close(pooled.detach().cpu().transpose(1, 2), ref, rtol=1e-5, atol=1e-6)
+    q = ops.l2_normalize_last(pooled @ hd.t()).permute(0, 3, 2, 1)                      # (B,D,T,SP)
+    torch.testing.assert_close(q.detach().cpu(), fx["sp_feats"], rtol=1e-4, atol=2e-6)
+    proj = torch.randn(q.shape, generator=torch.Generator().manual_seed(c["seed"] + 7))
+    (q * proj.to(DEV)).sum().backward()
+    assert relmax(md.grad.cpu(), fx["grad_maps"]) < 1e-4
+    assert relmax(hd.grad.cpu(), fx["grad_head"]) < 1e-4
+
+
+def test_dilated_superpixels_reference_default_element(ops):
+    """The reference's default element (51 x 51 diamond, utils/arguments.py:209-210) at the BASELINE config 3 shape: a
+    frame against the oracle, a 1 x 1 element is the undilated pooling, constants are reproduced for every label present,
+    dilated sizes never shrink, and the module routes --dilate-superpixels here."""
+    B, C, T, SP = 2, 128, 4, 196
+    g = torch.Generator().manual_seed(11)
+    lab = cases.voronoi_labels(B, T, SP, 256, g, one_based=True)
+    maps = torch.randn(B, C, T, 32, 32, generator=g)
+    md, ld = maps.to(DEV), lab.to(DEV)
+    out = ops.segment_mean_dilated(md, ld, SP, 51, "L1")
+    ref = O.segment_mean_dilated(maps[:1, :, :1], lab[:1, :1], SP, 51, "L1")
+    torch.testing.assert_close(out[:1, :, :1].cpu().transpose(1, 2), ref, rtol=1e-5, atol=1e-6)
+    assert torch.equal(ops.segment_mean_dilated(md, ld, SP, 1, "circle"), ops.segment_mean(md, ld, SP))
+    ones = ops.segment_mean_dilated(torch.ones_like(md), ld, SP, 51, "cross")
+    present = torch.zeros(B, T, SP, device=DEV).scatter_(2, ld.flatten(2), 1.0).transpose(1, 2)
+    torch.testing.assert_close(ones[..., 0], present, rtol=1e-6, atol=1e-6)
+    with pytest.raises(Exception):
+        ops.segment_mean_dilated(md, ld, 300, 51, "L1")                                  # SP <= 255 in the dilated path
+    with pytest.raises(ValueError):
+        ops.segment_mean_dilated(md, ld, SP, 51, "square")
+
+
 def test_segmean_config3_shape_properties(ops):
     """BASELINE config 3 shape: constants are reproduced, sizes partition the image, empty labels give zero rows."""
     B, C, T, SP = 2, 512, 8, 196

@@ -30,6 +30,8 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert lib.crw_walk_workspace_bytes(20, 49, 4, 128, 0) > 0
     assert lib.crw_walk_workspace_bytes(20, 49, 4, 128, _lib.WALK_FORCE_GENERAL) > 0
     assert lib.crw_segmean_workspace_bytes(2, 3, 32, 32, 256, 256, 100) > 0
+    assert lib.crw_segmean_dilated_workspace_bytes(2, 3, 32, 32, 256, 256, 100) > lib.crw_segmean_workspace_bytes(2, 3, 32, 32, 256, 256, 100)
+    assert lib.crw_segmean_dilated_workspace_bytes(2, 3, 32, 32, 256, 256, 256) == 0          # SP <= 255 in the dilated path
 
 
 def test_flag_constants_match_the_header():
@@ -99,5 +101,10 @@ def test_crw_module_surface_on_cpu():
     assert torch.equal(crw.xent_targets(torch.zeros(2, 5, 5)), torch.arange(5).repeat(2))
     with pytest.raises(RuntimeError):
         crw(torch.zeros(1, 4, 6, 64, 64))                       # CPU input: refused, no fallback
-    with pytest.raises(NotImplementedError):
-        CRW(argparse.Namespace(**{**vars(args), "dilate_superpixels": True}))
+    assert crw.dilation is None
+    dil = CRW(argparse.Namespace(**{**vars(args), "dilate_superpixels": True}))
+    assert dil.dilation == (51, "L1")                             # utils/arguments.py:209-210 defaults
+    with pytest.raises(AssertionError):                          # utils/__init__.py:591
+        CRW(argparse.Namespace(**{**vars(args), "dilate_superpixels": True, "dilation_kernel_size": 50}))
+    with pytest.raises(ValueError):
+        CRW(argparse.Namespace(**{**vars(args), "dilate_superpixels": True, "dilation_kernel_shape": "square"}))

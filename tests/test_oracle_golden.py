@@ -49,6 +49,26 @@ def test_walk_matches_reference(name):
     torch.testing.assert_close(torch.stack(A21), fx["A21"], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", list(cases.SPD_CASES))
+def test_dilated_superpixel_matches_reference(name):
+    """--dilate-superpixels (model.py:303-309): the oracle's run-free restatement against the reference's fp16 depthwise
+    convolution, for the three structuring elements of utils/__init__.py:590-608."""
+    c = cases.SPD_CASES[name]
+    fx = load(name)
+    maps, lab3, head_w = cases.sp_inputs(c)
+    pooled = O.segment_mean_dilated(maps, lab3[:, :, 0], c["SP"], c["ksize"], c["shape"])       # (B,T,SP,C)
+    f = pooled @ head_w.t()
+    q = (f / f.norm(dim=-1, keepdim=True).clamp_min(1e-12)).permute(0, 3, 1, 2)
+    torch.testing.assert_close(q, fx["sp_feats"], rtol=1e-4, atol=2e-6)
+    if c["one_based"]:
+        assert q[:, :, :, 0].abs().max() == 0
+    # the element is symmetric, R wide on its centre row and a single pixel on its first and last rows
+    hw = O.dilation_halfwidths(c["ksize"], c["shape"])
+    R = c["ksize"] // 2
+    assert len(hw) == c["ksize"] and hw[R] == R and hw == hw[::-1] and hw[0] == 0
+    assert c["shape"] != "cross" or set(hw[:R]) == {0}
+
+
 @pytest.mark.parametrize("name", list(cases.SP_CASES))
 def test_superpixel_matches_reference(name):
     c = cases.SP_CASES[name]

@@ -225,6 +225,66 @@ def test_segmean_bulk_copy_path_vs_oracle(sim, B, T, C, Hm, scale, SP):
     torch.testing.assert_close(gm, m2.grad, rtol=1e-4, atol=1e-6)
 
 
+DILATE = {"L1": 0, "circle": 1, "cross": 2}
+
+
+@pytest.mark.parametrize("name", list(cases.SPD_CASES))
+def test_segmean_dilated_vs_reference_golden(sim, name):
+    """--dilate-superpixels (model.py:303-309): the run-dilating kernels against the reference's conv2d-dilated pooling,
+    forward through the head to the golden node embeddings, backward to the golden gradient of the maps."""
+    c = cases.SPD_CASES[name]
+    fx = load(name)
+    maps, lab3, head_w = cases.sp_inputs(c)
+    B, Ce, T = maps.shape[:3]
+    SP = c["SP"]
+    wsb = sim.crw_segmean_dilated_workspace_bytes(B, T, 32, 32, 256, 256, SP)
+    assert wsb > sim.crw_segmean_workspace_bytes(B, T, 32, 32, 256, 256, SP)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    out = torch.empty(B, SP, T, Ce)
+    lab = lab3[:, :, 0]
+    sb, st, sy, sx = lab.stride()
+    sim.check(sim.crw_segmean_dilated_fwd(ptr(maps), ptr(lab), sb, st, sy, sx, B, Ce, T, 32, 32, 256, 256, SP, c["ksize"],
+                                          DILATE[c["shape"]], ptr(out), ptr(ws), wsb, None))
+    torch.testing.assert_close(out.transpose(1, 2), O.segment_mean_dilated(maps, lab, SP, c["ksize"], c["shape"]), rtol=1e-5, atol=1e-6)
+    pooled = out.clone().requires_grad_(True)
+    f = pooled @ head_w.t()
+    q = (f / f.norm(dim=-1, keepdim=True).clamp_min(1e-12)).permute(0, 3, 2, 1)
+    torch.testing.assert_close(q.detach(), fx["sp_feats"], rtol=1e-4, atol=2e-6)
+    g = torch.Generator().manual_seed(c["seed"] + 7)
+    proj = torch.randn(q.shape, generator=g)                    # the functional gen_spd differentiated
+    (q * proj).sum().backward()
+    gm = torch.empty_like(maps)
+    sim.check(sim.crw_segmean_dilated_bwd(ptr(pooled.grad.contiguous()), ptr(ws), wsb, B, Ce, T, 32, 32, 256, 256, SP, ptr(gm), None))
+    torch.testing.assert_close(gm, fx["grad_maps"], rtol=1e-4, atol=1e-6)
+
+
+def test_segmean_dilated_edges(sim):
+    """ksize 1 is the undilated pooling; out-of-range labels dilate nothing; rectangular cells and a non-square image;
+    arguments the kernels cannot take are refused."""
+    g = torch.Generator().manual_seed(77)
+    B, T, C, Hm, Wm, sy, sx, SP = 1, 2, 8, 6, 10, 4, 2, 9
+    h, w = Hm * sy, Wm * sx
+    maps = torch.randn(B, C, T, Hm, Wm, generator=g)
+    lab = torch.randint(0, SP, (B, T, h // 3, w // 4 + 1), generator=g).repeat_interleave(3, 2).repeat_interleave(4, 3)[..., :h, :w].contiguous()
+    lab[:, :, :2, :3] = SP + 1
+    lab[:, :, -1, :] = -5
+    sb, st, ss_y, ss_x = lab.stride()
+    wsb = sim.crw_segmean_dilated_workspace_bytes(B, T, Hm, Wm, h, w, SP)
+    for ksize, shape in [(1, "L1"), (5, "L1"), (7, "circle"), (9, "cross"), (2 * h + 1, "circle")]:
+        ws = torch.zeros(wsb, dtype=torch.uint8)
+        out = torch.empty(B, SP, T, C)
+        sim.check(sim.crw_segmean_dilated_fwd(ptr(maps), ptr(lab), sb, st, ss_y, ss_x, B, C, T, Hm, Wm, h, w, SP, ksize, DILATE[shape],
+                                              ptr(out), ptr(ws), wsb, None))
+        ref = O.segment_mean(maps, lab, SP) if ksize == 1 else O.segment_mean_dilated(maps, lab, SP, ksize, shape)
+        torch.testing.assert_close(out.transpose(1, 2), ref, rtol=1e-5, atol=1e-6)
+    out = torch.empty(B, SP, T, C)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    assert sim.crw_segmean_dilated_fwd(ptr(maps), ptr(lab), sb, st, ss_y, ss_x, B, C, T, Hm, Wm, h, w, SP, 4, 0, ptr(out), ptr(ws), wsb, None) != 0
+    assert sim.crw_segmean_dilated_fwd(ptr(maps), ptr(lab), sb, st, ss_y, ss_x, B, C, T, Hm, Wm, h, w, SP, 5, 3, ptr(out), ptr(ws), wsb, None) != 0
+    assert sim.crw_segmean_dilated_fwd(ptr(maps), ptr(lab), sb, st, ss_y, ss_x, B, C, T, Hm, Wm, h, w, SP, 129, 0, ptr(out), ptr(ws), wsb, None) != 0
+    assert sim.crw_segmean_dilated_workspace_bytes(B, T, Hm, Wm, h, w, 256) == 0
+
+
 def check_label_images(cls, rgb, pred, lbl_set, c, fx):
     """Class map / label image of the kernel against the reference's dump_predictions output.  OpenCV's vectorised resize
     may fuse or reorder the two interpolation passes, so a pixel may legitimately differ only where the two best classes of
