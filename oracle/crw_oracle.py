@@ -299,6 +299,8 @@ def segment_mean_dilated(maps: torch.Tensor, labels: torch.Tensor, SP: int, ksiz
             onehot[lab[ys, xs], ys, xs] = True
             dil = torch.zeros_like(onehot)
             for i, dy in enumerate(range(-R, R + 1)):
+                if abs(dy) >= h:
+                    continue
                 # rows shifted by dy, dilated horizontally by hw_[i]
                 src = torch.zeros_like(onehot)
                 if dy >= 0:

@@ -129,6 +129,7 @@ struct DilArgs {
     unsigned* runs;              // (B*T, h, w): label << 16 | x0 of every run, in x order (x1 = next x0 - 1)
     int* nruns;                  // (B*T, h)
     unsigned char hw[kDilMaxR + 1];
+    int NW, cpc, nxc;            // pass 2 strips: 32-column words and cells per strip, strips per row of cells
 };
 
 // pass 1: one warp per label row
@@ -163,78 +164,76 @@ __global__ void __launch_bounds__(256) segdil_runs_kernel(DilArgs a, int64_t tot
     }
 }
 
-// pass 2: one warp per feature cell; lanes own the cell's pixels (two each), their label sets live in shared memory
-__global__ void __launch_bounds__(256) segdil_count_kernel(DilArgs a, SegWs ws, int64_t total_cells) {
-    __shared__ unsigned sbits[8][64][kDilWords + 1];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int cells = a.Hm * a.Wm, npix = a.sy * a.sx;
-    unsigned (*bits)[kDilWords + 1] = sbits[wib];
-    for (int64_t gc = warp; gc < total_cells; gc += nw) {
-        const int64_t bt = gc / cells;
-        const int cell = (int)(gc - bt * cells);
-        const int cy = cell / a.Wm, cx = cell - cy * a.Wm;
-        int py[2], px[2];
-        bool live[2];
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int pix = lane + 32 * h2;
-            live[h2] = pix < npix;
-            const int ly = live[h2] ? pix / a.sx : 0;
-            py[h2] = cy * a.sy + ly;
-            px[h2] = cx * a.sx + (live[h2] ? pix - ly * a.sx : 0);
-#pragma unroll
-            for (int k = 0; k < kDilWords; ++k) bits[pix][k] = 0u;
-        }
-        __syncwarp();
-        const int ylo = max(0, cy * a.sy - a.R), yhi = min(a.h - 1, cy * a.sy + a.sy - 1 + a.R);
-        for (int yy = ylo; yy <= yhi; ++yy) {
-            const int64_t row = bt * a.h + yy;
-            const unsigned* rr = a.runs + row * a.w;
-            const int nr = __ldg(a.nruns + row);
-            int wv[2];
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                const int dy = abs(yy - py[h2]);
-                wv[h2] = (live[h2] && dy <= a.R) ? (int)a.hw[dy] : -1;         // -1: this row cannot reach the pixel
-            }
-            unsigned rec = nr > 0 ? __ldg(rr) : 0u;
-            for (int i = 0; i < nr; ++i) {
-                const unsigned nxt = i + 1 < nr ? __ldg(rr + i + 1) : 0u;
-                const unsigned lab = rec >> 16;
-                const int x0 = (int)(rec & 0xffffu), x1 = i + 1 < nr ? (int)(nxt & 0xffffu) - 1 : a.w - 1;
-                if (lab != kDilBadLabel) {
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2)
-                        if (wv[h2] >= 0 && px[h2] >= x0 - wv[h2] && px[h2] <= x1 + wv[h2])
-                            bits[lane + 32 * h2][lab >> 5] |= 1u << (lab & 31u);
+// pass 2: one CTA per (clip, frame, row of cells, chunk of <= 256 pixel columns).  The dilated masks of that strip are built
+// as BITMAPS in shared memory, cov[pixel row][32-column word][label]: a half-warp takes one label row the strip can see,
+// each lane one run of it, and ORs the run's widened interval into the bitmap of every pixel row it reaches (the work is
+// shared by all the cells of the strip instead of being repeated per cell).  A warp then turns one cell into its
+// (label, count) list: lanes own labels, a count is the popcount of the cell's columns over its pixel rows, and ballots
+// compact the list in label order - the same lists the undilated kernel writes.
+__global__ void __launch_bounds__(256) segdil_count_kernel(DilArgs a, SegWs ws) {
+    CRW_DYN_SMEM(smem_raw);
+    unsigned* cov = reinterpret_cast<unsigned*>(smem_raw);              // [sy][NW][SP]
+    __shared__ int shw[kDilMaxR + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int blk = blockIdx.x;
+    const int xc = blk % a.nxc;
+    blk /= a.nxc;
+    const int cy = blk % a.Hm, bt = blk / a.Hm;
+    const int cells = a.Hm * a.Wm;
+    const int cx_lo = xc * a.cpc, ncell = min(a.cpc, a.Wm - cx_lo);
+    const int X0 = cx_lo * a.sx, X1 = X0 + ncell * a.sx - 1, py0 = cy * a.sy;
+    for (int i = tid; i < a.sy * a.NW * a.SP; i += 256) cov[i] = 0u;
+    if (tid <= kDilMaxR) shw[tid] = a.hw[tid];
+    __syncthreads();
+    const int ylo = max(0, py0 - a.R), yhi = min(a.h - 1, py0 + a.sy - 1 + a.R);
+    for (int yy = ylo + (tid >> 4); yy <= yhi; yy += 16) {
+        const int wmax = shw[max(0, max(py0 - yy, yy - (py0 + a.sy - 1)))];     // the widest reach of this row into the strip
+        const int64_t row = (int64_t)bt * a.h + yy;
+        const unsigned* rr = a.runs + row * a.w;
+        const int nr = __ldg(a.nruns + row);
+        for (int i = tid & 15; i < nr; i += 16) {
+            const unsigned rec = __ldg(rr + i);
+            const unsigned lab = rec >> 16;
+            const int x0 = (int)(rec & 0xffffu);
+            const int x1 = i + 1 < nr ? (int)(__ldg(rr + i + 1) & 0xffffu) - 1 : a.w - 1;
+            if (lab == kDilBadLabel || x1 + wmax < X0 || x0 - wmax > X1) continue;
+            for (int ly = 0; ly < a.sy; ++ly) {
+                const int dy = abs(yy - (py0 + ly));
+                if (dy > a.R) continue;
+                const int wv = shw[dy];
+                const int lo = max(x0 - wv, X0) - X0, hi = min(x1 + wv, X1) - X0;
+                unsigned* base = cov + (size_t)ly * a.NW * a.SP + lab;
+                for (int wd = lo >> 5; wd <= hi >> 5; ++wd) {          // empty when lo > hi
+                    const int b0 = max(lo, wd * 32) - wd * 32, b1 = min(hi, wd * 32 + 31) - wd * 32;
+                    if (b0 <= b1) atomicOr(base + (size_t)wd * a.SP, (0xffffffffu >> (31 - (b1 - b0))) << b0);
                 }
-                rec = nxt;
             }
         }
-        __syncwarp();
-        // the cell's (label, count) list, labels ascending
+    }
+    __syncthreads();
+    const unsigned colmask = a.sx == 32 ? 0xffffffffu : (1u << a.sx) - 1u;
+    for (int c = warp; c < ncell; c += 8) {
+        const int cell = cy * a.Wm + cx_lo + c;
+        const int bit = c * a.sx, wd = bit >> 5, off = bit & 31;
+        const bool two = off + a.sx > 32;                               // the cell's columns straddle two words
         int n = 0;
-        for (int k = 0; k < kDilWords; ++k) {
-            const unsigned b0 = bits[lane][k], b1 = bits[lane + 32][k];
-            unsigned u = b0 | b1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) u |= __shfl_xor_sync(kFull, u, o);
-            while (u) {
-                const int bit = __ffs((int)u) - 1;
-                u &= u - 1;
-                const int cnt = __popc(__ballot_sync(kFull, (b0 >> bit) & 1u)) + __popc(__ballot_sync(kFull, (b1 >> bit) & 1u));
-                const int lab = k * 32 + bit;
-                if (lane == 0) {
-                    ws.ent[((int64_t)bt * ws.cap + n) * cells + cell] = ((unsigned)lab << 8) | (unsigned)cnt;
-                    atomicAdd(ws.size + bt * a.SP + lab, cnt);
+        for (int s0 = 0; s0 < a.SP; s0 += 32) {
+            const int lab = s0 + lane;
+            int cnt = 0;
+            if (lab < a.SP)
+                for (int ly = 0; ly < a.sy; ++ly) {
+                    const unsigned* q = cov + ((size_t)ly * a.NW + wd) * a.SP + lab;
+                    cnt += __popc(__funnelshift_r(q[0], two ? q[a.SP] : 0u, off) & colmask);
                 }
-                ++n;
+            const unsigned have = __ballot_sync(kFull, cnt > 0);
+            if (cnt > 0) {
+                const int pos = n + __popc(have & ((1u << lane) - 1u));
+                ws.ent[((int64_t)bt * ws.cap + pos) * cells + cell] = ((unsigned)lab << 8) | (unsigned)cnt;
+                atomicAdd(ws.size + bt * a.SP + lab, cnt);
             }
+            n += __popc(have);
         }
-        if (lane == 0) ws.nent[bt * cells + cell] = (unsigned char)n;
-        __syncwarp();
+        if (lane == 0) ws.nent[(int64_t)bt * cells + cell] = (unsigned char)n;
     }
 }
 
@@ -800,8 +799,9 @@ static int segdil_check(int B, int C, int T, int Hm, int Wm, int h, int w, int S
         set_error("segmean_dilated: kernel size %d must be odd and positive, shape %d one of CRW_DILATE_*", ksize, shape);
         return CRW_ERR_SHAPE;
     }
-    if (SP > 255 || w > 65535 || ksize / 2 > kDilMaxR) {
-        set_error("segmean_dilated: unsupported SP=%d (<= 255), width=%d or kernel size %d (<= %d)", SP, w, ksize, 2 * kDilMaxR + 1);
+    if (SP > 255 || w > 65535 || ksize / 2 > kDilMaxR || w / Wm > 32) {
+        set_error("segmean_dilated: unsupported SP=%d (<= 255), width=%d, cell width %d (<= 32) or kernel size %d (<= %d)", SP, w, w / Wm, ksize,
+                  2 * kDilMaxR + 1);
         return CRW_ERR_UNSUPPORTED;
     }
     return CRW_OK;
@@ -842,13 +842,25 @@ extern "C" int crw_segmean_dilated_fwd(const float* maps, const int64_t* labels,
         a.hw[dy] = (unsigned char)wv;
     }
     cudaMemsetAsync(ws.size, 0, sizeof(int) * (size_t)B * T * SP, (cudaStream_t)stream);
-    const int64_t rows = (int64_t)B * T * h, total = (int64_t)B * T * cells;
+    const int64_t rows = (int64_t)B * T * h;
     const int grid0 = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
     CRW_LAUNCH(segdil_runs_kernel, grid0, 256, 0, stream, a, rows);
     e = check_launch("segdil_runs");
     if (e != CRW_OK) return e;
-    const int grid1 = (int)((total + 7) / 8 < 148 * 8 ? (total + 7) / 8 : 148 * 8);
-    CRW_LAUNCH(segdil_count_kernel, grid1, 256, 0, stream, a, ws, total);
+    {   // strips of whole cells, at most 256 columns, bitmap at most 160 KB
+        const size_t col_bytes = (size_t)a.sy * SP * sizeof(unsigned);
+        int nw = (Wm * a.sx + 31) / 32;
+        if (nw > 8) nw = 8;
+        if ((size_t)nw * col_bytes > 160 * 1024) nw = (int)((160 * 1024) / col_bytes);
+        a.NW = nw < 1 ? 1 : nw;
+        a.cpc = a.NW * 32 / a.sx;
+        if (a.cpc > Wm) a.cpc = Wm;
+        a.nxc = (Wm + a.cpc - 1) / a.cpc;
+        const size_t smem = (size_t)a.NW * col_bytes;
+        auto k = segdil_count_kernel;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CRW_LAUNCH(k, B * T * Hm * a.nxc, 256, smem, stream, a, ws);
+    }
     e = check_launch("segdil_count");
     if (e != CRW_OK) return e;
     return seg_fwd_tail(maps, ws, B, C, T, cells, SP, out, stream);

@@ -168,6 +168,7 @@ static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mas
 // atomics: fibers are cooperatively scheduled on one OS thread, so plain RMW is atomic
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o | v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; *p = o > v ? o : v; return o; }
 static inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *p = (o >= lim) ? 0 : o + 1; return o; }
 static inline unsigned atomicExch(unsigned* p, unsigned v) { unsigned o = *p; *p = v; return o; }
@@ -189,6 +190,8 @@ static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; 
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31u; return sh ? (lo >> sh) | (hi << (32u - sh)) : lo; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 template <class T> static inline T __ldg(const T* p) { return *p; }

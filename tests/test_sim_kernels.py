@@ -285,6 +285,25 @@ def test_segmean_dilated_edges(sim):
     assert sim.crw_segmean_dilated_workspace_bytes(B, T, Hm, Wm, h, w, 256) == 0
 
 
+@pytest.mark.parametrize("Hm,Wm,sy,sx,SP,ksize,shape", [(3, 40, 2, 8, 30, 13, "L1"),      # two strips of 32 cells
+                                                         (4, 14, 3, 5, 11, 9, "circle"),    # cells straddling bitmap words
+                                                         (2, 70, 1, 4, 40, 31, "cross"),    # 280 columns, one pixel row per cell
+                                                         (5, 3, 2, 32, 7, 21, "L1")])       # 32-pixel-wide cells
+def test_segmean_dilated_strips(sim, Hm, Wm, sy, sx, SP, ksize, shape):
+    g = torch.Generator().manual_seed(Hm * 1000 + Wm)
+    B, T, C = 1, 2, 4
+    h, w = Hm * sy, Wm * sx
+    maps = torch.randn(B, C, T, Hm, Wm, generator=g)
+    lab = torch.randint(0, SP, (B, T, (h + 1) // 2, (w + 4) // 5), generator=g).repeat_interleave(2, 2).repeat_interleave(5, 3)[..., :h, :w].contiguous()
+    sb, st, ss_y, ss_x = lab.stride()
+    wsb = sim.crw_segmean_dilated_workspace_bytes(B, T, Hm, Wm, h, w, SP)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    out = torch.empty(B, SP, T, C)
+    sim.check(sim.crw_segmean_dilated_fwd(ptr(maps), ptr(lab), sb, st, ss_y, ss_x, B, C, T, Hm, Wm, h, w, SP, ksize, DILATE[shape],
+                                          ptr(out), ptr(ws), wsb, None))
+    torch.testing.assert_close(out.transpose(1, 2), O.segment_mean_dilated(maps, lab, SP, ksize, shape), rtol=1e-5, atol=1e-6)
+
+
 def check_label_images(cls, rgb, pred, lbl_set, c, fx):
     """Class map / label image of the kernel against the reference's dump_predictions output.  OpenCV's vectorised resize
     may fuse or reorder the two interpolation passes, so a pixel may legitimately differ only where the two best classes of

@@ -42,6 +42,14 @@ def main():
         f = timed(lambda: ops.segment_mean_dilated(maps.detach(), lab, SP, ksize, shape))
         fb = timed(lambda: run(lambda: ops.segment_mean_dilated(maps, lab, SP, ksize, shape)))
         print("dilated %-6s %d fwd %.3f ms  fwd+bwd %.3f ms" % (shape, ksize, f, fb))
+    # per-kernel device times of one dilated forward + backward (torch.profiler, in situ)
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            run(lambda: ops.segment_mean_dilated(maps, lab, SP, ksize, "L1"))
+        torch.cuda.synchronize()
+    for ev in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:8]:
+        print("  %-60s %8.1f us x %d" % (ev.key[:60], ev.device_time_total / max(ev.count, 1), ev.count))
     # what the reference does instead: one-hot masks, fp16 depthwise convolution, threshold (model.py:303-309)
     oh = (lab[:1, :, None] == torch.arange(SP, device="cuda")[None, None, :, None, None]).flatten(1, 2).half()
     k = torch.ones(T * SP, 1, ksize, ksize, device="cuda", dtype=torch.half)
