@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
 // the cell's pixels can see, builds the pixels' label sets as bitsets in shared memory and emits the cell's (label, count)
 // list - the same lists the undilated path produces, so the CSR / accumulate / backward kernels are shared.
 constexpr int kDilMaxR = 63;            // structuring element up to 127 x 127
-constexpr int kDilWords = 8;            // label bitset: SP <= 255 in the dilated path
 constexpr unsigned kDilBadLabel = 0x3ffu;
 
 struct DilArgs {
@@ -368,13 +367,50 @@ __device__ __forceinline__ void seg_issue_meta(const SegWs& ws, const SegCursor&
     cp_async_commit();
 }
 
+// A chunk with more CSR entries than the staging buffer holds (dilated masks: a cell carries ten and more labels).  The
+// entries stay in L2; a warp fetches 32 of a label with one coalesced load - the next label's first batch while the current
+// label is reduced - and hands them round by shuffles.  Same summation order as the staged path.
+template <int LMAX>
+__device__ __forceinline__ void seg_reduce_chunk_l2(float2 (&acc)[LMAX], const float* tl0, const float* tl1, const int* pst,
+                                                    const uint2* csr_bt, int SP, int warp, int lane) {
+    uint2 nxt = make_uint2(0u, 0u);
+    if (warp < SP && pst[warp] + lane < pst[warp + 1]) nxt = csr_bt[pst[warp] + lane];
+#pragma unroll
+    for (int i = 0; i < LMAX; ++i) {
+        const int s = warp + 32 * i;
+        if (s < SP) {
+            const int e0 = pst[s], e1 = pst[s + 1];
+            uint2 cur = nxt;
+            if (i + 1 < LMAX && s + 32 < SP) {
+                const int f0 = pst[s + 32] + lane;
+                nxt = f0 < pst[s + 33] ? csr_bt[f0] : make_uint2(0u, 0u);
+            }
+            float2 a = acc[i];
+            for (int base = e0; base < e1; base += 32) {
+                if (base != e0) cur = base + lane < e1 ? csr_bt[base + lane] : make_uint2(0u, 0u);
+                const int n = min(32, e1 - base);
+                for (int j = 0; j < n; ++j) {
+                    const float wgt = __uint_as_float(__shfl_sync(kFull, cur.x, j));
+                    const unsigned cl = __shfl_sync(kFull, cur.y, j);
+                    a = ffma2(wgt, make_float2(tl0[cl], tl1[cl]), a);
+                }
+            }
+            acc[i] = a;
+        }
+    }
+}
+
 template <int LMAX>
 __device__ __forceinline__ void seg_reduce_chunk(float2 (&acc)[LMAX], const float* tile, const uint2* est, const int* pst,
                                                  const uint2* csr_bt, int SP, int warp, int lane) {
     const float* tl0 = tile + lane * kSegLDC;
     const float* tl1 = tl0 + 32 * kSegLDC;
     const int eb = pst[0];
-    const uint2* ents = (pst[SP] - eb <= kSegEntCap) ? est - eb : csr_bt;          // indexed by the CSR position
+    if (pst[SP] - eb > kSegEntCap) {
+        seg_reduce_chunk_l2<LMAX>(acc, tl0, tl1, pst, csr_bt, SP, warp, lane);
+        return;
+    }
+    const uint2* ents = est - eb;                                                   // indexed by the CSR position
 #pragma unroll
     for (int i = 0; i < LMAX; ++i) {
         const int s = warp + 32 * i;
@@ -591,6 +627,9 @@ __global__ void __launch_bounds__(1024, 1) segmean_accum_kernel(const float* __r
 // contiguous bytes per channel.  A gather: deterministic.
 constexpr int kSegLDB = kSegCT + 4;
 
+// kCrowded (dilated masks, ten and more labels per cell): the cell's 32 channels are summed in registers over all its
+// entries and written once, instead of one read-modify-write round of the output per four entries.
+template <bool kCrowded>
 __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restrict__ gout, SegWs ws, int C, int T, int cells,
                                                           int SP, float* __restrict__ gmaps) {
     CRW_DYN_SMEM(smem_raw);
@@ -636,6 +675,35 @@ __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restric
         int nmax = ne;                                                        // slots are taken four at a time, for as long as any lane of the warp has some
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, o));
+        if constexpr (kCrowded) {
+            float acc[kSegCT];
+#pragma unroll
+            for (int c = 0; c < kSegCT; ++c) acc[c] = 0.f;
+            for (int base = 0; base < nmax; base += 4) {
+                float cnt[4];
+                const float4* row[4];
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    const unsigned e = base + sl < ne ? __ldg(ent + (int64_t)(base + sl) * cells + cell) : 0u;
+                    cnt[sl] = (float)(e & 255u);
+                    row[sl] = reinterpret_cast<const float4*>(wg + (e >> 8) * kSegLDB);
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < kSegCT / 4; ++c4) {
+                    const float4 v0 = row[0][c4], v1 = row[1][c4], v2 = row[2][c4], v3 = row[3][c4];
+                    acc[4 * c4 + 0] = fmaf(cnt[3], v3.x, fmaf(cnt[2], v2.x, fmaf(cnt[1], v1.x, fmaf(cnt[0], v0.x, acc[4 * c4 + 0]))));
+                    acc[4 * c4 + 1] = fmaf(cnt[3], v3.y, fmaf(cnt[2], v2.y, fmaf(cnt[1], v1.y, fmaf(cnt[0], v0.y, acc[4 * c4 + 1]))));
+                    acc[4 * c4 + 2] = fmaf(cnt[3], v3.z, fmaf(cnt[2], v2.z, fmaf(cnt[1], v1.z, fmaf(cnt[0], v0.z, acc[4 * c4 + 2]))));
+                    acc[4 * c4 + 3] = fmaf(cnt[3], v3.w, fmaf(cnt[2], v2.w, fmaf(cnt[1], v1.w, fmaf(cnt[0], v0.w, acc[4 * c4 + 3]))));
+                }
+            }
+            if (live) {
+                float* d = dst0 + cell;
+#pragma unroll
+                for (int c = 0; c < kSegCT; ++c)
+                    if (c < nc) d[c * cstride] = acc[c];
+            }
+        } else
         for (int base = 0; base < nmax || base == 0; base += 4) {
             float cnt[4];
             const float4* row[4];
@@ -766,7 +834,8 @@ static int seg_fwd_tail(const float* maps, const SegWs& ws, int B, int C, int T,
     return check_launch("segmean_accum");
 }
 
-static int seg_bwd_run(const float* grad_out, const SegWs& ws, int B, int C, int T, int cells, int SP, float* grad_maps, crw_stream_t stream);
+static int seg_bwd_run(const float* grad_out, const SegWs& ws, int B, int C, int T, int cells, int SP, float* grad_maps, bool crowded,
+                       crw_stream_t stream);
 
 extern "C" int crw_segmean_bwd(const float* grad_out, const void* workspace, size_t workspace_bytes,
                                int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
@@ -777,15 +846,22 @@ extern "C" int crw_segmean_bwd(const float* grad_out, const void* workspace, siz
     const int cells = Hm * Wm;
     SegWs ws = seg_ws(const_cast<void*>(workspace), B, T, cells, SP, cap);
     if (!workspace || workspace_bytes < ws.bytes) { set_error("segmean_bwd: workspace too small"); return CRW_ERR_SHAPE; }
-    return seg_bwd_run(grad_out, ws, B, C, T, cells, SP, grad_maps, stream);
+    return seg_bwd_run(grad_out, ws, B, C, T, cells, SP, grad_maps, false, stream);
 }
 
-static int seg_bwd_run(const float* grad_out, const SegWs& ws, int B, int C, int T, int cells, int SP, float* grad_maps, crw_stream_t stream) {
+static int seg_bwd_run(const float* grad_out, const SegWs& ws, int B, int C, int T, int cells, int SP, float* grad_maps, bool crowded,
+                       crw_stream_t stream) {
     const size_t smem = ((size_t)SP * kSegLDB + 2 * (size_t)SP) * sizeof(float);
-    auto k = segmean_bwd_kernel;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((C + kSegCT - 1) / kSegCT, B * T);
-    CRW_LAUNCH(k, grid, 256, smem, stream, grad_out, ws, C, T, cells, SP, grad_maps);
+    if (crowded) {
+        auto k = segmean_bwd_kernel<true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CRW_LAUNCH(k, grid, 256, smem, stream, grad_out, ws, C, T, cells, SP, grad_maps);
+    } else {
+        auto k = segmean_bwd_kernel<false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CRW_LAUNCH(k, grid, 256, smem, stream, grad_out, ws, C, T, cells, SP, grad_maps);
+    }
     return check_launch("segmean_bwd");
 }
 
@@ -875,5 +951,5 @@ extern "C" int crw_segmean_dilated_bwd(const float* grad_out, const void* worksp
     int* nruns;
     SegWs ws = segdil_ws(const_cast<void*>(workspace), B, T, Hm * Wm, h, w, SP, &runs, &nruns);
     if (!workspace || workspace_bytes < ws.bytes) { set_error("segmean_dilated_bwd: workspace too small"); return CRW_ERR_SHAPE; }
-    return seg_bwd_run(grad_out, ws, B, C, T, Hm * Wm, SP, grad_maps, stream);
+    return seg_bwd_run(grad_out, ws, B, C, T, Hm * Wm, SP, grad_maps, true, stream);
 }

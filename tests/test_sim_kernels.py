@@ -288,10 +288,12 @@ def test_segmean_dilated_edges(sim):
 @pytest.mark.parametrize("Hm,Wm,sy,sx,SP,ksize,shape", [(3, 40, 2, 8, 30, 13, "L1"),      # two strips of 32 cells
                                                          (4, 14, 3, 5, 11, 9, "circle"),    # cells straddling bitmap words
                                                          (2, 70, 1, 4, 40, 31, "cross"),    # 280 columns, one pixel row per cell
-                                                         (5, 3, 2, 32, 7, 21, "L1")])       # 32-pixel-wide cells
+                                                         (5, 3, 2, 32, 7, 21, "L1"),        # 32-pixel-wide cells
+                                                         (16, 16, 2, 2, 70, 15, "circle"),  # > 1024 CSR entries in a chunk (TMA path)
+                                                         (16, 20, 2, 2, 40, 13, "L1")])     # the same on the cp.async path
 def test_segmean_dilated_strips(sim, Hm, Wm, sy, sx, SP, ksize, shape):
     g = torch.Generator().manual_seed(Hm * 1000 + Wm)
-    B, T, C = 1, 2, 4
+    B, T, C = 1, 2, (64 if Hm == 16 else 4)
     h, w = Hm * sy, Wm * sx
     maps = torch.randn(B, C, T, Hm, Wm, generator=g)
     lab = torch.randint(0, SP, (B, T, (h + 1) // 2, (w + 4) // 5), generator=g).repeat_interleave(2, 2).repeat_interleave(5, 3)[..., :h, :w].contiguous()
