@@ -306,6 +306,41 @@ def label_prop_bench(dev):
                                  "split issues 3 MMAs per product and whole 16x8 query windows, so the tensor pipe does ~8x this"}}
 
 
+def superpixel_pool_bench(dev):
+    """BASELINE configs[2] shape (8 clips x 8 frames, 196 superpixels on 256x256, 512-channel 32x32 maps): superpixel pooling
+    forward + backward, plain and with the reference's default --dilate-superpixels element (51x51 'L1')."""
+    from sapienza_video_contrastive_b200 import ops
+    B, T, C, SP, size = 8, 8, 512, 196, 256
+    g = torch.Generator(device=dev).manual_seed(0)
+    pts = torch.rand(B, T, SP, 2, generator=g, device=dev) * size
+    yx = torch.stack(torch.meshgrid(torch.arange(size, device=dev), torch.arange(size, device=dev), indexing="ij"), -1).float()
+    lab = torch.stack([torch.cdist(yx.reshape(1, -1, 2).expand(T, -1, -1), pts[b]).argmin(-1) for b in range(B)]).reshape(B, T, size, size)
+    maps = torch.randn(B, C, T, 32, 32, generator=g, device=dev, requires_grad=True)
+    gout = torch.randn(B, SP, T, C, generator=g, device=dev)
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    def step(fn):
+        fn().backward(gout)
+        maps.grad = None
+
+    plain = timed(lambda: step(lambda: ops.segment_mean(maps, lab, SP)))
+    dil = timed(lambda: step(lambda: ops.segment_mean_dilated(maps, lab, SP, 51, "L1")))
+    return {"config": "B=%d T=%d C=%d SP=%d labels %dx%d maps 32x32, forward + backward" % (B, T, C, SP, size, size),
+            "plain_ms": plain, "plain_clips_per_s": B / plain * 1e3,
+            "dilated_L1_51_ms": dil, "dilated_clips_per_s": B / dil * 1e3}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     dev = torch.device("cuda", local_rank)
@@ -426,6 +461,10 @@ def run_ours(args, rank, world, local_rank):
             out["label_prop"] = label_prop_bench(dev)
         except Exception as e:                                   # the headline line must still print
             out["label_prop"] = {"error": repr(e)}
+        try:
+            out["superpixel_pooling"] = superpixel_pool_bench(dev)
+        except Exception as e:
+            out["superpixel_pooling"] = {"error": repr(e)}
     print(json.dumps(out), flush=True)
 
 
