@@ -106,6 +106,23 @@ int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float tempe
                      uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
                      float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
+/* ---- f3: teacher-student walk, teacherstudent.py:472-580 (CRWTeacherStudent.forward) + :270-292 (SoftCrossEntropyLoss) ----
+ * The same walk with two additions, both on the chain products W_i (B,T-2,N,N) = the palindrome products `aar` (`aal`
+ * with CRW_WALK_FLIP) of walks i = 1..T-2:
+ *   chains_out != NULL      W_i are copied out before the loss (the TEACHER call: rate 0, grad_feats NULL);
+ *   teacher_chains != NULL  the STUDENT call: ts_xent[i] = mean over rows of  -sum_m teacher[m] * log_softmax(W_i row)[m]
+ *                           (the student's chain probabilities are the logits there, as in the reference), ts_xent[T-2] their
+ *                           mean, xent[T-2] = alpha * mean_i xent_i + (1 - alpha) * ts_xent[T-2]  (teacherstudent.py:572-575),
+ *                           and grad_feats is the gradient of THAT loss.
+ * Runs the batched multi-kernel path: size the workspace with crw_walk_workspace_bytes(..., flags | CRW_WALK_FORCE_GENERAL).
+ * The reference's CRWBase transition matrix is the softmax one: pass CRW_WALK_SOFTMAX for it. */
+int crw_walk_ts_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,
+                        const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
+                        uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags,
+                        const float* teacher_chains, float alpha, float* chains_out,
+                        float* q, float* xent, float* ts_xent, float* acc,
+                        float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+
 /* ---- a1: the projection head, model.py:117 (nn.Linear(C_e,128,bias=False)) ------------------------------------------
  * out (R,D) = x (R,C) weight^T, grad_x (R,C) = grad_out (R,D) weight, with R = B*N*T rows, on the fused tcgen05 kind::tf32
  * GEMM (fp32-faithful: tf32 big + small operand parts, error ~2^-22 |a||b|).  err_word: one zero-initialised device word

@@ -142,12 +142,11 @@ def walk_matrices(q, tau, p, u12, u21p, softmax=False):
     return A12, A21
 
 
-def walk_loss(q, tau, p, u12=None, u21p=None, flip=False, softmax=False):
-    """model.py:366-413.  Returns (loss[1], xents list, accs list, names list)."""
+def walk_chain_products(q, tau, p, u12=None, u21p=None, flip=False, softmax=False):
+    """model.py:376-382 / teacherstudent.py:507-515: the palindrome products `aar` (`aal` with flip) of walks 1..T-2."""
     B, D, T, N = q.shape
     A12, A21 = walk_matrices(q, tau, p, u12, u21p, softmax)
-    xents, accs, names = [], [], []
-    tgt = torch.arange(N, device=q.device)
+    out = []
     for i in range(1, T - 1):                                    # shortest cycle skipped (F7)
         chain = A12[: i + 1] + A21[: i + 1][::-1]
         if flip:
@@ -155,6 +154,34 @@ def walk_loss(q, tau, p, u12=None, u21p=None, flip=False, softmax=False):
         W = chain[0]
         for M in chain[1:]:
             W = W @ M
+        out.append(W)
+    return out
+
+
+def teacher_student_loss(q_s, q_t, tau, p, alpha, us12=None, us21p=None, ut12=None, ut21p=None, flip=False, softmax=True):
+    """teacherstudent.py:494-577 (CRWTeacherStudent.forward from the node embeddings on).  q_s, q_t (B,D,T,N) unit-norm student /
+    teacher nodes.  Edge dropout is applied to the TEACHER as well (stoch_mat's do_dropout defaults to True at :527-528,
+    whatever the comment above those lines says), with its own draws made after the student's.
+    -> (loss [1], walk xents list, teacher-student xents list)."""
+    B, D, T, N = q_s.shape
+    Ws = walk_chain_products(q_s, tau, p, us12, us21p, flip, softmax)
+    Wt = walk_chain_products(q_t, tau, p, ut12, ut21p, flip, softmax)
+    xents, ts = [], []
+    for A, At in zip(Ws, Wt):
+        diag = torch.diagonal(A, dim1=-2, dim2=-1)
+        xents.append((-(torch.log(diag + EPS_LOG) - torch.log((A + EPS_LOG).sum(-1)))).mean())
+        ts.append((-(At * torch.log_softmax(A, dim=-1)).sum(-1)).mean())          # SoftCrossEntropyLoss, :270-292
+    zero = torch.zeros(1, device=q_s.device)
+    loss = alpha * (sum(xents, zero) / max(1, len(xents))) + (1 - alpha) * (sum(ts, zero) / max(1, len(ts)))
+    return loss, xents, ts
+
+
+def walk_loss(q, tau, p, u12=None, u21p=None, flip=False, softmax=False):
+    """model.py:366-413.  Returns (loss[1], xents list, accs list, names list)."""
+    B, D, T, N = q.shape
+    xents, accs, names = [], [], []
+    tgt = torch.arange(N, device=q.device)
+    for i, W in enumerate(walk_chain_products(q, tau, p, u12, u21p, flip, softmax), start=1):
         diag = torch.diagonal(W, dim1=-2, dim2=-1)
         rows = (W + EPS_LOG).sum(-1)
         xents.append((-(torch.log(diag + EPS_LOG) - torch.log(rows))).mean())

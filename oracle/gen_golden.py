@@ -144,6 +144,34 @@ def gen_spd(ref_model, ref_utils):
         print("golden", name, tuple(sp_feats.shape))
 
 
+def gen_ts(ref_model, ref_utils):
+    """CRWTeacherStudent.forward (teacherstudent.py:472-580) from the node embeddings on.  The class needs a pretrained
+    checkpoint to construct, so an instance is made without __init__ and given exactly the attributes forward reads; the two
+    pixels_to_nodes methods return fixed unit-norm embeddings (B,C,T,N)."""
+    import teacherstudent as ts_mod
+    import torch.nn.functional as F
+    for name, c in cases.TS_CASES.items():
+        fs, ft = cases.ts_inputs(c)
+        obj = ts_mod.CRWTeacherStudent.__new__(ts_mod.CRWTeacherStudent)
+        nn.Module.__init__(obj)
+        obj.args = argparse.Namespace(device="cpu")
+        obj.edgedrop_rate, obj.temperature, obj.flip, obj.alpha, obj.vis = c["p"], c["tau"], c["flip"], c["alpha"], None
+        obj._xent_targets = dict()
+        obj.xent = nn.CrossEntropyLoss(reduction="none")
+        obj.soft_xent = ts_mod.SoftCrossEntropyLoss()
+        fs_req = fs.clone().requires_grad_(True)
+        obj.pixels_to_nodes = lambda x: (F.normalize(fs_req, p=2, dim=-1).permute(0, 3, 2, 1), None)
+        obj.pixels_to_nodes_tchr = lambda x: (F.normalize(ft, p=2, dim=-1).permute(0, 3, 2, 1), None)
+        x = torch.zeros(c["B"], c["T"], c["N"] * 3, 8, 8)
+        torch.manual_seed(c["seed"] + 1000)
+        q, loss, diags = obj(x)
+        loss.sum().backward()
+        fx = dict(q=q.detach().clone(), loss=loss.detach().clone(), diags={k: v.detach().clone() for k, v in diags.items()},
+                  grad_feats=fs_req.grad.clone())
+        torch.save(fx, os.path.join(OUT, name + ".pt"))
+        print("golden", name, float(loss))
+
+
 def gen_lp(ref_model, ref_utils, ref_tu):
     """Runs the reference's own evaluator loop (test.py:67-160) on a fake loader / fake encoder and
     captures (Ws, Is) from mem_efficient_batched_affinity and each `pred` handed to dump_predictions."""
@@ -249,11 +277,15 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "spd":            # only the dilated-superpixel fixtures (added later)
         gen_spd(ref_model, ref_utils)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "ts":             # only the teacher-student fixtures (added later)
+        gen_ts(ref_model, ref_utils)
+        return
     gen_misc(ref_model, ref_utils, ref_tu)
     gen_post(ref_model, ref_utils, ref_tu)
     gen_walk(ref_model, ref_utils)
     gen_sp(ref_model, ref_utils)
     gen_spd(ref_model, ref_utils)
+    gen_ts(ref_model, ref_utils)
     gen_lp(ref_model, ref_utils, ref_tu)
     gen_cfg1(ref_model, ref_utils)
 

@@ -12,6 +12,9 @@ __version__ = "0.1.0"
 _LAZY = {
     "CRW": ("model", "CRW"),
     "ZeroSoftmax": ("model", "ZeroSoftmax"),
+    "CRWBase": ("teacherstudent", "CRWBase"),
+    "CRWTeacherStudent": ("teacherstudent", "CRWTeacherStudent"),
+    "SoftCrossEntropyLoss": ("teacherstudent", "SoftCrossEntropyLoss"),
     "make_encoder": ("resnet", "make_encoder"),
     "From3D": ("resnet", "From3D"),
     "context_index_bank": ("test_utils", "context_index_bank"),
@@ -25,7 +28,7 @@ _LAZY = {
 
 
 def __getattr__(name):
-    if name in ("ops", "model", "test_utils", "resnet"):
+    if name in ("ops", "model", "test_utils", "resnet", "teacherstudent"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name in _LAZY:

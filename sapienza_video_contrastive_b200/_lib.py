@@ -48,6 +48,9 @@ _SIGNATURES = {
     "crw_walk_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_uint64,
                                  c_uint64, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    "crw_walk_ts_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_uint64,
+                                    c_uint64, c_uint32, c_void_p, c_uint32, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_philox_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint32, c_void_p]),
     "crw_lp_upsample_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "crw_bmm_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -33,6 +33,11 @@ struct WalkParams {
     float *ws_invn, *ws_nrm;                   // (B,T,N)
     float *ws_dqa, *ws_dqb;                    // (B,T-1,N,D) per-pair contributions to dQ_i / dQ_{i+1}
     unsigned* ws_clipcnt;                      // (B,T) per-frame tickets of the pair-backward CTAs (zero between launches)
+    // teacher-student walk (teacherstudent.py:472-580), general path only
+    const float* ts_target;    // teacher chain products (B,T-2,N,N): adds the soft cross-entropy against them, or nullptr
+    float ts_alpha;            // loss = alpha * walk loss + (1 - alpha) * teacher-student loss
+    float* ts_xent;            // (T-2 + 1) per-walk soft cross-entropies and their mean
+    float* chains_out;         // (B,T-2,N,N): the chain products of this call (a teacher's), or nullptr
 };
 
 struct FusedLayout {

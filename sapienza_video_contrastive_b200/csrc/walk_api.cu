@@ -64,10 +64,48 @@ extern "C" size_t crw_walk_workspace_bytes(int B, int N, int T, int D, unsigned 
     return ws_layout(B, N, T, D, flags).total;
 }
 
+namespace {
+struct TsArgs {
+    const float* teacher_chains;
+    float alpha;
+    float* ts_xent;
+    float* chains_out;
+};
+
+int walk_run(const float* feats, int B, int N, int T, int D, float temperature, float rate,
+             const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
+             uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
+             float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream, const TsArgs* ts);
+}  // namespace
+
 extern "C" int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,
                                 const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
                                 uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
                                 float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
+    return walk_run(feats, B, N, T, D, temperature, rate, u12, u21p, philox_seed, philox_offset, philox_threads, philox_state_dev, flags,
+                    q, xent, acc, grad_feats, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int crw_walk_ts_fwd_bwd(const float* feats, int B, int N, int T, int D, float temperature, float rate,
+                                   const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
+                                   uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags,
+                                   const float* teacher_chains, float alpha, float* chains_out,
+                                   float* q, float* xent, float* ts_xent, float* acc,
+                                   float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
+    if (teacher_chains && (!ts_xent || !(alpha >= 0.f && alpha <= 1.f))) {
+        set_error("walk_ts: a teacher needs ts_xent and 0 <= alpha <= 1 (got %g)", (double)alpha);
+        return CRW_ERR_SHAPE;
+    }
+    const TsArgs ts{teacher_chains, alpha, ts_xent, chains_out};
+    return walk_run(feats, B, N, T, D, temperature, rate, u12, u21p, philox_seed, philox_offset, philox_threads, philox_state_dev,
+                    flags | CRW_WALK_FORCE_GENERAL, q, xent, acc, grad_feats, workspace, workspace_bytes, stream, &ts);
+}
+
+namespace {
+int walk_run(const float* feats, int B, int N, int T, int D, float temperature, float rate,
+             const float* u12, const float* u21p, uint64_t philox_seed, uint64_t philox_offset,
+             uint32_t philox_threads, uint64_t* philox_state_dev, unsigned flags, float* q, float* xent, float* acc,
+             float* grad_feats, void* workspace, size_t workspace_bytes, crw_stream_t stream, const TsArgs* ts) {
     if (B <= 0 || N <= 0 || T <= 0 || D <= 0) { set_error("walk: bad shape B=%d N=%d T=%d D=%d", B, N, T, D); return CRW_ERR_SHAPE; }
     if (!(temperature > 0.f)) { set_error("walk: temperature must be > 0"); return CRW_ERR_SHAPE; }
     if ((u12 == nullptr) != (u21p == nullptr)) { set_error("walk: u12 and u21p must both be given or both be NULL"); return CRW_ERR_SHAPE; }
@@ -106,5 +144,9 @@ extern "C" int crw_walk_fwd_bwd(const float* feats, int B, int N, int T, int D, 
         p.ws_invn = (float*)(ws + w.o_invn); p.ws_nrm = (float*)(ws + w.o_nrm);
         p.ws_dqa = (float*)(ws + w.o_dqa); p.ws_dqb = (float*)(ws + w.o_dqb);
     }
+    if (ts) {
+        p.ts_target = ts->teacher_chains; p.ts_alpha = ts->alpha; p.ts_xent = ts->ts_xent; p.chains_out = ts->chains_out;
+    }
     return w.fused ? launch_walk_fused(p, stream) : launch_walk_general(p, stream);
 }
+}  // namespace

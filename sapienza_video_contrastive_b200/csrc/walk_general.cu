@@ -281,20 +281,26 @@ __global__ void __launch_bounds__(256) stoch_rows_kernel(StochArgs s) {
 }
 
 // ---- loss rows: W -> dW in place, per-row loss and accuracy -------------------------------------------------------
+// With a teacher (Wt != nullptr, teacherstudent.py:270-292, 545-548) the row also carries the soft cross-entropy of the
+// teacher's row against log_softmax of the student's row - the student's chain PROBABILITIES are the logits there - and
+// dW = alpha * d(walk loss) + (1 - alpha) * d(soft cross-entropy).
 __global__ void __launch_bounds__(256) loss_rows_kernel(float* __restrict__ W, float* __restrict__ rowloss,
-                                                        float* __restrict__ rowacc, int64_t rows, int N, float cgrad, int need_grad) {
+                                                        float* __restrict__ rowacc, int64_t rows, int N, float cgrad, int need_grad,
+                                                        const float* __restrict__ Wt, float* __restrict__ rowts, float alpha) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = warp; row < rows; row += nw) {
         const int n = (int)(row % N);
         float* w = W + row * N;
-        float rs = 0.f, best = -INFINITY;
+        const float* wt = Wt ? Wt + row * N : nullptr;
+        float rs = 0.f, best = -INFINITY, dot = 0.f, st = 0.f;
         int bi = 0x7fffffff;
         for (int m = lane; m < N; m += 32) {
             const float v = w[m];
             rs += v + kEpsLog;
             if (v > best) { best = v; bi = m; }
+            if (wt) { const float t = wt[m]; dot = fmaf(t, v, dot); st += t; }
         }
         rs = warp_sum(rs);
 #pragma unroll
@@ -304,11 +310,30 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(float* __restrict__ W, f
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
         const float dg = w[n] + kEpsLog;
+        float se = 0.f;
+        if (wt) {
+            dot = warp_sum(dot);
+            st = warp_sum(st);
+            for (int m = lane; m < N; m += 32) se += expf(w[m] - best);
+            se = warp_sum(se);
+        }
         __syncwarp();
-        if (lane == 0) { rowloss[row] = logf(rs) - logf(dg); rowacc[row] = (bi == n) ? 1.f : 0.f; }
+        if (lane == 0) {
+            rowloss[row] = logf(rs) - logf(dg);
+            rowacc[row] = (bi == n) ? 1.f : 0.f;
+            if (wt) rowts[row] = (best + logf(se)) * st - dot;              // sum_m t_m (logsumexp - w_m)
+        }
         if (need_grad) {
             const float ir = 1.0f / rs, idg = 1.0f / dg;
-            for (int m = lane; m < N; m += 32) w[m] = cgrad * (ir - (m == n ? idg : 0.f));
+            if (wt) {
+                const float ca = alpha * cgrad, cb = (1.f - alpha) * cgrad, ise = st / se;
+                for (int m = lane; m < N; m += 32) {
+                    const float v = w[m];
+                    w[m] = ca * (ir - (m == n ? idg : 0.f)) + cb * (expf(v - best) * ise - wt[m]);
+                }
+            } else {
+                for (int m = lane; m < N; m += 32) w[m] = cgrad * (ir - (m == n ? idg : 0.f));
+            }
         }
     }
 }
@@ -317,36 +342,51 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(float* __restrict__ W, f
 // the last CTA to finish (ticket) adds the J results in order -> deterministic
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ rowloss, const float* __restrict__ rowacc,
                                                           float* __restrict__ xent, float* __restrict__ acc, int B, int J, int N,
-                                                          const unsigned* __restrict__ tc_err, unsigned* __restrict__ ticket) {
-    __shared__ float sl[256], sa[256];
+                                                          const unsigned* __restrict__ tc_err, unsigned* __restrict__ ticket,
+                                                          const float* __restrict__ rowts, float* __restrict__ ts, float alpha) {
+    __shared__ float sl[256], sa[256], st[256];
     __shared__ unsigned last;
     const int j = blockIdx.x;
-    float l = 0.f, a = 0.f;
+    float l = 0.f, a = 0.f, t = 0.f;
     for (int64_t e = threadIdx.x; e < (int64_t)B * N; e += 256) {
         const int64_t b = e / N, n = e - b * N;
         l += rowloss[(b * J + j) * N + n];
         a += rowacc[(b * J + j) * N + n];
+        if (rowts) t += rowts[(b * J + j) * N + n];
     }
     sl[threadIdx.x] = l;
     sa[threadIdx.x] = a;
+    st[threadIdx.x] = t;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) { sl[threadIdx.x] += sl[threadIdx.x + s]; sa[threadIdx.x] += sa[threadIdx.x + s]; }
+        if ((int)threadIdx.x < s) {
+            sl[threadIdx.x] += sl[threadIdx.x + s];
+            sa[threadIdx.x] += sa[threadIdx.x + s];
+            st[threadIdx.x] += st[threadIdx.x + s];
+        }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         xent[j] = sl[0] / ((float)B * N);
         acc[j] = sa[0] / ((float)B * N);
+        if (rowts) ts[j] = st[0] / ((float)B * N);
         __threadfence();
         last = atomicAdd(ticket, 1u) == (unsigned)J - 1u ? 1u : 0u;
     }
     __syncthreads();
     if (last && threadIdx.x == 0) {
         __threadfence();
-        float tot = 0.f;
+        float tot = 0.f, tts = 0.f;
         for (int jj = 0; jj < J; ++jj) tot += ld_cg(xent + jj);
+        tot /= (float)J;                                                                  // the loss of model.py:413
+        if (rowts) {
+            for (int jj = 0; jj < J; ++jj) tts += ld_cg(ts + jj);
+            tts /= (float)J;
+            ts[J] = tts;
+            tot = alpha * tot + (1.f - alpha) * tts;                                      // teacherstudent.py:575
+        }
         // a tensor-core pipeline that timed out (gemm_tc.cu) left garbage behind: poison the loss instead of returning it
-        xent[J] = (tc_err && *tc_err) ? __int_as_float(0x7fc00000) : tot / (float)J;          // the loss itself (model.py:413)
+        xent[J] = (tc_err && *tc_err) ? __int_as_float(0x7fc00000) : tot;
         *ticket = 0u;
     }
 }
@@ -436,9 +476,9 @@ static GenLayout gen_layout(int B, int N, int T) {
 
 size_t walk_general_mats_floats(int B, int N, int T) { return (size_t)gen_layout(B, N, T).total; }
 
-// s12, s21 (B(T-1)N each) | invn, nrm (B N T each) | rowloss, rowacc (B (T-2) N each)
+// s12, s21 (B(T-1)N each) | invn, nrm (B N T each) | rowloss, rowacc, rowts (B (T-2) N each)
 size_t walk_general_stat_floats(int B, int N, int T) {
-    return (size_t)B * N * (2 * (T > 1 ? T - 1 : 0) + 2 * T + 2 * (T >= 3 ? T - 2 : 0));
+    return (size_t)B * N * (2 * (T > 1 ? T - 1 : 0) + 2 * T + 3 * (T >= 3 ? T - 2 : 0));       // + rowts (teacher-student rows)
 }
 
 #define CRW_TRY(x) do { int _e = (x); if (_e != CRW_OK) return _e; } while (0)
@@ -456,6 +496,7 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
     float* nrm = invn + (int64_t)B * N * T;
     float* rowloss = nrm + (int64_t)B * N * T;
     float* rowacc = rowloss + (int64_t)B * t2 * N;
+    float* rowts = rowacc + (int64_t)B * t2 * N;
     unsigned char* codesF = p.ws_codes;                          // (B,T-1,N,N), orientation of A
     unsigned char* codesG = p.ws_codes + (int64_t)B * s1;        // orientation of A^T
     const int softmax = (p.flags & CRW_WALK_SOFTMAX) ? 1 : 0;
@@ -533,9 +574,12 @@ int launch_walk_general(const WalkParams& p, crw_stream_t stream) {
     const int need_grad = p.grad != nullptr;
     const float cgrad = 1.0f / ((float)t2 * (float)B * (float)N);
     const int64_t lrows = (int64_t)B * t2 * N;
-    CRW_LAUNCH(loss_rows_kernel, rows_grid(lrows), 256, 0, stream, W, rowloss, rowacc, lrows, N, cgrad, need_grad);
+    if (p.chains_out) cudaMemcpyAsync(p.chains_out, W, sizeof(float) * (size_t)B * s2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    const float* Wt = p.ts_target;
+    CRW_LAUNCH(loss_rows_kernel, rows_grid(lrows), 256, 0, stream, W, rowloss, rowacc, lrows, N, cgrad, need_grad, Wt, rowts, p.ts_alpha);
     CRW_TRY(check_launch("loss_rows"));
-    CRW_LAUNCH(loss_reduce_kernel, t2, 256, 0, stream, rowloss, rowacc, p.xent, p.acc, B, t2, N, (const unsigned*)p.ws_tc, p.ws_counter);
+    CRW_LAUNCH(loss_reduce_kernel, t2, 256, 0, stream, rowloss, rowacc, p.xent, p.acc, B, t2, N, (const unsigned*)p.ws_tc, p.ws_counter,
+               Wt ? (const float*)rowts : (const float*)nullptr, p.ts_xent, p.ts_alpha);
     CRW_TRY(check_launch("loss_reduce"));
     if (!need_grad) return CRW_OK;
 

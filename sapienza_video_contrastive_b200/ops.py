@@ -365,7 +365,7 @@ def philox_replay_ok(device) -> bool:
 # ------------------------------------------------------------------------------------------------------------------
 class _Walk(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, tau, rate, flags, rng, u12, u21p, rng_state):
+    def forward(ctx, feats, tau, rate, flags, rng, u12, u21p, rng_state, ts=None):
         _need_cuda(feats, u12, u21p)
         check_device(feats.device)
         feats = _f32c(feats)
@@ -411,13 +411,33 @@ class _Walk(torch.autograd.Function):
         xent = torch.empty(nw + 1, dtype=torch.float32, device=dev) if nw > 0 else torch.zeros(1, dtype=torch.float32, device=dev)
         acc = torch.empty(max(nw, 1), dtype=torch.float32, device=dev)
         grad = torch.empty_like(feats) if (need_grad and nw > 0) else None
-        L.check(L.crw_walk_fwd_bwd(feats.data_ptr(), B, N, T, D, float(tau), float(rate),
-                                   u12.data_ptr() if u12 is not None else None,
-                                   u21p.data_ptr() if u21p is not None else None,
-                                   seed, off, thr, rng_state.data_ptr() if (rng == "device" and rate > 0) else None,
-                                   flags, q.data_ptr(), xent.data_ptr(), acc.data_ptr(),
-                                   grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(), _stream()),
-                "walk_fwd_bwd")
+        if ts is None:
+            L.check(L.crw_walk_fwd_bwd(feats.data_ptr(), B, N, T, D, float(tau), float(rate),
+                                       u12.data_ptr() if u12 is not None else None,
+                                       u21p.data_ptr() if u21p is not None else None,
+                                       seed, off, thr, rng_state.data_ptr() if (rng == "device" and rate > 0) else None,
+                                       flags, q.data_ptr(), xent.data_ptr(), acc.data_ptr(),
+                                       grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(), _stream()),
+                    "walk_fwd_bwd")
+        else:
+            # teacher-student call (teacherstudent.py:472-580): `ts` carries the teacher's chain products and / or asks for ours
+            teacher = ts.get("teacher")
+            if teacher is not None:
+                teacher = _f32c(teacher)
+                if tuple(teacher.shape) != (B, nw, N, N):
+                    raise ValueError("teacher chains must be (B,T-2,N,N) = %s, got %s" % ((B, nw, N, N), tuple(teacher.shape)))
+                ts["ts_xent"] = torch.zeros(nw + 1, dtype=torch.float32, device=dev)
+            if ts.get("want_chains"):
+                ts["chains"] = torch.empty(B, nw, N, N, dtype=torch.float32, device=dev)
+            L.check(L.crw_walk_ts_fwd_bwd(feats.data_ptr(), B, N, T, D, float(tau), float(rate),
+                                          u12.data_ptr() if u12 is not None else None,
+                                          u21p.data_ptr() if u21p is not None else None,
+                                          seed, off, thr, rng_state.data_ptr() if (rng == "device" and rate > 0) else None,
+                                          flags, teacher.data_ptr() if teacher is not None else None, float(ts.get("alpha", 1.0)),
+                                          ts["chains"].data_ptr() if ts.get("want_chains") else None,
+                                          q.data_ptr(), xent.data_ptr(), ts["ts_xent"].data_ptr() if teacher is not None else None,
+                                          acc.data_ptr(), grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(),
+                                          _stream()), "walk_ts_fwd_bwd")
         loss = xent[nw:nw + 1]                                 # model.py:413 (zeros when there is no walk)
         xent, acc = xent[:nw], acc[:nw]
         ctx.save_for_backward(grad if grad is not None else torch.empty(0, device=dev), q, feats)
@@ -447,7 +467,7 @@ class _Walk(torch.autograd.Function):
             out = extra if out is None else out + extra
         if out is None:
             out = torch.zeros_like(feats)
-        return out, None, None, None, None, None, None, None
+        return out, None, None, None, None, None, None, None, None
 
 
 def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = False, softmax: bool = False,
@@ -468,7 +488,60 @@ def walk(feats: torch.Tensor, temperature: float, rate: float, flip: bool = Fals
     flags |= WALK_NO_TF32 if no_tf32 else 0
     if u12 is not None:
         rng = "torch"
-    return _Walk.apply(feats, float(temperature), float(rate), flags, rng, u12, u21p, rng_state)
+    return _Walk.apply(feats, float(temperature), float(rate), flags, rng, u12, u21p, rng_state, None)
+
+
+def walk_chains(feats: torch.Tensor, temperature: float, rate: float = 0.0, flip: bool = False, softmax: bool = True,
+                rng: str = "philox", u12: Optional[torch.Tensor] = None, u21p: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The teacher side of teacherstudent.py:523-538: feats (B,N,T,D) -> the palindrome chain products (B,T-2,N,N) of walks
+    1..T-2 (`aar`, or `aal` with flip); no gradient.  Edge dropout as in `walk` (the reference drops the teacher's edges too:
+    stoch_mat's do_dropout defaults to True at teacherstudent.py:527-528)."""
+    flags = (WALK_FLIP if flip else 0) | (WALK_SOFTMAX if softmax else 0) | WALK_FORCE_GENERAL
+    if u12 is not None:
+        rng = "torch"
+    ts = {"want_chains": True}
+    with torch.no_grad():
+        _Walk.apply(feats.detach(), float(temperature), float(rate), flags, rng, u12, u21p, None, ts)
+    return ts["chains"]
+
+
+def walk_teacher_student(feats: torch.Tensor, teacher_feats: torch.Tensor, temperature: float, rate: float, alpha: float,
+                         flip: bool = False, softmax: bool = True, rng: str = "philox", uniforms=None):
+    """teacherstudent.py:494-577 from the node vectors on: feats / teacher_feats (B,N,T,D) before normalisation.  The walk
+    loss of `walk` blended with the soft cross-entropy of the teacher's chain products against log_softmax of the student's
+    (SoftCrossEntropyLoss, :270-292): loss = alpha * walk loss + (1 - alpha) * teacher-student loss.
+    `uniforms` = (us12, us21p, ut12, ut21p) supplies the dropout draws; otherwise they are made in the reference's order
+    (the student's 2(T-1) draws, then the teacher's) by torch.rand ('torch') or by replaying the generator in the kernels
+    ('philox').  -> (q, loss [1], xent (T-2), acc (T-2), ts_xent (T-2)); the gradient of `loss` with respect to `feats` comes
+    out of the same launch."""
+    _need_cuda(feats, teacher_feats)
+    B, N, T, D = feats.shape
+    flags = (WALK_FLIP if flip else 0) | (WALK_SOFTMAX if softmax else 0) | WALK_FORCE_GENERAL
+    us12 = us21p = ut12 = ut21p = None
+    dropping = rate > 0 and T > 1
+    if uniforms is not None:
+        us12, us21p, ut12, ut21p = uniforms
+        rng = "torch"
+    elif dropping and rng == "torch":
+        us12, us21p, ut12, ut21p = (torch.stack([torch.rand(B, N, N, device=feats.device) for _ in range(T - 1)]) for _ in range(4))
+    if dropping and rng == "philox":
+        # the teacher's chains are needed first but its draws come second: run it on the later part of the generator stream
+        idx = feats.device.index if feats.device.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        off = gen.get_offset()
+        span = 2 * (T - 1) * torch_rand_offset_increment(B * N * N, torch_rand_threads(B * N * N, idx))
+        gen.set_offset(off + span)
+        teacher = walk_chains(teacher_feats, temperature, rate, flip, softmax, "philox")
+        gen.set_offset(off)
+    elif rng in ("philox", "torch"):
+        teacher = walk_chains(teacher_feats, temperature, rate if dropping else 0.0, flip, softmax, rng, ut12, ut21p)
+    else:
+        raise ValueError("rng must be 'torch' or 'philox'")
+    ts = {"teacher": teacher, "alpha": float(alpha)}
+    q, loss, xent, acc = _Walk.apply(feats, float(temperature), float(rate), flags, rng, us12, us21p, None, ts)
+    if dropping and rng == "philox":
+        gen.set_offset(off + 2 * span)
+    return q, loss, xent, acc, ts["ts_xent"][:-1]
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -32,6 +32,13 @@ SPD_CASES = {
     "spd_cross":  dict(B=2, T=1, SP=20, Ce=8, one_based=False, ksize=21, shape="cross", seed=53),
 }
 
+# teacher-student walk cases (teacherstudent.py:472-580): node vectors in, softmax transition matrices
+TS_CASES = {
+    "ts_basic":  dict(B=2, T=4, N=25, D=32, p=0.1, tau=0.07, alpha=0.5, flip=False, seed=61),
+    "ts_flip":   dict(B=1, T=5, N=16, D=16, p=0.2, tau=0.05, alpha=0.25, flip=True, seed=62),
+    "ts_nodrop": dict(B=2, T=3, N=36, D=32, p=0.0, tau=0.07, alpha=0.8, flip=False, seed=63),
+}
+
 # label-propagation cases (test_utils.py:148-179, test.py:141-160)
 LP_CASES = {
     "lp_small":   dict(C=16, h=12, w=17, n_ctx=4, n_tgt=6, long_mem=[0], radius=3, k=5, tau=0.07, L=3,
@@ -72,6 +79,15 @@ def walk_inputs(c):
     maps = torch.randn(c["B"] * c["N"], c["Ce"], c["T"], 8, 8, generator=g)
     head_w = torch.randn(128, c["Ce"], generator=g) / c["Ce"] ** 0.5
     return maps, head_w
+
+
+def ts_inputs(c):
+    """-> student, teacher node vectors before normalisation, each (B, N, T, D); the teacher is a perturbed student.
+    The walk RNG seed is c['seed'] + 1000."""
+    g = torch.Generator().manual_seed(c["seed"])
+    fs = torch.randn(c["B"], c["N"], c["T"], c["D"], generator=g)
+    ft = fs + 0.5 * torch.randn(c["B"], c["N"], c["T"], c["D"], generator=g)
+    return fs, ft
 
 
 def voronoi_labels(B, T, SP, size, g, one_based):

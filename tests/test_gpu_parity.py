@@ -354,6 +354,57 @@ def test_superpixel_nodes_and_walk_match_reference(ops, name):
     assert relmax(md.grad.cpu(), fx["grad_maps"]) < 1e-4
 
 
+@pytest.mark.parametrize("name", list(cases.TS_CASES))
+def test_teacher_student_walk_matches_reference(ops, name):
+    """teacherstudent.py:472-580 from the node vectors on (crw_walk_ts_fwd_bwd): loss, walk diags and the gradient of the
+    student's node vectors against the reference's CRWTeacherStudent.forward; teacher-student terms against the oracle."""
+    c = cases.TS_CASES[name]
+    fx = load(name)
+    fs, ft = cases.ts_inputs(c)
+    B, N, T, D = fs.shape
+    torch.manual_seed(c["seed"] + 1000)
+    us12, us21p = O.draw_uniforms(B, N, T)
+    ut12, ut21p = O.draw_uniforms(B, N, T)
+    fd = fs.to(DEV).requires_grad_(True)
+    uni = tuple(u.to(DEV) for u in (us12, us21p, ut12, ut21p))
+    q, loss, xent, acc, tsx = ops.walk_teacher_student(fd, ft.to(DEV), c["tau"], c["p"], c["alpha"], flip=c["flip"], uniforms=uni)
+    torch.testing.assert_close(q.permute(0, 3, 2, 1).cpu(), fx["q"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(loss.cpu(), fx["loss"], rtol=1e-5, atol=0)
+    names = [("l%d" if c["flip"] else "r%d") % i for i in range(1, T - 1)]
+    for j, nm in enumerate(names):
+        torch.testing.assert_close(xent[j].cpu(), fx["diags"]["8 xent cyc %s" % nm], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(acc[j].cpu(), fx["diags"]["8 acc cyc %s" % nm], rtol=0, atol=1e-6)
+    qt = torch.nn.functional.normalize(ft, dim=-1).permute(0, 3, 2, 1)
+    _, _, ts_o = O.teacher_student_loss(fx["q"], qt, c["tau"], c["p"], c["alpha"], us12, us21p, ut12, ut21p, flip=c["flip"])
+    torch.testing.assert_close(tsx.cpu(), torch.stack(ts_o), rtol=1e-5, atol=0)
+    loss.sum().backward()
+    assert relmax(fd.grad.cpu(), fx["grad_feats"]) < 1e-4
+    chains = ops.walk_chains(ft.to(DEV), c["tau"], c["p"], c["flip"], True, u12=uni[2], u21p=uni[3])
+    Wt = torch.stack(O.walk_chain_products(qt, c["tau"], c["p"], ut12, ut21p, flip=c["flip"], softmax=True), 1)
+    torch.testing.assert_close(chains.cpu(), Wt, rtol=1e-4, atol=1e-7)
+
+
+def test_teacher_student_walk_generator_order(ops):
+    """Without explicit draws the student's 2(T-1) dropout draws come first in the generator stream and the teacher's second,
+    as in the reference - although the teacher's chains are computed first: 'philox' (in-kernel replay) and 'torch'
+    (torch.rand) give the same numbers from the same seed and leave the generator in the same state."""
+    if not ops.philox_replay_ok(DEV):
+        pytest.skip("torch's CUDA rand launch geometry is not the one the replay assumes")
+    B, N, T, D = 3, 70, 4, 64                                     # a large-graph shape: tensor-core GEMMs inside
+    g = torch.Generator().manual_seed(5)
+    fs, ft = torch.randn(B, N, T, D, generator=g).to(DEV), torch.randn(B, N, T, D, generator=g).to(DEV)
+    outs = []
+    for rng in ("torch", "philox"):
+        torch.manual_seed(77)
+        f = fs.clone().requires_grad_(True)
+        q, loss, xent, acc, tsx = ops.walk_teacher_student(f, ft, 0.07, 0.2, 0.3, rng=rng)
+        loss.sum().backward()
+        outs.append((loss.detach(), tsx, f.grad, torch.rand(4, device=DEV)))
+    for a, b in zip(*outs):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-9)
+    assert torch.equal(outs[0][3], outs[1][3])
+
+
 @pytest.mark.parametrize("name", list(cases.SPD_CASES))
 def test_dilated_superpixel_nodes_match_reference(ops, name):
     """--dilate-superpixels (model.py:303-309): pooled features against the oracle, node embeddings and the gradients of

@@ -108,3 +108,35 @@ def test_crw_module_surface_on_cpu():
         CRW(argparse.Namespace(**{**vars(args), "dilate_superpixels": True, "dilation_kernel_size": 50}))
     with pytest.raises(ValueError):
         CRW(argparse.Namespace(**{**vars(args), "dilate_superpixels": True, "dilation_kernel_shape": "square"}))
+
+
+def test_teacher_student_module_surface_on_cpu(tmp_path):
+    """teacherstudent.py:11-53, 294-341: biased head, softmax walk, frozen teacher loaded from args.path_to_pretrained,
+    the reference's state-dict names, alpha checked; no CPU forward."""
+    import argparse
+    from sapienza_video_contrastive_b200 import CRWBase, CRWTeacherStudent, SoftCrossEntropyLoss
+    torch.manual_seed(0)
+    args = argparse.Namespace(device="cpu", dropout=0.1, featdrop=0.0, temp=0.07, head_depth=0, model_type="scratch",
+                              remove_layers=[], dilate_superpixels=False, flip=False, sk_targets=False,
+                              alpha_teacher_student=0.5, path_to_pretrained=str(tmp_path / "pretrained.pth"))
+    base = CRWBase(args)
+    assert base.use_softmax and base.selfsim_fc[0].bias is not None
+    assert "selfsim_fc.0.bias" in base.state_dict()
+    torch.save({"model": base.state_dict()}, args.path_to_pretrained)
+    ts = CRWTeacherStudent(args)
+    assert all(not p.requires_grad for p in ts.teacher.parameters()) and any(p.requires_grad for p in ts.parameters())
+    for k, v in base.state_dict().items():
+        assert torch.equal(ts.state_dict()["teacher." + k], v)
+    assert {k.split(".")[0] for k in ts.state_dict()} == {"encoder", "selfsim_fc", "teacher"}
+    with pytest.raises(AssertionError):
+        CRWTeacherStudent(argparse.Namespace(**{**vars(args), "alpha_teacher_student": 1.5}), teacher=base)
+    with pytest.raises(RuntimeError):
+        ts(torch.zeros(1, 4, 6, 64, 64))
+    # SoftCrossEntropyLoss (:270-292): hard targets reduce to the usual cross-entropy
+    x = torch.randn(5, 7)
+    y = torch.randint(0, 7, (5,))
+    onehot = torch.nn.functional.one_hot(y, 7).float()
+    torch.testing.assert_close(SoftCrossEntropyLoss()(x, onehot), torch.nn.functional.cross_entropy(x, y))
+    assert SoftCrossEntropyLoss(reduction="none")(x, onehot).shape == (5,)
+    with pytest.raises(ValueError):
+        SoftCrossEntropyLoss(reduction="median")(x, onehot)

@@ -49,6 +49,27 @@ def test_walk_matches_reference(name):
     torch.testing.assert_close(torch.stack(A21), fx["A21"], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", list(cases.TS_CASES))
+def test_teacher_student_loss_matches_reference(name):
+    """CRWTeacherStudent.forward (teacherstudent.py:472-580) run unmodified from the node embeddings on: loss, walk diags and
+    the gradient of the student's node vectors."""
+    c = cases.TS_CASES[name]
+    fx = load(name)
+    fs, ft = cases.ts_inputs(c)
+    fs = fs.clone().requires_grad_(True)
+    nrm = lambda f: torch.nn.functional.normalize(f, p=2, dim=-1).permute(0, 3, 2, 1)          # (B,D,T,N)
+    torch.manual_seed(c["seed"] + 1000)
+    us12, us21p = O.draw_uniforms(c["B"], c["N"], c["T"])
+    ut12, ut21p = O.draw_uniforms(c["B"], c["N"], c["T"])        # the teacher's matrices are dropped out too, with later draws
+    loss, xents, ts = O.teacher_student_loss(nrm(fs), nrm(ft), c["tau"], c["p"], c["alpha"], us12, us21p, ut12, ut21p, flip=c["flip"])
+    torch.testing.assert_close(loss, fx["loss"], rtol=1e-5, atol=0)
+    names = [("l%d" if c["flip"] else "r%d") % i for i in range(1, c["T"] - 1)]
+    for n, xe in zip(names, xents):
+        torch.testing.assert_close(xe, fx["diags"]["%d xent cyc %s" % (8, n)], rtol=1e-5, atol=1e-7)
+    loss.sum().backward()
+    assert float((fs.grad - fx["grad_feats"]).abs().max() / fx["grad_feats"].abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize("name", list(cases.SPD_CASES))
 def test_dilated_superpixel_matches_reference(name):
     """--dilate-superpixels (model.py:303-309): the oracle's run-free restatement against the reference's fp16 depthwise

@@ -113,6 +113,60 @@ def test_walk_vs_oracle_grad(sim, B, N, T, D, p, flags):
     assert g2 is None and torch.equal(xe2, xe)
 
 
+@pytest.mark.parametrize("name", list(cases.TS_CASES))
+def test_teacher_student_walk_vs_reference_golden(sim, name):
+    """crw_walk_ts_fwd_bwd: the teacher call hands out its chain products (checked against the oracle's), the student call
+    blends the walk loss with the soft cross-entropy against them; loss, diags and the gradient of the student's node
+    vectors against the reference's CRWTeacherStudent.forward."""
+    c = cases.TS_CASES[name]
+    fx = load(name)
+    fs, ft = cases.ts_inputs(c)
+    B, N, T, D = fs.shape
+    J = T - 2
+    torch.manual_seed(c["seed"] + 1000)
+    us12, us21p = O.draw_uniforms(B, N, T)
+    ut12, ut21p = O.draw_uniforms(B, N, T)
+    flags = _lib.WALK_SOFTMAX | (_lib.WALK_FLIP if c["flip"] else 0)
+    wsb = sim.crw_walk_workspace_bytes(B, N, T, D, flags | _lib.WALK_FORCE_GENERAL)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    q = torch.empty_like(fs)
+    xe, ac, tsx = torch.zeros(J + 1), torch.zeros(J), torch.zeros(J + 1)
+    chains = torch.empty(B, J, N, N)
+    p = c["p"]
+    sim.check(sim.crw_walk_ts_fwd_bwd(ptr(ft), B, N, T, D, c["tau"], p, ptr(ut12) if p > 0 else None, ptr(ut21p) if p > 0 else None,
+                                      0, 0, 0, None, flags, None, 1.0, ptr(chains), ptr(q), ptr(xe), None, ptr(ac), None,
+                                      ptr(ws), wsb, None), "teacher")
+    qt = torch.nn.functional.normalize(ft, dim=-1).permute(0, 3, 2, 1)
+    Wt = torch.stack(O.walk_chain_products(qt, c["tau"], p, ut12, ut21p, flip=c["flip"], softmax=True), 1)
+    torch.testing.assert_close(chains, Wt, rtol=1e-4, atol=1e-7)
+    g = torch.empty_like(fs)
+    for _ in range(2):                                           # the workspace is reusable as it is
+        sim.check(sim.crw_walk_ts_fwd_bwd(ptr(fs), B, N, T, D, c["tau"], p, ptr(us12) if p > 0 else None, ptr(us21p) if p > 0 else None,
+                                          0, 0, 0, None, flags, ptr(chains), c["alpha"], None, ptr(q), ptr(xe), ptr(tsx), ptr(ac), ptr(g),
+                                          ptr(ws), wsb, None), "student")
+    torch.testing.assert_close(q.permute(0, 3, 2, 1), fx["q"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(xe[J:], fx["loss"], rtol=1e-5, atol=0)
+    names = [("l%d" if c["flip"] else "r%d") % i for i in range(1, T - 1)]
+    for j, nm in enumerate(names):
+        torch.testing.assert_close(xe[j], fx["diags"]["8 xent cyc %s" % nm], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(ac[j], fx["diags"]["8 acc cyc %s" % nm], rtol=0, atol=1e-6)
+    _, _, ts_o = O.teacher_student_loss(fx["q"], qt, c["tau"], p, c["alpha"], us12, us21p, ut12, ut21p, flip=c["flip"])
+    torch.testing.assert_close(tsx[:J], torch.stack(ts_o), rtol=1e-5, atol=0)
+    assert abs(float(tsx[J]) - float(tsx[:J].mean())) < 1e-6
+    assert float((g - fx["grad_feats"]).abs().max() / fx["grad_feats"].abs().max()) < 1e-4
+    # alpha = 1 is the plain walk: same loss and gradient as crw_walk_fwd_bwd on the general path
+    g1 = torch.empty_like(fs)
+    sim.check(sim.crw_walk_ts_fwd_bwd(ptr(fs), B, N, T, D, c["tau"], p, ptr(us12) if p > 0 else None, ptr(us21p) if p > 0 else None,
+                                      0, 0, 0, None, flags, ptr(chains), 1.0, None, ptr(q), ptr(xe), ptr(tsx), ptr(ac), ptr(g1),
+                                      ptr(ws), wsb, None), "alpha 1")
+    _, xe0, _, g0 = run_walk(sim, fs, c["tau"], p, us12, us21p, flags | _lib.WALK_FORCE_GENERAL)
+    torch.testing.assert_close(xe[:J], xe0, rtol=1e-6, atol=0)
+    torch.testing.assert_close(g1, g0, rtol=1e-5, atol=1e-9)
+    # a teacher without somewhere to put its losses, or alpha outside [0, 1], is refused
+    assert sim.crw_walk_ts_fwd_bwd(ptr(fs), B, N, T, D, c["tau"], 0.0, None, None, 0, 0, 0, None, flags, ptr(chains), 1.5, None, ptr(q),
+                                   ptr(xe), ptr(tsx), ptr(ac), None, ptr(ws), wsb, None) != 0
+
+
 def test_walk_empty_nodes(sim):
     """all-zero node vectors (empty superpixels): zero ZeroSoftmax rows, loss row = log N, finite grads (F5)."""
     torch.manual_seed(3)
