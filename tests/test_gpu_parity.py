@@ -300,6 +300,65 @@ def test_crw_dropin_config1_matches_reference(ops):
     assert relmax(crw.encoder.model.conv1.weight.grad.cpu(), fx["grad_conv1"]) < 0.3   # 20 conv/BN layers on cuDNN vs CPU at random init: not the path under test
 
 
+def test_crw_module_dilated_superpixels(ops):
+    """CRW(args) with --dilate-superpixels (model.py:38, 303-309): image_to_nodes pools with the dilated masks (checked
+    against the oracle on the module's own feature maps) and the full forward / backward runs."""
+    from sapienza_video_contrastive_b200 import CRW
+    torch.manual_seed(0)
+    crw = CRW(make_args(dilate_superpixels=True, dilation_kernel_size=11, dilation_kernel_shape="circle", dropout=0.0)).to(DEV)
+    assert crw.dilation == (11, "circle")
+    B, T, SP = 1, 3, 12
+    g = torch.Generator().manual_seed(4)
+    lab = cases.voronoi_labels(B, T, SP, 256, g, one_based=False)
+    sp_mask = lab[:, :, None].repeat(1, 1, 3, 1, 1).to(DEV)
+    x = torch.randn(B, T, 3, 256, 256, generator=g).to(DEV)
+    with torch.no_grad():
+        feats, maps = crw.image_to_nodes(x, sp_mask, SP)
+    assert feats.shape == (B, 128, T, SP) and maps.shape == (B, 512, T, 32, 32)
+    pooled = O.segment_mean_dilated(maps.cpu(), lab, SP, 11, "circle")                     # (B,T,SP,C)
+    f = pooled @ crw.selfsim_fc[0].weight.detach().cpu().t()
+    ref = (f / f.norm(dim=-1, keepdim=True).clamp_min(1e-12)).permute(0, 3, 1, 2)
+    torch.testing.assert_close(feats.cpu(), ref, rtol=1e-3, atol=1e-4)                     # tf32-split head vs fp32 matmul
+    plain = CRW(make_args(dropout=0.0)).to(DEV)
+    plain.load_state_dict(crw.state_dict())
+    with torch.no_grad():
+        feats0, _ = plain.image_to_nodes(x, sp_mask, SP)
+    assert float((feats0 - feats).abs().max()) > 1e-3                                     # the dilation does change the nodes
+    q, loss, diags = crw(x, sp_mask, SP)
+    loss.mean().backward()
+    assert q.shape == (B, 128, T, SP) and torch.isfinite(loss).all()
+    assert crw.selfsim_fc[0].weight.grad is not None and torch.isfinite(crw.encoder.model.conv1.weight.grad).all()
+
+
+def test_teacher_student_module_forward(ops):
+    """CRWTeacherStudent.forward (teacherstudent.py:472-580) through the module: loss against the oracle evaluated on the
+    module's own node vectors, gradients reach the student only, the reference's diag names."""
+    from sapienza_video_contrastive_b200 import CRWBase, CRWTeacherStudent
+    torch.manual_seed(0)
+    args = make_args(alpha_teacher_student=0.4, dropout=0.1)
+    teacher = CRWBase(args)
+    ts = CRWTeacherStudent(args, teacher=teacher).to(DEV)
+    B, T, N = 2, 4, 9
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, T, N * 3, 64, 64, generator=g).to(DEV)
+    torch.manual_seed(21)
+    uni = O.draw_uniforms(B, N, T) + O.draw_uniforms(B, N, T)
+    q, loss, diags = ts(x, walk_uniforms=tuple(u.to(DEV) for u in uni))
+    assert q.shape == (B, 128, T, N) and loss.shape == (1,)
+    assert sorted(diags) == ["64 acc cyc r1", "64 acc cyc r2", "64 xent cyc r1", "64 xent cyc r2"]
+    with torch.no_grad():
+        xr = x.transpose(1, 2).reshape(B, N, 3, T, 64, 64)
+        fs = ts._patch_nodes_prenorm(xr)[0].cpu()
+        ft = ts.teacher._patch_nodes_prenorm(xr)[0].cpu()
+    nrm = lambda f: torch.nn.functional.normalize(f, dim=-1).permute(0, 3, 2, 1)
+    loss_o, xents_o, _ = O.teacher_student_loss(nrm(fs), nrm(ft), 0.07, 0.1, 0.4, *uni)
+    torch.testing.assert_close(loss.detach().cpu(), loss_o, rtol=1e-4, atol=0)
+    torch.testing.assert_close(diags["64 xent cyc r1"].cpu(), xents_o[0], rtol=1e-4, atol=0)
+    loss.mean().backward()
+    assert ts.selfsim_fc[0].weight.grad is not None and ts.selfsim_fc[0].bias.grad is not None
+    assert all(p.grad is None for p in ts.teacher.parameters())
+
+
 def test_crw_dropin_api_surface(ops):
     from sapienza_video_contrastive_b200 import CRW
     torch.manual_seed(0)
