@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(1024, 1) segmean_accum_tma_kernel(const CRW_GR
     uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * meta_words);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nchunks = ws.nchunks, ntiles = C / kSegCTF;
-    const int64_t cstride = (int64_t)T * cells;
+    [[maybe_unused]] const int64_t cstride = (int64_t)T * cells;      // the host simulator's stand-in for the tensor copy
     SegCursor cur;
     int total;
     seg_first_cursor<LMAX>(cur, total, BT, C, T, nchunks);

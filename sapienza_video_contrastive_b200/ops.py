@@ -530,9 +530,11 @@ def walk_teacher_student(feats: torch.Tensor, teacher_feats: torch.Tensor, tempe
         gen = torch.cuda.default_generators[idx]
         off = gen.get_offset()
         span = 2 * (T - 1) * torch_rand_offset_increment(B * N * N, torch_rand_threads(B * N * N, idx))
-        gen.set_offset(off + span)
-        teacher = walk_chains(teacher_feats, temperature, rate, flip, softmax, "philox")
-        gen.set_offset(off)
+        try:
+            gen.set_offset(off + span)
+            teacher = walk_chains(teacher_feats, temperature, rate, flip, softmax, "philox")
+        finally:
+            gen.set_offset(off)
     elif rng in ("philox", "torch"):
         teacher = walk_chains(teacher_feats, temperature, rate if dropping else 0.0, flip, softmax, rng, ut12, ut21p)
     else:
