@@ -167,6 +167,38 @@ def test_teacher_student_walk_vs_reference_golden(sim, name):
                                    ptr(xe), ptr(tsx), ptr(ac), None, ptr(ws), wsb, None) != 0
 
 
+@pytest.mark.parametrize("B,N,T,D,p,flags,alpha", [(2, 20, 4, 32, 0.2, 0, 0.3), (1, 70, 3, 64, 0.0, 2, 0.0), (1, 33, 5, 32, 0.1, 1, 1.0)])
+def test_teacher_student_walk_vs_oracle(sim, B, N, T, D, p, flags, alpha):
+    """ZeroSoftmax and softmax transition matrices, flip, the two ends of alpha, a graph beyond the fused kernels' size:
+    losses and the gradient against autograd through the oracle."""
+    g = torch.Generator().manual_seed(N * 10 + T)
+    fs, ft = torch.randn(B, N, T, D, generator=g), torch.randn(B, N, T, D, generator=g)
+    torch.manual_seed(N)
+    us12, us21p = O.draw_uniforms(B, N, T)
+    ut12, ut21p = O.draw_uniforms(B, N, T)
+    J = T - 2
+    nrm = lambda f: torch.nn.functional.normalize(f, dim=-1).permute(0, 3, 2, 1)
+    fo = fs.clone().requires_grad_(True)
+    loss_o, xents_o, ts_o = O.teacher_student_loss(nrm(fo), nrm(ft), 0.07, p, alpha, us12, us21p, ut12, ut21p, flip=bool(flags & 2),
+                                                   softmax=bool(flags & 1))
+    loss_o.sum().backward()
+    wsb = sim.crw_walk_workspace_bytes(B, N, T, D, flags | _lib.WALK_FORCE_GENERAL)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    q = torch.empty_like(fs)
+    xe, ac, tsx = torch.zeros(J + 1), torch.zeros(J), torch.zeros(J + 1)
+    chains = torch.empty(B, J, N, N)
+    up = lambda u: ptr(u) if p > 0 else None
+    sim.check(sim.crw_walk_ts_fwd_bwd(ptr(ft), B, N, T, D, 0.07, p, up(ut12), up(ut21p), 0, 0, 0, None, flags, None, 1.0, ptr(chains),
+                                      ptr(q), ptr(xe), None, ptr(ac), None, ptr(ws), wsb, None), "teacher")
+    gr = torch.empty_like(fs)
+    sim.check(sim.crw_walk_ts_fwd_bwd(ptr(fs), B, N, T, D, 0.07, p, up(us12), up(us21p), 0, 0, 0, None, flags, ptr(chains), alpha, None,
+                                      ptr(q), ptr(xe), ptr(tsx), ptr(ac), ptr(gr), ptr(ws), wsb, None), "student")
+    torch.testing.assert_close(xe[J:], loss_o.detach(), rtol=1e-5, atol=0)
+    torch.testing.assert_close(xe[:J], torch.stack(xents_o).detach(), rtol=1e-5, atol=0)
+    torch.testing.assert_close(tsx[:J], torch.stack(ts_o).detach(), rtol=1e-5, atol=0)
+    assert float((gr - fo.grad).abs().max() / fo.grad.abs().max()) < 1e-4
+
+
 def test_walk_empty_nodes(sim):
     """all-zero node vectors (empty superpixels): zero ZeroSoftmax rows, loss row = log N, finite grads (F5)."""
     torch.manual_seed(3)
@@ -344,7 +376,9 @@ def test_segmean_dilated_edges(sim):
                                                          (2, 70, 1, 4, 40, 31, "cross"),    # 280 columns, one pixel row per cell
                                                          (5, 3, 2, 32, 7, 21, "L1"),        # 32-pixel-wide cells
                                                          (16, 16, 2, 2, 70, 15, "circle"),  # > 1024 CSR entries in a chunk (TMA path)
-                                                         (16, 20, 2, 2, 40, 13, "L1")])     # the same on the cp.async path
+                                                         (16, 20, 2, 2, 40, 13, "L1"),      # the same on the cp.async path
+                                                         (1, 100, 64, 1, 255, 127, "circle"), # tallest cells, most labels, widest element: bitmap capped by shared memory
+                                                         (2, 3, 16, 4, 200, 9, "cross")])    # 16 x 4 cells
 def test_segmean_dilated_strips(sim, Hm, Wm, sy, sx, SP, ksize, shape):
     g = torch.Generator().manual_seed(Hm * 1000 + Wm)
     B, T, C = 1, 2, (64 if Hm == 16 else 4)
