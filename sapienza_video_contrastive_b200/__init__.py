@@ -24,6 +24,8 @@ _LAZY = {
     "RadiusMask": ("test_utils", "RadiusMask"),
     "LabelPropagator": ("test_utils", "LabelPropagator"),
     "propagate_labels": ("test_utils", "propagate_labels"),
+    "dump_predictions": ("test_utils", "dump_predictions"),
+    "davis_index_maps": ("test_utils", "davis_index_maps"),
 }
 
 

@@ -191,6 +191,28 @@ def dump_predictions(pred, lbl_set, img, prefix: Optional[str] = None, norm_mask
     return img_with_label, pred_lbl, None
 
 
+def davis_index_maps(cls: torch.Tensor, lbl_set, palette, size=None) -> torch.Tensor:
+    """eval/convert_davis.py:33-70 without the PNG round trip: the class maps the post-processing kernel already produced
+    (`cls` (..., H, W) uint8, slot l = colour lbl_set[l]) -> DAVIS palette indices, optionally resized to the ground truth's
+    (height, width) with OpenCV's INTER_NEAREST rule.  A colour that is not in the palette maps to 0, as in the reference
+    (`color2id` finds nothing and `lblidx2` keeps its zero).  Index arithmetic on a few bytes per pixel: plain tensor ops on
+    whatever device `cls` lives on; write the result with `Image.putpalette(palette.ravel())` as :68-70 does."""
+    lbl_set = torch.as_tensor(lbl_set).to(torch.int64).reshape(-1, 3)
+    pal = torch.as_tensor(palette).to(torch.int64).reshape(-1, 3)
+    match = (lbl_set[:, None, :] == pal[None, :, :]).all(-1)                       # (L, P)
+    ids = torch.arange(pal.shape[0])
+    lut = torch.where(match.any(1), (match.long() * ids).max(1).values, torch.zeros((), dtype=torch.int64)).to(torch.uint8)
+    out = lut.to(cls.device)[cls.long()]
+    if size is not None:
+        H, W = int(size[0]), int(size[1])
+        h, w = out.shape[-2:]
+        if (h, w) != (H, W):        # cv2 INTER_NEAREST: source = min(floor(dst * (src / dst)), src - 1), in double
+            ys = torch.clamp(torch.floor(torch.arange(H, dtype=torch.float64) * (h / H)).long(), max=h - 1).to(out.device)
+            xs = torch.clamp(torch.floor(torch.arange(W, dtype=torch.float64) * (w / W)).long(), max=w - 1).to(out.device)
+            out = out[..., ys[:, None], xs[None, :]]
+    return out
+
+
 class LabelPropagator:
     """Native evaluator: encoder features in, propagated soft label maps out, everything on the device.
 

@@ -140,3 +140,30 @@ def test_teacher_student_module_surface_on_cpu(tmp_path):
     assert SoftCrossEntropyLoss(reduction="none")(x, onehot).shape == (5,)
     with pytest.raises(ValueError):
         SoftCrossEntropyLoss(reduction="median")(x, onehot)
+
+
+def test_davis_index_maps_matches_convert_davis():
+    """eval/convert_davis.py:52-66 restated with numpy + cv2 on a synthetic label image: colour -> palette id, unknown
+    colours -> 0, INTER_NEAREST resize to the ground-truth size (up and down, non-integer ratios)."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from sapienza_video_contrastive_b200.test_utils import davis_index_maps
+    g = torch.Generator().manual_seed(0)
+    palette = torch.randint(0, 256, (40, 3), generator=g)
+    palette[0] = 0
+    lbl_set = torch.stack([palette[0], palette[7], palette[21], torch.tensor([1, 2, 3]), palette[39]])   # one colour off-palette
+    cls = torch.randint(0, 5, (2, 37, 53), generator=g).to(torch.uint8)
+    pal_np = palette.numpy().astype(np.uint8)
+    for size in (None, (37, 53), (60, 107), (19, 30), (480, 854)):
+        got = davis_index_maps(cls, lbl_set, palette, size)
+        for f in range(2):
+            lblimg = lbl_set.numpy().astype(np.uint8)[cls[f].numpy()]                # what dump_predictions wrote / imread returns
+            idx = np.zeros(lblimg.shape[:2])
+            for c in np.unique(lblimg.reshape(-1, 3), axis=0):
+                cid = np.arange(0, pal_np.shape[0])[np.all(pal_np == c, axis=-1)]
+                if len(cid) > 0:
+                    idx[np.all(lblimg == c, axis=-1)] = cid
+            idx = idx.astype(np.uint8)
+            if size is not None:
+                idx = cv2.resize(idx, (size[1], size[0]), interpolation=cv2.INTER_NEAREST)
+            assert np.array_equal(got[f].numpy(), idx), size
