@@ -204,6 +204,13 @@ int crw_lp_gather(float* lbls, const int64_t* key_frames_n, const float* Ws_n, c
 int crw_lp_upsample_argmax(const float* pred, int n, int h, int w, int L, int H, int W, int norm_mask,
                            const unsigned char* palette, unsigned char* cls, unsigned char* rgb, crw_stream_t stream);
 
+/* ---- f1, JHMDB branch: key-point coordinates, utils/test_utils.py:60-84 (process_pose) called at test.py:171-172 ------------
+ * pred (n, h, w, L) fp32 soft label maps, channel 0 = background.  For every frame and channel c = 1..L-1: the topk
+ * (default 3, at most 4; clipped to h*w) largest positions, values normalised to sum 1, coords[f][0][c-1] = sum x_i v_i,
+ * coords[f][1][c-1] = sum y_i v_i (fp32, in rank order), or -1, -1 when the channel is zero everywhere.
+ * coords (n, 2, L-1) fp32.  Equal values rank by position (torch.topk leaves that order unspecified). */
+int crw_lp_pose_coords(const float* pred, int n, int h, int w, int L, int topk, float* coords, crw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -343,3 +343,26 @@ def segment_mean_dilated(maps: torch.Tensor, labels: torch.Tensor, SP: int, ksiz
             wgt = cnt / (size + EPS_LOG)[:, None, None]
             out[b, t] = torch.einsum("sij,cij->sc", wgt, maps[b, :, t].double())
     return out.float()
+
+
+def process_pose(pred: torch.Tensor, lbl_set, topk: int = 3):
+    """utils/test_utils.py:60-84 restated: pred (h,w,L) soft maps, channel 0 = background -> (coords (2,L-1) float32 with
+    -1 for channels that are zero everywhere, sharp (h,w,3) float64 image with lbl_set[c] at each key point).  Ties between
+    equal values rank by position here (torch.topk leaves their order unspecified)."""
+    import numpy as np
+    h, w, L = pred.shape
+    flat = pred[..., 1:].reshape(h * w, L - 1).float()
+    k = min(h * w, topk)
+    order = torch.argsort(flat, dim=0, descending=True, stable=True)[:k]              # (k, L-1), smaller position first on ties
+    vals = torch.gather(flat, 0, order)
+    vals = vals / vals.sum(0)[None]
+    xx, yy = order % w, order // w
+    coords = torch.stack([(xx * vals).sum(0), (yy * vals).sum(0)], dim=0)
+    coords[:, flat.sum(0) == 0] = -1
+    sharp = np.zeros((h, w, 3))
+    lbl = np.asarray(lbl_set)
+    for t in range(L - 1):
+        x, y = int(coords[0, t]), int(coords[1, t])
+        if x >= 0 and y >= 0:
+            sharp[y, x, :] = lbl[t + 1]
+    return coords, sharp

@@ -172,6 +172,15 @@ def gen_ts(ref_model, ref_utils):
         print("golden", name, float(loss))
 
 
+def gen_pose(ref_model, ref_utils, ref_tu):
+    """utils/test_utils.py:60-84 (process_pose), the JHMDB branch of test.py:171-172."""
+    for name, c in cases.POSE_CASES.items():
+        pred, lbl_set = cases.pose_inputs(c)
+        coords, sharp = ref_tu.process_pose(pred.clone(), lbl_set.numpy())
+        torch.save(dict(coords=coords.clone(), sharp=torch.from_numpy(sharp)), os.path.join(OUT, name + ".pt"))
+        print("golden", name, tuple(coords.shape))
+
+
 def gen_lp(ref_model, ref_utils, ref_tu):
     """Runs the reference's own evaluator loop (test.py:67-160) on a fake loader / fake encoder and
     captures (Ws, Is) from mem_efficient_batched_affinity and each `pred` handed to dump_predictions."""
@@ -277,6 +286,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "spd":            # only the dilated-superpixel fixtures (added later)
         gen_spd(ref_model, ref_utils)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "pose":           # only the key-point fixtures (added later)
+        gen_pose(ref_model, ref_utils, ref_tu)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "ts":             # only the teacher-student fixtures (added later)
         gen_ts(ref_model, ref_utils)
         return
@@ -286,6 +298,7 @@ def main():
     gen_sp(ref_model, ref_utils)
     gen_spd(ref_model, ref_utils)
     gen_ts(ref_model, ref_utils)
+    gen_pose(ref_model, ref_utils, ref_tu)
     gen_lp(ref_model, ref_utils, ref_tu)
     gen_cfg1(ref_model, ref_utils)
 

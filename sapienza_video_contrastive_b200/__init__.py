@@ -26,6 +26,7 @@ _LAZY = {
     "propagate_labels": ("test_utils", "propagate_labels"),
     "dump_predictions": ("test_utils", "dump_predictions"),
     "davis_index_maps": ("test_utils", "davis_index_maps"),
+    "process_pose": ("test_utils", "process_pose"),
 }
 
 

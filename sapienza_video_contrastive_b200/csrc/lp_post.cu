@@ -96,6 +96,87 @@ __global__ void __launch_bounds__(256) lp_post_kernel(LpPostArgs a) {
 
 using namespace crw;
 
+// ---- JHMDB key points (utils/test_utils.py:60-84, process_pose) ----------------------------------------------------------
+// Per frame and key-point channel c = 1..L-1: the top-k (k = min(hw, topk) <= 4) positions of the soft map, their values
+// normalised to sum 1, and the value-weighted mean of their (x, y) - or (-1, -1) for a channel that is zero everywhere.
+// One CTA per (frame, channel): every thread keeps the best k of its strided share, a shared-memory tree merges the sorted
+// lists (larger value first, then the smaller position), thread 0 does the reference's float arithmetic in its order.
+constexpr int kPoseK = 4;
+struct PoseTop {
+    float v[kPoseK];
+    int p[kPoseK];
+};
+__device__ __forceinline__ bool pose_before(float va, int pa, float vb, int pb) { return va > vb || (va == vb && pa < pb); }
+__device__ __forceinline__ void pose_insert(PoseTop& t, int k, float v, int p) {
+    if (!pose_before(v, p, t.v[k - 1], t.p[k - 1])) return;
+    int i = k - 1;
+    while (i > 0 && pose_before(v, p, t.v[i - 1], t.p[i - 1])) { t.v[i] = t.v[i - 1]; t.p[i] = t.p[i - 1]; --i; }
+    t.v[i] = v;
+    t.p[i] = p;
+}
+
+__global__ void __launch_bounds__(256) lp_pose_kernel(const float* __restrict__ pred, int hw, int w, int L, int k, float* __restrict__ coords) {
+    __shared__ float sv[256][kPoseK];
+    __shared__ int sp[256][kPoseK];
+    __shared__ int snz[256];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x % (L - 1), f = blockIdx.x / (L - 1);
+    const float* src = pred + (int64_t)f * hw * L + (c + 1);
+    PoseTop t;
+#pragma unroll
+    for (int i = 0; i < kPoseK; ++i) { t.v[i] = -INFINITY; t.p[i] = 0x7fffffff; }
+    int nz = 0;
+    for (int p = tid; p < hw; p += 256) {
+        const float v = src[(int64_t)p * L];
+        nz |= v != 0.f;
+        pose_insert(t, k, v, p);
+    }
+#pragma unroll
+    for (int i = 0; i < kPoseK; ++i) { sv[tid][i] = t.v[i]; sp[tid][i] = t.p[i]; }
+    snz[tid] = nz;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) {
+            for (int i = 0; i < k; ++i) pose_insert(t, k, sv[tid + s][i], sp[tid + s][i]);
+            nz |= snz[tid + s];
+        }
+        __syncthreads();
+        if (tid < s) {
+#pragma unroll
+            for (int i = 0; i < kPoseK; ++i) { sv[tid][i] = t.v[i]; sp[tid][i] = t.p[i]; }
+            snz[tid] = nz;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        float x = -1.f, y = -1.f;
+        if (nz) {                                    // flatlbls.sum(0) == 0 -> -1 (non-negative soft labels: the sum is 0 iff all are)
+            float tot = 0.f;
+            for (int i = 0; i < k; ++i) tot = __fadd_rn(tot, t.v[i]);
+            x = 0.f;
+            y = 0.f;
+            for (int i = 0; i < k; ++i) {
+                const float wgt = __fdiv_rn(t.v[i], tot);
+                x = __fadd_rn(x, __fmul_rn((float)(t.p[i] % w), wgt));
+                y = __fadd_rn(y, __fmul_rn((float)(t.p[i] / w), wgt));
+            }
+        }
+        float* o = coords + (int64_t)f * 2 * (L - 1);
+        o[c] = x;
+        o[(L - 1) + c] = y;
+    }
+}
+
+extern "C" int crw_lp_pose_coords(const float* pred, int n, int h, int w, int L, int topk, float* coords, crw_stream_t stream) {
+    if (n < 0 || h <= 0 || w <= 0 || L < 1 || topk < 1) { set_error("lp_pose_coords: bad shape"); return CRW_ERR_SHAPE; }
+    const int64_t hw = (int64_t)h * w;
+    const int k = hw < topk ? (int)hw : topk;
+    if (k > kPoseK || hw > 0x7ffffffe) { set_error("lp_pose_coords: top-k up to %d, got %d", kPoseK, k); return CRW_ERR_UNSUPPORTED; }
+    if (n == 0 || L == 1) return CRW_OK;
+    CRW_LAUNCH(lp_pose_kernel, n * (L - 1), 256, 0, stream, pred, (int)hw, w, L, k, coords);
+    return check_launch("lp_pose_coords");
+}
+
 extern "C" int crw_lp_upsample_argmax(const float* pred, int n, int h, int w, int L, int H, int W, int norm_mask,
                                       const unsigned char* palette, unsigned char* cls, unsigned char* rgb, crw_stream_t stream) {
     if (n < 0 || h <= 0 || w <= 0 || L <= 0 || H <= 0 || W <= 0) { set_error("lp_upsample_argmax: bad shape"); return CRW_ERR_SHAPE; }

@@ -741,3 +741,18 @@ def lp_upsample_argmax(preds: torch.Tensor, size: Tuple[int, int], palette: Opti
     L.check(L.crw_lp_upsample_argmax(preds.data_ptr(), n, h, w, Lb, H, W, int(norm_mask), pal.data_ptr() if pal is not None else None,
                                      cls.data_ptr(), rgb.data_ptr() if rgb is not None else None, _stream()), "lp_upsample_argmax")
     return cls, rgb
+
+
+def lp_pose_coords(preds: torch.Tensor, topk: int = 3) -> torch.Tensor:
+    """utils/test_utils.py:60-84 (process_pose) on the device: preds (n,h,w,L) or (h,w,L) soft label maps, channel 0 =
+    background -> key-point coordinates (n,2,L-1) float32 ((x, y) rows; -1 for channels that are zero everywhere)."""
+    _need_cuda(preds)
+    check_device(preds.device)
+    if preds.dim() == 3:
+        preds = preds[None]
+    preds = _f32c(preds)
+    n, h, w, Lb = preds.shape
+    coords = torch.empty(n, 2, max(Lb - 1, 0), dtype=torch.float32, device=preds.device)
+    L = _lib.lib()
+    L.check(L.crw_lp_pose_coords(preds.data_ptr(), n, h, w, Lb, int(topk), coords.data_ptr(), _stream()), "lp_pose_coords")
+    return coords

@@ -191,6 +191,24 @@ def dump_predictions(pred, lbl_set, img, prefix: Optional[str] = None, norm_mask
     return img_with_label, pred_lbl, None
 
 
+def process_pose(pred, lbl_set, topk: int = 3):
+    """utils/test_utils.py:60-84 with the reference's signature and return values: pred (h,w,L) soft maps of one frame ->
+    (current_coord (2,L-1) CPU float32, pred_val_sharp (h,w,3) float64 numpy image with lbl_set[c] at every key point).
+    The top-k search and the weighted coordinates run in one kernel (ops.lp_pose_coords); painting at most L-1 pixels is
+    left to the host as in the reference."""
+    import numpy as np
+    p = torch.as_tensor(pred, dtype=torch.float32)
+    dev = p.device if p.is_cuda else torch.device("cuda")
+    coords = ops.lp_pose_coords(p.to(dev), topk)[0].cpu()
+    sharp = np.zeros((int(p.shape[0]), int(p.shape[1]), 3))
+    lbl = np.asarray(lbl_set.cpu() if torch.is_tensor(lbl_set) else lbl_set)
+    for t in range(len(lbl) - 1):
+        x, y = int(coords[0, t]), int(coords[1, t])
+        if x >= 0 and y >= 0:
+            sharp[y, x, :] = lbl[t + 1]
+    return coords, sharp
+
+
 def davis_index_maps(cls: torch.Tensor, lbl_set, palette, size=None) -> torch.Tensor:
     """eval/convert_davis.py:33-70 without the PNG round trip: the class maps the post-processing kernel already produced
     (`cls` (..., H, W) uint8, slot l = colour lbl_set[l]) -> DAVIS palette indices, optionally resized to the ground truth's

@@ -39,6 +39,13 @@ TS_CASES = {
     "ts_nodrop": dict(B=2, T=3, N=36, D=32, p=0.0, tau=0.07, alpha=0.8, flip=False, seed=63),
 }
 
+# key-point cases (utils/test_utils.py:60-84, process_pose): distinct values, an all-zero channel, fewer positions than top-k
+POSE_CASES = {
+    "pose_jhmdb": dict(h=40, w=53, L=16, zero=[3], seed=71),
+    "pose_small": dict(h=1, w=2, L=4, zero=[], seed=72),
+    "pose_wide":  dict(h=7, w=300, L=3, zero=[1], seed=73),
+}
+
 # label-propagation cases (test_utils.py:148-179, test.py:141-160)
 LP_CASES = {
     "lp_small":   dict(C=16, h=12, w=17, n_ctx=4, n_tgt=6, long_mem=[0], radius=3, k=5, tau=0.07, L=3,
@@ -88,6 +95,18 @@ def ts_inputs(c):
     fs = torch.randn(c["B"], c["N"], c["T"], c["D"], generator=g)
     ft = fs + 0.5 * torch.randn(c["B"], c["N"], c["T"], c["D"], generator=g)
     return fs, ft
+
+
+def pose_inputs(c):
+    """-> pred (h, w, L) non-negative soft maps with distinct values per channel, lbl_set (L, 3)."""
+    g = torch.Generator().manual_seed(c["seed"])
+    hw = c["h"] * c["w"]
+    pred = torch.stack([torch.randperm(hw, generator=g).float() + 1 for _ in range(c["L"])], -1).reshape(c["h"], c["w"], c["L"])
+    pred = pred / pred.sum((0, 1), keepdim=True) * torch.rand(c["L"], generator=g)
+    for z in c["zero"]:
+        pred[..., z] = 0
+    lbl_set = torch.randint(0, 256, (c["L"], 3), generator=g)
+    return pred, lbl_set
 
 
 def voronoi_labels(B, T, SP, size, g, one_based):

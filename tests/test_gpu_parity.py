@@ -413,6 +413,25 @@ def test_superpixel_nodes_and_walk_match_reference(ops, name):
     assert relmax(md.grad.cpu(), fx["grad_maps"]) < 1e-4
 
 
+@pytest.mark.parametrize("name", list(cases.POSE_CASES))
+def test_pose_coords_match_reference(ops, name):
+    """utils/test_utils.py:60-84 (process_pose, the JHMDB branch of test.py:171-172): key-point coordinates bit-equal to the
+    reference's, through the operator (several frames per launch) and through the reference-signature mirror."""
+    from sapienza_video_contrastive_b200 import test_utils as TU
+    c = cases.POSE_CASES[name]
+    fx = load(name)
+    pred, lbl_set = cases.pose_inputs(c)
+    batch = torch.stack([pred, pred.flip(0), pred * 0.5]).to(DEV)
+    coords = ops.lp_pose_coords(batch).cpu()
+    assert torch.equal(coords[0], fx["coords"])
+    assert torch.equal(coords[1], O.process_pose(pred.flip(0), lbl_set.numpy())[0])
+    assert torch.equal(coords[2], O.process_pose(pred * 0.5, lbl_set.numpy())[0])
+    cc, sharp = TU.process_pose(pred, lbl_set.numpy())
+    assert torch.equal(cc, fx["coords"]) and torch.equal(torch.from_numpy(sharp), fx["sharp"])
+    for k in (1, 4):
+        assert torch.equal(ops.lp_pose_coords(pred.to(DEV), k)[0].cpu(), O.process_pose(pred, lbl_set.numpy(), topk=k)[0])
+
+
 @pytest.mark.parametrize("name", list(cases.TS_CASES))
 def test_teacher_student_walk_matches_reference(ops, name):
     """teacherstudent.py:472-580 from the node vectors on (crw_walk_ts_fwd_bwd): loss, walk diags and the gradient of the

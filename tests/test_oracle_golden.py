@@ -49,6 +49,20 @@ def test_walk_matches_reference(name):
     torch.testing.assert_close(torch.stack(A21), fx["A21"], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", list(cases.POSE_CASES))
+def test_process_pose_matches_reference(name):
+    """utils/test_utils.py:60-84 run unmodified: key-point coordinates (bit-equal: same float operations in the same order)
+    and the sharp key-point image."""
+    c = cases.POSE_CASES[name]
+    fx = load(name)
+    pred, lbl_set = cases.pose_inputs(c)
+    coords, sharp = O.process_pose(pred, lbl_set.numpy())
+    assert torch.equal(coords, fx["coords"])
+    assert torch.equal(torch.from_numpy(sharp), fx["sharp"])
+    for z in c["zero"]:
+        assert coords[0, z - 1] == -1 and coords[1, z - 1] == -1
+
+
 @pytest.mark.parametrize("name", list(cases.TS_CASES))
 def test_teacher_student_loss_matches_reference(name):
     """CRWTeacherStudent.forward (teacherstudent.py:472-580) run unmodified from the node embeddings on: loss, walk diags and

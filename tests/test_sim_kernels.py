@@ -394,6 +394,30 @@ def test_segmean_dilated_strips(sim, Hm, Wm, sy, sx, SP, ksize, shape):
     torch.testing.assert_close(out.transpose(1, 2), O.segment_mean_dilated(maps, lab, SP, ksize, shape), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", list(cases.POSE_CASES))
+def test_pose_coords_vs_reference_golden(sim, name):
+    """crw_lp_pose_coords against the reference's process_pose (utils/test_utils.py:60-84): bit-equal coordinates, several
+    frames in one launch, top-k 1..4, and the documented tie rule (equal values rank by position)."""
+    c = cases.POSE_CASES[name]
+    fx = load(name)
+    pred, lbl_set = cases.pose_inputs(c)
+    h, w, L = pred.shape
+    batch = torch.stack([pred, pred.flip(0), pred * 0.5]).contiguous()
+    coords = torch.full((3, 2, L - 1), 7.0)
+    sim.check(sim.crw_lp_pose_coords(ptr(batch), 3, h, w, L, 3, ptr(coords), None))
+    assert torch.equal(coords[0], fx["coords"])
+    assert torch.equal(coords[1], O.process_pose(pred.flip(0), lbl_set.numpy())[0])
+    assert torch.equal(coords[2], O.process_pose(pred * 0.5, lbl_set.numpy())[0])
+    for k in (1, 2, 4):
+        sim.check(sim.crw_lp_pose_coords(ptr(batch), 1, h, w, L, k, ptr(coords), None))
+        assert torch.equal(coords[0], O.process_pose(pred, lbl_set.numpy(), topk=k)[0]), k
+    tied = torch.zeros(h, w, L)
+    tied[..., 1:] = 0.25
+    sim.check(sim.crw_lp_pose_coords(ptr(tied), 1, h, w, L, 3, ptr(coords), None))
+    assert torch.equal(coords[0], O.process_pose(tied, lbl_set.numpy())[0])
+    assert sim.crw_lp_pose_coords(ptr(batch), 1, h, w, L, 5, ptr(coords), None) != 0 or h * w < 5
+
+
 def check_label_images(cls, rgb, pred, lbl_set, c, fx):
     """Class map / label image of the kernel against the reference's dump_predictions output.  OpenCV's vectorised resize
     may fuse or reorder the two interpolation passes, so a pixel may legitimately differ only where the two best classes of
