@@ -86,6 +86,16 @@ int crw_affinity(const float* x1, const float* x2, int BT, int N1, int N2, int D
 int crw_stoch_mat(float* A, const float* drop_uniform, float rate, float temperature, unsigned flags,
                   int64_t R, int N, int M, float* out, crw_stream_t stream);
 
+/* ---- a5, Sinkhorn branch: utils/__init__.py:615-641 (sinkhorn_knopp) as called by stoch_mat(do_sinkhorn=True), model.py:83-87 ----
+ * A (R, N, M) contiguous, IN PLACE: optionally A <- exp(A / temperature), A <- A / sum(A) per matrix, then sweeps of
+ * "L1-normalise the columns, L1-normalise the rows" (F.normalize semantics, eps 1e-12) while the unbiased standard
+ * deviation of all R*M column sums exceeds tol, at least one and at most max_iter sweeps (the reference's own stop rule).
+ * The stop rule is evaluated on the HOST once per sweep, as in the reference: this call synchronises `stream`.
+ * *iterations (host, may be NULL) receives the number of sweeps. */
+size_t crw_sinkhorn_workspace_bytes(int64_t R, int N, int M);
+int crw_sinkhorn_knopp(float* A, int64_t R, int N, int M, int apply_exp, float temperature, float tol, int max_iter,
+                       int* iterations, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+
 /* ---- a5/a6: the walk, model.py:366-413, forward AND backward in one call -------------------------------
  * feats (B,N,T,D) fp32, NOT yet normalised (output of selfsim_fc, model.py:117); the L2 normalisation of
  * model.py:118 is folded in.  Edge dropout: either u12/u21p (each (T-1,B,N,N), the reference's rand_like

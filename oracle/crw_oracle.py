@@ -366,3 +366,15 @@ def process_pose(pred: torch.Tensor, lbl_set, topk: int = 3):
         if x >= 0 and y >= 0:
             sharp[y, x, :] = lbl[t + 1]
     return coords, sharp
+
+
+def sinkhorn_knopp(A: torch.Tensor, tol: float = 0.01, max_iter: int = 1000):
+    """utils/__init__.py:615-641 restated (3-D input): -> (A2, number of sweeps)."""
+    A = A / A.sum(-1).sum(-1)[:, None, None]
+    A2 = A
+    it = 0
+    while (A2.sum(-2).std() > tol and it < max_iter) or it == 0:
+        A1 = F.normalize(A2, p=1, dim=-2)
+        A2 = F.normalize(A1, p=1, dim=-1)
+        it += 1
+    return A2, it

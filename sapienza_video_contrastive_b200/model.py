@@ -113,13 +113,20 @@ class CRW(nn.Module):
 
     def stoch_mat(self, A, zero_diagonal=False, do_dropout=True, do_sinkhorn=False):
         """model.py:74-90.  Like the reference, dropout overwrites the caller's tensor (or view) with -1e20."""
-        if do_sinkhorn:
-            raise NotImplementedError("the Sinkhorn branch (model.py:83-87) is dead in the reference's forward and not built")
         if zero_diagonal:
             A = self.zeroout_diag(A)
         u = None
         if do_dropout and self.edgedrop_rate > 0:
             u = torch.rand_like(A)                     # same draw, same layout rule as the reference (SURVEY F6)
+        if do_sinkhorn:
+            # model.py:83-87: sinkhorn_knopp((A / tau).exp(), tol=0.01, max_iter=100) after the in-place edge drop.  Never
+            # reached from the reference's forward; forward-only here (the result carries no gradient).
+            if u is not None:
+                with torch.no_grad():
+                    A[u < self.edgedrop_rate] = -1e20
+            flat = A.detach().reshape(-1, *A.shape[-2:]) if A.dim() != 3 else A.detach()
+            out, _ = ops.sinkhorn_knopp(flat, tol=0.01, max_iter=100, exp_temperature=self.temperature)
+            return out.reshape(A.shape)
         work = A.detach().contiguous()
         aliased = work.data_ptr() == A.data_ptr()
         if not aliased:

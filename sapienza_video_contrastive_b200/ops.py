@@ -756,3 +756,24 @@ def lp_pose_coords(preds: torch.Tensor, topk: int = 3) -> torch.Tensor:
     L = _lib.lib()
     L.check(L.crw_lp_pose_coords(preds.data_ptr(), n, h, w, Lb, int(topk), coords.data_ptr(), _stream()), "lp_pose_coords")
     return coords
+
+
+def sinkhorn_knopp(A: torch.Tensor, tol: float = 0.01, max_iter: int = 1000, exp_temperature: Optional[float] = None):
+    """utils/__init__.py:615-641: A (R,N,M) or (N,M) positive -> the Sinkhorn-Knopp normalised matrix (new tensor, no
+    gradient) and the number of sweeps.  `exp_temperature` = tau first maps A -> exp(A / tau) (the argument stoch_mat passes
+    at model.py:84).  The stop rule is the reference's (std of all column sums > tol) and is read back once per sweep."""
+    import ctypes
+    _need_cuda(A)
+    check_device(A.device)
+    squeeze = A.dim() == 2
+    work = _f32c(A.detach()).clone()
+    if squeeze:
+        work = work[None]
+    R, N, M = work.shape
+    L = _lib.lib()
+    nbytes = L.crw_sinkhorn_workspace_bytes(R, N, M)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=work.device)
+    n_it = ctypes.c_int(0)
+    L.check(L.crw_sinkhorn_knopp(work.data_ptr(), R, N, M, int(exp_temperature is not None), float(exp_temperature or 1.0), float(tol),
+                                 int(max_iter), ctypes.addressof(n_it), ws.data_ptr(), nbytes, _stream()), "sinkhorn_knopp")
+    return (work[0] if squeeze else work), n_it.value

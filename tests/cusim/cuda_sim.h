@@ -62,7 +62,8 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "sim"; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
-enum cudaMemcpyKind { cudaMemcpyDeviceToDevice = 3 };
+enum cudaMemcpyKind { cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxThreadsPerMultiProcessor = 39, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };

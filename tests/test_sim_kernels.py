@@ -235,6 +235,33 @@ def test_affinity_and_stoch_mat(sim):
     torch.testing.assert_close(y2, torch.softmax(A0 / 0.07, -1), rtol=1e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize("R,N,M,tol,max_iter,use_exp", [(3, 12, 12, 0.01, 100, True), (2, 49, 49, 1e-4, 1000, True), (1, 7, 20, 0.01, 3, False),
+                                                        (4, 33, 33, 0.0, 5, True)])
+def test_sinkhorn_knopp(sim, R, N, M, tol, max_iter, use_exp):
+    """crw_sinkhorn_knopp against the reference's function (utils/__init__.py:615-641; imported when the reference tree is
+    present, else its restatement in the oracle): same number of sweeps, same matrix."""
+    import ctypes
+    from oracle import ref_import
+    g = torch.Generator().manual_seed(R * 100 + N)
+    A = torch.randn(R, N, M, generator=g) * 0.3
+    if use_exp:
+        A[0, 1, 2] = -1e20                                       # a dropped edge (model.py:81): exp -> 0
+    x = (A / 0.07).exp() if use_exp else A.abs() + 0.1
+    ref, its = O.sinkhorn_knopp(x, tol, max_iter)
+    if ref_import.available():
+        _, ref_utils, _ = ref_import.load()
+        torch.testing.assert_close(ref, ref_utils.sinkhorn_knopp(x, tol=tol, max_iter=max_iter), rtol=0, atol=0)
+    work = A.clone() if use_exp else x.clone()
+    wsb = sim.crw_sinkhorn_workspace_bytes(R, N, M)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    n_it = ctypes.c_int(0)
+    sim.check(sim.crw_sinkhorn_knopp(ptr(work), R, N, M, int(use_exp), 0.07, tol, max_iter, ctypes.addressof(n_it), ptr(ws), wsb, None))
+    assert n_it.value == its
+    torch.testing.assert_close(work, ref, rtol=2e-5, atol=1e-9)
+    torch.testing.assert_close(work.sum(-1), torch.ones(R, N), rtol=1e-5, atol=1e-6)
+    assert sim.crw_sinkhorn_knopp(ptr(work), R, N, M, 1, 0.0, tol, max_iter, None, ptr(ws), wsb, None) != 0
+
+
 def test_philox_known_answers(sim):
     """Philox4x32-10 against the Random123 known-answer vectors, through the uniform mapping: element e of a draw with
     `threads` >= n uses counter (offset/4, 0, e, 0), component 0."""
