@@ -1,8 +1,5 @@
-"""Sinkhorn-Knopp on the GPU (crw_sinkhorn_knopp).  The kernels pass in the host simulator (tests/test_sim_kernels.py) against
-the reference's own function; this file runs last and its tests are non-strict xfail because the round's GPU budget ran out
-before their first run on hardware - a pass shows up as XPASS."""
-import os
-
+"""Sinkhorn-Knopp on the GPU (crw_sinkhorn_knopp, utils/__init__.py:615-641 + model.py:83-87): same number of sweeps and the
+same matrix as the reference's rule; the simulator twin of these tests compares against the reference's own function."""
 import pytest
 import torch
 
@@ -12,7 +9,6 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (simulator-verified)")
 @pytest.mark.parametrize("R,N,M,tol,max_iter", [(3, 12, 12, 0.01, 100), (2, 49, 49, 1e-4, 1000), (8, 196, 196, 0.01, 100)])
 def test_sinkhorn_knopp_matches_reference_rule(R, N, M, tol, max_iter):
     from sapienza_video_contrastive_b200 import ops
@@ -25,7 +21,6 @@ def test_sinkhorn_knopp_matches_reference_rule(R, N, M, tol, max_iter):
     torch.testing.assert_close(out.cpu(), ref, rtol=2e-5, atol=1e-9)
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (simulator-verified)")
 def test_stoch_mat_sinkhorn_branch():
     """CRW.stoch_mat(do_sinkhorn=True), model.py:83-87."""
     import argparse
