@@ -191,6 +191,24 @@ def dump_predictions(pred, lbl_set, img, prefix: Optional[str] = None, norm_mask
     return img_with_label, pred_lbl, None
 
 
+def hard_prop(pred: torch.Tensor) -> torch.Tensor:
+    """utils/test_utils.py:51-56: keep, per position, only the classes that reach the maximum over dim 0, share the mass
+    equally between them; IN PLACE like the reference, and returned.  A handful of elementwise tensor ops (not called from
+    test.py); kept for callers of the reference module."""
+    top = pred.max(dim=0)[0]
+    below = pred < top
+    pred.masked_fill_(below, 0)
+    pred.masked_fill_(pred >= top, 1)          # evaluated after the zeroing, as in the reference (matters for maxima <= 0)
+    pred /= pred.sum(0)[None]
+    return pred
+
+
+def infer_downscale(model=None):
+    """utils/test_utils.py:212-216: the reference hard-codes 320 // 40 for both axes."""
+    import numpy as np
+    return 320 // np.array([40, 40])
+
+
 def process_pose(pred, lbl_set, topk: int = 3):
     """utils/test_utils.py:60-84 with the reference's signature and return values: pred (h,w,L) soft maps of one frame ->
     (current_coord (2,L-1) CPU float32, pred_val_sharp (h,w,3) float64 numpy image with lbl_set[c] at every key point).

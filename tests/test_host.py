@@ -167,3 +167,26 @@ def test_davis_index_maps_matches_convert_davis():
             if size is not None:
                 idx = cv2.resize(idx, (size[1], size[0]), interpolation=cv2.INTER_NEAREST)
             assert np.array_equal(got[f].numpy(), idx), size
+
+
+def test_small_test_utils_mirrors():
+    """hard_prop (utils/test_utils.py:51-56) against the reference's three in-place statements; infer_downscale (:212-216)."""
+    from sapienza_video_contrastive_b200.test_utils import hard_prop, infer_downscale
+    g = torch.Generator().manual_seed(2)
+    pred = torch.rand(4, 5, 6, generator=g)
+    pred[1, 0, 0] = pred[2, 0, 0] = 2.0                           # a tie shares the mass
+    ref = pred.clone()
+    mx = ref.max(axis=0)[0]
+    ref[ref < mx] = 0
+    ref[ref >= mx] = 1
+    ref /= ref.sum(0)[None]
+    out = hard_prop(pred)
+    assert out is pred and torch.equal(pred, ref) and float(pred[1, 0, 0]) == 0.5
+    neg = -torch.rand(3, 2, 2, generator=g) - 0.5                # negative maxima: the zeroed entries pass the second test too
+    ref = neg.clone()
+    mx = ref.max(axis=0)[0]
+    ref[ref < mx] = 0
+    ref[ref >= mx] = 1
+    ref /= ref.sum(0)[None]
+    assert torch.equal(hard_prop(neg), ref)
+    assert list(infer_downscale()) == [8, 8]
