@@ -24,8 +24,7 @@ import this module.  The product package never does (tests/test_host.py greps fo
 """
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 import torch.nn.functional as F
