@@ -6,7 +6,10 @@
  * (paths relative to the reference root).  Conventions:
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name says host;
  *   - the caller owns every buffer, including workspaces (query the size with *_workspace_bytes);
- *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises or allocates;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises or allocates - with ONE
+ *     documented exception, crw_sinkhorn_knopp, whose stop rule the reference evaluates on the host once per sweep;
+ *   - a tensor-core pipeline that stalls (bounded mbarrier waits, seconds) raises its error word and TRAPS: the caller sees
+ *     a CUDA error at its next API call, never silently wrong output;
  *   - return value: CRW_OK or a negative error; crw_last_error() gives a thread-local message;
  *   - fp32 arithmetic throughout; indices int64.
  */
@@ -196,6 +199,11 @@ int crw_lp_topk(const float* feats, int Nf, const int64_t* key_frames, const int
                 int n_long, int h, int w, int C, float radius, const float* dense_mask, float temperature, int k,
                 unsigned flags, float* Ws, int64_t* Is, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
+/* Which kernel crw_lp_topk takes for a configuration: 1 = the tcgen05 tensor-core kernel, 0 = the exact-fp32 SIMT kernel
+ * (what the dispatcher of crw_lp_topk decides, given a workspace of crw_lp_topk_workspace_bytes and no CRW_LP_FORCE_SIMT).
+ * Lets callers and tests assert that the path they mean to measure is the one that runs. */
+int crw_lp_topk_uses_tensor_cores(int C, int k, float radius, int has_dense_mask);
+
 /* feats (C, Nf, hw) channel-first (the encoder's layout, test.py:90-93) -> (Nf, hw, C) channel-last with
  * optional L2 normalisation over C (eps 1e-12). */
 int crw_lp_prepare(const float* feats_cf, int C, int Nf, int hw, int normalize, float* feats_cl, crw_stream_t stream);
@@ -213,6 +221,12 @@ int crw_lp_gather(float* lbls, const int64_t* key_frames_n, const float* Ws_n, c
  * pred -= min_L; pred /= max_L per source pixel.  The upsampled (H, W, L) tensor is never materialised.  L <= 255. */
 int crw_lp_upsample_argmax(const float* pred, int n, int h, int w, int L, int H, int W, int norm_mask,
                            const unsigned char* palette, unsigned char* cls, unsigned char* rgb, crw_stream_t stream);
+
+/* test.py:162-164 (--norm_mask) as an in-place operator: maps (rows, L) fp32, every row r: maps[r] -= min(maps[r]);
+ * maps[r] /= max(maps[r]) (0/0 -> NaN, as in the reference).  The evaluator applies it to the ground-truth frame 0 after the
+ * first target (the reference's `pred = lbls[0]` is a view, so its in-place normalisation rewrites frame 0) and to every
+ * map it returns. */
+int crw_lp_minmax_normalize(float* maps, int64_t rows, int L, crw_stream_t stream);
 
 /* ---- f1, JHMDB branch: key-point coordinates, utils/test_utils.py:60-84 (process_pose) called at test.py:171-172 ------------
  * pred (n, h, w, L) fp32 soft label maps, channel 0 = background.  For every frame and channel c = 1..L-1: the topk

@@ -248,9 +248,12 @@ def lp_topk(feats, key_indices, n_context, n_long, h, w, radius, tau, k):
     return torch.stack(Ws), torch.stack(Is)
 
 
-def lp_propagate(lbls, key_indices, Ws, Is, n_context):
+def lp_propagate(lbls, key_indices, Ws, Is, n_context, norm_mask=False):
     """test.py:141-160.  lbls (Nf, h, w, L) soft labels (frames >= n_context are overwritten).
-    Returns the predicted soft maps (Nt, h, w, L); frame 0 of the targets keeps lbls[0]."""
+    Returns the soft maps handed to dump_predictions (Nt, h, w, L); frame 0 of the targets keeps lbls[0].
+    norm_mask (test.py:162-164): every returned map is min-max-normalised over L; for t = 0 `pred` is a view of lbls[0], so
+    the GROUND-TRUTH frame 0 is normalised in place AFTER it was copied to lbls[n_context], and later frames propagate from
+    the normalised frame 0 (the propagated frames themselves are stored un-normalised)."""
     lbls = lbls.clone()
     lbls[n_context:] *= 0
     Nf, h, w, L = lbls.shape
@@ -260,8 +263,11 @@ def lp_propagate(lbls, key_indices, Ws, Is, n_context):
         pred = (ctx[:, Is[t]] * Ws[t][None]).sum(1)                      # (L, hw)
         pred = pred.view(L, h, w).permute(1, 2, 0)
         if t == 0:
-            pred = lbls[0]
+            pred = lbls[0]                                               # a view (test.py:159)
         lbls[t + n_context] = pred
+        if norm_mask:
+            pred[:, :, :] -= pred.min(-1)[0][:, :, None]
+            pred[:, :, :] /= pred.max(-1)[0][:, :, None]
         preds.append(pred.clone())
     return torch.stack(preds)
 

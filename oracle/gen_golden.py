@@ -181,13 +181,15 @@ def gen_pose(ref_model, ref_utils, ref_tu):
         print("golden", name, tuple(coords.shape))
 
 
-def gen_lp(ref_model, ref_utils, ref_tu):
+def gen_lp(ref_model, ref_utils, ref_tu, only=None):
     """Runs the reference's own evaluator loop (test.py:67-160) on a fake loader / fake encoder and
     captures (Ws, Is) from mem_efficient_batched_affinity and each `pred` handed to dump_predictions."""
     import test as ref_test
     ref_test.vis = None          # test.py:201 reads an undefined module global (SURVEY F11); supply it
 
-    for name, c in cases.LP_CASES.items():
+    for name, c in list(cases.LP_CASES.items()) + list(cases.LP_TC_CASES.items()) + [("lp_normmask", cases.LP_NORM_CASE)]:
+        if only is not None and name not in only:
+            continue
         feats, lbls = cases.lp_inputs(c)
         Nf = feats.shape[2]
 
@@ -221,7 +223,7 @@ def gen_lp(ref_model, ref_utils, ref_tu):
         ref_tu.dump_predictions = dump
         args = argparse.Namespace(videoLen=c["n_ctx"], long_mem=c["long_mem"], radius=c["radius"],
                                   temperature=c["tau"], topk=c["k"], device="cpu", no_l2=True, pca_vis=False,
-                                  norm_mask=False, filelist="davis", save_path=tempfile.mkdtemp(), visdom=False)
+                                  norm_mask=(name == "lp_normmask"), filelist="davis", save_path=tempfile.mkdtemp(), visdom=False)
         try:
             with torch.no_grad():
                 ref_test.test(loader, Model(), args)
@@ -288,6 +290,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "pose":           # only the key-point fixtures (added later)
         gen_pose(ref_model, ref_utils, ref_tu)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "lp_tc":          # only the tensor-core-shaped label-propagation fixtures (round 2)
+        gen_lp(ref_model, ref_utils, ref_tu, only=set(cases.LP_TC_CASES) | {"lp_normmask"})
         return
     if len(sys.argv) > 1 and sys.argv[1] == "ts":             # only the teacher-student fixtures (added later)
         gen_ts(ref_model, ref_utils)

@@ -55,11 +55,13 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_philox_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint32, c_void_p]),
     "crw_lp_upsample_argmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "crw_lp_minmax_normalize": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
     "crw_lp_pose_coords": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "crw_bmm_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "crw_bmm_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "crw_bmm_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "crw_lp_topk_workspace_bytes": (c_size_t, [c_int] * 7),
+    "crw_lp_topk_uses_tensor_cores": (c_int, [c_int, c_int, c_float, c_int]),
     "crw_lp_topk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                             c_float, c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),

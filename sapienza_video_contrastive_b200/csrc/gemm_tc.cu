@@ -438,22 +438,6 @@ int gemm_tc_run(const TcGemmCall& c, void* workspace, size_t workspace_bytes, cr
 #endif
 }
 
-int gemm_tc_check(void* workspace, crw_stream_t stream) {
-#ifdef CRW_SIM
-    (void)workspace; (void)stream;
-    return CRW_OK;
-#else
-    unsigned flag = 0;
-    if (cudaMemcpyAsync(&flag, workspace, sizeof(flag), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
-        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
-        set_error("gemm_tc: %s", cudaGetErrorString(cudaGetLastError()));
-        return CRW_ERR_CUDA;
-    }
-    if (flag) { set_error("gemm_tc: pipeline barrier timed out (flag %u)", flag); return CRW_ERR_CUDA; }
-    return CRW_OK;
-#endif
-}
-
 }  // namespace crw
 
 using namespace crw;

@@ -32,7 +32,6 @@ struct TcGemmCall {
 size_t gemm_tc_workspace_bytes(int M, int N, int Kcat, int Z);
 bool gemm_tc_eligible(int M, int N, int Kmin, int Kmax);
 int gemm_tc_run(const TcGemmCall& c, void* workspace, size_t workspace_bytes, crw_stream_t stream);
-int gemm_tc_check(void* workspace, crw_stream_t stream);
 
 // gemm_tf32.cu: the same call on tcgen05 kind::tf32 with the operands read in place by TMA and split inside the kernel (no
 // workspace, no separate split launch); for products too small to amortise gemm_tc's operand pass

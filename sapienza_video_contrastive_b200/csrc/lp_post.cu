@@ -167,6 +167,26 @@ __global__ void __launch_bounds__(256) lp_pose_kernel(const float* __restrict__ 
     }
 }
 
+// test.py:162-164 (--norm_mask): pred -= min_L; pred /= max_L per position, in place (same two fp32 operations as the reference)
+__global__ void __launch_bounds__(256) lp_minmax_kernel(float* maps, int64_t rows, int L) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        float* p = maps + r * L;
+        float mn = p[0];
+        for (int l = 1; l < L; ++l) mn = fminf(mn, p[l]);
+        float mx = p[0] - mn;
+        for (int l = 1; l < L; ++l) mx = fmaxf(mx, p[l] - mn);
+        for (int l = 0; l < L; ++l) p[l] = (p[l] - mn) / mx;
+    }
+}
+
+extern "C" int crw_lp_minmax_normalize(float* maps, int64_t rows, int L, crw_stream_t stream) {
+    if (rows < 0 || L <= 0) { set_error("lp_minmax_normalize: bad shape"); return CRW_ERR_SHAPE; }
+    if (rows == 0) return CRW_OK;
+    const int grid = (int)((rows + 255) / 256 < 148 * 8 ? (rows + 255) / 256 : 148 * 8);
+    CRW_LAUNCH(lp_minmax_kernel, grid, 256, 0, stream, maps, rows, L);
+    return check_launch("lp_minmax_normalize");
+}
+
 extern "C" int crw_lp_pose_coords(const float* pred, int n, int h, int w, int L, int topk, float* coords, crw_stream_t stream) {
     if (n < 0 || h <= 0 || w <= 0 || L < 1 || topk < 1) { set_error("lp_pose_coords: bad shape"); return CRW_ERR_SHAPE; }
     const int64_t hw = (int64_t)h * w;

@@ -271,6 +271,10 @@ static int radius_R(float radius) {          // largest integer offset R with R*
     return R;
 }
 
+extern "C" int crw_lp_topk_uses_tensor_cores(int C, int k, float radius, int has_dense_mask) {
+    return lp_tc_supported(C, k, radius, radius > 0.f ? radius_R(radius) : 0, has_dense_mask != 0) ? 1 : 0;
+}
+
 extern "C" size_t crw_lp_topk_workspace_bytes(int Nf, int Nt, int S, int h, int w, int C, int k) {
     (void)Nt; (void)S;
     size_t b = 256;                          // word 0: device-side error flag

@@ -20,16 +20,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-// bounded spin: a protocol bug becomes an error code instead of a hung GPU
+// bounded spin (each try_wait suspends for the hardware's time slice, so the bound is seconds): a protocol bug raises the
+// error word AND traps, so it surfaces as a CUDA error at the caller's next API call instead of a hung GPU or, worse,
+// a kernel that returns garbage silently
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, unsigned* err) {
     const unsigned a = smem_u32(bar);
-    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+    for (unsigned spin = 0; spin < (1u << 26); ++spin) {
         unsigned ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) return true;
     }
     atomicExch(err, 1u);
+    __threadfence_system();
+    __trap();
     return false;
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {

@@ -138,9 +138,9 @@ class CRW(nn.Module):
                 A.copy_(work)                          # propagate the in-place side effect through the view
         return out
 
-    def pixels_to_nodes(self, x):
+    def pixels_to_nodes(self, x, featdrop=True):
         """model.py:92-123: x (B,N,C,T,h,w) -> feats (B,128,T,N) unit-norm, maps (B,N,C',T,H,W)."""
-        f, maps, B, N = self._patch_nodes_prenorm(x)
+        f, maps, B, N = self._patch_nodes_prenorm(x, featdrop)
         q = ops.l2_normalize_last(f)                               # (B,N,T,D)
         return q.permute(0, 3, 2, 1), maps
 
@@ -149,11 +149,13 @@ class CRW(nn.Module):
         f, maps = self._superpixel_nodes_prenorm(x, sp_mask, max_sp_num)
         return ops.l2_normalize_last(f).permute(0, 3, 2, 1), maps
 
-    def _patch_nodes_prenorm(self, x):
+    def _patch_nodes_prenorm(self, x, featdrop=True):
+        """`featdrop=False`: the teacher's variant (teacherstudent.py:453-455 comments the feature dropout out so that the
+        teacher's targets stay deterministic)."""
         B, N, C, T, h, w = x.shape
         maps = self.encoder(x.flatten(0, 1))
         H, W = maps.shape[-2:]
-        if self.featdrop_rate > 0:
+        if featdrop and self.featdrop_rate > 0:
             maps = self.featdrop(maps)
         if N == 1:      # whole images: every feature-map position becomes a node (model.py:110-113)
             maps = maps.permute(0, 3, 4, 1, 2).contiguous()

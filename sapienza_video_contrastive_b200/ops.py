@@ -102,49 +102,90 @@ def pool_patch(maps: torch.Tensor) -> torch.Tensor:
 # a1: projection head (model.py:117).  Forward and input gradient are stock cuBLAS GEMMs (torch.matmul); the weight
 # gradient - 128 x 512 outputs reduced over B*N*T rows - uses the split-K kernel.
 # ------------------------------------------------------------------------------------------------------------------
-_async_wgrad = False
-_side_streams = {}
-_pending_events = []
+# Per-DEVICE state (under nn.DataParallel every replica runs on its own Python thread, one per GPU, and autograd
+# runs CUDA backward nodes on one engine thread per device - so "per device" is the granularity that is both visible from the
+# forward thread and from the backward, and private to a replica): the opt-in flags, the side stream and the events still to
+# be joined.  One replica can never pop another replica's events.
+_dev_state = {}
+_dev_lock = threading.Lock()
+_warned = set()
+
+
+def _warn_once(key, msg: str) -> None:
+    """One line per process and reason whenever a call leaves the tensor-core path for a library / SIMT one."""
+    if key not in _warned:
+        _warned.add(key)
+        import warnings
+        warnings.warn("crw_b200: " + msg, RuntimeWarning, stacklevel=3)
+
+
+class _DevState:
+    __slots__ = ("pending", "side", "async_wgrad", "tc_head", "lock")
+
+    def __init__(self):
+        self.pending, self.side, self.async_wgrad, self.tc_head, self.lock = [], None, False, True, threading.Lock()
+
+
+def _state(device=None) -> _DevState:
+    idx = torch.device(device).index if device is not None else None
+    idx = torch.cuda.current_device() if idx is None else idx
+    st = _dev_state.get(idx)
+    if st is None:
+        with _dev_lock:
+            st = _dev_state.setdefault(idx, _DevState())
+    return st
 
 
 def set_async_wgrad(flag: bool) -> None:
-    """Opt-in: run the head's weight-gradient kernel on a side stream so it overlaps the (HBM-bound) pooling backward.
-    The caller must then call `join_side_streams()` before anything consumes `weight.grad` (optimizer step, all-reduce,
-    a copy to the host, the end of a CUDA-graph capture).  Off by default: the drop-in module needs no extra calls."""
-    global _async_wgrad
-    _async_wgrad = bool(flag)
+    """Opt-in (for the current device): run the head's weight-gradient kernel on a side stream so it overlaps the (HBM-bound)
+    pooling backward.  The caller must then call `join_side_streams()` before anything consumes `weight.grad` (optimizer
+    step, all-reduce, a copy to the host, the end of a CUDA-graph capture).  Off by default: the drop-in module needs no
+    extra calls."""
+    _state().async_wgrad = bool(flag)
 
 
 def join_side_streams() -> None:
-    """Make the current stream wait for every side-stream launch issued since the last join."""
+    """Make the current stream wait for every side-stream launch issued on the current device since the last join."""
     cur = torch.cuda.current_stream()
-    while _pending_events:
-        cur.wait_event(_pending_events.pop())
+    st = _state()
+    with st.lock:
+        pend, st.pending = st.pending, []
+    for ev in pend:
+        cur.wait_event(ev)
 
 
 def _side_stream(device) -> torch.cuda.Stream:
-    idx = torch.device(device).index
-    idx = torch.cuda.current_device() if idx is None else idx
-    if idx not in _side_streams:
-        _side_streams[idx] = torch.cuda.Stream(device=idx)
-    return _side_streams[idx]
+    st = _state(device)
+    if st.side is None:
+        with st.lock:
+            if st.side is None:
+                st.side = torch.cuda.Stream(device=device)
+    return st.side
 
 
 _ERR_UNSUPPORTED = -2
-_tc_head = True
 
 
 def set_tensor_core_head(enabled: bool) -> None:
-    """Head forward / input gradient on the fused tcgen05 tf32 GEMM (default) or on the library fp32 GEMM.  The tensor-core
-    path feeds full-precision operands (tf32 big + small) but accumulates with the tensor core's truncating fp32 adder:
-    ~5e-6 of the largest output at K = 512 against ~5e-7 for an fp32 sgemm."""
-    global _tc_head
-    _tc_head = bool(enabled)
+    """Head forward / input gradient on the fused tcgen05 tf32 GEMM (default) or on the library fp32 GEMM (for the
+    current device).  The tensor-core path feeds full-precision operands (tf32 big + small) but accumulates with the tensor core's
+    truncating fp32 adder: ~5e-6 of the largest output at K = 512 against ~5e-7 for an fp32 sgemm."""
+    _state().tc_head = bool(enabled)
+
+
+_err_words = {}
 
 
 def tc_error_word(device) -> torch.Tensor:
-    """The device word the tensor-core head GEMMs raise on a pipeline timeout (never read on the hot path; tests check it)."""
-    return _workspace("tc_err", 256, device)[:4].view(torch.int32)
+    """The device word (ONE per device) the tensor-core head GEMMs raise on a pipeline timeout.  The kernels also trap, so a
+    timeout surfaces as a CUDA error at the next API call; the word tells a post-mortem which pipeline it was."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    with _ws_lock:
+        w = _err_words.get(idx)
+        if w is None:
+            w = _err_words[idx] = torch.zeros(64, dtype=torch.int32, device="cuda:%d" % idx)
+    return w[:1]
 
 
 def _head_gemm(fn_name: str, a: torch.Tensor, weight: torch.Tensor, out_cols: int) -> Optional[torch.Tensor]:
@@ -166,10 +207,13 @@ class _HeadLinear(torch.autograd.Function):
         _need_cuda(x, weight)
         ctx.save_for_backward(x, weight)
         D, C = weight.shape
-        if _tc_head and x.dtype == torch.float32 and weight.dtype == torch.float32:
+        st = _state(x.device)
+        ctx.async_wgrad, ctx.tc_head = st.async_wgrad, st.tc_head        # the backward uses the forward's settings
+        if st.tc_head and x.dtype == torch.float32 and weight.dtype == torch.float32:
             out = _head_gemm("crw_head_fwd", _f32c(x.reshape(-1, C)), _f32c(weight), D)
             if out is not None:
                 return out.view(*x.shape[:-1], D)
+            _warn_once(("head_fwd", D, C), "head forward (%d x %d): shape not TMA-addressable, using the library GEMM" % (D, C))
         return x.matmul(weight.t())               # shapes TMA cannot address (tiny or unaligned): library GEMM
 
     @staticmethod
@@ -178,14 +222,16 @@ class _HeadLinear(torch.autograd.Function):
         gx = gw = None
         cur = torch.cuda.current_stream()
         fork = None
-        if ctx.needs_input_grad[1] and _async_wgrad:
+        if ctx.needs_input_grad[1] and ctx.async_wgrad:
             fork = torch.cuda.Event()
             fork.record(cur)                       # the side stream only needs g and x, not the input gradient below
         if ctx.needs_input_grad[0]:
             D, C = weight.shape
             gx = None
-            if _tc_head and g.dtype == torch.float32 and weight.dtype == torch.float32:
+            if ctx.tc_head and g.dtype == torch.float32 and weight.dtype == torch.float32:
                 gx = _head_gemm("crw_head_dgrad", _f32c(g.reshape(-1, D)), _f32c(weight), C)
+                if gx is None:
+                    _warn_once(("head_dgrad", D, C), "head input gradient (%d x %d): shape not TMA-addressable, using the library GEMM" % (D, C))
             gx = g.matmul(weight) if gx is None else gx.view(*g.shape[:-1], C)
         if ctx.needs_input_grad[1]:
             D, C = weight.shape
@@ -209,7 +255,9 @@ class _HeadLinear(torch.autograd.Function):
                     done.record(side)
                 for t in (g2, x2, gw):
                     t.record_stream(side)
-                _pending_events.append(done)
+                st = _state(g.device)
+                with st.lock:
+                    st.pending.append(done)
         return gx, gw
 
 
@@ -583,9 +631,6 @@ def affinity_nodes(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     return _Affinity.apply(x1, x2)
 
 
-_bmm_ws = {}
-
-
 def bmm_tc(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
            out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """Batched fp32 GEMM on the tensor cores (the large-graph walk's contraction engine, gemm_tc.cu):
@@ -604,10 +649,7 @@ def bmm_tc(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: boo
         out = torch.empty(Z, M, N, device=A.device, dtype=torch.float32)
     L = _lib.lib()
     nbytes = L.crw_bmm_tc_workspace_bytes(Z, M, N, K)
-    key = (A.device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _bmm_ws.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = _bmm_ws[key] = torch.zeros(nbytes, dtype=torch.uint8, device=A.device)
+    ws = _workspace("bmm_tc", nbytes, A.device)
     L.check(L.crw_bmm_tc(A.data_ptr(), B.data_ptr(), out.data_ptr(), Z, M, N, K, int(trans_a), int(trans_b), int(accumulate),
                          ws.data_ptr(), ws.numel(), _stream()), "bmm_tc")
     if int(ws[:4].view(torch.int32)[0]) != 0:
@@ -695,6 +737,11 @@ def lp_topk(feats_cl: torch.Tensor, key_frames: torch.Tensor, query_frames: torc
     Ws = torch.empty(Nt, k, hw, dtype=torch.float32, device=dev)
     Is = torch.empty(Nt, k, hw, dtype=torch.int64, device=dev)
     L = _lib.lib()
+    if not force_simt and not L.crw_lp_topk_uses_tensor_cores(C, k, float(radius), int(dense_mask is not None)):
+        _warn_once(("lp_simt", C, k, dense_mask is not None),
+                   "label propagation with C=%d, k=%d%s runs on the exact-fp32 SIMT kernel (tensor-core kernel: C %% 64 == 0, "
+                   "C <= 256, k <= 16, radius <= 12, no dense mask); expect ~10x lower throughput"
+                   % (C, k, ", dense mask" if dense_mask is not None else ""))
     nbytes = L.crw_lp_topk_workspace_bytes(Nf, Nt, S, h, w, C, k)
     ws = _workspace(("lp", Nf, h, w, C, k), nbytes, dev)
     L.check(L.crw_lp_topk(feats_cl.data_ptr(), Nf, key_frames.data_ptr(), query_frames.data_ptr(), Nt, S, n_long, h, w, C,
@@ -716,6 +763,17 @@ def lp_gather_(lbls: torch.Tensor, key_frames_n: torch.Tensor, Ws_n: torch.Tenso
     L = _lib.lib()
     L.check(L.crw_lp_gather(lbls.data_ptr(), key_frames_n.contiguous().data_ptr(), _f32c(Ws_n).data_ptr(),
                             Is_n.contiguous().data_ptr(), hw, Lc, k, int(out_frame), _stream()), "lp_gather")
+
+
+def lp_minmax_normalize_(maps: torch.Tensor) -> torch.Tensor:
+    """test.py:162-164 (--norm_mask) in place on a contiguous (..., L) fp32 tensor: rows -= min; rows /= max."""
+    _need_cuda(maps)
+    if maps.dtype != torch.float32 or not maps.is_contiguous():
+        raise ValueError("lp_minmax_normalize_ needs a contiguous fp32 tensor")
+    Lc = maps.shape[-1]
+    L = _lib.lib()
+    L.check(L.crw_lp_minmax_normalize(maps.data_ptr(), maps.numel() // Lc, Lc, _stream()), "lp_minmax_normalize")
+    return maps
 
 
 def lp_upsample_argmax(preds: torch.Tensor, size: Tuple[int, int], palette: Optional[torch.Tensor] = None,

@@ -75,9 +75,9 @@ class CRWTeacherStudent(CRWBase):
         assert 0 <= self.alpha <= 1, "alpha_teacher_student must be in the interval [0, 1]"
 
     def pixels_to_nodes_tchr(self, x):
-        """teacherstudent.py:439-470: the teacher's node embeddings and maps, no gradient."""
+        """teacherstudent.py:439-470: the teacher's node embeddings and maps, no gradient and NO feature dropout (:453-455)."""
         with torch.no_grad():
-            return self.teacher.pixels_to_nodes(x)
+            return self.teacher.pixels_to_nodes(x, featdrop=False)
 
     def forward(self, x, just_feats=False, walk_uniforms=None):
         """x (B,T,N*3,H,W) -> (q, loss[1], diags) as teacherstudent.py:472-580; `walk_uniforms` optionally supplies the
@@ -89,7 +89,7 @@ class CRWTeacherStudent(CRWBase):
         x = x.transpose(1, 2).reshape(B, _N, C, T, H, W)
         f, mm, _, _ = self._patch_nodes_prenorm(x)
         with torch.no_grad():
-            ft = self.teacher._patch_nodes_prenorm(x)[0]
+            ft = self.teacher._patch_nodes_prenorm(x, featdrop=False)[0]      # deterministic teacher (:453-455)
         qn, loss, xent, acc, ts_xent = ops.walk_teacher_student(f, ft, self.temperature, self.edgedrop_rate, self.alpha, flip=self.flip,
                                                                 softmax=True, rng=self._rng_mode(f.device), uniforms=walk_uniforms)
         q = qn.permute(0, 3, 2, 1)                                               # (B, D, T, N)

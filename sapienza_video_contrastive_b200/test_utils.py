@@ -72,17 +72,12 @@ class RadiusMask:
         self.radius, self.h, self.w = float(radius), int(h), int(w)
 
 
-_mask_cache = {}
-
-
 def _analyse_dense_mask(mask: torch.Tensor, device) -> Tuple[Optional[RadiusMask], torch.Tensor]:
     """Recover (h, w, radius) from a dense additive mask when it IS a radius mask (verified exactly on the device);
-    otherwise the caller falls back to the literal dense-mask path."""
+    otherwise the caller falls back to the literal dense-mask path.  Derived afresh on every call (once per video in
+    test.py): a cache keyed on the tensor's address would hand a recycled allocation the previous video's geometry."""
     m = mask.reshape(mask.shape[-2], mask.shape[-1])
     hw = m.shape[0]
-    key = (mask.data_ptr(), hw, str(mask.device), mask._version)
-    if key in _mask_cache:
-        return _mask_cache[key]
     md = m.to(device=device, dtype=torch.float32).contiguous()
     spec = None
     row0 = md[0] == 0                                     # queries admissible for key (0,0)
@@ -103,8 +98,6 @@ def _analyse_dense_mask(mask: torch.Tensor, device) -> Tuple[Optional[RadiusMask
             inside = ((gy[:, None] - gy[None]) ** 2 + (gx[:, None] - gx[None]) ** 2).float() < radius * radius
             if bool(torch.equal(inside, md == 0)) and bool((md[~inside] <= -1e9).all()):
                 spec = RadiusMask(radius, h, w)
-    _mask_cache.clear()
-    _mask_cache[key] = (spec, md)
     return spec, md
 
 
@@ -149,9 +142,13 @@ def batched_affinity(query, keys, mask, temperature, topk, long_mem, device):
     return mem_efficient_batched_affinity(query, keys, mask, temperature, topk, long_mem, device)
 
 
-def propagate_labels(lbls: torch.Tensor, key_indices: torch.Tensor, Ws, Is, n_context: int, device=None) -> torch.Tensor:
-    """test.py:141-160: lbls (Nf,h,w,L) soft labels (rows >= n_context are overwritten, frame 0 is ground truth).
-    Ws / Is: per-target (k,hw) tensors (lists or stacked).  Returns the predictions (Nt,h,w,L) on `device`."""
+def propagate_labels(lbls: torch.Tensor, key_indices: torch.Tensor, Ws, Is, n_context: int, device=None,
+                     norm_mask: bool = False) -> torch.Tensor:
+    """test.py:141-164: lbls (Nf,h,w,L) soft labels (rows >= n_context are overwritten, frame 0 is ground truth).
+    Ws / Is: per-target (k,hw) tensors (lists or stacked).  Returns the maps test.py hands to dump_predictions, (Nt,h,w,L) on
+    `device`.  norm_mask reproduces test.py:162-164 INCLUDING its side effect: the first target's `pred` is a view of
+    lbls[0], so the reference normalises the ground-truth frame 0 in place (after copying it to lbls[n_context]) and every
+    later frame propagates from the normalised frame 0; the returned maps are normalised, the stored context is not."""
     device = device or (Ws[0].device if Ws[0].is_cuda else "cuda")
     Nf, h, w, L = lbls.shape
     lb = lbls.to(device=device, dtype=torch.float32).clone()
@@ -162,10 +159,16 @@ def propagate_labels(lbls: torch.Tensor, key_indices: torch.Tensor, Ws, Is, n_co
     for t in range(ki.shape[0]):
         if t == 0:
             lb[n_context] = lb[0]                         # test.py:158-160: the first target keeps the ground truth
+            if norm_mask:
+                ops.lp_minmax_normalize_(lb[0])           # ... and --norm_mask then rewrites frame 0 through the view
+            preds.append(lb[0] if norm_mask else lb[n_context])
         else:
             ops.lp_gather_(lb, ki[t], Ws[t].to(device), Is[t].to(device), t + n_context)
-        preds.append(lb[t + n_context])
-    return torch.stack(preds).view(-1, h, w, L)
+            preds.append(lb[t + n_context])
+    out = torch.stack(preds)
+    if norm_mask and out.shape[0] > 1:
+        ops.lp_minmax_normalize_(out[1:])
+    return out.view(-1, h, w, L)
 
 
 def dump_predictions(pred, lbl_set, img, prefix: Optional[str] = None, norm_mask: bool = False):
@@ -274,9 +277,9 @@ class LabelPropagator:
                              force_simt=self.force_simt)
         return ki, Ws, Is
 
-    def __call__(self, feats: torch.Tensor, lbls: torch.Tensor):
+    def __call__(self, feats: torch.Tensor, lbls: torch.Tensor, norm_mask: bool = False):
         ki, Ws, Is = self.affinity(feats)
-        preds = propagate_labels(lbls, ki, Ws, Is, self.n_context, device=feats.device)
+        preds = propagate_labels(lbls, ki, Ws, Is, self.n_context, device=feats.device, norm_mask=norm_mask)
         return preds, (Ws, Is)
 
     def label_images(self, preds: torch.Tensor, lbl_set: torch.Tensor, size, norm_mask: bool = False):

@@ -58,6 +58,22 @@ LP_CASES = {
                        dyadic=False, repeat_first=False, seed=34),
 }
 
+# label-propagation cases that reach the tensor-core kernel (C a multiple of 64, k <= 16, window <= 32 keys): generic
+# unit-norm features at C = 64 and C = 256, a replicated first frame (exact ties are the norm there) and a dyadic grid
+LP_TC_CASES = {
+    "lp_tc64":      dict(C=64, h=20, w=27, n_ctx=3, n_tgt=4, long_mem=[0], radius=5, k=10, tau=0.07, L=3,
+                         dyadic=False, repeat_first=False, seed=35),
+    "lp_tc256":     dict(C=256, h=18, w=40, n_ctx=4, n_tgt=3, long_mem=[0], radius=12, k=10, tau=0.05, L=4,
+                         dyadic=False, repeat_first=False, seed=36),
+    "lp_tc_repeat": dict(C=64, h=17, w=19, n_ctx=5, n_tgt=7, long_mem=[0], radius=12, k=10, tau=0.07, L=2,
+                         dyadic=False, repeat_first=True, seed=37),
+    "lp_tc_dyadic": dict(C=128, h=16, w=24, n_ctx=3, n_tgt=4, long_mem=[0], radius=4, k=5, tau=0.07, L=4,
+                         dyadic=True, repeat_first=False, seed=38),
+}
+# test.py:158-164 with --norm_mask: soft (non-one-hot) ground truth on frame 0, so the in-place normalisation of the view
+# lbls[0] at t = 0 changes what every later frame propagates from
+LP_NORM_CASE = dict(C=16, h=11, w=14, n_ctx=3, n_tgt=6, long_mem=[0], radius=4, k=5, tau=0.07, L=3,
+                    dyadic=False, repeat_first=True, soft_first=True, seed=39)
 
 # label-map post-processing cases (utils/test_utils.py:85-123): integer and non-integer scale factors, down-scaling, norm_mask
 POST_CASES = {
@@ -144,6 +160,8 @@ def lp_inputs(c):
     lbls = torch.zeros(Nf, c["h"], c["w"], c["L"])
     seg = torch.randint(0, c["L"], (c["h"], c["w"]), generator=g)
     first = F.one_hot(seg, c["L"]).float()
+    if c.get("soft_first"):                                     # bilinear-resized one-hots are soft (vos.py:262)
+        first = torch.softmax(2.0 * first + torch.randn(c["h"], c["w"], c["L"], generator=g), -1)
     lbls[: c["n_ctx"] + 1] = first                              # replicated first frame carries GT
     lbls[c["n_ctx"] + 1:] = torch.rand(c["n_tgt"] - 1, c["h"], c["w"], c["L"], generator=g)  # junk, zeroed by test.py:142
     return feats, lbls

@@ -1,0 +1,219 @@
+"""Round-2 pins: parity tests of exactly the kernels and configurations behind the published numbers.
+
+  * label propagation THROUGH THE TENSOR-CORE KERNEL (lp_tc.cu) against goldens of the unmodified reference's test.test()
+    (code/test.py:67-160) at C = 64 / 128 / 256, with the tie audit and the propagated label maps;
+  * the same at the full DAVIS shape (C=256, 60x107, 20 context frames, radius 12, k=10) against the oracle;
+  * bench.py's HotPath exactly as it is timed (rng='device', whole-step CUDA graph, cluster chain, side-stream wgrad)
+    against the oracle fed with the same Philox draws;
+  * the large-graph walk (N in {512, 1024}, T in {8, 16}) and BASELINE configs[2] (T=8, SP in {100,196,256}) against the
+    oracle (code/model.py:366-413), not against another path of this repository.
+
+Tolerances: north_star - loss / gradients 1e-4 relative in fp32; top-k indices bit-exact apart from ties.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import crw_oracle as O
+from tests.golden import cases
+from tests.test_sim_kernels import load
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from sapienza_video_contrastive_b200 import ops as _ops
+    _ops.check_device(DEV)
+    return _ops
+
+
+def relmax(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def uses_tc(C, k, radius):
+    from sapienza_video_contrastive_b200 import _lib
+    return bool(_lib.lib().crw_lp_topk_uses_tensor_cores(C, k, float(radius), 0))
+
+
+def audit_picks(feats, ki, Is, Is_ref, c, gap_tol):
+    """Index audit against the reference's picks.  Scores are recomputed in float64 from the inputs.  Every pick of ours
+    must (1) be admissible, (2) be duplicate-free per query, (3) where it differs from the reference's pick at the same rank,
+    carry a float64 score within `gap_tol` of the reference's pick (0 = exact ties only).
+    -> (number of differing picks, largest score gap among them, set of (target, query) with a differing pick)."""
+    hw = c["h"] * c["w"]
+    f = feats[0].flatten(-2).double()
+    add = O.radius_mask_additive(c["h"], c["w"], c["radius"])[0, 0].double()
+    n_long = len(c["long_mem"])
+    n_diff, worst, where = 0, 0.0, set()
+    for n in range(Is.shape[0]):
+        assert (Is[n] >= 0).all() and (Is[n] < ki.shape[1] * hw).all()
+        sc = torch.cat([f[:, ki[n, s]].t() @ f[:, n + c["n_ctx"]] + (add if s >= n_long else 0) for s in range(ki.shape[1])], 0) / c["tau"]
+        mine, ref = torch.gather(sc, 0, Is[n]), torch.gather(sc, 0, Is_ref[n])
+        assert float(mine.min()) > -1e6, "a masked key was selected"
+        srt = Is[n].sort(0).values
+        assert (srt[1:] != srt[:-1]).all(), "duplicate index"
+        neq = Is[n] != Is_ref[n]
+        if neq.any():
+            gap = (mine - ref).abs()[neq]
+            worst = max(worst, float(gap.max()))
+            n_diff += int(neq.sum())
+            where |= {(n, int(q)) for q in neq.any(0).nonzero().flatten()}
+        assert float((mine - ref).abs().max()) <= gap_tol, "target %d: a pick differs from the reference's by more than a tie" % n
+    return n_diff, worst, where
+
+
+@pytest.mark.parametrize("name", list(cases.LP_TC_CASES))
+def test_label_prop_tensor_core_kernel_matches_reference_golden(ops, name):
+    """goldens of the unmodified reference that reach lp_topk_tc_kernel, index audit AND label maps."""
+    from sapienza_video_contrastive_b200 import LabelPropagator, context_index_bank
+    c = cases.LP_TC_CASES[name]
+    assert uses_tc(c["C"], c["k"], c["radius"]), "this case must run on the tensor-core kernel"
+    fx = load(name)
+    feats, lbls = cases.lp_inputs(c)
+    lp = LabelPropagator(c["n_ctx"], c["long_mem"], c["radius"], c["k"], c["tau"], normalize=False)
+    preds, (Ws, Is) = lp(feats.to(DEV), lbls)
+    ki = torch.cat(context_index_bank(c["n_ctx"], c["long_mem"], c["n_tgt"]), -1)
+    # exact ties only where arithmetic is exact (dyadic grid) or keys are replicated; float rounding of a 64..256-term fp32
+    # dot product (ours vs the reference's sgemm order) otherwise: 2e-6 on the cosine
+    tol = 0.0 if c["dyadic"] else 2e-6 / c["tau"]
+    n_diff, worst, where = audit_picks(feats, ki, Is.cpu(), fx["Is"], c, tol)
+    if not (c["dyadic"] or c["repeat_first"]):
+        assert n_diff <= 2, (n_diff, worst)
+    torch.testing.assert_close(Ws.cpu(), fx["Ws"], rtol=2e-5, atol=1e-6)
+    # label maps: everywhere when ties carry equal labels (replicated frames) or there are no differing picks
+    p, r = preds.cpu(), fx["preds"]
+    if n_diff == 0 or c["repeat_first"]:
+        torch.testing.assert_close(p, r, rtol=1e-5, atol=1e-6)
+    else:
+        bad = (p - r).abs().amax(-1) > 1e-5
+        assert int(bad.sum()) <= 4 * len(where) * c["n_tgt"], "label maps differ beyond what the tied picks explain"
+
+
+def test_label_prop_davis_shape_tensor_core_vs_oracle(ops):
+    """BASELINE configs[3] at full size (C=256, 60x107 = 6420 nodes, 20 context frames + long memory, radius 12, k=10), three
+    target frames: tensor-core path vs oracle (test_utils.py:148-179 + test.py:141-160 restated), picks AND label maps."""
+    from sapienza_video_contrastive_b200 import LabelPropagator
+    C, h, w, n_ctx, n_tgt, k, r, tau, L = 256, 60, 107, 20, 3, 10, 12, 0.07, 4
+    assert uses_tc(C, k, r)
+    g = torch.Generator().manual_seed(0)
+    feats = torch.nn.functional.normalize(torch.randn(1, C, n_ctx + n_tgt, h, w, generator=g), dim=1)
+    lbls = torch.rand(n_ctx + n_tgt, h, w, L, generator=g)
+    lbls = lbls / lbls.sum(-1, keepdim=True)
+    c = dict(h=h, w=w, radius=r, long_mem=[0], n_ctx=n_ctx, tau=tau)
+    lp = LabelPropagator(n_ctx, [0], r, k, tau, normalize=False)
+    preds, (Ws, Is) = lp(feats.to(DEV), lbls)
+    ki = O.context_index_bank(n_ctx, [0], n_tgt)
+    Wo, Io = O.lp_topk(feats[0].flatten(-2), ki, n_ctx, 1, h, w, r, tau, k)
+    po = O.lp_propagate(lbls, ki, Wo, Io, n_ctx)
+    n_diff, worst, where = audit_picks(feats, ki, Is.cpu(), Io, c, 2e-6 / tau)
+    total = Io.numel()
+    print("DAVIS-shape tensor-core picks: %d of %d differ from the oracle's (largest score gap %.3g)" % (n_diff, total, worst))
+    assert n_diff <= total * 1e-5 + 2
+    torch.testing.assert_close(Ws.cpu(), Wo, rtol=2e-5, atol=1e-6)
+    p = preds.cpu()
+    bad = (p - po).abs().amax(-1) > 1e-5                      # (n_tgt, h, w)
+    # a differing (tied) pick changes its own query and, through the recurrence, whoever reads that position later
+    assert int(bad.sum()) <= 50 * len(where), (int(bad.sum()), len(where))
+
+
+def test_bench_hot_path_graph_replay_matches_oracle(ops):
+    """the configuration bench.py times - rng='device', the whole step replayed as a CUDA graph, chain on
+    4-CTA clusters, weight gradient on a side stream - against the oracle (model.py:92-123, 366-413) fed with the Philox
+    draws the device-side generator state promises."""
+    sys.path.insert(0, ROOT)
+    import bench
+    ops.set_async_wgrad(True)
+    try:
+        hp = bench.HotPath(torch.device(DEV, torch.cuda.current_device()), 0, use_graph=True)
+        hp.prepare()
+        assert hp.graph is not None
+        c = bench.CFG
+        B, N, T = c["B"], c["N"], c["T"]
+        for rep in range(2):
+            torch.cuda.synchronize()
+            seed, off = (int(v) for v in hp.rng_state.tolist())
+            loss = hp.step()
+            torch.cuda.synchronize()
+            numel = B * N * N
+            thr = ops.torch_rand_threads(numel, DEV)
+            inc = ops.torch_rand_offset_increment(numel, thr)
+            draws = [ops.philox_uniform(numel, seed, off + j * inc, thr, DEV).view(B, N, N) for j in range(2 * (T - 1))]
+            assert int(hp.rng_state[1]) == off + 2 * (T - 1) * inc          # the kernel advanced the state itself
+            u12, u21p = torch.stack(draws[: T - 1]), torch.stack(draws[T - 1:])
+            mo = hp.maps_in.detach().permute(0, 2, 1, 3, 4).clone().requires_grad_(True)       # logical (BN, C, T, H, W)
+            ho = hp.head.weight.detach().clone().requires_grad_(True)
+            qo = O.patch_nodes(mo, ho, B)
+            loss_o, xents, accs, _ = O.walk_loss(qo, c["tau"], c["p"], u12, u21p)
+            loss_o.sum().backward()
+            torch.testing.assert_close(loss.detach().reshape(1), loss_o.detach().reshape(1), rtol=1e-5, atol=0)
+            assert relmax(hp.head.weight.grad, ho.grad) < 1e-4
+            assert relmax(hp.maps_in.grad.permute(0, 2, 1, 3, 4), mo.grad) < 1e-4
+            assert 1.0 < float(loss) < 12.0
+    finally:
+        ops.set_async_wgrad(False)
+
+
+@pytest.mark.parametrize("B,N,T,p", [(1, 512, 8, 0.1), (1, 1024, 4, 0.1), (1, 1024, 16, 0.1), (2, 512, 16, 0.0), (2, 640, 5, 0.2)])
+def test_large_graph_walk_matches_oracle(ops, B, N, T, p):
+    """N >= 512 (the fp16-split tcgen05 GEMM path) and the configs[4] extremes against the ORACLE
+    (model.py:366-413 restated; run in fp32 on the device for speed, explicit dropout draws)."""
+    torch.manual_seed(N + T)
+    f = torch.randn(B, N, T, 128, device=DEV)
+    u12, u21p = O.draw_uniforms(B, N, T, device=DEV)
+    fo = f.clone().requires_grad_(True)
+    qo = (fo / fo.norm(dim=-1, keepdim=True).clamp_min(1e-12)).permute(0, 3, 2, 1)
+    loss_o, xents, accs, _ = O.walk_loss(qo, 0.07, p, u12, u21p)
+    loss_o.sum().backward()
+    fd = f.clone().requires_grad_(True)
+    q, loss, xent, acc = ops.walk(fd, 0.07, p, u12=u12, u21p=u21p)
+    loss.sum().backward()
+    torch.testing.assert_close(xent, torch.stack(xents).detach(), rtol=2e-5, atol=0)
+    torch.testing.assert_close(loss.reshape(1), loss_o.detach().reshape(1), rtol=1e-5, atol=0)
+    assert float((acc - torch.stack(accs)).abs().max()) <= 2.0 / (B * N) + 1e-6
+    assert relmax(fd.grad, fo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("SP", [100, 196, 256])
+def test_superpixel_config3_step_matches_oracle(ops, SP):
+    """BASELINE configs[2]: ~100-256 superpixel nodes per frame via segment-mean pooling, palindrome walk, clip_len 8
+    (model.py:260-332 + 366-413) against the oracle: pooled nodes, loss, and the gradients of maps and head."""
+    B, T, Ce = 2, 8, 64
+    g = torch.Generator().manual_seed(SP)
+    maps = torch.randn(B, Ce, T, 32, 32, generator=g)
+    head_w = torch.randn(128, Ce, generator=g) / Ce ** 0.5
+    lab = cases.voronoi_labels(B, T, SP, 256, g, one_based=(SP == 196))          # SP=196: node 0 is empty
+    u12, u21p = O.draw_uniforms(B, SP, T, generator=g)
+    mo, ho = maps.clone().requires_grad_(True), head_w.clone().requires_grad_(True)
+    q_o = O.superpixel_nodes(mo, lab, SP, ho)
+    loss_o, xents, accs, _ = O.walk_loss(q_o, 0.07, 0.1, u12, u21p)
+    loss_o.sum().backward()
+    md, hd = maps.to(DEV).requires_grad_(True), head_w.to(DEV).requires_grad_(True)
+    pooled = ops.segment_mean(md, lab.to(DEV), SP)
+    f = ops.head_linear(pooled, hd)
+    q, loss, xent, acc = ops.walk(f, 0.07, 0.1, u12=u12.to(DEV), u21p=u21p.to(DEV))
+    loss.sum().backward()
+    torch.testing.assert_close(q.permute(0, 3, 2, 1).cpu(), q_o.detach(), rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(xent.cpu(), torch.stack(xents).detach(), rtol=2e-5, atol=0)
+    assert relmax(hd.grad.cpu(), ho.grad) < 1e-4
+    assert relmax(md.grad.cpu(), mo.grad) < 1e-4
+
+
+def test_norm_mask_side_effect_matches_reference(ops):
+    """test.py:158-164: with --norm_mask the first target's `pred` is a VIEW of lbls[0], so the reference min-max-normalises the
+    ground-truth frame 0 in place and every later frame propagates from the normalised labels (VERDICT r1 missing #8)."""
+    from sapienza_video_contrastive_b200 import LabelPropagator
+    c = cases.LP_NORM_CASE
+    fx = load("lp_normmask")
+    feats, lbls = cases.lp_inputs(c)
+    lp = LabelPropagator(c["n_ctx"], c["long_mem"], c["radius"], c["k"], c["tau"], normalize=False)
+    preds, _ = lp(feats.to(DEV), lbls, norm_mask=True)
+    torch.testing.assert_close(preds.cpu(), fx["preds"], rtol=1e-5, atol=1e-6)
+    plain, _ = lp(feats.to(DEV), lbls)
+    plain = ops.lp_minmax_normalize_(plain.contiguous()).cpu()
+    assert float((plain - fx["preds"]).abs().max()) > 1e-3          # normalising the outputs alone does not reproduce it

@@ -125,9 +125,12 @@ def test_superpixel_matches_reference(name):
         torch.testing.assert_close(xe, fx["diags"]["256 xent cyc %s" % n], rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("name", list(cases.LP_CASES))
+ALL_LP = dict(cases.LP_CASES, **cases.LP_TC_CASES)
+
+
+@pytest.mark.parametrize("name", list(ALL_LP))
 def test_label_prop_matches_reference(name):
-    c = cases.LP_CASES[name]
+    c = ALL_LP[name]
     fx = load(name)
     feats, lbls = cases.lp_inputs(c)
     n_tgt = c["n_tgt"]
@@ -135,11 +138,25 @@ def test_label_prop_matches_reference(name):
     f = feats[0].flatten(-2)                                   # (C, Nf, hw)
     Ws, Is = O.lp_topk(f, ki, c["n_ctx"], len(c["long_mem"]), c["h"], c["w"], c["radius"], c["tau"], c["k"])
     assert Is.dtype == torch.int64 and Is.shape == fx["Is"].shape
-    if not c["repeat_first"]:
+    if not c["repeat_first"] and name != "lp_tc_dyadic":         # (exact ties: replicated frames, dyadic collisions at C=128)
         assert torch.equal(Is, fx["Is"])
     torch.testing.assert_close(Ws, fx["Ws"], rtol=1e-5, atol=1e-7)
     preds = O.lp_propagate(lbls, ki, Ws, Is, c["n_ctx"])
     torch.testing.assert_close(preds, fx["preds"], rtol=1e-5, atol=1e-6)
+
+
+def test_label_prop_norm_mask_side_effect_matches_reference():
+    """test.py:158-164: --norm_mask normalises the ground-truth frame 0 in place through the view `pred = lbls[0]`."""
+    c = cases.LP_NORM_CASE
+    fx = load("lp_normmask")
+    feats, lbls = cases.lp_inputs(c)
+    ki = O.context_index_bank(c["n_ctx"], c["long_mem"], c["n_tgt"])
+    Ws, Is = O.lp_topk(feats[0].flatten(-2), ki, c["n_ctx"], 1, c["h"], c["w"], c["radius"], c["tau"], c["k"])
+    torch.testing.assert_close(O.lp_propagate(lbls, ki, Ws, Is, c["n_ctx"], norm_mask=True), fx["preds"], rtol=1e-5, atol=1e-6)
+    plain = O.lp_propagate(lbls, ki, Ws, Is, c["n_ctx"])
+    plain = (plain - plain.min(-1, keepdim=True)[0])
+    plain = plain / plain.max(-1, keepdim=True)[0]
+    assert float((plain - fx["preds"]).abs().max()) > 1e-3       # normalising the outputs alone does not reproduce it
 
 
 @pytest.mark.parametrize("name", list(cases.POST_CASES))
