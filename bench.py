@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py - CRW walk fwd+bwd clips/s on the Kinetics-shaped batch (BASELINE.json configs[1]) and, as extra keys,
-DAVIS-shaped label-propagation frames/s (configs[3]).
+"""bench.py - CRW walk fwd+bwd clips/s on the Kinetics-shaped batch (BASELINE.json configs[1]) and DAVIS-shaped
+label-propagation frames/s (configs[3]), with the reference beside them.
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
+    python bench.py --gpus N --steps K --warmup W                    # our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the UNMODIFIED reference on the host cores
 
-One "step" = one pass of the hot path over one batch per GPU: patch mean-pool (a1) -> Linear head (stock cuBLAS) ->
-fused walk forward+backward (a4-a6) -> head backward -> pool backward, on precomputed encoder maps
-(B=20 clips/GPU, N=49, T=4, C_e=512, 8x8 maps, tau 0.07, edge dropout 0.1).  Prints ONE JSON line.
+One "step" (M1) = one pass of the hot path over one batch per GPU: patch mean-pool (a1) -> Linear head -> fused walk
+forward+backward (a4-a6) -> head backward -> pool backward, on precomputed encoder maps (B=20 clips/GPU, N=49, T=4, C_e=512,
+8x8 maps, tau 0.07, edge dropout 0.1).  Prints ONE JSON line.  Extra keys (one GPU): `label_prop` (M2, with
+its own roofline / cpu_baseline / torch_gpu_baseline / e2e / clocks), `torch_gpu_baseline` (the reference's own PyTorch code
+on the same B200), `superpixel` (configs[2]), `sweep` (configs[4] points), `e2e_module` (CRW(args)(x) with the ResNet-18).
+Every leg is timed for >= 50 ms with CUDA events and reports a per-iteration median.
 """
 from __future__ import annotations
 
@@ -26,7 +29,10 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(B=20, N=49, T=4, Ce=512, D=128, H=8, W=8, tau=0.07, p=0.1)
 LP = dict(C=256, h=60, w=107, n_ctx=20, n_tgt=37, k=10, radius=12, tau=0.07, L=4)   # 37 targets x 56 query tiles = 14 x 148 CTAs
+SP = dict(B=8, T=8, C=512, SP=196, size=256)                                        # BASELINE configs[2]
+SWEEP = [dict(T=4, N=49, B=2048), dict(T=8, N=256, B=256), dict(T=16, N=1024, B=16)]   # BASELINE configs[4]: B sized for >= 50 ms of work
 RESNET18_GRAD_FLOATS = 11_176_512 + 512 * 128          # encoder + head parameters (44.97 MB)
+MIN_MS = 50.0
 
 
 def peaks():
@@ -74,55 +80,110 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
+def timed_median(fn, min_ms=MIN_MS, warm=3, max_iters=5000, min_iters=5):
+    """CUDA-event time of fn(), one event pair per iteration, repeated until the timed iterations add up to >= min_ms.
+    -> (median ms, iterations, total ms)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts, total = [], 0.0
+    while (total < min_ms or len(ts) < min_iters) and len(ts) < max_iters:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+        total += ts[-1]
+    ts.sort()
+    return ts[len(ts) // 2], len(ts), total
+
+
+def count_kernels(fn):
+    """Kernels one call of fn() launches, counted by the CUDA profiler (kineto), not assumed: -> (ours, others, names)."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
+                 and not e.name.lower().startswith(("memcpy", "memset"))]
+        ours = [n for n in names if "crw::" in n or n.startswith("crw")]
+        return len(ours), len(names) - len(ours), sorted(set(n.split("(")[0][:60] for n in names))
+    except Exception as e:                                       # pragma: no cover - profiler unavailable
+        return None, None, ["profiler unavailable: %r" % (e,)]
+
+
 # --------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path, timed on the host cores
+# reference arm: the unmodified reference (oracle/_ref, via oracle/ref_harness.py) or, if it is not in place, the oracle port
 # --------------------------------------------------------------------------------------------------------------
-def cpu_step_fn(B):
-    from oracle import crw_oracle as O
+def reference_walk_step(B, device):
+    """-> (step(i) -> loss, kind): forward + backward of the reference's own CRW on the configs[1] maps on `device`."""
     c = CFG
     g = torch.Generator().manual_seed(1000)
-    maps = torch.randn(B * c["N"], c["Ce"], c["T"], c["H"], c["W"], generator=g).requires_grad_(True)
+    maps = torch.randn(B * c["N"], c["Ce"], c["T"], c["H"], c["W"], generator=g).to(device).requires_grad_(True)
     torch.manual_seed(0)
-    head = torch.nn.Linear(c["Ce"], c["D"], bias=False)
+    head = torch.nn.Linear(c["Ce"], c["D"], bias=False).to(device)
+    from oracle import ref_harness as RH
+    if RH.available():
+        return RH.walk_step(maps, head.weight.detach(), B, c["N"], c["T"], c["tau"], c["p"], device), "reference"
+    from oracle import crw_oracle as O
 
     def step(i):
         torch.manual_seed(123 + i)
         q = O.patch_nodes(maps, head.weight, B)
-        u12, u21p = O.draw_uniforms(B, c["N"], c["T"])
+        u12, u21p = O.draw_uniforms(B, c["N"], c["T"], device=device)
         loss, *_ = O.walk_loss(q, c["tau"], c["p"], u12, u21p)
         maps.grad = None
         head.weight.grad = None
         loss.mean().backward()
-        return float(loss)
+        return loss
 
-    return step
+    return step, "port"
 
 
-def time_cpu(B, steps, warmup):
-    step = cpu_step_fn(B)
+def time_cpu_walk(B, steps, warmup):
+    step, kind = reference_walk_step(B, "cpu")
     for i in range(warmup):
         step(i)
     t0 = time.perf_counter()
     for i in range(steps):
         step(warmup + i)
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps * 1e3
+    return B * steps / dt, dt / steps * 1e3, kind
+
+
+def host_threads():
+    """All host cores, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     c = CFG
-    cores = torch.get_num_threads()
-    steps, warmup = min(args.steps, 40), min(max(args.warmup, 1), 3)     # bounded: ~0.25 s per 20-clip step on 8 cores
-    val, ms = time_cpu(c["B"], steps, warmup)
+    cores = host_threads()
+    steps, warmup = args.steps, args.warmup
+    note = None
+    if steps > 400:                                   # bounded: ~50 ms per 20-clip step on 16 cores
+        note = "steps capped at 400 (asked %d)" % steps
+        steps = 400
+    val, ms, kind = time_cpu_walk(c["B"], steps, warmup)
+    what = ("the unmodified reference CRW.forward + backward (code/model.py:334-415, encoder swapped for the precomputed maps)"
+            if kind == "reference" else "oracle/crw_oracle.py port (oracle/_ref not built)")
     out = {"metric": "crw_walk_fwd_bwd_clips_per_s", "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "impl": "reference",
            "config": workload_config(1),
-           "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
-                            "sample": "%d steps of the full %d-clip batch (oracle/crw_oracle.py: pool+head+walk fwd+bwd)" % (steps, c["B"])},
+           "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": kind,
+                            "sample": "%d steps of the full %d-clip batch: %s" % (steps, c["B"], what)},
            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if note:
+        out["note"] = note
     print(json.dumps(out), flush=True)
 
 
@@ -233,7 +294,7 @@ def time_gpu_steps(fn, steps, warmup, world, after=None, finish=None):
 
 def kernel_roofline(dev):
     """The dominant kernels of the step are the two HBM streams over the 514 MB of maps.  Timed live with CUDA events
-    on the launching stream; achieved = algorithmic bytes / time."""
+    on the launching stream (>= 50 ms each); achieved = algorithmic bytes / median launch time."""
     from sapienza_video_contrastive_b200 import _lib
     c = CFG
     L = _lib.lib()
@@ -245,100 +306,283 @@ def kernel_roofline(dev):
     res = {}
     for name, fn in (("pool_patch_fwd", lambda: L.crw_pool_patch_fwd(maps.data_ptr(), pooled.data_ptr(), rows, hw, st)),
                      ("pool_patch_bwd", lambda: L.crw_pool_patch_bwd(pooled.data_ptr(), gm.data_ptr(), rows, hw, st))):
-        for _ in range(5):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 30
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / n * 1e3
+        med, n, total = timed_median(fn, warm=5)
         bytes_alg = rows * hw * 4 + rows * 4
-        res[name] = {"us": us, "algorithmic_bytes": bytes_alg, "gbs": bytes_alg / us / 1e3}
+        res[name] = {"us": med * 1e3, "launches_timed": n, "algorithmic_bytes": bytes_alg, "gbs": bytes_alg / med / 1e6}
     return res
 
 
-def label_prop_bench(dev):
-    """BASELINE configs[3]: DAVIS-480p-shaped label propagation, features resident, top-k for n_tgt target frames."""
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture of THIS round (profiles/ncu_summary.json; offline - a
+    number taken under the profiler is never a bench value, so it is only quoted next to the live measurement)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            d = json.load(f)
+        ent = d.get(kernel, {})
+        return ent.get("dram_bytes_per_launch"), d.get("_source", "profiles/ncu_summary.json")
+    except Exception:
+        return None, None
+
+
+# ---- M2: label propagation ----------------------------------------------------------------------------------------------
+def lp_inputs(replicate_first, n_tgt=None, seed=0):
+    c = LP
+    n_tgt = n_tgt or c["n_tgt"]
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.nn.functional.normalize(torch.randn(1, c["C"], c["n_ctx"] + n_tgt, c["h"], c["w"], generator=g), dim=1)
+    if replicate_first:
+        feats[:, :, : c["n_ctx"] + 1] = feats[:, :, :1]                     # vos.py:148-149 replicates frame 0 videoLen times
+    lbls = torch.zeros(c["n_ctx"] + n_tgt, c["h"], c["w"], c["L"])
+    lbls[: c["n_ctx"] + 1] = torch.nn.functional.one_hot(torch.randint(0, c["L"], (c["h"], c["w"]), generator=g), c["L"]).float()
+    return feats, lbls
+
+
+def lp_issued_flops(stats):
+    """Tensor-core work the label-propagation kernels ISSUE per call (to set beside the algorithmic 2*C*pairs)."""
+    c = LP
+    R = 11                                                                    # radius 12: offsets up to 11
+    per_tile = 0
+    for ty in range((c["h"] + 15) // 16):
+        rows = min(ty * 16 + 15 + R, c["h"] - 1) - max(ty * 16 - R, 0) + 1
+        per_tile_keys = c["n_ctx"] * rows * 32 + ((c["h"] * c["w"] + 31) // 32) * 32
+        per_tile += ((c["w"] + 7) // 8) * 128 * per_tile_keys * c["C"] * 2
+    pre = per_tile * c["n_tgt"]
+    tiles = max(stats.get("tiles", 1), 1)
+    return pre + 3 * pre * stats.get("listed_tiles", 0) / tiles
+
+
+def label_prop_bench(dev, cpu=True, gpu_baseline=True):
+    """BASELINE configs[3]: DAVIS-480p-shaped label propagation (C=256, 60x107, 20 context frames + long memory, radius 12,
+    top-k 10).  Device-resident value, host-buffer e2e, roofline, the reference on the host cores and on this GPU."""
     from sapienza_video_contrastive_b200 import LabelPropagator
     c = LP
-    g = torch.Generator().manual_seed(0)
-    feats = torch.randn(1, c["C"], c["n_ctx"] + c["n_tgt"], c["h"], c["w"], generator=g).to(dev)
-    lbls = torch.zeros(c["n_ctx"] + c["n_tgt"], c["h"], c["w"], c["L"])
-    lbls[: c["n_ctx"] + 1, :, :, 0] = 1
-    lp = LabelPropagator(c["n_ctx"], [0], c["radius"], c["k"], c["tau"], normalize=True)
-    lp(feats, lbls)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
-    e0.record()
-    for _ in range(reps):
-        lp(feats, lbls)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    fps = c["n_tgt"] / ms * 1e3
-    # the step right after it in test.py (SURVEY 8f rank 1): full-resolution hard label images of every target frame
-    preds, _ = lp(feats, lbls)
-    pal = torch.randint(0, 256, (c["L"], 3), generator=g)
-    lp.label_images(preds, pal, (c["h"] * 8, c["w"] * 8))
-    torch.cuda.synchronize()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(10):
-        lp.label_images(preds, pal, (c["h"] * 8, c["w"] * 8))
-    p1.record()
-    torch.cuda.synchronize()
-    post_ms = p0.elapsed_time(p1) / 10
+    hbm, tf, src = peaks()
     useful_flops = 2 * c["C"] * 90_214_480           # SURVEY 8d: in-radius + long-memory score pairs per target frame
-    _, tf, _ = peaks()
-    return {"metric": "label_prop_frames_per_s", "value": fps, "unit": "frames/s", "ms_per_frame": ms / c["n_tgt"],
-            "postprocess": {"what": "upsample x8 (cv2 bilinear rule) + arg-max + colour table for the %d frames, one launch" % c["n_tgt"],
-                            "ms": post_ms, "frames_per_s": c["n_tgt"] / post_ms * 1e3},
-            "config": "C=%d %dx%d, %d context + long-mem [0], radius %d, top-k %d, %d target frames per call (layout + hi/lo split + tcgen05 top-k + gathers)"
-                      % (c["C"], c["h"], c["w"], c["n_ctx"], c["radius"], c["k"], c["n_tgt"]),
-            "roofline": {"bound": "tensor", "achieved": useful_flops * fps / 1e12, "peak": tf, "unit": "TFLOP/s",
-                         "frac": useful_flops * fps / 1e12 / tf,
-                         "note": "algorithmic flops = 2*C*(in-radius + long-memory pairs) per frame; the fp32-faithful fp16 hi/lo "
-                                 "split issues 3 MMAs per product and whole 16x8 query windows, so the tensor pipe does ~8x this"}}
+    lp = LabelPropagator(c["n_ctx"], [0], c["radius"], c["k"], c["tau"], normalize=True)
+    out = {"metric": "label_prop_frames_per_s", "unit": "frames/s",
+           "config": "BASELINE configs[3]: C=%d %dx%d, %d context + long-mem [0], radius %d, top-k %d, %d target frames per call "
+                     "(layout + fp16 split + tcgen05 pre-ranking + exact fp32 re-ranking + certification + gathers)"
+                     % (c["C"], c["h"], c["w"], c["n_ctx"], c["radius"], c["k"], c["n_tgt"])}
+    variants = {}
+    with ClockSampler(dev.index or 0) as clk:
+        for name, rep in (("distinct_frames", False), ("replicated_first_frame", True)):
+            feats, lbls = lp_inputs(rep)
+            fd, ld = feats.to(dev), lbls.to(dev)
+            med, n, total = timed_median(lambda: lp(fd, ld))
+            st = dict(lp.stats)
+            variants[name] = {"frames_per_s": c["n_tgt"] / med * 1e3, "ms_per_call": med, "calls_timed": n, "ms_timed": total,
+                              "certification": st}
+            if not rep:
+                main_med, main_stats = med, st
+                # ---- e2e: host feats / labels in (pinned), label maps out (pinned), copies inside the timed region ----
+                hf, hl = feats.pin_memory(), lbls.pin_memory()
+                hout = torch.empty(c["n_tgt"], c["h"], c["w"], c["L"]).pin_memory()
+
+                def e2e_call():
+                    preds, _ = lp(hf.to(dev, non_blocking=True), hl.to(dev, non_blocking=True))
+                    hout.copy_(preds, non_blocking=True)
+
+                emed, en, etot = timed_median(e2e_call)
+                out["e2e"] = {"value": c["n_tgt"] / emed * 1e3, "unit": "frames/s", "ms_per_call": emed, "calls_timed": en,
+                              "h2d_bytes_per_call": hf.numel() * 4 + hl.numel() * 4, "d2h_bytes_per_call": hout.numel() * 4,
+                              "note": "pinned host encoder features + labels -> device -> LabelPropagator -> soft label maps back to host"}
+                # the step right after it in test.py (SURVEY 8f rank 1): full-resolution hard label images of every target frame
+                preds, _ = lp(fd, ld)
+                pal = torch.randint(0, 256, (c["L"], 3))
+                pmed, pn, _ = timed_median(lambda: lp.label_images(preds, pal, (c["h"] * 8, c["w"] * 8)))
+                out["postprocess"] = {"what": "upsample x8 (cv2 bilinear rule) + arg-max + colour table for the %d frames, one launch" % c["n_tgt"],
+                                      "ms": pmed, "frames_per_s": c["n_tgt"] / pmed * 1e3}
+    fps = c["n_tgt"] / main_med * 1e3
+    out.update(value=fps, ms_per_frame=main_med / c["n_tgt"], clocks=clk.summary(), variants=variants)
+    issued = lp_issued_flops(main_stats)
+    out["roofline"] = {"bound": "tensor", "achieved": useful_flops * fps / 1e12, "peak": tf, "unit": "TFLOP/s",
+                       "frac": useful_flops * fps / 1e12 / tf, "peak_source": src,
+                       "issued_over_algorithmic": issued / (useful_flops * c["n_tgt"]),
+                       "hbm_bound_frames_per_s": hbm * 1e9 / 144.6e6,
+                       "note": "algorithmic flops = 2*C*(in-radius + long-memory pairs) per frame (SURVEY 8d: 46.2 GFLOP); the "
+                               "kernel issues whole 16x8 query windows once on the fp16 hi planes, plus 3 MMAs per step on the listed tiles"}
+    if cpu:
+        from oracle import ref_harness as RH
+        cores = host_threads()
+        n_cpu = 2
+        feats, lbls = lp_inputs(False, n_tgt=n_cpu)
+        feats = torch.nn.functional.normalize(feats, dim=1)
+        if RH.available():
+            _, _, _, dt = RH.lp_video(feats, lbls, c["n_ctx"], [0], c["radius"], c["k"], c["tau"], "cpu")
+            kind = "reference"
+        else:
+            from oracle import crw_oracle as O
+            t0 = time.perf_counter()
+            ki = O.context_index_bank(c["n_ctx"], [0], n_cpu)
+            Wo, Io = O.lp_topk(feats[0].flatten(-2), ki, c["n_ctx"], 1, c["h"], c["w"], c["radius"], c["tau"], c["k"])
+            O.lp_propagate(lbls, ki, Wo, Io, c["n_ctx"])
+            dt, kind = time.perf_counter() - t0, "port"
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+                               "sample": "%d target frames of the same shape through code/test.py's loop (key bank, radius mask, "
+                                         "mem_efficient_batched_affinity, label gather), %.1f s" % (n_cpu, dt)}
+    if gpu_baseline:
+        try:
+            from oracle import ref_harness as RH
+            n_g = 8
+            feats, lbls = lp_inputs(False, n_tgt=n_g)
+            feats = torch.nn.functional.normalize(feats, dim=1)
+            if RH.available():
+                RH.lp_video(feats[:, :, : c["n_ctx"] + 2], lbls[: c["n_ctx"] + 2], c["n_ctx"], [0], c["radius"], c["k"], c["tau"], dev)   # warm-up
+                _, _, _, dt = RH.lp_video(feats, lbls, c["n_ctx"], [0], c["radius"], c["k"], c["tau"], dev)
+                out["torch_gpu_baseline"] = {"value": n_g / dt, "unit": "frames/s", "kind": "reference",
+                                             "sample": "the unmodified code/test.py loop with args.device = this B200 (features start on the host as in "
+                                                       "the reference, chunks are moved per 2 frames), %d target frames, %.2f s wall" % (n_g, dt)}
+        except Exception as e:
+            out["torch_gpu_baseline"] = {"error": repr(e)[:300]}
+    return out
 
 
-def superpixel_pool_bench(dev):
-    """BASELINE configs[2] shape (8 clips x 8 frames, 196 superpixels on 256x256, 512-channel 32x32 maps): superpixel pooling
-    forward + backward, plain and with the reference's default --dilate-superpixels element (51x51 'L1')."""
+# ---- configs[2]: superpixel graph ------------------------------------------------------------------------------------------
+def superpixel_bench(dev):
+    """BASELINE configs[2] shape (8 clips x 8 frames, 196 superpixels on 256x256, 512-channel 32x32 maps): the whole step
+    (segment-mean pooling -> head -> walk fwd+bwd -> head bwd -> pooling bwd) and the pooling kernels alone, plain and with the
+    reference's default --dilate-superpixels element (51x51 'L1')."""
     from sapienza_video_contrastive_b200 import ops
-    B, T, C, SP, size = 8, 8, 512, 196, 256
+    B, T, C, SPn, size = SP["B"], SP["T"], SP["C"], SP["SP"], SP["size"]
+    hbm, _, _ = peaks()
     g = torch.Generator(device=dev).manual_seed(0)
-    pts = torch.rand(B, T, SP, 2, generator=g, device=dev) * size
+    pts = torch.rand(B, T, SPn, 2, generator=g, device=dev) * size
     yx = torch.stack(torch.meshgrid(torch.arange(size, device=dev), torch.arange(size, device=dev), indexing="ij"), -1).float()
     lab = torch.stack([torch.cdist(yx.reshape(1, -1, 2).expand(T, -1, -1), pts[b]).argmin(-1) for b in range(B)]).reshape(B, T, size, size)
     maps = torch.randn(B, C, T, 32, 32, generator=g, device=dev, requires_grad=True)
-    gout = torch.randn(B, SP, T, C, generator=g, device=dev)
+    gout = torch.randn(B, SPn, T, C, generator=g, device=dev)
+    torch.manual_seed(0)
+    w = torch.nn.Linear(C, 128, bias=False).to(dev).weight
+    ones = torch.ones(1, device=dev)
 
-    def timed(fn, iters=10):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
-
-    def step(fn):
+    def pool_step(fn):
         fn().backward(gout)
         maps.grad = None
 
-    plain = timed(lambda: step(lambda: ops.segment_mean(maps, lab, SP)))
-    dil = timed(lambda: step(lambda: ops.segment_mean_dilated(maps, lab, SP, 51, "L1")))
-    return {"config": "B=%d T=%d C=%d SP=%d labels %dx%d maps 32x32, forward + backward" % (B, T, C, SP, size, size),
-            "plain_ms": plain, "plain_clips_per_s": B / plain * 1e3,
-            "dilated_L1_51_ms": dil, "dilated_clips_per_s": B / dil * 1e3}
+    def full_step():
+        maps.grad = None
+        w.grad = None
+        f = ops.head_linear(ops.segment_mean(maps, lab, SPn), w)
+        q, loss, xent, acc = ops.walk(f, 0.07, 0.1, rng="philox")
+        loss.backward(ones)
+
+    step_ms, n, _ = timed_median(full_step)
+    fwd_ms, _, _ = timed_median(lambda: ops.segment_mean(maps.detach(), lab, SPn))
+    plain, _, _ = timed_median(lambda: pool_step(lambda: ops.segment_mean(maps, lab, SPn)))
+    dil, _, _ = timed_median(lambda: pool_step(lambda: ops.segment_mean_dilated(maps, lab, SPn, 51, "L1")))
+    dil_fwd, _, _ = timed_median(lambda: ops.segment_mean_dilated(maps.detach(), lab, SPn, 51, "L1"))
+    bytes_alg = maps.numel() * 4 + lab.numel() * 8
+    return {"config": "BASELINE configs[2]: B=%d T=%d C=%d SP=%d labels %dx%d maps 32x32" % (B, T, C, SPn, size, size),
+            "step_ms": step_ms, "step_clips_per_s": B / step_ms * 1e3, "steps_timed": n,
+            "pool_fwd_ms": fwd_ms, "pool_fwd_gbs": bytes_alg / fwd_ms / 1e6, "pool_fwd_hbm_frac": bytes_alg / fwd_ms / 1e6 / hbm,
+            "pool_fwd_bwd_ms": plain, "pool_fwd_bwd_clips_per_s": B / plain * 1e3,
+            "dilated_L1_51_fwd_ms": dil_fwd, "dilated_L1_51_fwd_bwd_ms": dil, "dilated_clips_per_s": B / dil * 1e3}
+
+
+# ---- configs[4]: sweep points ------------------------------------------------------------------------------------------------
+def sweep_bench(dev):
+    from sapienza_video_contrastive_b200 import ops
+    _, tf, _ = peaks()
+    res = []
+    for pt in SWEEP:
+        B, N, T, D = pt["B"], pt["N"], pt["T"], 128
+        try:
+            f = torch.randn(B, N, T, D, device=dev, requires_grad=True)
+            ones = torch.ones(1, device=dev)
+
+            def step():
+                f.grad = None
+                q, loss, xent, acc = ops.walk(f, 0.07, 0.1, rng="philox")
+                loss.backward(ones)
+
+            ms, n, total = timed_median(step, warm=2, min_iters=3)
+            flops = 3 * (2 * (T - 1) * N * N * D + 2 * N ** 3 * 3 * (T - 2)) * B          # SURVEY 8d: fwd + 2x bwd, minimal chain count
+            res.append({"B": B, "N": N, "T": T, "ms": ms, "iters_timed": n, "clips_per_s": B / ms * 1e3,
+                        "algorithmic_tflops": flops / ms / 1e9, "tensor_frac": flops / ms / 1e9 / tf})
+            del f
+            torch.cuda.empty_cache()
+        except Exception as e:
+            res.append({"B": B, "N": N, "T": T, "error": repr(e)[:200]})
+    return res
+
+
+# ---- the reference's own PyTorch code on this GPU (SURVEY 2b: "the bar is the stock PyTorch/cuBLAS sequence on the same B200") ----
+def torch_gpu_walk_baseline(dev):
+    c = CFG
+    step, kind = reference_walk_step(c["B"], dev)
+    i = [0]
+
+    def fn():
+        step(i[0])
+        i[0] += 1
+
+    med, n, total = timed_median(fn)
+    ours, others, _ = count_kernels(fn)
+    return {"value": c["B"] / med * 1e3, "unit": "clips/s", "ms_per_step": med, "steps_timed": n, "kind": kind,
+            "kernel_launches_per_step": (ours or 0) + (others or 0),
+            "what": "the reference's CRW.forward + backward (eager PyTorch: ATen / cuBLAS kernels) on the same maps, device-resident"}
+
+
+# ---- module-level end to end: CRW(args)(x) with the stock ResNet-18 -------------------------------------------------------------
+def module_e2e(dev, world, steps=10):
+    """SURVEY 8d config 2 'end-to-end variant' (code/train.py:58-81): x (20,4,147,64,64) per GPU from pinned host memory ->
+    CRW(args)(x) -> loss.backward(), stock ResNet-18 on cuDNN, DistributedDataParallel when world > 1; the reference module (or the
+    port) on the same GPU beside it (one GPU only)."""
+    import argparse as ap
+    from sapienza_video_contrastive_b200 import CRW
+    c = CFG
+    ns = ap.Namespace(device=str(dev), dropout=c["p"], featdrop=0.0, temp=c["tau"], head_depth=0, model_type="scratch",
+                      remove_layers=[], dilate_superpixels=False, flip=False, sk_targets=False)
+    torch.manual_seed(0)
+    crw = CRW(ns).to(dev)
+    model = crw
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(crw, device_ids=[dev.index])
+    hx = [torch.randn(c["B"], c["T"], c["N"] * 3, 64, 64).pin_memory() for _ in range(2)]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def run(m, i):
+        x = hx[i & 1].to(dev, non_blocking=True)
+        for p_ in m.parameters():
+            p_.grad = None
+        q, loss, diags = m(x, None, None)
+        loss.mean().backward()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    k = [0]
+
+    def ours():
+        run(model, k[0])
+        k[0] += 1
+
+    med, n, _ = timed_median(ours, min_ms=200.0, warm=2, min_iters=3)
+    out = {"value": c["B"] * world / med * 1e3, "unit": "clips/s", "ms_per_step": med, "steps_timed": n,
+           "h2d_bytes_per_step": hx[0].numel() * 4, "d2h_bytes_per_step": 4,
+           "what": "CRW(args)(x) + backward, x (20,4,147,64,64) fp32 per GPU from pinned host memory, stock ResNet-18 (cuDNN) + the "
+                   "sm_100a hot path" + (", DistributedDataParallel over %d GPUs" % world if world > 1 else "")}
+    if world == 1:
+        try:
+            from oracle import ref_import
+            if ref_import.available():
+                import contextlib
+                import io
+                ref_model, _, _ = ref_import.load()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    torch.manual_seed(0)
+                    ref = ref_model.CRW(ref_import.namespace(device=str(dev), dropout=c["p"], temp=c["tau"])).to(dev)
+                ref.load_state_dict(crw.state_dict())
+                j = [0]
+
+                def theirs():
+                    run(ref, j[0])
+                    j[0] += 1
+
+                rmed, rn, _ = timed_median(theirs, min_ms=200.0, warm=2, min_iters=3)
+                out["reference_module_same_gpu"] = {"value": c["B"] / rmed * 1e3, "unit": "clips/s", "ms_per_step": rmed, "steps_timed": rn,
+                                                    "what": "the unmodified reference CRW (code/model.py) with the same weights on the same B200"}
+        except Exception as e:
+            out["reference_module_same_gpu"] = {"error": repr(e)[:300]}
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -370,8 +614,13 @@ def run_ours(args, rank, world, local_rank):
 
     with ClockSampler(local_rank) as clk:
         ms = time_gpu_steps(hp.step, args.steps, args.warmup, world, after if world > 1 else None, finish if world > 1 else None)
+        # the same step, one event pair per step, for >= 50 ms: the per-step median next to the contract's K-step mean
+        med_ms, med_n, _ = timed_median(hp.step, warm=0) if world == 1 else (None, None, None)
     clocks = clk.summary()
     value = c["B"] * world * args.steps / ms * 1e3
+    loss_now = float(hp.step().detach())
+    if not (1.0 < loss_now < 12.0):                                  # random init: near log(49) = 3.9
+        raise SystemExit("bench.py: the timed step produced loss %r - not a valid run" % loss_now)
 
     # ---- end to end through the public operator API with HOST buffers (pinned), copies inside the timed region ----
     host = [torch.randn(hp.maps.shape, pin_memory=True) for _ in range(2)]
@@ -413,7 +662,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(3, min(args.steps, 10))
+    n_e2e = max(6, min(args.steps, 10))                              # ~9 ms per step: >= 50 ms timed
     e0.record()
     e2e_loop(n_e2e)
     e1.record()
@@ -425,58 +674,72 @@ def run_ours(args, rank, world, local_rank):
         ms_e2e = float(t)
     e2e_val = c["B"] * world * n_e2e / ms_e2e * 1e3
 
+    mod = None
+    if args.e2e_module:
+        mod = module_e2e(dev, world)
+
     if rank != 0:
         return
     hbm, tf, src = peaks()
     kr = kernel_roofline(dev)
     dom = max(kr, key=lambda k: kr[k]["us"])
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    traffic, traffic_src = ncu_traffic(dom)
+    n_ours, n_other, knames = count_kernels(hp._step_eager)
     out = {"metric": "crw_walk_fwd_bwd_clips_per_s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
            "launch": "eager" if args.eager else "cuda_graph",
            "clocks": clocks,
-           "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": n_e2e,
+                   "ms_timed": ms_e2e,
                    "note": "pinned host maps -> device (double-buffered copy stream) -> hot path -> loss + head grad back to host"},
-           "gpu_launches": 9 * args.steps,
-           "gpu_launches_note": "per step: crw pool_fwd, gemm_tf32 (head fwd), walk_pairs_fwd, walk_chain_cluster, walk_pairs_bwd, "
-                                "gemm_tf32 (head dgrad), gemm_tf32 (split-K head wgrad), splitk_reduce, pool_bwd; "
-                                "plus one torch elementwise scale of the walk gradient",
+           "gpu_launches": (n_ours or 0) * args.steps,
+           "gpu_launches_note": "counted with the CUDA profiler on one step: %s kernels of libcrw_b200.so + %s others (torch elementwise) per step; "
+                                "kernels: %s" % (n_ours, n_other, ", ".join(knames)),
            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kr[dom]["gbs"], "peak": hbm, "unit": "GB/s",
-                        "frac": kr[dom]["gbs"] / hbm, "traffic": traffic, "peak_source": src,
+                        "frac": kr[dom]["gbs"] / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": src,
                         "step_hbm_frac": (2 * kr[dom]["algorithmic_bytes"]) / (ms / args.steps * 1e-3) / 1e9 / hbm},
-           "kernels": kr}
+           "kernels": kr, "loss": loss_now}
+    if med_ms is not None:
+        out["ms_per_step_median"] = med_ms
+        out["value_median"] = c["B"] / med_ms * 1e3
+        out["median_steps_timed"] = med_n
+    if mod is not None:
+        out["e2e_module"] = mod
     if world == 1 and not args.no_cpu:
-        cores = torch.get_num_threads()
-        val, cms = time_cpu(c["B"], 20, 1)
-        out["cpu_baseline"] = {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
-                               "sample": "20 steps of the full %d-clip batch (oracle/crw_oracle.py), %.0f ms/step" % (c["B"], cms)}
-    if world == 1 and not args.no_lp:
-        try:
-            out["label_prop"] = label_prop_bench(dev)
-        except Exception as e:                                   # the headline line must still print
-            out["label_prop"] = {"error": repr(e)}
-        try:
-            out["superpixel_pooling"] = superpixel_pool_bench(dev)
-        except Exception as e:
-            out["superpixel_pooling"] = {"error": repr(e)}
+        cores = host_threads()
+        val, cms, kind = time_cpu_walk(c["B"], 20, 2)
+        out["cpu_baseline"] = {"value": val, "unit": "clips/s", "cores": cores, "kind": kind,
+                               "sample": "20 steps of the full %d-clip batch (%s), %.0f ms/step"
+                                         % (c["B"], "unmodified reference CRW.forward + backward on the precomputed maps" if kind == "reference"
+                                            else "oracle/crw_oracle.py port", cms)}
+    if world == 1 and not args.no_extras:
+        for key, fn in (("torch_gpu_baseline", lambda: torch_gpu_walk_baseline(dev)),
+                        ("label_prop", lambda: label_prop_bench(dev, cpu=not args.no_cpu)),
+                        ("superpixel", lambda: superpixel_bench(dev)),
+                        ("sweep", lambda: sweep_bench(dev)),
+                        ("e2e_module", (lambda: module_e2e(dev, 1)) if mod is None else None)):
+            if fn is None or (key == "label_prop" and args.no_lp):
+                continue
+            try:
+                out[key] = fn()
+            except Exception as e:                                   # the headline line must still print
+                out[key] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
     print(json.dumps(out), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="launch the step op by op instead of replaying a CUDA graph")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-lp", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the host-core baselines")
+    ap.add_argument("--no-lp", action="store_true", help="skip the label-propagation leg")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only (no label_prop / superpixel / sweep / baselines on the GPU)")
+    ap.add_argument("--e2e-module", action="store_true", help="also time CRW(args)(x) with the ResNet-18 (DDP when several GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

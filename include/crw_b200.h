@@ -37,6 +37,7 @@ extern "C" {
 #define CRW_WALK_NO_TF32 64u      /* large-graph path: always the fp16 hi/lo-split GEMM, never the fused kind::tf32 one */
 #define CRW_WALK_NO_CLUSTER 32u   /* small-graph path: one CTA per clip for the chain instead of a 4-CTA cluster */
 #define CRW_LP_FORCE_SIMT 1u      /* label propagation: exact-fp32 SIMT scores instead of the tcgen05 kernel */
+#define CRW_LP_EXACT_ONLY 2u      /* label propagation, tensor-core path: skip the fp16 pre-ranking pass, every tile on the 3-MMA fp32-faithful pass */
 
 typedef void* crw_stream_t;
 
@@ -189,11 +190,16 @@ int crw_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, ui
  * semantics for an arbitrary mask, without the window skipping.
  * Ws (Nt,k,hw) fp32 softmax over the k best scores / temperature; Is (Nt,k,hw) int64 = slot*hw + key_pos,
  * sorted by descending score, ties broken by ascending index.
- * Two implementations with identical results: a tcgen05/TMEM/TMA tensor-core kernel (C % 64 == 0, C <= 256, k <= 16,
- * radius <= 13, no dense mask; fp16 hi/lo split operands, fp32 accumulation, see csrc/lp_tc.cu) and an exact-fp32 SIMT
- * kernel for everything else (or when flags has CRW_LP_FORCE_SIMT).  feats holds Nf frames.  After the stream has
- * drained, the first 32-bit word of the workspace is non-zero if the tensor-core kernel hit an internal barrier
- * timeout (results invalid). */
+ * Two implementations with identical results.  (1) The tensor-core path (C % 64 == 0, C <= 256, k <= 12, radius <= 12, no
+ * dense mask; |feats| < 6e4, csrc/lp_tc.cu): a tcgen05/TMEM/TMA kernel pre-ranks every admissible key on the fp16 "hi" part of
+ * the features (one MMA per 16 channels) and keeps a 16-key shortlist per query; a second kernel re-scores the shortlist in
+ * exact fp32 (sequential fmaf over the channels), ranks it and PROVES the result equal to a full exact evaluation from the
+ * error bound of the pre-scores (|pre - exact| <= 1.05e-3 |q| max|k|); tiles holding a query that cannot be certified (exact
+ * ties of replicated frames, vos.py:148-149; CRW_LP_EXACT_ONLY) are redone on the fp32-faithful pass (fp16 hi/lo
+ * split, three MMAs per step, ~2^-22 relative) and re-ranked the same way.  (2) An exact-fp32 SIMT kernel for everything else
+ * (or CRW_LP_FORCE_SIMT); both rank by the same fp32 scores, so Ws and Is agree bit for bit.  feats holds Nf frames.
+ * Workspace header (32-bit words, valid once the stream has drained): [0] error (1 = internal barrier timeout - the kernel
+ * also traps -, 2 = features outside the fp16 range), [1] tiles sent to the fp32-faithful pass, [4] queries not certified. */
 size_t crw_lp_topk_workspace_bytes(int Nf, int Nt, int S, int h, int w, int C, int k);
 int crw_lp_topk(const float* feats, int Nf, const int64_t* key_frames, const int64_t* query_frames, int Nt, int S,
                 int n_long, int h, int w, int C, float radius, const float* dense_mask, float temperature, int k,

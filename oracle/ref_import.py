@@ -4,7 +4,8 @@ The reference imports a handful of plotting / image packages at module import ti
 absent here and unused on the hot path; they are replaced by empty stub
 modules.  Nothing from the reference is copied into this repository: this module only makes
 `import model`, `import utils.test_utils` resolve so oracle/gen_golden.py can execute it.
-/root/reference does not exist on the GPU box; available() is False there.
+/root/reference does not exist on the GPU box; there the byte-identical files that oracle/build_ref.py placed under the
+git-ignored oracle/_ref/code/ are imported instead (bench.py's reference arm only - the -m gpu tests never need them).
 """
 from __future__ import annotations
 
@@ -14,10 +15,16 @@ import sys
 import types
 
 REF_ROOT = "/root/reference/code"
+REF_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "code")      # oracle/build_ref.py
+
+
+def root() -> str:
+    """/root/reference/code in the authoring container, else the byte-identical files placed by oracle/build_ref.py."""
+    return REF_ROOT if os.path.isfile(os.path.join(REF_ROOT, "model.py")) else REF_BUILT
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "model.py"))
+    return os.path.isfile(os.path.join(root(), "model.py"))
 
 
 class _Any:
@@ -63,7 +70,7 @@ def load():
     # the reference's top-level package is called `utils`; make sure ours / others do not shadow it
     for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k in ("model", "resnet")]:
         del sys.modules[k]
-    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, root())
     hook = sys.excepthook
     import model as ref_model            # noqa: E402
     import utils as ref_utils            # noqa: E402

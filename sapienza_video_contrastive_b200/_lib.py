@@ -27,6 +27,7 @@ WALK_FORCE_TC = 16
 WALK_NO_CLUSTER = 32
 WALK_NO_TF32 = 64
 LP_FORCE_SIMT = 1
+LP_EXACT_ONLY = 2
 DILATE_SHAPES = {"L1": 0, "circle": 1, "cross": 2}                # CRW_DILATE_* (utils/__init__.py:590-608 kernel names)
 
 _SIGNATURES = {

@@ -276,9 +276,9 @@ extern "C" int crw_lp_topk_uses_tensor_cores(int C, int k, float radius, int has
 }
 
 extern "C" size_t crw_lp_topk_workspace_bytes(int Nf, int Nt, int S, int h, int w, int C, int k) {
-    (void)Nt; (void)S;
+    (void)S;
     size_t b = 256;                          // word 0: device-side error flag
-    if (lp_tc_supported(C, k, 1.f, 0, false)) b = lp_tc_workspace_bytes(Nf, h, w, C);
+    if (lp_tc_supported(C, k, 1.f, 0, false)) b = lp_tc_workspace_bytes(Nf, Nt, h, w, C);
     return b;
 }
 
@@ -295,7 +295,7 @@ extern "C" int crw_lp_topk(const float* feats, int Nf, const int64_t* key_frames
     if (!workspace || workspace_bytes < 256) { set_error("lp_topk: workspace missing"); return CRW_ERR_SHAPE; }
     const int Rr = radius > 0.f ? radius_R(radius) : 0;
     if (!(flags & CRW_LP_FORCE_SIMT) && lp_tc_supported(C, k, radius, Rr, dense_mask != nullptr) &&
-        workspace_bytes >= lp_tc_workspace_bytes(Nf, h, w, C)) {
+        workspace_bytes >= lp_tc_workspace_bytes(Nf, Nt, h, w, C)) {
         LpTcArgs t{};
         t.key_frames = key_frames; t.query_frames = query_frames;
         t.Nt = Nt; t.S = S; t.n_long = n_long; t.h = h; t.w = w; t.C = C; t.k = k; t.R = Rr;
@@ -304,7 +304,7 @@ extern "C" int crw_lp_topk(const float* feats, int Nf, const int64_t* key_frames
         int r2i = 0;
         while ((float)(r2i + 1) < radius * radius) ++r2i;
         t.r2i = radius > 0.f ? r2i : 0;
-        t.tau = temperature; t.Ws = Ws; t.Is = Is;
+        t.tau = temperature; t.Ws = Ws; t.Is = Is; t.flags = flags;
         return launch_lp_tc(feats, Nf, t, workspace, workspace_bytes, stream);
     }
     cudaMemsetAsync(workspace, 0, 4, (cudaStream_t)stream);

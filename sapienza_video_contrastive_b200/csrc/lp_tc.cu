@@ -2,27 +2,36 @@
 // Reference semantics: code/utils/test_utils.py:148-179 (affinity, mask, /T, topk, softmax) with the radius mask of
 // code/utils/__init__.py:377-391 + code/test.py:118-122 evaluated as an integer test.  Same results as lp_simt.cu.
 //
-// fp32-faithful scores on fp16 tensor cores: every feature is split x = hi + lo * 2^-11 (hi = fp16(x),
-// lo = fp16((x - hi) * 2^11)); a score is  <q,k> = qhi.khi + (qhi.klo + qlo.khi) * 2^-11  with fp32 accumulation in
-// TMEM (two accumulators, three tcgen05.mma per 16-channel step); the dropped lo.lo term is ~2^-22 relative.
-// Dyadic inputs (lo = 0) are reproduced exactly.
+// Three kernels per call (round 2: one third of the tensor-core work of round 1, results certified exact):
+//   1. lp_topk_tc_kernel<PRE>    pre-ranking on the fp16 "hi" planes only: ONE tcgen05.mma per 16-channel step.  With
+//      x = hi + dx, |dx| <= 2^-11 |x|, a pre-score differs from the exact dot product by at most
+//      eps = 1.05e-3 |q| max|k| (+ a denormal term).  The kernel keeps, per query, the 16 best pre-scores (the shortlist).
+//   2. lp_rescore_kernel<CHECK>  exact fp32 scores of the 16 shortlisted keys (sequential fmaf over the channels, the very
+//      order of the SIMT kernel), ranking by (score desc, index asc), softmax over the k winners -> Ws, Is.  Every key
+//      outside the shortlist has pre-score <= the 16th, hence exact score <= pre16 + eps: when the k-th exact score
+//      exceeds that bound the top-k is PROVEN identical to a full exact evaluation.  Otherwise the query's tile is put
+//      on a device-side work list (exact ties - replicated first frames, vos.py:148-149 - always land here).
+//   3. lp_topk_tc_kernel<EXACT> + lp_rescore_kernel<NOCHECK> over the listed tiles only: fp32-faithful scores from the fp16
+//      hi/lo split, x = hi + lo * 2^-11, <q,k> = qhi.khi + (qhi.klo + qlo.khi) * 2^-11 with fp32 accumulation in two TMEM
+//      accumulators (three tcgen05.mma per step, dropped term ~2^-22 relative, dyadic inputs exact) - round 1's kernel -
+//      producing a shortlist that goes through the same exact re-ranking.  (k > 12 is left to the SIMT kernel.)
 //
 // One CTA = one target frame x one 16x8 block of 128 queries (the M = 128 rows / TMEM lanes of the MMA):
-//   TMEM     the query tile itself (hi and lo planes, 2 x C/2 columns) lives in tensor memory for the CTA's lifetime
-//            (tcgen05.mma with the A operand in TMEM): it is re-used by every key tile, so it is never re-read from
-//            shared memory, which would otherwise bound small-N MMAs.  The remaining 256 columns hold two accumulator
-//            stages (main + correction, 64 keys each).
+//   TMEM     the query tile itself (hi, and lo in EXACT mode; C/2 columns per plane) lives in tensor memory for the CTA's
+//            lifetime (tcgen05.mma with the A operand in TMEM): it is re-used by every key tile, so it is never re-read
+//            from shared memory, which would otherwise bound small-N MMAs.  256 further columns hold two accumulator
+//            stages (main [+ correction], 64 keys each).
 //   warp 0   TMA producer: the query tile once (staged in shared memory, copied to TMEM by the epilogue warps), then a
-//            3-stage ring of 64-key tiles (hi+lo planes, 128B-swizzled).  A tile is two 32-key runs: restricted slots
-//            only visit the rows of the block's (16+2R) x (8+2R) window, one run per window row; long-memory slots
-//            sweep the frame linearly.
-//   warp 1   MMA issuer (one elected thread): per key tile 3 x C/16 tcgen05.mma (M128 N64 K16, kind::f16, A from TMEM,
-//            B from shared memory) into the main / correction accumulators of one of two ping-pong stages.
-//   warps 2-9  epilogue: thread = (query = TMEM lane, one 32-key run of the tile).  tcgen05.ld pulls main + correction
-//            values into registers; validity + the radius test are folded into a branch-free running max, and only
-//            when some lane's max beats its k-th best does the warp extract candidates into the register-resident
-//            sorted top-k list.  The two half-lists of a query are merged once at the end through shared memory; the
-//            affinity matrix never leaves the SM.  Final softmax over the k winners.
+//            ring of 64-key tiles (128B-swizzled; 6 stages of the hi plane in PRE mode, 3 stages of hi+lo in EXACT mode).
+//            A tile is two 32-key runs: restricted slots only visit the rows of the block's (16+2R) x (8+2R) window, one
+//            run per window row; long-memory slots sweep the frame linearly.
+//   warp 1   MMA issuer (one elected thread): per key tile 1 or 3 x C/16 tcgen05.mma (M128 N64 K16, kind::f16, A from
+//            TMEM, B from shared memory) into one of two ping-pong accumulator stages.
+//   warps 2-9  epilogue: thread = (query = TMEM lane, one 32-key run of the tile).  tcgen05.ld pulls the scores into
+//            registers; validity + the radius test are one bit mask per run, folded into a branch-free running max, and
+//            only when some lane's max beats its 16th best does the warp extract candidates into the register-resident
+//            sorted list.  The two half-lists of a query are merged once at the end through shared memory; the affinity
+//            matrix never leaves the SM.
 #include "common.cuh"
 
 #include "tc_common.cuh"
@@ -34,30 +43,57 @@ constexpr int TC_M = 128;        // queries per CTA (16 rows x 8 cols)
 constexpr int TC_QH = 16, TC_QW = 8;
 constexpr int TC_NS = 32;        // keys per run (one TMA box)
 constexpr int TC_NT = 64;        // keys per tile = MMA N (two runs)
-constexpr int TC_STAGES = 3;     // key ring depth
 constexpr int TC_EPI_WARPS = 8;  // two epilogue warps per TMEM lane quarter, each owning half of a sub-tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int LP_SHORT = 16;     // shortlist length per query
+constexpr int LP_PRE_MAX_K = 12; // the pre-ranking pass needs spare shortlist entries below the k-th to certify a query
+constexpr int MODE_PRE = 0, MODE_EXACT = 1;
+// workspace header words
+constexpr int HDR_ERR = 0, HDR_COUNT = 1, HDR_KNORM2 = 2, HDR_MAXABS = 3, HDR_FLAGGED = 4, HDR_BYTES = 1024;
+// |pre-score - exact fp32 score| <= LP_EPS_REL |q| max|k| + LP_EPS_ABS (|q| + max|k|):  2 * 2^-11 (1 + 2^-12) from rounding
+// both operands to fp16, 2e-5 for the tensor core's truncating fp32 accumulation over <= 256 channels, 1.6e-5 for the fp32
+// rounding of the exact score itself; the absolute term covers fp16 subnormals (|x| < 6.1e-5: error <= 2^-25 per element)
+constexpr float LP_EPS_REL = 1.05e-3f, LP_EPS_ABS = 1e-6f;
 
 #ifndef CRW_SIM
 
-// ---- split kernel: fp32 channel-last features -> fp16 hi / lo planes ----------------------------------------------
-__global__ void __launch_bounds__(256) lp_split_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, int64_t n4) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(x + i);
-        const float f[4] = {v.x, v.y, v.z, v.w};
-        __half h[4], l[4];
+// ---- split kernel: fp32 channel-last features -> fp16 hi / lo planes; also max squared row norm and max |x| ---------
+__global__ void __launch_bounds__(256) lp_split_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                       int64_t rows, int c4, unsigned* hdr) {
+    const int lane = threadIdx.x & 31;
+    float best_ss = 0.f, best_abs = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+        float ss = 0.f;
+        for (int i = lane; i < c4; i += 32) {
+            const float4 v = __ldg(x + r * c4 + i);
+            const float f[4] = {v.x, v.y, v.z, v.w};
+            __half h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            h[j] = __float2half_rn(f[j]);
-            l[j] = __float2half_rn((f[j] - __half2float(h[j])) * 2048.0f);
+            for (int j = 0; j < 4; ++j) {
+                h[j] = __float2half_rn(f[j]);
+                l[j] = __float2half_rn((f[j] - __half2float(h[j])) * 2048.0f);
+                ss = fmaf(f[j], f[j], ss);
+                best_abs = fmaxf(best_abs, fabsf(f[j]));
+            }
+            uint2 ho, lo_;
+            ho.x = (unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16);
+            ho.y = (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16);
+            lo_.x = (unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16);
+            lo_.y = (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16);
+            hi[r * c4 + i] = ho;
+            lo[r * c4 + i] = lo_;
         }
-        uint2 ho, lo_;
-        ho.x = (unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16);
-        ho.y = (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16);
-        lo_.x = (unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16);
-        lo_.y = (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16);
-        hi[i] = ho;
-        lo[i] = lo_;
+        best_ss = fmaxf(best_ss, warp_sum(ss));
+    }
+    best_abs = warp_max(best_abs);
+    __shared__ float sh[16];
+    if (lane == 0) { sh[threadIdx.x >> 5] = best_ss; sh[8 + (threadIdx.x >> 5)] = best_abs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a = fmaxf(a, sh[i]); b = fmaxf(b, sh[8 + i]); }
+        atomicMax(hdr + HDR_KNORM2, __float_as_uint(a));             // non-negative floats order like their bit patterns
+        atomicMax(hdr + HDR_MAXABS, __float_as_uint(b));
     }
 }
 
@@ -103,60 +139,60 @@ struct SubIter {
     }
 };
 
-template <int K>
-struct RegTopK {
-    float v[K];
-    int idx[K];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int i = 0; i < K; ++i) { v[i] = -INFINITY; idx[i] = 0x7fffffff; }
-    }
-    __device__ __forceinline__ void push(float x, int id) {      // candidates arrive with ascending id
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const bool better = x > v[i];
-            const float tv = better ? v[i] : x;
-            const int ti = better ? idx[i] : id;
-            v[i] = better ? x : v[i];
-            idx[i] = better ? id : idx[i];
-            x = tv;
-            id = ti;
-        }
-    }
-};
+// bits j = 0..15 set where key column j of a 16-key part is admissible
+__device__ __forceinline__ unsigned range_mask16(int jlo, int jhi) {
+    jlo = max(jlo, 0);
+    jhi = min(jhi, 15);
+    return jhi < jlo ? 0u : ((0xffffu >> (15 - jhi)) & (0xffffu << jlo)) & 0xffffu;
+}
 
-template <int K>
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                   const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo, LpTcArgs a) {
+    constexpr int K = LP_SHORT;
+    constexpr int PLANES = MODE == MODE_EXACT ? 2 : 1;
+    constexpr int STAGES = MODE == MODE_EXACT ? 3 : 6;
     extern __shared__ unsigned char smem_dyn[];
+    const int tiles_x = (a.w + TC_QW - 1) / TC_QW;
+    const int tiles = tiles_x * ((a.h + TC_QH - 1) / TC_QH);
+    int n, tile;
+    if (a.list) {                                                 // work list written by the certification pass
+        if (blockIdx.x >= *a.count) return;
+        const int e = a.list[blockIdx.x];
+        n = e / tiles;
+        tile = e - n * tiles;
+    } else {
+        n = blockIdx.y;
+        tile = blockIdx.x;
+    }
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int C = a.C, KC = C / 64, hw = a.h * a.w;
     const unsigned q_chunk = (unsigned)TC_M * 128;                // staged query tile: one 64-channel chunk = 128 rows x 128 B
     const unsigned q_plane = (unsigned)KC * q_chunk;
     const unsigned k_chunk = (unsigned)TC_NT * 128;               // key tile: one chunk = 64 rows x 128 B
     const unsigned k_plane = (unsigned)KC * k_chunk;
-    const unsigned k_stage = 2 * k_plane;
+    const unsigned k_stage = PLANES * k_plane;
     unsigned char* k_smem = smem;                                 // [stage][hi|lo][chunk][64 rows][128 B]
     unsigned char* q_smem = smem;                                 // staging of the query tile (aliases the first stages)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(k_smem + TC_STAGES * k_stage);
+    float* lists_v = reinterpret_cast<float*>(k_smem + STAGES * k_stage);     // [128 queries][2 halves][16] candidate scores
+    int* lists_i = reinterpret_cast<int*>(lists_v + TC_M * 2 * LP_SHORT);      // ... and ids
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists_i + TC_M * 2 * LP_SHORT);
     uint64_t* q_full = bars;
     uint64_t* q_ready = bars + 1;
     uint64_t* k_full = bars + 2;
-    uint64_t* k_empty = k_full + TC_STAGES;
-    uint64_t* t_full = k_empty + TC_STAGES;
+    uint64_t* k_empty = k_full + STAGES;
+    uint64_t* t_full = k_empty + STAGES;
     uint64_t* t_empty = t_full + 2;
     unsigned* tmem_base_smem = reinterpret_cast<unsigned*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.y;
-    const int tiles_x = (a.w + TC_QW - 1) / TC_QW;
-    const int qy0 = (blockIdx.x / tiles_x) * TC_QH, qx0 = (blockIdx.x % tiles_x) * TC_QW;
+    const int qy0 = (tile / tiles_x) * TC_QH, qx0 = (tile % tiles_x) * TC_QW;
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         mbar_init(q_ready, 32 * TC_EPI_WARPS);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -171,13 +207,13 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     const unsigned tm_qhi = tmem_base, tm_qlo = tmem_base + (unsigned)(C / 2), tm_acc = tmem_base + 256u;
 
     if (warp == 0) {
-        // ===================== TMA producer (whole warp: one lane per box, so a tile's 16 loads issue in parallel) ==========
+        // ===================== TMA producer (whole warp: one lane per box, so a tile's loads issue in parallel) ==========
         {
             const int64_t qrow0 = a.query_frames[n] * (int64_t)hw;
-            if (lane == 0) mbar_expect_tx(q_full, 2 * q_plane);
+            if (lane == 0) mbar_expect_tx(q_full, PLANES * q_plane);
             __syncwarp();
-            for (int op = lane; op < TC_QH * KC * 2; op += 32) {
-                const int yy = op / (KC * 2), rem = op - yy * (KC * 2), c = rem >> 1, pl = rem & 1;
+            for (int op = lane; op < TC_QH * KC * PLANES; op += 32) {
+                const int yy = op / (KC * PLANES), rem = op - yy * (KC * PLANES), c = rem / PLANES, pl = rem - c * PLANES;
                 const int row = (int)(qrow0 + (int64_t)(qy0 + yy) * a.w + qx0);
                 tma_load_2d(q_smem + (pl ? q_plane : 0u) + c * q_chunk + yy * 1024, pl ? &map_q_lo : &map_q_hi, c * 64, row, q_full);
             }
@@ -185,7 +221,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             SubIter it;
             it.init(&a, qy0, qx0);
             for (unsigned t = 0; ok && !it.done(); ++t) {
-                const unsigned st = t % TC_STAGES, ph = (t / TC_STAGES) & 1u;
+                const unsigned st = t % STAGES, ph = (t / STAGES) & 1u;
                 ok = mbar_wait(k_empty + st, ph ^ 1u, a.err);
                 if (!ok) break;
                 unsigned char* dst = k_smem + st * k_stage;
@@ -193,10 +229,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 int nrun = 0;
                 for (; nrun < 2 && !it.done(); ++nrun, it.next())
                     rows[nrun] = (int)(a.key_frames[(int64_t)n * a.S + it.slot] * (int64_t)hw + it.kidx0());
-                if (lane == 0) mbar_expect_tx(k_full + st, (unsigned)nrun * 2u * (unsigned)KC * (TC_NS * 128u));
+                if (lane == 0) mbar_expect_tx(k_full + st, (unsigned)nrun * (unsigned)PLANES * (unsigned)KC * (TC_NS * 128u));
                 __syncwarp();
-                if (lane < nrun * KC * 2) {
-                    const int r = lane / (KC * 2), rem = lane - r * (KC * 2), c = rem >> 1, pl = rem & 1;
+                if (lane < nrun * KC * PLANES) {
+                    const int r = lane / (KC * PLANES), rem = lane - r * (KC * PLANES), c = rem / PLANES, pl = rem - c * PLANES;
                     tma_load_2d(dst + (pl ? k_plane : 0u) + c * k_chunk + r * (TC_NS * 128), pl ? &map_k_lo : &map_k_hi, c * 64,
                                 rows[r], k_full + st);
                 }
@@ -218,7 +254,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             const unsigned k_base = __shfl_sync(kFull, smem_u32(k_smem), 0);
             for (unsigned t = 0; ok && t < ntiles; ++t) {
                 const unsigned as = t & 1u, aph = (t >> 1) & 1u;
-                const unsigned st = t % TC_STAGES, ph = (t / TC_STAGES) & 1u;
+                const unsigned st = t % STAGES, ph = (t / STAGES) & 1u;
                 ok = mbar_wait(t_empty + as, aph ^ 1u, a.err);
                 if (!ok) break;
                 ok = mbar_wait(k_full + st, ph, a.err);
@@ -232,11 +268,14 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                     for (int cch = 0; cch < KC; ++cch) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t k_hi = desc_make(lk_hi + 2u * kk), k_lo = desc_make(lk_lo + 2u * kk);
+                            const uint64_t k_hi = desc_make(lk_hi + 2u * kk);
                             const unsigned accum = (cch | kk) ? 1u : 0u;
                             tc_mma_f16_ts(d_main, a_hi + 8u * kk, k_hi, idesc, accum);
-                            tc_mma_f16_ts(d_corr, a_hi + 8u * kk, k_lo, idesc, accum);
-                            tc_mma_f16_ts(d_corr, a_lo + 8u * kk, k_hi, idesc, 1u);
+                            if (MODE == MODE_EXACT) {
+                                const uint64_t k_lo = desc_make(lk_lo + 2u * kk);
+                                tc_mma_f16_ts(d_corr, a_hi + 8u * kk, k_lo, idesc, accum);
+                                tc_mma_f16_ts(d_corr, a_lo + 8u * kk, k_hi, idesc, 1u);
+                            }
                         }
                         lk_hi += k_chunk >> 4; lk_lo += k_chunk >> 4;
                         a_hi += 32u; a_lo += 32u;
@@ -259,23 +298,39 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         bool ok = mbar_wait(q_full, 0, a.err);
         // move this query row's plane (half 0: hi, half 1: lo) from the swizzled staging tile to TMEM: 8 fp16 = 4 columns per 16 B
         {
-            const unsigned char* src = q_smem + (half ? q_plane : 0u) + (unsigned)q * 128u;
-            const unsigned dstc = (half ? tm_qlo : tm_qhi) + lane_sel;
-            for (int c = 0; c < KC; ++c) {
-                unsigned r[32];
+            if (MODE == MODE_EXACT || half == 0) {
+                const unsigned char* src = q_smem + (half ? q_plane : 0u) + (unsigned)q * 128u;
+                const unsigned dstc = (half ? tm_qlo : tm_qhi) + lane_sel;
+                for (int c = 0; c < KC; ++c) {
+                    unsigned r[32];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(src + c * q_chunk + ((ch ^ (q & 7)) << 4));
-                    r[ch * 4 + 0] = v.x; r[ch * 4 + 1] = v.y; r[ch * 4 + 2] = v.z; r[ch * 4 + 3] = v.w;
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(src + c * q_chunk + ((ch ^ (q & 7)) << 4));
+                        r[ch * 4 + 0] = v.x; r[ch * 4 + 1] = v.y; r[ch * 4 + 2] = v.z; r[ch * 4 + 3] = v.w;
+                    }
+                    tc_st32(dstc + (unsigned)c * 32u, r);
                 }
-                tc_st32(dstc + (unsigned)c * 32u, r);
+                tc_wait_st();
             }
-            tc_wait_st();
             tc_fence_before();
             mbar_arrive(q_ready);
         }
-        RegTopK<K> top;
-        top.init();
+        // Per-thread sorted candidate lists live in shared memory ([query][half][16], values and ids) and are updated
+        // COOPERATIVELY: a candidate of lane s is inserted by the 16 lanes of its half-warp, lane r holding rank r (one LDS,
+        // one ballot for the position, one shuffle for the shift, one STS) - a register-resident list costs the whole warp
+        // ~150 instructions per insertion while 31 lanes idle, and with 32 lanes x 16 keys per step some lane has a candidate
+        // on almost every step, which made the epilogue, not the tensor pipe, the bottleneck (measured: 473 us per CTA with
+        // register lists against 130 us of MMA work).  thr = the thread's current 16th best (its admission threshold).
+        float* lv = lists_v + (size_t)(q * 2 + half) * K;
+        int* li = lists_i + (size_t)(q * 2 + half) * K;
+        const volatile float* other16 = lists_v + (size_t)(q * 2 + (half ^ 1)) * K + (K - 1);
+#pragma unroll
+        for (int r = 0; r < K; ++r) { lv[r] = -INFINITY; li[r] = 0x7fffffff; }
+        asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");      // (the other half's list is read below)
+        float thr = -INFINITY;
+        const int hbase = lane & 16, r16 = lane & 15;
+        // rows of the window this warp's four query rows can reach at all (warp-uniform skip of the others)
+        const int wqy0 = qy0 + quarter * 4;
         SubIter it;
         it.init(&a, qy0, qx0);
         if (half && !it.done()) it.next();                             // this warp's run of tile 0
@@ -286,77 +341,96 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             ok = mbar_wait(t_full + as, aph, a.err);
             if (!ok) break;
             tc_fence_after();
+            bool live = mine_exists;
+            unsigned adm = 0u;
+            int base_id = 0;
             if (mine_exists) {
                 const bool restricted = a.restricted && it.slot >= a.n_long;
-#pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    unsigned m[16], c[16];
-                    const unsigned col = tm_acc + as * 128u + (unsigned)half * 32u + (unsigned)part * 16u + lane_sel;
-                    tc_ld16(col, m);
-                    tc_ld16(col + 64u, c);
+                // admissible key columns of this run, as one 32-bit mask (bit j = key kidx0 + j)
+                if (restricted) {
+                    const int wy = it.row_y();
+                    live = wy >= wqy0 - a.R && wy <= wqy0 + 3 + a.R;    // warp-uniform
+                    const int dy = wy - qy;
+                    const int rem = a.r2i - dy * dy;                   // admissible iff dx^2 <= rem
+                    if (rem >= 0 && qvalid) {
+                        const int dxm = (int)sqrtf((float)rem);        // exact floor for these small integers
+                        const int jlo = max(qx - dxm, 0) - it.x0, jhi = min(qx + dxm, a.w - 1) - it.x0;
+                        adm = range_mask16(jlo, jhi) | (range_mask16(jlo - 16, jhi - 16) << 16);
+                    }
+                } else {
+                    const int nvalid = hw - it.kidx0();
+                    adm = !qvalid ? 0u : (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
+                }
+                base_id = it.slot * hw + it.kidx0();
+            }
+            float sv[32];
+            if (live) {
+                // pull the whole 32-key run into registers, then release the accumulator stage BEFORE the selection work:
+                // the MMA of tile t+2 only waits for the loads, not for the insertions
+                unsigned m0[16], m1[16];
+                const unsigned col = tm_acc + as * 128u + (unsigned)half * 32u + lane_sel;
+                tc_ld16(col, m0);
+                tc_ld16(col + 16u, m1);
+                if (MODE == MODE_EXACT) {
+                    unsigned c0[16], c1[16];
+                    tc_ld16(col + 64u, c0);
+                    tc_ld16(col + 80u, c1);
                     tc_wait_ld();
-                    const int kidx0 = it.kidx0() + part * 16;
-                    const int base_id = it.slot * hw + kidx0;
-                    float sv[16];
-                    float mx = -INFINITY;
-                    if (restricted) {
-                        const int dy = it.row_y() - qy;
-                        const int rem = a.r2i - dy * dy;               // admissible iff dx^2 <= rem
-                        const int kx0 = it.x0 + part * 16, dx0 = kx0 - qx;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int kx = kx0 + j, dx = dx0 + j;
-                            const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
-                            const bool adm = (unsigned)kx < (unsigned)a.w && dx * dx <= rem;
-                            sv[j] = adm ? sc : -INFINITY;
-                            mx = fmaxf(mx, sv[j]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float sc = fmaf(__uint_as_float(c[j]), 4.8828125e-4f, __uint_as_float(m[j]));
-                            sv[j] = (kidx0 + j < hw) ? sc : -INFINITY;
-                            mx = fmaxf(mx, sv[j]);
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        sv[j] = fmaf(__uint_as_float(c0[j]), 4.8828125e-4f, __uint_as_float(m0[j]));
+                        sv[16 + j] = fmaf(__uint_as_float(c1[j]), 4.8828125e-4f, __uint_as_float(m1[j]));
                     }
-                    // rare path: extract candidates in descending value (equal values: ascending column) while one beats the k-th best
-                    while (__any_sync(kFull, mx > top.v[K - 1])) {
-                        if (mx > top.v[K - 1]) {
-                            int jm = 0;
+                } else {
+                    tc_wait_ld();
 #pragma unroll
-                            for (int j = 15; j >= 0; --j) jm = (sv[j] == mx) ? j : jm;
-                            top.push(mx, base_id + jm);
-                            float nm = -INFINITY;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                sv[j] = (j == jm) ? -INFINITY : sv[j];
-                                nm = fmaxf(nm, sv[j]);
-                            }
-                            mx = nm;
-                        }
-                    }
+                    for (int j = 0; j < 16; ++j) { sv[j] = __uint_as_float(m0[j]); sv[16 + j] = __uint_as_float(m1[j]); }
                 }
             }
             tc_fence_before();
             mbar_arrive(t_empty + as);
+            if (live) {
+                thr = fmaxf(thr, *other16);                            // the other half's 16th best bounds the query's too
+                if (__any_sync(kFull, adm != 0u)) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = sv[j];
+                        unsigned b = __ballot_sync(kFull, ((adm >> j) & 1u) && x > thr);
+                        while (b) {                                    // warp-uniform; each half-warp serves its lowest candidate lane
+                            const unsigned bh = (b >> hbase) & 0xffffu;
+                            const int s = bh ? hbase + __ffs(bh) - 1 : -1;
+                            const float xs = __shfl_sync(kFull, x, s < 0 ? lane : s);
+                            float* sl = lists_v + (size_t)((quarter * 32 + (s < 0 ? lane : s)) * 2 + half) * K;
+                            int* si = lists_i + (size_t)((quarter * 32 + (s < 0 ? lane : s)) * 2 + half) * K;
+                            const float v = sl[r16];
+                            const int id = si[r16];
+                            const unsigned ge = (__ballot_sync(kFull, v >= xs) >> hbase) & 0xffffu;   // equal scores: the earlier (lower id) stays ahead
+                            const int pos = __popc(ge);
+                            const float vu = __shfl_up_sync(kFull, v, 1, 16);
+                            const int iu = __shfl_up_sync(kFull, id, 1, 16);
+                            const float nv = r16 < pos ? v : (r16 == pos ? xs : vu);
+                            const int ni = r16 < pos ? id : (r16 == pos ? base_id + j : iu);
+                            if (s >= 0 && r16 >= pos) { sl[r16] = nv; si[r16] = ni; }
+                            const float t16 = __shfl_sync(kFull, nv, hbase + 15);
+                            if (lane == s) thr = fmaxf(thr, t16);
+                            __syncwarp();
+                            b &= ~(((bh ? (1u << (__ffs(bh) - 1)) : 0u) << hbase) |
+                                   ((((b >> (hbase ^ 16)) & 0xffffu) ? (1u << (__ffs((b >> (hbase ^ 16)) & 0xffffu) - 1)) : 0u) << (hbase ^ 16)));
+                        }
+                    }
+                }
+            }
             // advance to this warp's run of the next tile
             if (!it.done()) it.next();
             if (!it.done()) it.next();
         }
-        // merge the two half-lists of each query (sorted by value desc; equal values: lower index first) and write out.
-        // All MMAs are complete (the last t_full was observed), so the key ring's shared memory is free.
-        float* mv = reinterpret_cast<float*>(smem);                    // [128 queries][2 halves][K]
-        int* mi = reinterpret_cast<int*>(smem + (size_t)TC_M * 2 * K * sizeof(float));
-        asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");
-#pragma unroll
-        for (int r = 0; r < K; ++r) { mv[(q * 2 + half) * K + r] = top.v[r]; mi[(q * 2 + half) * K + r] = top.idx[r]; }
+        // merge the two half-lists of each query (sorted by value desc; equal values: lower index first) and write the shortlist
         asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");
         if (ok && qvalid && half == 0) {
-            const int64_t obase = (int64_t)n * a.k * hw + qy * a.w + qx;
-            const float* v0 = mv + (q * 2 + 0) * K;
-            const float* v1 = mv + (q * 2 + 1) * K;
-            const int* i0 = mi + (q * 2 + 0) * K;
-            const int* i1 = mi + (q * 2 + 1) * K;
+            const float* v0 = lists_v + (size_t)(q * 2 + 0) * K;
+            const float* v1 = lists_v + (size_t)(q * 2 + 1) * K;
+            const int* i0 = lists_i + (size_t)(q * 2 + 0) * K;
+            const int* i1 = lists_i + (size_t)(q * 2 + 1) * K;
             int h0 = 0, h1 = 0;
             float vals[K];
             int ids[K];
@@ -370,20 +444,13 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 h0 += first ? 1 : 0;
                 h1 += first ? 0 : 1;
             }
-            float mxv = 0.f, den = 0.f;
+            const int64_t obase = ((int64_t)n * hw + qy * a.w + qx) * K;
+            float4* ov = reinterpret_cast<float4*>(a.short_v + obase);
+            int4* oi = reinterpret_cast<int4*>(a.short_i + obase);
 #pragma unroll
-            for (int r = 0; r < K; ++r) {
-                vals[r] = vals[r] / a.tau;
-                if (r == 0) mxv = vals[0];
-            }
-#pragma unroll
-            for (int r = 0; r < K; ++r) { vals[r] = r < a.k ? expf(vals[r] - mxv) : 0.f; den += vals[r]; }
-#pragma unroll
-            for (int r = 0; r < K; ++r) {
-                if (r < a.k) {
-                    a.Ws[obase + (int64_t)r * hw] = vals[r] / den;
-                    a.Is[obase + (int64_t)r * hw] = ids[r] == 0x7fffffff ? 0 : ids[r];
-                }
+            for (int r = 0; r < K / 4; ++r) {
+                ov[r] = make_float4(vals[4 * r], vals[4 * r + 1], vals[4 * r + 2], vals[4 * r + 3]);
+                oi[r] = make_int4(ids[4 * r], ids[4 * r + 1], ids[4 * r + 2], ids[4 * r + 3]);
             }
         }
     }
@@ -393,6 +460,156 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+// ---- exact re-ranking of the shortlists ---------------------------------------------------------------------------------
+// One warp = two queries x 16 shortlisted keys (lane = (query, candidate)).  The key rows are staged through shared memory
+// 64 channels at a time with coalesced 256-byte row reads; each lane then runs the SAME sequential fmaf chain over the channels
+// as lp_simt.cu, so the scores - and therefore the order, the ties and the softmax weights - are bit-identical to the SIMT
+// kernel's.  CHECK: certify the query (see the file header) or put its tile on the work list.  !CHECK: one CTA per listed tile.
+struct LpRescoreArgs {
+    const float* feats;          // (Nf, hw, C) fp32
+    const int64_t* key_frames;   // (Nt, S)
+    const int64_t* query_frames; // (Nt)
+    const float* short_v;        // (Nt*hw, 16) pre-scores, descending
+    const int* short_i;          // (Nt*hw, 16) flat ids slot*hw + pos
+    int Nt, S, h, w, C, k;
+    float tau;
+    float* Ws;
+    int64_t* Is;
+    unsigned* hdr;               // workspace header
+    unsigned* flags;             // (Nt*tiles) tile already listed
+    int* list;                   // (Nt*tiles) work list
+};
+
+constexpr int RS_WARPS = 4, RS_CH = 64, RS_LD = RS_CH + 4;
+
+template <int CHECK>
+__global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs a) {
+    __shared__ __align__(16) float rows_s[RS_WARPS][32][RS_LD];
+    __shared__ __align__(16) float q_s[RS_WARPS][2][RS_CH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hw = a.h * a.w;
+    const int tiles_x = (a.w + TC_QW - 1) / TC_QW;
+    const int tiles = tiles_x * ((a.h + TC_QH - 1) / TC_QH);
+    const int qq = lane >> 4, cand = lane & 15;
+    const float kmax = sqrtf(__uint_as_float(a.hdr[HDR_KNORM2]));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && __uint_as_float(a.hdr[HDR_MAXABS]) >= 60000.f) atomicExch(a.hdr + HDR_ERR, 2u);
+
+    int64_t pair0, pair1, stride;                                  // this warp's range of query pairs
+    int tile_n = 0, tile_qy0 = 0, tile_qx0 = 0;
+    if (CHECK) {
+        const int64_t npairs = ((int64_t)a.Nt * hw + 1) / 2;
+        pair0 = (int64_t)blockIdx.x * RS_WARPS + warp;
+        pair1 = npairs;
+        stride = (int64_t)gridDim.x * RS_WARPS;
+    } else {
+        if (blockIdx.x >= a.hdr[HDR_COUNT]) return;
+        const int e = a.list[blockIdx.x];
+        tile_n = e / tiles;
+        const int tile = e - tile_n * tiles;
+        tile_qy0 = (tile / tiles_x) * TC_QH;
+        tile_qx0 = (tile % tiles_x) * TC_QW;
+        pair0 = warp;
+        pair1 = TC_M / 2;
+        stride = RS_WARPS;
+    }
+    for (int64_t pr = pair0; pr < pair1; pr += stride) {
+        // the query of this half-warp
+        int n, qpos;
+        bool qok;
+        if (CHECK) {
+            const int64_t g = pr * 2 + qq;
+            qok = g < (int64_t)a.Nt * hw;
+            n = qok ? (int)(g / hw) : 0;
+            qpos = qok ? (int)(g - (int64_t)n * hw) : 0;
+        } else {
+            const int ql = (int)pr * 2 + qq;                           // 0..127 inside the 16x8 block
+            const int qy = tile_qy0 + (ql >> 3), qx = tile_qx0 + (ql & 7);
+            qok = qy < a.h && qx < a.w;
+            n = tile_n;
+            qpos = qok ? qy * a.w + qx : 0;
+        }
+        const int64_t sbase = ((int64_t)n * hw + qpos) * LP_SHORT + cand;
+        const int id = qok ? a.short_i[sbase] : 0x7fffffff;
+        const float pre = qok ? a.short_v[sbase] : -INFINITY;
+        const bool valid = id != 0x7fffffff;
+        const int slot = valid ? id / hw : 0;
+        const int pos = valid ? id - slot * hw : 0;
+        const float* krow = a.feats + (a.key_frames[(int64_t)n * a.S + slot] * (int64_t)hw + pos) * a.C;
+        const float* qrow = a.feats + (a.query_frames[n] * (int64_t)hw + qpos) * a.C;
+        float acc = 0.f, qn2 = 0.f;
+        for (int c0 = 0; c0 < a.C; c0 += RS_CH) {
+            __syncwarp();
+            // stage 32 key rows x 64 channels: a half-warp reads one row's 256 bytes
+#pragma unroll 8
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + (lane >> 4);
+                const float* src = reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)krow, r));
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + c0) + (lane & 15));
+                *reinterpret_cast<float4*>(&rows_s[warp][r][(lane & 15) * 4]) = v;
+            }
+            {
+                const float* src = reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)qrow, (lane >> 4) * 16));
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + c0) + (lane & 15));
+                *reinterpret_cast<float4*>(&q_s[warp][lane >> 4][(lane & 15) * 4]) = v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < RS_CH; c += 4) {
+                const float4 kv = *reinterpret_cast<const float4*>(&rows_s[warp][lane][c]);
+                const float4 qv = *reinterpret_cast<const float4*>(&q_s[warp][qq][c]);
+                acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc); acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+                qn2 = fmaf(qv.x, qv.x, qn2); qn2 = fmaf(qv.y, qv.y, qn2); qn2 = fmaf(qv.z, qv.z, qn2); qn2 = fmaf(qv.w, qv.w, qn2);
+            }
+        }
+        const float raw = valid ? acc : -INFINITY;
+        const float v = valid ? acc / a.tau : -INFINITY;              // the SIMT kernel ranks sc / tau
+        // rank inside the half-warp by (value desc, index asc, lane asc)
+        int rank = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float ov = __shfl_sync(kFull, v, (lane & 16) + i);
+            const int oi = __shfl_sync(kFull, id, (lane & 16) + i);
+            rank += (ov > v || (ov == v && (oi < id || (oi == id && i < cand)))) ? 1 : 0;
+        }
+        // softmax over the k winners, summed in rank order like the SIMT kernel
+        const unsigned half_mask = 0xffffu << (lane & 16);
+        const unsigned b0 = __ballot_sync(kFull, rank == 0) & half_mask;
+        const float mxv = __shfl_sync(kFull, v, __ffs(b0) - 1);
+        const float e = rank < a.k ? expf(v - mxv) : 0.f;
+        float den = 0.f;
+        for (int r = 0; r < a.k; ++r) {
+            const unsigned b = __ballot_sync(kFull, rank == r) & half_mask;
+            den += __shfl_sync(kFull, e, __ffs(b) - 1);
+        }
+        if (qok && rank < a.k) {
+            const int64_t o = ((int64_t)n * a.k + rank) * hw + qpos;
+            a.Ws[o] = e / den;
+            a.Is[o] = valid ? id : 0;
+        }
+        if (CHECK) {
+            // certification: every key outside the shortlist has pre-score <= pre16, hence exact score <= pre16 + eps
+            const unsigned bk = __ballot_sync(kFull, rank == a.k - 1) & half_mask;
+            const float tk = __shfl_sync(kFull, raw, __ffs(bk) - 1);
+            const float pre16 = __shfl_sync(kFull, pre, (lane & 16) + 15);
+            const float qn = sqrtf(qn2);
+            const float eps = LP_EPS_REL * qn * kmax + LP_EPS_ABS * (qn + kmax);
+            const bool certified = pre16 == -INFINITY || tk > pre16 + eps;
+            if (qok && cand == 0 && !certified) {
+                const int qy = qpos / a.w, qx = qpos - qy * a.w;
+                const int e_ = n * tiles + (qy / TC_QH) * tiles_x + qx / TC_QW;
+                atomicAdd(a.hdr + HDR_FLAGGED, 1u);
+                if (atomicExch(a.flags + e_, 1u) == 0u) a.list[atomicAdd(a.hdr + HDR_COUNT, 1u)] = e_;
+            }
+        }
+    }
+}
+
+__global__ void lp_fill_list_kernel(int* list, unsigned* count, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) list[i] = i;
+    if (i == 0) *count = (unsigned)n;
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
@@ -407,53 +624,108 @@ static bool make_map(CUtensorMap* m, const void* base, int C, int64_t rows, int 
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-size_t lp_tc_workspace_bytes(int Nf, int h, int w, int C) { return 2 * (size_t)Nf * h * w * C * 2 + 256; }
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static int lp_tiles(int h, int w) { return ((w + TC_QW - 1) / TC_QW) * ((h + TC_QH - 1) / TC_QH); }
+
+size_t lp_tc_workspace_bytes(int Nf, int Nt, int h, int w, int C) {
+    const size_t plane = align256((size_t)Nf * h * w * C * 2);
+    const size_t sl = align256((size_t)Nt * h * w * LP_SHORT * 4);
+    const size_t tl = align256((size_t)Nt * lp_tiles(h, w) * 4);
+    return HDR_BYTES + 2 * plane + 2 * sl + 2 * tl;
+}
 
 bool lp_tc_supported(int C, int k, float radius, int R, bool dense) {
-    return !dense && C % 64 == 0 && C >= 64 && C <= 256 && k >= 1 && k <= 16 && (radius <= 0.f || TC_QW + 2 * R <= TC_NS);
+    // k <= 12: the 16-key shortlist must hold spare entries below the k-th for the certification to mean anything
+    return !dense && C % 64 == 0 && C >= 64 && C <= 256 && k >= 1 && k <= LP_PRE_MAX_K && (radius <= 0.f || TC_QW + 2 * R <= TC_NS);
+}
+
+template <int MODE>
+static int launch_tc_pass(const CUtensorMap& mqh, const CUtensorMap& mql, const CUtensorMap& mkh, const CUtensorMap& mkl,
+                          const LpTcArgs& a, cudaStream_t st) {
+    constexpr int PLANES = MODE == MODE_EXACT ? 2 : 1, STAGES = MODE == MODE_EXACT ? 3 : 6;
+    const size_t ring = (size_t)STAGES * PLANES * TC_NT * a.C * 2, stagingq = (size_t)PLANES * TC_M * a.C * 2;
+    const size_t lists = (size_t)TC_M * 2 * LP_SHORT * 8;
+    const size_t body = (ring > stagingq ? ring : stagingq) + lists;
+    const size_t smem = 1024 + body + 256;
+    if (smem > 227 * 1024) { set_error("lp_topk: shared memory budget exceeded (%zu bytes)", smem); return CRW_ERR_UNSUPPORTED; }
+    auto k = lp_topk_tc_kernel<MODE>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int tiles = lp_tiles(a.h, a.w);
+    dim3 grid = a.list ? dim3((unsigned)(tiles * a.Nt), 1) : dim3((unsigned)tiles, (unsigned)a.Nt);
+    k<<<grid, TC_THREADS, smem, st>>>(mqh, mql, mkh, mkl, a);
+    return check_launch(MODE == MODE_EXACT ? "lp_topk_tc<exact>" : "lp_topk_tc<pre>");
 }
 
 int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace, size_t workspace_bytes, crw_stream_t stream) {
     const int hw = a0.h * a0.w, C = a0.C;
-    const size_t plane = (size_t)Nf * hw * C * 2;
-    if (workspace_bytes < 2 * plane + 256) { set_error("lp_topk: workspace too small for the tensor-core path"); return CRW_ERR_SHAPE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (workspace_bytes < lp_tc_workspace_bytes(Nf, a0.Nt, a0.h, a0.w, C)) {
+        set_error("lp_topk: workspace too small for the tensor-core path");
+        return CRW_ERR_SHAPE;
+    }
+    const size_t plane = align256((size_t)Nf * hw * C * 2);
+    const size_t sl = align256((size_t)a0.Nt * hw * LP_SHORT * 4);
+    const int tiles = lp_tiles(a0.h, a0.w);
+    const size_t tl = align256((size_t)a0.Nt * tiles * 4);
     unsigned char* ws = (unsigned char*)workspace;
-    unsigned* err = (unsigned*)ws;
-    void* hi = ws + 256;
-    void* lo = ws + 256 + plane;
-    cudaMemsetAsync(err, 0, 4, (cudaStream_t)stream);
-    const int64_t n4 = (int64_t)Nf * hw * C / 4;
-    const int sgrid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    lp_split_kernel<<<sgrid, 256, 0, (cudaStream_t)stream>>>((const float4*)feats, (uint2*)hi, (uint2*)lo, n4);
+    unsigned* hdr = (unsigned*)ws;
+    void* hi = ws + HDR_BYTES;
+    void* lo = ws + HDR_BYTES + plane;
+    float* short_v = (float*)(ws + HDR_BYTES + 2 * plane);
+    int* short_i = (int*)(ws + HDR_BYTES + 2 * plane + sl);
+    unsigned* flags = (unsigned*)(ws + HDR_BYTES + 2 * plane + 2 * sl);
+    int* list = (int*)(ws + HDR_BYTES + 2 * plane + 2 * sl + tl);
+    cudaMemsetAsync(hdr, 0, HDR_BYTES, st);
+    cudaMemsetAsync(flags, 0, (size_t)a0.Nt * tiles * 4, st);
+    const int64_t rows = (int64_t)Nf * hw;
+    const int sgrid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
+    lp_split_kernel<<<sgrid, 256, 0, st>>>((const float4*)feats, (uint2*)hi, (uint2*)lo, rows, C / 4, hdr);
     int e = check_launch("lp_split");
     if (e != CRW_OK) return e;
     CUtensorMap mqh, mql, mkh, mkl;
-    const int64_t rows = (int64_t)Nf * hw;
     if (!make_map(&mqh, hi, C, rows, TC_QW) || !make_map(&mql, lo, C, rows, TC_QW) || !make_map(&mkh, hi, C, rows, TC_NS) ||
         !make_map(&mkl, lo, C, rows, TC_NS)) {
         set_error("lp_topk: cuTensorMapEncodeTiled failed");
         return CRW_ERR_CUDA;
     }
     LpTcArgs a = a0;
-    a.err = err;
-    size_t ring = TC_STAGES * 2 * (size_t)TC_NT * C * 2, stagingq = 2 * (size_t)TC_M * C * 2;
-    const size_t smem = 1024 + (ring > stagingq ? ring : stagingq) + 256;
-    dim3 grid(((a.w + TC_QW - 1) / TC_QW) * ((a.h + TC_QH - 1) / TC_QH), a.Nt);
-    if (a.k == 10) {
-        auto k = lp_topk_tc_kernel<10>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mqh, mql, mkh, mkl, a);
-    } else {
-        auto k = lp_topk_tc_kernel<16>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mqh, mql, mkh, mkl, a);
+    a.err = hdr + HDR_ERR;
+    a.short_v = short_v;
+    a.short_i = short_i;
+    LpRescoreArgs r{};
+    r.feats = feats; r.key_frames = a.key_frames; r.query_frames = a.query_frames; r.short_v = short_v; r.short_i = short_i;
+    r.Nt = a.Nt; r.S = a.S; r.h = a.h; r.w = a.w; r.C = C; r.k = a.k; r.tau = a.tau; r.Ws = a.Ws; r.Is = a.Is;
+    r.hdr = hdr; r.flags = flags; r.list = list;
+    const bool pre = !(a.flags & CRW_LP_EXACT_ONLY);
+    if (pre) {
+        a.list = nullptr; a.count = nullptr;
+        e = launch_tc_pass<MODE_PRE>(mqh, mql, mkh, mkl, a, st);
+        if (e != CRW_OK) return e;
+        const int64_t npairs = ((int64_t)a.Nt * hw + 1) / 2;
+        const int64_t want = (npairs + RS_WARPS - 1) / RS_WARPS;
+        const int rgrid = (int)(want < 148 * 12 ? want : 148 * 12);
+        lp_rescore_kernel<1><<<rgrid, 32 * RS_WARPS, 0, st>>>(r);
+        e = check_launch("lp_rescore<check>");
+        if (e != CRW_OK) return e;
+        a.list = list; a.count = hdr + HDR_COUNT;
+        e = launch_tc_pass<MODE_EXACT>(mqh, mql, mkh, mkl, a, st);
+        if (e != CRW_OK) return e;
+        lp_rescore_kernel<0><<<tiles * a.Nt, 32 * RS_WARPS, 0, st>>>(r);
+        return check_launch("lp_rescore<listed>");
     }
-    return check_launch("lp_topk_tc");
+    // every tile on the fp32-faithful path (on request): fill the work list with all tiles first
+    a.list = nullptr; a.count = nullptr;
+    e = launch_tc_pass<MODE_EXACT>(mqh, mql, mkh, mkl, a, st);
+    if (e != CRW_OK) return e;
+    lp_fill_list_kernel<<<(tiles * a.Nt + 255) / 256, 256, 0, st>>>(list, hdr + HDR_COUNT, tiles * a.Nt);
+    lp_rescore_kernel<0><<<tiles * a.Nt, 32 * RS_WARPS, 0, st>>>(r);
+    return check_launch("lp_rescore<all>");
 }
 
 #else   // CRW_SIM: the tensor-core path needs real hardware; the host simulator always takes the SIMT kernel
 
-size_t lp_tc_workspace_bytes(int, int, int, int) { return 256; }
+size_t lp_tc_workspace_bytes(int, int, int, int, int) { return 256; }
 bool lp_tc_supported(int, int, float, int, bool) { return false; }
 int launch_lp_tc(const float*, int, const LpTcArgs&, void*, size_t, crw_stream_t) { return CRW_ERR_UNSUPPORTED; }
 

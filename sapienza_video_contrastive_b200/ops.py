@@ -718,8 +718,13 @@ def lp_prepare(feats_cf: torch.Tensor, normalize: bool) -> torch.Tensor:
 
 def lp_topk(feats_cl: torch.Tensor, key_frames: torch.Tensor, query_frames: torch.Tensor, n_long: int, h: int, w: int,
             radius: float, temperature: float, k: int, dense_mask: Optional[torch.Tensor] = None, force_simt: bool = False,
-            check: bool = True):
-    """feats_cl (Nf,hw,C); key_frames (Nt,S) int64; query_frames (Nt) int64 -> Ws (Nt,k,hw) fp32, Is (Nt,k,hw) int64."""
+            check: bool = True, exact_only: bool = False, stats: Optional[dict] = None):
+    """feats_cl (Nf,hw,C); key_frames (Nt,S) int64; query_frames (Nt) int64 -> Ws (Nt,k,hw) fp32, Is (Nt,k,hw) int64.
+
+    Tensor-core path (C % 64 == 0, C <= 256, k <= 12, radius <= 12, no dense mask): fp16 pre-ranking on tcgen05, exact fp32
+    re-ranking of a 16-key shortlist per query, certification, and the fp32-faithful 3-MMA pass for the tiles that could not
+    be certified (`exact_only` sends every tile there).  `stats`, if given, receives {"tensor_cores", "tiles", "listed_tiles",
+    "uncertified_queries"} (needs `check`, which reads the workspace header back and therefore synchronises)."""
     _need_cuda(feats_cl, key_frames, query_frames, dense_mask)
     check_device(feats_cl.device)
     feats_cl = _f32c(feats_cl)
@@ -737,19 +742,29 @@ def lp_topk(feats_cl: torch.Tensor, key_frames: torch.Tensor, query_frames: torc
     Ws = torch.empty(Nt, k, hw, dtype=torch.float32, device=dev)
     Is = torch.empty(Nt, k, hw, dtype=torch.int64, device=dev)
     L = _lib.lib()
-    if not force_simt and not L.crw_lp_topk_uses_tensor_cores(C, k, float(radius), int(dense_mask is not None)):
+    on_tc = bool(L.crw_lp_topk_uses_tensor_cores(C, k, float(radius), int(dense_mask is not None))) and not force_simt
+    if not force_simt and not on_tc:
         _warn_once(("lp_simt", C, k, dense_mask is not None),
                    "label propagation with C=%d, k=%d%s runs on the exact-fp32 SIMT kernel (tensor-core kernel: C %% 64 == 0, "
-                   "C <= 256, k <= 16, radius <= 12, no dense mask); expect ~10x lower throughput"
+                   "C <= 256, k <= 12, radius <= 12, no dense mask); expect ~10x lower throughput"
                    % (C, k, ", dense mask" if dense_mask is not None else ""))
     nbytes = L.crw_lp_topk_workspace_bytes(Nf, Nt, S, h, w, C, k)
-    ws = _workspace(("lp", Nf, h, w, C, k), nbytes, dev)
+    ws = _workspace(("lp", Nf, Nt, h, w, C, k), nbytes, dev)
+    flags = (_lib.LP_FORCE_SIMT if force_simt else 0) | (_lib.LP_EXACT_ONLY if exact_only else 0)
     L.check(L.crw_lp_topk(feats_cl.data_ptr(), Nf, key_frames.data_ptr(), query_frames.data_ptr(), Nt, S, n_long, h, w, C,
                           float(radius), dense_mask.data_ptr() if dense_mask is not None else None, float(temperature), k,
-                          _lib.LP_FORCE_SIMT if force_simt else 0, Ws.data_ptr(), Is.data_ptr(), ws.data_ptr(), ws.numel(),
-                          _stream()), "lp_topk")
-    if check and int(ws[:4].view(torch.int32)[0]) != 0:          # device-side barrier watchdog of the tensor-core kernel
-        raise _lib.CrwError("lp_topk: tensor-core kernel reported an internal barrier timeout")
+                          flags, Ws.data_ptr(), Is.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "lp_topk")
+    if check:
+        hdr = ws[:32].view(torch.int32).tolist()          # one small read-back: error word + certification counters
+        if hdr[0] == 2:
+            raise _lib.CrwError("lp_topk: features exceed the fp16 range of the tensor-core path (|x| >= 6e4); L2-normalise "
+                                "them (test.py:93) or pass force_simt=True")
+        if hdr[0] != 0:
+            raise _lib.CrwError("lp_topk: tensor-core kernel reported an internal barrier timeout")
+        if stats is not None:
+            tiles = ((w + 7) // 8) * ((h + 15) // 16) * Nt
+            stats.update(tensor_cores=on_tc, tiles=tiles, listed_tiles=hdr[1] if on_tc else 0,
+                         uncertified_queries=hdr[4] if on_tc else 0)
     return Ws, Is
 
 

@@ -260,8 +260,9 @@ class LabelPropagator:
     """
 
     def __init__(self, n_context: int, long_mem: Sequence[int], radius: float, topk: int, temperature: float,
-                 normalize: bool = True, force_simt: bool = False):
-        self.force_simt = force_simt
+                 normalize: bool = True, force_simt: bool = False, exact_only: bool = False):
+        self.force_simt, self.exact_only = force_simt, exact_only
+        self.stats = {}                 # certification counters of the last call (ops.lp_topk)
         self.n_context, self.long_mem = int(n_context), list(long_mem)
         self.radius, self.topk, self.temperature, self.normalize = float(radius), int(topk), float(temperature), normalize
 
@@ -274,7 +275,7 @@ class LabelPropagator:
         ki = torch.cat(context_index_bank(self.n_context, self.long_mem, Nt), dim=-1).to(feats.device)
         qf = torch.arange(Nt, device=feats.device) + self.n_context
         Ws, Is = ops.lp_topk(cl, ki, qf, len(self.long_mem), h, w, self.radius, self.temperature, self.topk,
-                             force_simt=self.force_simt)
+                             force_simt=self.force_simt, exact_only=self.exact_only, stats=self.stats)
         return ki, Ws, Is
 
     def __call__(self, feats: torch.Tensor, lbls: torch.Tensor, norm_mask: bool = False):

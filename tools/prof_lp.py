@@ -10,9 +10,9 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-bench.label_prop_bench(dev)
+bench.label_prop_bench(dev, cpu=False, gpu_baseline=False)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    r = bench.label_prop_bench(dev)
+    r = bench.label_prop_bench(dev, cpu=False, gpu_baseline=False)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
 print(r["value"], "frames/s")
