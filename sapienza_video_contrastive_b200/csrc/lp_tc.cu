@@ -46,6 +46,7 @@ constexpr int TC_NT = 64;        // keys per tile = MMA N (two runs)
 constexpr int TC_EPI_WARPS = 8;  // two epilogue warps per TMEM lane quarter, each owning half of a sub-tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int LP_SHORT = 16;     // shortlist length per query
+constexpr int LP_HALF = 12;      // candidates each of a query's two epilogue threads keeps (>= LP_PRE_MAX_K: the k best may all sit in one half)
 constexpr int LP_PRE_MAX_K = 12; // the pre-ranking pass needs spare shortlist entries below the k-th to certify a query
 constexpr int MODE_PRE = 0, MODE_EXACT = 1;
 // workspace header words
@@ -153,6 +154,11 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     constexpr int K = LP_SHORT;
     constexpr int PLANES = MODE == MODE_EXACT ? 2 : 1;
     constexpr int STAGES = MODE == MODE_EXACT ? 3 : 6;
+    // accumulator stages in tensor memory: the pre-ranking pass needs 64 columns per stage and its query tile 128, so SIX stages
+    // fit - the MMA warp then runs up to six tiles ahead of the slowest epilogue warp, which turns "every tile waits for the
+    // unluckiest warp's insertions" into "throughput = average epilogue rate"; the fp32-faithful pass (128 + 256 columns) has two
+    constexpr unsigned ACC_STAGES = MODE == MODE_EXACT ? 2u : 6u, ACC_STRIDE = MODE == MODE_EXACT ? 128u : 64u;
+    constexpr unsigned ACC_BASE = MODE == MODE_EXACT ? 256u : 128u;
     extern __shared__ unsigned char smem_dyn[];
     const int tiles_x = (a.w + TC_QW - 1) / TC_QW;
     const int tiles = tiles_x * ((a.h + TC_QH - 1) / TC_QH);
@@ -175,16 +181,16 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     const unsigned k_stage = PLANES * k_plane;
     unsigned char* k_smem = smem;                                 // [stage][hi|lo][chunk][64 rows][128 B]
     unsigned char* q_smem = smem;                                 // staging of the query tile (aliases the first stages)
-    float* lists_v = reinterpret_cast<float*>(k_smem + STAGES * k_stage);     // [128 queries][2 halves][16] candidate scores
-    int* lists_i = reinterpret_cast<int*>(lists_v + TC_M * 2 * LP_SHORT);      // ... and ids
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists_i + TC_M * 2 * LP_SHORT);
+    float* park_s = reinterpret_cast<float*>(k_smem + STAGES * k_stage);      // [8][256 epilogue threads][4] scores of the run in hand
+    float* thr_s = park_s + 32 * 32 * TC_EPI_WARPS;                           // [128 queries][2 halves] published 12th-best scores
+    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + TC_M * 2);
     uint64_t* q_full = bars;
     uint64_t* q_ready = bars + 1;
     uint64_t* k_full = bars + 2;
     uint64_t* k_empty = k_full + STAGES;
     uint64_t* t_full = k_empty + STAGES;
-    uint64_t* t_empty = t_full + 2;
-    unsigned* tmem_base_smem = reinterpret_cast<unsigned*>(t_empty + 2);
+    uint64_t* t_empty = t_full + ACC_STAGES;
+    unsigned* tmem_base_smem = reinterpret_cast<unsigned*>(t_empty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qy0 = (tile / tiles_x) * TC_QH, qx0 = (tile % tiles_x) * TC_QW;
@@ -193,7 +199,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         mbar_init(q_full, 1);
         mbar_init(q_ready, 32 * TC_EPI_WARPS);
         for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 32 * TC_EPI_WARPS); }
+        for (unsigned s = 0; s < ACC_STAGES; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -204,7 +210,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_base = *tmem_base_smem;
-    const unsigned tm_qhi = tmem_base, tm_qlo = tmem_base + (unsigned)(C / 2), tm_acc = tmem_base + 256u;
+    const unsigned tm_qhi = tmem_base, tm_qlo = tmem_base + (unsigned)(C / 2), tm_acc = tmem_base + ACC_BASE;
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp: one lane per box, so a tile's loads issue in parallel) ==========
@@ -245,7 +251,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         {
             const unsigned idesc = umma_idesc_f16(TC_M, TC_NT);
             const unsigned tb = __shfl_sync(kFull, tmem_base, 0);
-            const unsigned u_qhi = tb, u_qlo = tb + (unsigned)(C / 2), u_acc = tb + 256u;
+            const unsigned u_qhi = tb, u_qlo = tb + (unsigned)(C / 2), u_acc = tb + ACC_BASE;
             bool ok = mbar_wait(q_ready, 0, a.err);
             tc_fence_after();
             SubIter it;
@@ -253,7 +259,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             const unsigned ntiles = (unsigned)((it.total_runs() + 1) / 2);
             const unsigned k_base = __shfl_sync(kFull, smem_u32(k_smem), 0);
             for (unsigned t = 0; ok && t < ntiles; ++t) {
-                const unsigned as = t & 1u, aph = (t >> 1) & 1u;
+                const unsigned as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1u;
                 const unsigned st = t % STAGES, ph = (t / STAGES) & 1u;
                 ok = mbar_wait(t_empty + as, aph ^ 1u, a.err);
                 if (!ok) break;
@@ -261,7 +267,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 if (!ok) break;
                 tc_fence_after();
                 const unsigned ka = k_base + st * k_stage;
-                const unsigned d_main = u_acc + as * 128u, d_corr = d_main + 64u;
+                const unsigned d_main = u_acc + as * ACC_STRIDE, d_corr = d_main + 64u;
                 if (elect_one()) {
                     unsigned lk_hi = desc_lo(ka), lk_lo = desc_lo(ka + k_plane);
                     unsigned a_hi = u_qhi, a_lo = u_qlo;
@@ -315,60 +321,81 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             tc_fence_before();
             mbar_arrive(q_ready);
         }
-        // Per-thread sorted candidate lists live in shared memory ([query][half][16], values and ids) and are updated
-        // COOPERATIVELY: a candidate of lane s is inserted by the 16 lanes of its half-warp, lane r holding rank r (one LDS,
-        // one ballot for the position, one shuffle for the shift, one STS) - a register-resident list costs the whole warp
-        // ~150 instructions per insertion while 31 lanes idle, and with 32 lanes x 16 keys per step some lane has a candidate
-        // on almost every step, which made the epilogue, not the tensor pipe, the bottleneck (measured: 473 us per CTA with
-        // register lists against 130 us of MMA work).  thr = the thread's current 16th best (its admission threshold).
-        float* lv = lists_v + (size_t)(q * 2 + half) * K;
-        int* li = lists_i + (size_t)(q * 2 + half) * K;
-        const volatile float* other16 = lists_v + (size_t)(q * 2 + (half ^ 1)) * K + (K - 1);
+        // Per-thread candidate list: the LP_HALF best (score, id) pairs of this thread's half of the key stream, sorted, in
+        // registers.  Per 32-key run: (1) one compare per key builds a per-lane candidate bit mask (score > thr, admissible);
+        // (2) if any lane has a candidate, the run's scores are parked in shared memory (so that a lane can fetch "its j-th
+        // score" with a run-time j) and the warp loops: every lane with a candidate left pops its lowest bit and runs the
+        // 12-stage compare-and-shift insertion - candidates of DIFFERENT lanes are inserted in the same pass.
+        // thr = this thread's admission threshold = max(its own 12th best, the other half's 12th best, published through
+        // shared memory once per run): a key below either bound cannot be among the query's 16 best.
+        // What was tried and measured on the way (ncu: the epilogue warps, not the tensor pipe, set the pace - 1.8 M warp
+        // instructions per CTA in round 1): extraction of the running maximum per 16-key part, 150 instructions per pass,
+        // 473 us per CTA; lists in shared memory updated cooperatively by a half-warp per candidate, one serial shuffle /
+        // vote / load chain per candidate, 1.5 ms; one fully unrolled insertion chain per key column, 36 KB of loop body
+        // (instruction-cache misses), 1.2 ms.
+        float tv[LP_HALF];
+        int ti[LP_HALF];
 #pragma unroll
-        for (int r = 0; r < K; ++r) { lv[r] = -INFINITY; li[r] = 0x7fffffff; }
-        asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");      // (the other half's list is read below)
+        for (int r = 0; r < LP_HALF; ++r) { tv[r] = -INFINITY; ti[r] = 0x7fffffff; }
+        volatile float* thr_pub = thr_s + (q * 2 + half);
+        const volatile float* thr_other = thr_s + (q * 2 + (half ^ 1));
+        *thr_pub = -INFINITY;
+        asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");      // (the other half's threshold is read below)
         float thr = -INFINITY;
-        const int hbase = lane & 16, r16 = lane & 15;
+        const int etid = threadIdx.x - 64;                             // 0..255 among the epilogue threads
+        float4* park4 = reinterpret_cast<float4*>(park_s) + etid;      // [8 groups of 4 columns][256 threads] float4: conflict-free stores
+        const float* park1 = park_s + etid * 4;
+        // Run enumeration (must match SubIter, which the producer and the issuer use): slots in order, long-memory slots sweep
+        // the frame in n_sweep runs, restricted slots visit the block's window rows wy0..wy1.  This warp owns runs
+        // half, half + 2, ... of the concatenated list, i.e. one run per tile.
+        const int n_sweep = (hw + TC_NS - 1) / TC_NS;
+        const int wy0 = max(qy0 - a.R, 0), wy1 = min(qy0 + TC_QH - 1 + a.R, a.h - 1);
+        const int n_rows = wy1 - wy0 + 1, wx0 = qx0 - a.R;
+        const int n_unres = a.restricted ? a.n_long : a.S;
+        const unsigned total_runs = (unsigned)(n_unres * n_sweep + (a.S - n_unres) * n_rows);
+        const unsigned ntiles = (total_runs + 1u) / 2u;
         // rows of the window this warp's four query rows can reach at all (warp-uniform skip of the others)
-        const int wqy0 = qy0 + quarter * 4;
-        SubIter it;
-        it.init(&a, qy0, qx0);
-        if (half && !it.done()) it.next();                             // this warp's run of tile 0
-        const unsigned ntiles = (unsigned)((it.total_runs() + 1) / 2);
+        const int wq_lo = qy0 + quarter * 4 - a.R, wq_hi = qy0 + quarter * 4 + 3 + a.R;
+        // half-width of the disc per row offset, 4 bits each (radius <= 12): dx^2 <= r2i - dy^2
+        unsigned long long dxm_lut = 0ull;
+        for (int d = 0; d <= a.R; ++d) dxm_lut |= (unsigned long long)((int)sqrtf((float)(a.r2i - d * d))) << (4 * d);
+        int slot = 0, step = half;
+        int nsteps = slot < n_unres ? n_sweep : n_rows;
+        while (slot < a.S && step >= nsteps) { step -= nsteps; ++slot; nsteps = slot < n_unres ? n_sweep : n_rows; }
         for (unsigned t = 0; ok && t < ntiles; ++t) {
-            const bool mine_exists = !it.done();                       // the last tile may hold a single run
-            const unsigned as = t & 1u, aph = (t >> 1) & 1u;
-            ok = mbar_wait(t_full + as, aph, a.err);
-            if (!ok) break;
-            tc_fence_after();
+            const bool mine_exists = slot < a.S;                       // the last tile may hold a single run
+            const unsigned as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1u;
             bool live = mine_exists;
             unsigned adm = 0u;
             int base_id = 0;
             if (mine_exists) {
-                const bool restricted = a.restricted && it.slot >= a.n_long;
                 // admissible key columns of this run, as one 32-bit mask (bit j = key kidx0 + j)
-                if (restricted) {
-                    const int wy = it.row_y();
-                    live = wy >= wqy0 - a.R && wy <= wqy0 + 3 + a.R;    // warp-uniform
-                    const int dy = wy - qy;
-                    const int rem = a.r2i - dy * dy;                   // admissible iff dx^2 <= rem
-                    if (rem >= 0 && qvalid) {
-                        const int dxm = (int)sqrtf((float)rem);        // exact floor for these small integers
-                        const int jlo = max(qx - dxm, 0) - it.x0, jhi = min(qx + dxm, a.w - 1) - it.x0;
-                        adm = range_mask16(jlo, jhi) | (range_mask16(jlo - 16, jhi - 16) << 16);
+                if (slot >= n_unres) {
+                    const int wy = wy0 + step;
+                    live = wy >= wq_lo && wy <= wq_hi;                 // warp-uniform
+                    const int dy = abs(wy - qy);
+                    if (dy <= a.R && qvalid) {
+                        const int dxm = (int)((dxm_lut >> (4 * dy)) & 15ull);
+                        const int jlo = max(qx - dxm, 0) - wx0, jhi = min(qx + dxm, a.w - 1) - wx0;      // 0 <= jlo <= jhi <= 29
+                        adm = (0xffffffffu >> (31 - jhi)) & (0xffffffffu << jlo);
                     }
+                    base_id = slot * hw + wy * a.w + wx0;
                 } else {
-                    const int nvalid = hw - it.kidx0();
-                    adm = !qvalid ? 0u : (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
+                    const int nvalid = hw - step * TC_NS;
+                    adm = !qvalid ? 0u : (nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
+                    base_id = slot * hw + step * TC_NS;
                 }
-                base_id = it.slot * hw + it.kidx0();
             }
+            live = live && __any_sync(kFull, adm != 0u);
+            ok = mbar_wait(t_full + as, aph, a.err);
+            if (!ok) break;
+            tc_fence_after();
             float sv[32];
             if (live) {
                 // pull the whole 32-key run into registers, then release the accumulator stage BEFORE the selection work:
-                // the MMA of tile t+2 only waits for the loads, not for the insertions
+                // the MMA into this stage only waits for the loads, not for the insertions
                 unsigned m0[16], m1[16];
-                const unsigned col = tm_acc + as * 128u + (unsigned)half * 32u + lane_sel;
+                const unsigned col = tm_acc + as * ACC_STRIDE + (unsigned)half * 32u + lane_sel;
                 tc_ld16(col, m0);
                 tc_ld16(col + 16u, m1);
                 if (MODE == MODE_EXACT) {
@@ -390,60 +417,75 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             tc_fence_before();
             mbar_arrive(t_empty + as);
             if (live) {
-                thr = fmaxf(thr, *other16);                            // the other half's 16th best bounds the query's too
-                if (__any_sync(kFull, adm != 0u)) {
+                // (>= the other half's bound, > the own one: a key that TIES with the other half's 12th best may still carry the
+                // lower index, so it must get in - nextafter turns ">=" into the single ">" the mask loop evaluates)
+                thr = fmaxf(thr, nextafterf(*thr_other, -INFINITY));
+                // candidate mask: bit j = sign(thr - score_j), shifted in from the top column down (two instructions per key)
+                unsigned cm = 0u;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = sv[j];
-                        unsigned b = __ballot_sync(kFull, ((adm >> j) & 1u) && x > thr);
-                        while (b) {                                    // warp-uniform; each half-warp serves its lowest candidate lane
-                            const unsigned bh = (b >> hbase) & 0xffffu;
-                            const int s = bh ? hbase + __ffs(bh) - 1 : -1;
-                            const float xs = __shfl_sync(kFull, x, s < 0 ? lane : s);
-                            float* sl = lists_v + (size_t)((quarter * 32 + (s < 0 ? lane : s)) * 2 + half) * K;
-                            int* si = lists_i + (size_t)((quarter * 32 + (s < 0 ? lane : s)) * 2 + half) * K;
-                            const float v = sl[r16];
-                            const int id = si[r16];
-                            const unsigned ge = (__ballot_sync(kFull, v >= xs) >> hbase) & 0xffffu;   // equal scores: the earlier (lower id) stays ahead
-                            const int pos = __popc(ge);
-                            const float vu = __shfl_up_sync(kFull, v, 1, 16);
-                            const int iu = __shfl_up_sync(kFull, id, 1, 16);
-                            const float nv = r16 < pos ? v : (r16 == pos ? xs : vu);
-                            const int ni = r16 < pos ? id : (r16 == pos ? base_id + j : iu);
-                            if (s >= 0 && r16 >= pos) { sl[r16] = nv; si[r16] = ni; }
-                            const float t16 = __shfl_sync(kFull, nv, hbase + 15);
-                            if (lane == s) thr = fmaxf(thr, t16);
-                            __syncwarp();
-                            b &= ~(((bh ? (1u << (__ffs(bh) - 1)) : 0u) << hbase) |
-                                   ((((b >> (hbase ^ 16)) & 0xffffu) ? (1u << (__ffs((b >> (hbase ^ 16)) & 0xffffu) - 1)) : 0u) << (hbase ^ 16)));
+                for (int j = 31; j >= 0; --j) cm = __funnelshift_l(__float_as_uint(thr - sv[j]), cm, 1);
+                cm &= adm;
+                if (__any_sync(kFull, cm != 0u)) {
+                    __syncwarp();
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) park4[g4 * 256] = make_float4(sv[4 * g4], sv[4 * g4 + 1], sv[4 * g4 + 2], sv[4 * g4 + 3]);
+                    while (__any_sync(kFull, cm != 0u)) {
+                        if (cm != 0u) {
+                            const int j = __ffs(cm) - 1;
+                            cm &= cm - 1u;
+                            const float x = park1[(j >> 2) * 1024 + (j & 3)];
+                            const int id = base_id + j;
+                            // sorted insert with every comparison made against the SAME x (no serial compare-and-shift chain):
+                            // entries >= x stay (equal scores keep the earlier, lower id ahead), x lands behind them, the rest shift
+                            bool ge[LP_HALF];
+#pragma unroll
+                            for (int r = 0; r < LP_HALF; ++r) ge[r] = tv[r] >= x;
+#pragma unroll
+                            for (int r = LP_HALF - 1; r >= 1; --r) {
+                                tv[r] = ge[r] ? tv[r] : (ge[r - 1] ? x : tv[r - 1]);
+                                ti[r] = ge[r] ? ti[r] : (ge[r - 1] ? id : ti[r - 1]);
+                            }
+                            tv[0] = ge[0] ? tv[0] : x;
+                            ti[0] = ge[0] ? ti[0] : id;
                         }
                     }
+                    thr = fmaxf(thr, tv[LP_HALF - 1]);
+                    *thr_pub = tv[LP_HALF - 1];
                 }
             }
             // advance to this warp's run of the next tile
-            if (!it.done()) it.next();
-            if (!it.done()) it.next();
+            step += 2;
+            while (slot < a.S && step >= nsteps) { step -= nsteps; ++slot; nsteps = slot < n_unres ? n_sweep : n_rows; }
         }
-        // merge the two half-lists of each query (sorted by value desc; equal values: lower index first) and write the shortlist
+        // All MMAs are complete (the last t_full was observed), so the key ring's shared memory is free: park the lists there
+        float* lists_v = reinterpret_cast<float*>(smem);                // [128 queries][2 halves][LP_HALF]
+        int* lists_i = reinterpret_cast<int*>(smem + (size_t)TC_M * 2 * LP_HALF * sizeof(float));
+        asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");
+#pragma unroll
+        for (int r = 0; r < LP_HALF; ++r) { lists_v[(q * 2 + half) * LP_HALF + r] = tv[r]; lists_i[(q * 2 + half) * LP_HALF + r] = ti[r]; }
+        // merge the two half-lists of each query (sorted by value desc; equal values: lower index first) into the 16-key
+        // shortlist.  Its last score is stored as the BOUND on every key that is not in the shortlist: such a key was either
+        // cut by the merge (score <= the 16th) or never admitted to a half-list (score <= that half's 12th best).
         asm volatile("bar.sync 1, %0;" :: "r"(32 * TC_EPI_WARPS) : "memory");
         if (ok && qvalid && half == 0) {
-            const float* v0 = lists_v + (size_t)(q * 2 + 0) * K;
-            const float* v1 = lists_v + (size_t)(q * 2 + 1) * K;
-            const int* i0 = lists_i + (size_t)(q * 2 + 0) * K;
-            const int* i1 = lists_i + (size_t)(q * 2 + 1) * K;
+            const float* v0 = lists_v + (size_t)(q * 2 + 0) * LP_HALF;
+            const float* v1 = lists_v + (size_t)(q * 2 + 1) * LP_HALF;
+            const int* i0 = lists_i + (size_t)(q * 2 + 0) * LP_HALF;
+            const int* i1 = lists_i + (size_t)(q * 2 + 1) * LP_HALF;
             int h0 = 0, h1 = 0;
             float vals[K];
             int ids[K];
 #pragma unroll
             for (int r = 0; r < K; ++r) {
-                const float a0 = h0 < K ? v0[h0] : -INFINITY, a1 = h1 < K ? v1[h1] : -INFINITY;
-                const int b0 = h0 < K ? i0[h0] : 0x7fffffff, b1 = h1 < K ? i1[h1] : 0x7fffffff;
+                const float a0 = h0 < LP_HALF ? v0[h0] : -INFINITY, a1 = h1 < LP_HALF ? v1[h1] : -INFINITY;
+                const int b0 = h0 < LP_HALF ? i0[h0] : 0x7fffffff, b1 = h1 < LP_HALF ? i1[h1] : 0x7fffffff;
                 const bool first = a0 > a1 || (a0 == a1 && b0 <= b1);
                 vals[r] = first ? a0 : a1;
                 ids[r] = first ? b0 : b1;
                 h0 += first ? 1 : 0;
                 h1 += first ? 0 : 1;
             }
+            vals[K - 1] = fmaxf(vals[K - 1], fmaxf(v0[LP_HALF - 1], v1[LP_HALF - 1]));     // (-inf while a half-list is not full)
             const int64_t obase = ((int64_t)n * hw + qy * a.w + qx) * K;
             float4* ov = reinterpret_cast<float4*>(a.short_v + obase);
             int4* oi = reinterpret_cast<int4*>(a.short_i + obase);
@@ -645,8 +687,9 @@ static int launch_tc_pass(const CUtensorMap& mqh, const CUtensorMap& mql, const 
                           const LpTcArgs& a, cudaStream_t st) {
     constexpr int PLANES = MODE == MODE_EXACT ? 2 : 1, STAGES = MODE == MODE_EXACT ? 3 : 6;
     const size_t ring = (size_t)STAGES * PLANES * TC_NT * a.C * 2, stagingq = (size_t)PLANES * TC_M * a.C * 2;
-    const size_t lists = (size_t)TC_M * 2 * LP_SHORT * 8;
-    const size_t body = (ring > stagingq ? ring : stagingq) + lists;
+    const size_t lists = (size_t)TC_M * 2 * LP_HALF * 8;                 // parked in the ring once the MMAs are done
+    size_t body = ring > stagingq ? ring : stagingq;
+    body = (body > lists ? body : lists) + (size_t)32 * 32 * TC_EPI_WARPS * 4 + (size_t)TC_M * 2 * 4;
     const size_t smem = 1024 + body + 256;
     if (smem > 227 * 1024) { set_error("lp_topk: shared memory budget exceeded (%zu bytes)", smem); return CRW_ERR_UNSUPPORTED; }
     auto k = lp_topk_tc_kernel<MODE>;

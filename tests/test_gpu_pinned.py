@@ -123,7 +123,7 @@ def test_label_prop_tensor_core_equals_simt_bit_for_bit(ops, C, h, w, n_ctx, n_t
     if repeat:
         assert st["listed_tiles"] > 0                       # exact ties cannot be certified from pre-scores
     else:
-        assert st["listed_tiles"] <= max(2, st["tiles"] // 4), st
+        assert st["uncertified_queries"] <= max(8, n_tgt * h * w // 50), st      # (k = 12 leaves 4 spare shortlist entries, k = 10 six)
 
 
 def test_label_prop_davis_shape_tensor_core_vs_oracle(ops):
