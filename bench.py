@@ -201,10 +201,15 @@ def workload_config(n):
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
 class HotPath:
-    """The step of the headline metric on one GPU, eager or as a captured CUDA graph."""
+    """The step of the headline metric on one GPU, eager or as a captured CUDA graph.
 
-    def __init__(self, dev, rank, use_graph=True):
+    parts == 1: the whole 20-clip batch as one chain of launches (pool -> head -> walk -> head bwd -> pool bwd).
+    parts >= 2: pipeline.PatchWalkPipeline - the clips split into micro-batches on staggered streams so that the HBM-bound pooling
+    of one micro-batch runs beside the latency-bound walk of another (pooling confined to `pool_sms` SMs)."""
+
+    def __init__(self, dev, rank, use_graph=True, parts=1, pool_sms=0, sizes=None):
         from sapienza_video_contrastive_b200 import ops
+        from sapienza_video_contrastive_b200.pipeline import PatchWalkPipeline
         self.ops, self.dev = ops, dev
         c = CFG
         g = torch.Generator(device="cpu").manual_seed(1000 + rank)
@@ -214,15 +219,44 @@ class HotPath:
         self.head = torch.nn.Linear(c["Ce"], c["D"], bias=False).to(dev)
         self.rng_state = torch.tensor([123, 0], dtype=torch.int64, device=dev)
         self.ones = torch.ones(1, device=dev)
-        self.maps_in = self.maps.clone().requires_grad_(True)
+        self.sizes = [int(x) for x in sizes] if sizes else None
+        self.parts = len(self.sizes) if self.sizes else int(parts)
+        if self.sizes is None and self.parts > 1:
+            self.sizes = [c["B"] // self.parts] * self.parts
+        self.autograd_chain = self.sizes is None          # one chain of torch.autograd operators; else the direct-call pipeline
         self.graph = None
         self.use_graph = use_graph
         self.loss = torch.zeros(1, device=dev)
-        self.gmaps = None
+        if self.autograd_chain:
+            self.maps_in = self.maps.clone().requires_grad_(True)
+            self.pipe = None
+        else:
+            self.maps_parts = self._split(self.maps, clone=True)
+            self.pipe = PatchWalkPipeline(self.head.weight, c["B"], c["N"], c["T"], c["tau"], c["p"], pool_sms=pool_sms, seed=123,
+                                          device=dev, sizes=self.sizes)
+            self.gmaps, self.ghead = None, None
+
+    def _split(self, maps, clone=False):
+        out, r0 = [], 0
+        for b in self.sizes:
+            r1 = r0 + b * CFG["N"]
+            out.append(maps[r0:r1].clone() if clone else maps[r0:r1].detach())
+            r0 = r1
+        return out
+
+    def set_inputs(self, maps):
+        """Point the step at another (BN, T, C, H, W) device tensor (the e2e loop's freshly uploaded batch)."""
+        if self.autograd_chain:
+            self.maps_in = maps
+        else:
+            self.maps_parts = self._split(maps)
 
     def _step_eager(self):
         c = CFG
         ops = self.ops
+        if self.pipe is not None:
+            self.loss, self.gmaps, self.ghead = self.pipe.step(self.maps_parts)       # per-micro-batch losses (weights b_i / B)
+            return self.loss
         self.maps_in.grad = None
         self.head.weight.grad = None
         pooled = ops.pool_patch(self.maps_in)                                        # (BN, T, Ce)
@@ -232,6 +266,15 @@ class HotPath:
         ops.join_side_streams()                       # the head's weight gradient ran beside the pooling backward
         self.loss = loss
         return loss
+
+    def head_grad(self):
+        return self.ghead if self.pipe is not None else self.head.weight.grad
+
+    def loss_value(self):
+        """float: the step's loss (mean over all clips)."""
+        if self.pipe is not None:
+            return float(self.pipe.loss())
+        return float(self.loss.detach())
 
     def prepare(self):
         if not self.use_graph:
@@ -594,7 +637,10 @@ def run_ours(args, rank, world, local_rank):
     ops.check_device(dev)
     c = CFG
     ops.set_async_wgrad(True)
-    hp = HotPath(dev, rank, use_graph=not args.eager)
+    sizes = [int(x) for x in args.part_sizes.split(",")] if args.part_sizes else None
+    if sizes is None and args.parts == 1:
+        args.pool_sms = 0
+    hp = HotPath(dev, rank, use_graph=not args.eager, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes)
     hp.prepare()
     grads = torch.zeros(RESNET18_GRAD_FLOATS, device=dev) if world > 1 else None
     pending = []
@@ -609,7 +655,7 @@ def run_ours(args, rank, world, local_rank):
         # NCCL's stream beside the NEXT step's pooling / walk kernels and is joined before the following exchange is issued
         # (and before the timed region closes), so every exchange is paid for inside the measurement.
         finish()
-        grads[: c["D"] * c["Ce"]].copy_(hp.head.weight.grad.view(-1))
+        grads[: c["D"] * c["Ce"]].copy_(hp.head_grad().view(-1))
         pending.append(dist.all_reduce(grads, async_op=True))
 
     with ClockSampler(local_rank) as clk:
@@ -618,7 +664,8 @@ def run_ours(args, rank, world, local_rank):
         med_ms, med_n, _ = timed_median(hp.step, warm=0) if world == 1 else (None, None, None)
     clocks = clk.summary()
     value = c["B"] * world * args.steps / ms * 1e3
-    loss_now = float(hp.step().detach())
+    hp.step()
+    loss_now = hp.loss_value()
     if not (1.0 < loss_now < 12.0):                                  # random init: near log(49) = 3.9
         raise SystemExit("bench.py: the timed step produced loss %r - not a valid run" % loss_now)
 
@@ -626,10 +673,13 @@ def run_ours(args, rank, world, local_rank):
     host = [torch.randn(hp.maps.shape, pin_memory=True) for _ in range(2)]
     dev_in = [torch.empty_like(hp.maps).requires_grad_(True) for _ in range(2)]
     copy_stream = torch.cuda.Stream()
-    loss_host = torch.zeros(1, pin_memory=True)
+    loss_host = torch.zeros(8, pin_memory=True)
     ghead_host = torch.zeros(c["D"], c["Ce"], pin_memory=True)
     h2d = host[0].numel() * 4
     d2h = 4 + ghead_host.numel() * 4
+
+    e2e = HotPath(dev, rank, use_graph=False, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes)      # same operators, eager, on uploaded inputs
+    e2e.head = hp.head
 
     def e2e_loop(n):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -645,16 +695,10 @@ def run_ours(args, rank, world, local_rank):
                     dev_in[nxt].data.copy_(host[nxt], non_blocking=True)
                     ready[nxt].record()
             torch.cuda.current_stream().wait_event(ready[cur])
-            x = dev_in[cur]
-            x.grad = None
-            hp.head.weight.grad = None
-            pooled = ops.pool_patch(x)
-            f = ops.head_linear(pooled, hp.head.weight).view(c["B"], c["N"], c["T"], c["D"])
-            q, loss, xent, acc = ops.walk(f, c["tau"], c["p"], rng="device", rng_state=hp.rng_state)
-            loss.backward(hp.ones)
-            ops.join_side_streams()
-            loss_host.copy_(loss.detach(), non_blocking=True)
-            ghead_host.copy_(hp.head.weight.grad, non_blocking=True)
+            e2e.set_inputs(dev_in[cur])
+            loss = e2e._step_eager()
+            loss_host[: loss.numel()].copy_(loss.detach(), non_blocking=True)
+            ghead_host.copy_(e2e.head_grad(), non_blocking=True)
             done[cur].record()
 
     e2e_loop(2)
@@ -685,10 +729,12 @@ def run_ours(args, rank, world, local_rank):
     dom = max(kr, key=lambda k: kr[k]["us"])
     traffic, traffic_src = ncu_traffic(dom)
     n_ours, n_other, knames = count_kernels(hp._step_eager)
+    step_desc = ("pipeline.PatchWalkPipeline: micro-batches of %s clips on staggered streams, pooling confined to %d SMs" % (hp.sizes, args.pool_sms)
+                 if hp.pipe is not None else "one chain of autograd operators")
     out = {"metric": "crw_walk_fwd_bwd_clips_per_s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-           "launch": "eager" if args.eager else "cuda_graph",
+           "launch": "eager" if args.eager else "cuda_graph", "parts": hp.sizes or [c["B"]], "pool_sms": args.pool_sms, "schedule": step_desc,
            "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": n_e2e,
                    "ms_timed": ms_e2e,
@@ -739,6 +785,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the host-core baselines")
     ap.add_argument("--no-lp", action="store_true", help="skip the label-propagation leg")
     ap.add_argument("--no-extras", action="store_true", help="headline line only (no label_prop / superpixel / sweep / baselines on the GPU)")
+    ap.add_argument("--parts", type=int, default=1, help="with --part-sizes '': equal micro-batches per step (1 = one chain of autograd operators)")
+    ap.add_argument("--part-sizes", default="5,5,5,5", help="clips per micro-batch on staggered streams (pipeline.PatchWalkPipeline), must add up to "
+                                                           "20; '' = use --parts.  Default: the best of the measured sweep (profiles/r02_split_sweep.jsonl)")
+    ap.add_argument("--pool-sms", type=int, default=108, help="SMs the pooling kernels are confined to while micro-batches overlap (0 = all)")
     ap.add_argument("--e2e-module", action="store_true", help="also time CRW(args)(x) with the ResNet-18 (DDP when several GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -49,6 +49,16 @@ const char* crw_last_error(void);
 int crw_pool_patch_fwd(const float* maps, float* pooled, int64_t rows, int hw, crw_stream_t stream);
 int crw_pool_patch_bwd(const float* grad_pooled, float* grad_maps, int64_t rows, int hw, crw_stream_t stream);
 
+/* The same two kernels confined to `sms` streaming multiprocessors (one 1024-thread CTA per SM, placed alone on its SM by a
+ * shared-memory reservation), so that kernels of ANOTHER stream - the walk of a different micro-batch, whose CTAs need a
+ * whole SM - run beside the HBM-bound pooling pass instead of behind it (sapienza_video_contrastive_b200/pipeline.py).
+ * sms <= 0, an unaligned base or hw not in {16, 32, 64}: identical to the unrestricted entry points. */
+int crw_pool_patch_fwd_sm(const float* maps, float* pooled, int64_t rows, int hw, int sms, crw_stream_t stream);
+int crw_pool_patch_bwd_sm(const float* gpooled, float* gmaps, int64_t rows, int hw, int sms, crw_stream_t stream);
+/* ... with the gradient scaled on the way: gmaps = gpooled * scale / hw (evaluated as gpooled / (hw / scale)), scale > 0 -
+ * the 1 / n of "mean over the clips of all n micro-batches". */
+int crw_pool_patch_bwd_scaled(const float* gpooled, float* gmaps, int64_t rows, int hw, float scale, int sms, crw_stream_t stream);
+
 /* ---- a2/a3: superpixel segment-mean pooling, model.py:296-325 + utils/__init__.py:433-584 -------------
  * maps (B,C,T,Hm,Wm) contiguous; labels int64 addressed as labels[b*ls_b + t*ls_t + y*ls_y + x*ls_x]
  * (so channel 0 of the (B,T,3,h,w) mask is passed without a copy, model.py:298); h = sy*Hm, w = sx*Wm.
@@ -151,6 +161,9 @@ int crw_head_dgrad(const float* grad_out, const float* weight, float* grad_x, in
 size_t crw_head_wgrad_workspace_bytes(int64_t R, int D, int C);
 int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, void* workspace,
                    size_t workspace_bytes, crw_stream_t stream);
+/* dW = beta * dW + alpha * grad_out^T x: accumulation of micro-batch contributions (pipeline.py) without a separate pass. */
+int crw_head_wgrad_axpby(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, float alpha, float beta,
+                         void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
 /* L2 normalisation of rows (F.normalize, eps 1e-12; model.py:118,329): q = f / max(|f|, eps).  inv_norm and norm
  * (rows each) are kept for the backward, which overwrites grad in place: g <- (g - q (q.g)) * inv_norm. */

@@ -35,6 +35,9 @@ _SIGNATURES = {
     "crw_last_error": (c_char_p, []),
     "crw_pool_patch_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_pool_patch_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "crw_pool_patch_fwd_sm": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "crw_pool_patch_bwd_sm": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "crw_pool_patch_bwd_scaled": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
     "crw_segmean_workspace_bytes": (c_size_t, [c_int] * 7),
     "crw_segmean_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64] + [c_int] * 8
                         + [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -69,6 +72,7 @@ _SIGNATURES = {
     "crw_head_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "crw_head_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "crw_head_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "crw_head_wgrad_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "crw_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_lp_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -29,8 +29,8 @@ __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
 }
 
 // L = lanes per row = hw / 4 (power of two, 4..32)
-template <int L>
-__global__ void __launch_bounds__(256) pool_fwd_kernel(const float4* __restrict__ maps, float* __restrict__ pooled,
+template <int L, int BLOCK = 256>
+__global__ void __launch_bounds__(BLOCK) pool_fwd_kernel(const float4* __restrict__ maps, float* __restrict__ pooled,
                                                        int64_t rows, float inv_hw_div) {
     constexpr int RPL = 32 / L;                     // rows covered by one warp-wide load
     const int lane = threadIdx.x & 31;
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const float4* __restrict_
     }
 }
 
-template <int L>
-__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ gpooled, float4* __restrict__ gmaps,
+template <int L, int BLOCK = 256>
+__global__ void __launch_bounds__(BLOCK) pool_bwd_kernel(const float* __restrict__ gpooled, float4* __restrict__ gmaps,
                                                        int64_t rows, float hw_div) {
     constexpr int RPL = 32 / L;
     const int lane = threadIdx.x & 31;
@@ -149,4 +149,57 @@ extern "C" int crw_pool_patch_bwd(const float* gpooled, float* gmaps, int64_t ro
     else if (vec && hw == 16) { auto k = pool_bwd_kernel<4>; CRW_LAUNCH(k, grid, 256, 0, stream, gpooled, (float4*)gmaps, rows, (float)hw); }
     else { CRW_LAUNCH(pool_bwd_generic, grid, 256, 0, stream, gpooled, gmaps, rows, hw); }
     return check_launch("pool_patch_bwd");
+}
+// SM-limited launches (crw_pool_patch_*_sm): `sms` CTAs of 1024 threads, each asking for more than half of an SM's shared
+// memory so that exactly one lands on an SM - the other SMs stay completely free for kernels of another stream (a walk CTA
+// needs a whole register file).  1024 threads x 16 outstanding 128-bit loads keep 256 KB in flight per SM.
+constexpr int kPoolBigBlock = 1024;
+constexpr int kPoolReserveSmem = 120 * 1024;
+
+template <typename K, typename... Args>
+static void launch_limited(K k, int sms, crw_stream_t stream, Args... args) {
+#ifndef CRW_SIM
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolReserveSmem);
+#endif
+    CRW_LAUNCH(k, sms, kPoolBigBlock, kPoolReserveSmem, stream, args...);
+}
+
+extern "C" int crw_pool_patch_fwd_sm(const float* maps, float* pooled, int64_t rows, int hw, int sms, crw_stream_t stream) {
+    if (sms <= 0) return crw_pool_patch_fwd(maps, pooled, rows, hw, stream);
+    if (rows < 0 || hw <= 0) { set_error("pool_patch_fwd: bad shape rows=%lld hw=%d", (long long)rows, hw); return CRW_ERR_SHAPE; }
+    if (rows == 0) return CRW_OK;
+    if ((((uintptr_t)maps) & 15) != 0 || (hw != 64 && hw != 32 && hw != 16)) return crw_pool_patch_fwd(maps, pooled, rows, hw, stream);
+    if (hw == 64) launch_limited(pool_fwd_kernel<16, kPoolBigBlock>, sms, stream, (const float4*)maps, pooled, rows, (float)hw);
+    else if (hw == 32) launch_limited(pool_fwd_kernel<8, kPoolBigBlock>, sms, stream, (const float4*)maps, pooled, rows, (float)hw);
+    else launch_limited(pool_fwd_kernel<4, kPoolBigBlock>, sms, stream, (const float4*)maps, pooled, rows, (float)hw);
+    return check_launch("pool_patch_fwd_sm");
+}
+
+extern "C" int crw_pool_patch_bwd_sm(const float* gpooled, float* gmaps, int64_t rows, int hw, int sms, crw_stream_t stream) {
+    return crw_pool_patch_bwd_scaled(gpooled, gmaps, rows, hw, 1.0f, sms, stream);
+}
+
+// gmaps = gpooled * scale / hw: the micro-batch pipeline folds the 1 / n_parts of "mean over all clips" into this pass
+// (evaluated as gpooled / (hw / scale): bit-identical to scaling first whenever scale is a power of two)
+extern "C" int crw_pool_patch_bwd_scaled(const float* gpooled, float* gmaps, int64_t rows, int hw, float scale, int sms,
+                                         crw_stream_t stream) {
+    if (rows < 0 || hw <= 0 || !(scale > 0.f)) { set_error("pool_patch_bwd: bad arguments rows=%lld hw=%d scale=%g", (long long)rows, hw, (double)scale); return CRW_ERR_SHAPE; }
+    if (rows == 0) return CRW_OK;
+    const float div = (float)hw / scale;
+    const bool vec = (((uintptr_t)gmaps) & 15) == 0 && (hw == 64 || hw == 32 || hw == 16);
+    if (!vec) {
+        if (scale != 1.0f) { set_error("pool_patch_bwd_scaled: scale needs 16-byte aligned maps and hw in {16, 32, 64}"); return CRW_ERR_UNSUPPORTED; }
+        return crw_pool_patch_bwd(gpooled, gmaps, rows, hw, stream);
+    }
+    if (sms <= 0) {
+        const int grid = pool_grid(rows);
+        if (hw == 64) { auto k = pool_bwd_kernel<16>; CRW_LAUNCH(k, grid, 256, 0, stream, gpooled, (float4*)gmaps, rows, div); }
+        else if (hw == 32) { auto k = pool_bwd_kernel<8>; CRW_LAUNCH(k, grid, 256, 0, stream, gpooled, (float4*)gmaps, rows, div); }
+        else { auto k = pool_bwd_kernel<4>; CRW_LAUNCH(k, grid, 256, 0, stream, gpooled, (float4*)gmaps, rows, div); }
+        return check_launch("pool_patch_bwd_scaled");
+    }
+    if (hw == 64) launch_limited(pool_bwd_kernel<16, kPoolBigBlock>, sms, stream, gpooled, (float4*)gmaps, rows, div);
+    else if (hw == 32) launch_limited(pool_bwd_kernel<8, kPoolBigBlock>, sms, stream, gpooled, (float4*)gmaps, rows, div);
+    else launch_limited(pool_bwd_kernel<4, kPoolBigBlock>, sms, stream, gpooled, (float4*)gmaps, rows, div);
+    return check_launch("pool_patch_bwd_sm");
 }

@@ -704,11 +704,13 @@ extern "C" int crw_stoch_mat(float* A, const float* drop_uniform, float rate, fl
 
 // ---- head weight gradient: dW (D,C) = g^T (D,R) x (R,C), split over R so the small output still fills the GPU ----
 namespace crw {
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
+// out = beta * out + alpha * sum_j part_j  (alpha = 1, beta = 0: plain reduction, bit-identical to the sum alone)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S,
+                                                            float alpha, float beta) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int j = 0; j < S; ++j) s += part[(int64_t)j * n + e];          // fixed order: deterministic
-        out[e] = s;
+        out[e] = beta == 0.f ? (alpha == 1.f ? s : alpha * s) : fmaf(alpha, s, beta * out[e]);
     }
 }
 static int wgrad_splits(int64_t R, int D, int C) {
@@ -744,6 +746,11 @@ extern "C" size_t crw_head_wgrad_workspace_bytes(int64_t R, int D, int C) {
 
 extern "C" int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, void* workspace,
                               size_t workspace_bytes, crw_stream_t stream) {
+    return crw_head_wgrad_axpby(grad_out, x, dW, R, D, C, 1.0f, 0.0f, workspace, workspace_bytes, stream);
+}
+
+extern "C" int crw_head_wgrad_axpby(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, float alpha, float beta,
+                                    void* workspace, size_t workspace_bytes, crw_stream_t stream) {
     if (R <= 0 || D <= 0 || C <= 0) { set_error("head_wgrad: bad shape"); return CRW_ERR_SHAPE; }
     if (!workspace || workspace_bytes < crw_head_wgrad_workspace_bytes(R, D, C)) { set_error("head_wgrad: workspace too small"); return CRW_ERR_SHAPE; }
     const int64_t n = (int64_t)D * C;
@@ -760,7 +767,7 @@ extern "C" int crw_head_wgrad(const float* grad_out, const float* x, float* dW, 
             unsigned* err = (unsigned*)((char*)workspace + sizeof(float) * (size_t)St * n);
             int e = gemm_tf32_run(c, err, stream);
             if (e != CRW_OK) return e;
-            CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256), 256, 0, stream, (const float*)workspace, dW, n, St);
+            CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256), 256, 0, stream, (const float*)workspace, dW, n, St, alpha, beta);
             return check_launch("head_wgrad_reduce");
         }
     }
@@ -773,7 +780,7 @@ extern "C" int crw_head_wgrad(const float* grad_out, const float* x, float* dW, 
     g.C = (float*)workspace; g.csb = 0; g.csj = (int64_t)D * C; g.ldc = C;
     int e = run_gemm(g, 1, stream);
     if (e != CRW_OK) return e;
-    CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256), 256, 0, stream, (const float*)workspace, dW, n, S);
+    CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256), 256, 0, stream, (const float*)workspace, dW, n, S, alpha, beta);
     return check_launch("head_wgrad_reduce");
 }
 

@@ -70,7 +70,7 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------------------------
 class _PoolPatch(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, maps):
+    def forward(ctx, maps, sm_limit):
         _need_cuda(maps)
         check_device(maps.device)
         maps = _f32c(maps)
@@ -78,8 +78,9 @@ class _PoolPatch(torch.autograd.Function):
         rows = maps.numel() // hw
         out = torch.empty(maps.shape[:-2], dtype=torch.float32, device=maps.device)
         L = _lib.lib()
-        L.check(L.crw_pool_patch_fwd(maps.data_ptr(), out.data_ptr(), rows, hw, _stream()), "pool_patch_fwd")
+        L.check(L.crw_pool_patch_fwd_sm(maps.data_ptr(), out.data_ptr(), rows, hw, sm_limit, _stream()), "pool_patch_fwd")
         ctx.shape = maps.shape
+        ctx.sm_limit = sm_limit
         return out
 
     @staticmethod
@@ -89,13 +90,14 @@ class _PoolPatch(torch.autograd.Function):
         hw = shape[-1] * shape[-2]
         gm = torch.empty(shape, dtype=torch.float32, device=g.device)
         L = _lib.lib()
-        L.check(L.crw_pool_patch_bwd(g.data_ptr(), gm.data_ptr(), g.numel(), hw, _stream()), "pool_patch_bwd")
-        return gm
+        L.check(L.crw_pool_patch_bwd_sm(g.data_ptr(), gm.data_ptr(), g.numel(), hw, ctx.sm_limit, _stream()), "pool_patch_bwd")
+        return gm, None
 
 
-def pool_patch(maps: torch.Tensor) -> torch.Tensor:
-    """(..., H, W) -> (...) spatial mean.  model.py:116."""
-    return _PoolPatch.apply(maps)
+def pool_patch(maps: torch.Tensor, sm_limit: int = 0) -> torch.Tensor:
+    """(..., H, W) -> (...) spatial mean.  model.py:116.  `sm_limit` > 0 confines the forward and the backward kernel to that
+    many SMs (see pipeline.PatchWalkPipeline); 0 = the whole GPU."""
+    return _PoolPatch.apply(maps, int(sm_limit))
 
 
 # ------------------------------------------------------------------------------------------------------------------

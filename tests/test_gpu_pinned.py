@@ -155,39 +155,49 @@ def test_label_prop_davis_shape_tensor_core_vs_oracle(ops):
     assert int(bad.sum()) <= 50 * len(where), (int(bad.sum()), len(where))
 
 
-def test_bench_hot_path_graph_replay_matches_oracle(ops):
+@pytest.mark.parametrize("sizes,pool_sms", [(None, 0), ([5, 5, 5, 5], 108), ([13, 7], 108)])
+def test_bench_hot_path_graph_replay_matches_oracle(ops, sizes, pool_sms):
     """the configuration bench.py times - rng='device', the whole step replayed as a CUDA graph, chain on
-    4-CTA clusters, weight gradient on a side stream - against the oracle (model.py:92-123, 366-413) fed with the Philox
-    draws the device-side generator state promises."""
+    4-CTA clusters, weight gradient on a side stream; by default the stream-staggered micro-batch pipeline (pipeline.py) - against
+    the oracle (model.py:92-123, 366-413) on the WHOLE 20-clip batch, fed with the Philox draws the device-side generator states
+    promise (one state per micro-batch)."""
     sys.path.insert(0, ROOT)
     import bench
     ops.set_async_wgrad(True)
     try:
-        hp = bench.HotPath(torch.device(DEV, torch.cuda.current_device()), 0, use_graph=True)
+        hp = bench.HotPath(torch.device(DEV, torch.cuda.current_device()), 0, use_graph=True, sizes=sizes, pool_sms=pool_sms)
         hp.prepare()
         assert hp.graph is not None
         c = bench.CFG
         B, N, T = c["B"], c["N"], c["T"]
+        part_sizes = sizes or [B]
+        states = hp.pipe.rng_states if hp.pipe is not None else [hp.rng_state]
+        maps_parts = hp.maps_parts if hp.pipe is not None else [hp.maps_in]
         for rep in range(2):
             torch.cuda.synchronize()
-            seed, off = (int(v) for v in hp.rng_state.tolist())
-            loss = hp.step()
+            before = [tuple(int(v) for v in st.tolist()) for st in states]
+            hp.step()
             torch.cuda.synchronize()
-            numel = B * N * N
-            thr = ops.torch_rand_threads(numel, DEV)
-            inc = ops.torch_rand_offset_increment(numel, thr)
-            draws = [ops.philox_uniform(numel, seed, off + j * inc, thr, DEV).view(B, N, N) for j in range(2 * (T - 1))]
-            assert int(hp.rng_state[1]) == off + 2 * (T - 1) * inc          # the kernel advanced the state itself
-            u12, u21p = torch.stack(draws[: T - 1]), torch.stack(draws[T - 1:])
-            mo = hp.maps_in.detach().permute(0, 2, 1, 3, 4).clone().requires_grad_(True)       # logical (BN, C, T, H, W)
+            u12, u21p = [], []
+            for (seed, off), b, st in zip(before, part_sizes, states):
+                numel = b * N * N
+                thr = ops.torch_rand_threads(numel, DEV)
+                inc = ops.torch_rand_offset_increment(numel, thr)
+                draws = [ops.philox_uniform(numel, seed, off + j * inc, thr, DEV).view(b, N, N) for j in range(2 * (T - 1))]
+                assert int(st[1]) == off + 2 * (T - 1) * inc               # the kernel advanced the state itself
+                u12.append(torch.stack(draws[: T - 1]))
+                u21p.append(torch.stack(draws[T - 1:]))
+            u12, u21p = torch.cat(u12, 1), torch.cat(u21p, 1)               # (T-1, B, N, N): the whole batch
+            mo = torch.cat([m.detach() for m in maps_parts]).permute(0, 2, 1, 3, 4).clone().requires_grad_(True)   # logical (BN, C, T, H, W)
             ho = hp.head.weight.detach().clone().requires_grad_(True)
             qo = O.patch_nodes(mo, ho, B)
             loss_o, xents, accs, _ = O.walk_loss(qo, c["tau"], c["p"], u12, u21p)
             loss_o.sum().backward()
-            torch.testing.assert_close(loss.detach().reshape(1), loss_o.detach().reshape(1), rtol=1e-5, atol=0)
-            assert relmax(hp.head.weight.grad, ho.grad) < 1e-4
-            assert relmax(hp.maps_in.grad.permute(0, 2, 1, 3, 4), mo.grad) < 1e-4
-            assert 1.0 < float(loss) < 12.0
+            assert abs(hp.loss_value() - float(loss_o)) <= 1e-5 * abs(float(loss_o))
+            assert relmax(hp.head_grad(), ho.grad) < 1e-4
+            gmaps = torch.cat(hp.gmaps) if hp.pipe is not None else hp.maps_in.grad
+            assert relmax(gmaps.permute(0, 2, 1, 3, 4), mo.grad) < 1e-4
+            assert 1.0 < hp.loss_value() < 12.0
     finally:
         ops.set_async_wgrad(False)
 
