@@ -789,6 +789,7 @@ def main():
     ap.add_argument("--part-sizes", default="5,5,5,5", help="clips per micro-batch on staggered streams (pipeline.PatchWalkPipeline), must add up to "
                                                            "20; '' = use --parts.  Default: the best of the measured sweep (profiles/r02_split_sweep.jsonl)")
     ap.add_argument("--pool-sms", type=int, default=108, help="SMs the pooling kernels are confined to while micro-batches overlap (0 = all)")
+    ap.add_argument("--nccl-ctas", type=int, default=16, help="NCCL_MAX_CTAS for the gradient all-reduce (several GPUs)")
     ap.add_argument("--e2e-module", action="store_true", help="also time CRW(args)(x) with the ResNet-18 (DDP when several GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -803,6 +804,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # The gradient exchange of step i runs beside step i+1, whose pooling kernels are HBM-bound and whose walk kernels need
+        # whole SMs: cap NCCL's CTAs (2 GPUs, ms/step with 4 / 8 / 16 / 32 CTAs: 0.58 / 0.35 / 0.291 / 0.294 -
+        # profiles/r02_multi_gpu.txt; below 16 the exchange itself outlasts the step).  An explicit NCCL_MAX_CTAS in the environment wins.
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, world, local_rank)
