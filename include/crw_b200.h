@@ -254,6 +254,16 @@ int crw_lp_minmax_normalize(float* maps, int64_t rows, int L, crw_stream_t strea
  * coords (n, 2, L-1) fp32.  Equal values rank by position (torch.topk leaves that order unspecified). */
 int crw_lp_pose_coords(const float* pred, int n, int h, int w, int L, int topk, float* coords, crw_stream_t stream);
 
+/* ---- f4: the patch-grid producer, code/utils/augs.py:59-82 (patch_grid) --------------------------------
+ * frames (F, H, W, 3) uint8, DEVICE: the frames of a batch of clips after the frame-level transforms.  The (H - win) / stride + 1
+ * by (W - win) / stride + 1 windows of win x win pixels (skimage view_as_windows order, augs.py:75-76) are each cropped to
+ * boxes[f][p] = {top, left, height, width} (the RandomResizedCrop(win, scale (0.7, 0.9)) parameters, drawn by the caller),
+ * resized to out_size x out_size with Pillow's BILINEAR rule (bit-exact on the 8-bit image), divided by 255 and normalised
+ * with mean3 / std3 (HOST pointers, 3 floats each; augs.py:10-12).  out (F, P * 3, out_size, out_size) fp32 - reshaped to
+ * (B, T, P * 3, out_size, out_size) it is the tensor CRW.forward takes (model.py:348-349).  win, out_size <= 64, out_size >= win. */
+int crw_patch_grid(const unsigned char* frames, const int* boxes, int F, int H, int W, int win, int stride, int out_size,
+                   const float* mean3, const float* std3, float* out, crw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -383,3 +383,63 @@ def sinkhorn_knopp(A: torch.Tensor, tol: float = 0.01, max_iter: int = 1000):
         A2 = F.normalize(A1, p=1, dim=-1)
         it += 1
     return A2, it
+
+
+# ----------------------------------------------------------------------------------------------
+# patch-grid producer: code/utils/augs.py:59-82
+# ----------------------------------------------------------------------------------------------
+def _pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Pillow 12.2 src/libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc for the BILINEAR (triangle) filter:
+    per output index the first tap and the fixed-point taps (PRECISION_BITS = 22).  Third-party arithmetic (Pillow is a
+    dependency of the reference, requirements.txt), restated from its published algorithm and pinned against PIL itself."""
+    import numpy as np
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    bounds, taps = [], []
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = []
+        for x in range(xmax):
+            v = abs((x + xmin - center + 0.5) / filterscale)
+            w.append(1.0 - v if v < 1.0 else 0.0)
+        ww = sum(w)
+        w = [c / ww if ww != 0 else c for c in w]
+        taps.append([int(0.5 + c * (1 << 22)) if c >= 0 else int(-0.5 + c * (1 << 22)) for c in w])
+        bounds.append(xmin)
+    return bounds, taps
+
+
+def patch_grid(frame, boxes, win=64, stride=32, out_size=64, mean=(0.4914, 0.4822, 0.4465), std=(0.2023, 0.1994, 0.2010)):
+    """augs.py:59-82 for one frame: frame (H, W, 3) uint8, boxes (P, 4) {top, left, height, width} per window (view_as_windows
+    order) -> (P * 3, out_size, out_size) fp32 = cat over windows of Normalize(ToTensor(resize(crop(window)))).  Integer
+    arithmetic of Pillow's two-pass 8-bit resampling, so the result is bit-exact."""
+    import numpy as np
+    frame = np.asarray(frame, dtype=np.uint8)
+    H, W = frame.shape[:2]
+    nwx, nwy = (W - win) // stride + 1, (H - win) // stride + 1
+    outs = []
+    for p in range(nwy * nwx):
+        wy, wx = (p // nwx) * stride, (p % nwx) * stride
+        i, j, h, w = (int(v) for v in boxes[p])
+        crop = frame[wy + i: wy + i + h, wx + j: wx + j + w].astype(np.int64)
+        bx, kx = _pil_bilinear_coeffs(w, out_size)
+        tmp = np.empty((h, out_size, 3), np.int64)
+        for xx in range(out_size):
+            acc = np.full((h, 3), 1 << 21, np.int64)
+            for t, c in enumerate(kx[xx]):
+                acc += crop[:, bx[xx] + t] * c
+            tmp[:, xx] = np.clip(acc >> 22, 0, 255)
+        by, ky = _pil_bilinear_coeffs(h, out_size)
+        res = np.empty((out_size, out_size, 3), np.int64)
+        for yy in range(out_size):
+            acc = np.full((out_size, 3), 1 << 21, np.int64)
+            for t, c in enumerate(ky[yy]):
+                acc += tmp[by[yy] + t] * c
+            res[yy] = np.clip(acc >> 22, 0, 255)
+        t = torch.from_numpy(res.astype(np.uint8)).permute(2, 0, 1).float().div(255)          # ToTensor
+        t = (t - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None]          # Normalize
+        outs.append(t)
+    return torch.cat(outs, 0)

@@ -260,6 +260,35 @@ def gen_post(ref_model, ref_utils, ref_tu):
         ref_tu.imageio, ref_tu.cm = orig_io, orig_cm
 
 
+def gen_pg(ref_model, ref_utils):
+    """The reference's own patch_grid (utils/augs.py:59-82) on a seeded frame.  skimage is absent here: its view_as_windows
+    (pure index math) is supplied by numpy's sliding_window_view with the same window shape and step.  The fixture stores the
+    8-bit patches (the float output is an exact function of them, checked below)."""
+    import numpy as np
+    from torchvision import transforms
+    augs = ref_utils.augs
+
+    def view_as_windows(x, shape, step):
+        v = np.lib.stride_tricks.sliding_window_view(x, tuple(int(s) for s in shape))
+        return v[::step[0], ::step[1], ::step[2]]
+
+    augs.skimage.util.view_as_windows = view_as_windows
+    c = cases.PG_CASE
+    frame = cases.pg_frame(c).numpy()
+    np.random.seed(c["np_seed"])
+    torch.manual_seed(c["torch_seed"])
+    aug = augs.patch_grid(transforms.Compose(augs.NORM), shape=np.array([64, 64, 3]))
+    out = aug(frame)                                                               # (P*3, 64, 64) fp32
+    mean = torch.tensor(augs.IMG_MEAN)[:, None, None]
+    std = torch.tensor(augs.IMG_STD)[:, None, None]
+    P = out.shape[0] // 3
+    u8 = torch.round((out.view(P, 3, 64, 64) * std + mean) * 255).to(torch.uint8)
+    back = ((u8.float().div(255) - mean) / std).view(-1, 64, 64)
+    assert torch.equal(back, out), "the float patches must be an exact function of the 8-bit ones"
+    torch.save(dict(patches_u8=u8), os.path.join(OUT, "pg_160x128.pt"))
+    print("golden pg", tuple(u8.shape))
+
+
 def gen_misc(ref_model, ref_utils, ref_tu):
     """Small known-answer vectors: ZeroSoftmax, radius mask, context_index_bank, affinity, stoch_mat."""
     g = torch.Generator().manual_seed(5)
@@ -294,6 +323,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "lp_tc":          # only the tensor-core-shaped label-propagation fixtures (round 2)
         gen_lp(ref_model, ref_utils, ref_tu, only=set(cases.LP_TC_CASES) | {"lp_normmask"})
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "pg":             # only the patch-grid fixture (round 2)
+        gen_pg(ref_model, ref_utils)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "ts":             # only the teacher-student fixtures (added later)
         gen_ts(ref_model, ref_utils)
         return
@@ -305,6 +337,7 @@ def main():
     gen_ts(ref_model, ref_utils)
     gen_pose(ref_model, ref_utils, ref_tu)
     gen_lp(ref_model, ref_utils, ref_tu)
+    gen_pg(ref_model, ref_utils)
     gen_cfg1(ref_model, ref_utils)
 
 

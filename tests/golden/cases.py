@@ -77,6 +77,15 @@ LP_TC_CASES = {
 LP_NORM_CASE = dict(C=16, h=11, w=14, n_ctx=3, n_tgt=6, long_mem=[0], radius=4, k=5, tau=0.07, L=3,
                     dyadic=False, repeat_first=False, soft_first=True, seed=39)
 
+# patch-grid producer (utils/augs.py:59-82): frame size, seeds of numpy's (stride draw) and torch's (crop draws) generators
+PG_CASE = dict(H=160, W=128, np_seed=3, torch_seed=5, frame_seed=91)
+
+
+def pg_frame(c):
+    g = torch.Generator().manual_seed(c["frame_seed"])
+    return torch.randint(0, 256, (c["H"], c["W"], 3), generator=g, dtype=torch.uint8)
+
+
 # label-map post-processing cases (utils/test_utils.py:85-123): integer and non-integer scale factors, down-scaling, norm_mask
 POST_CASES = {
     "post_x8":      dict(h=12, w=17, L=3, H=96, W=136, norm_mask=False, seed=41),

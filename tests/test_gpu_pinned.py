@@ -260,3 +260,37 @@ def test_norm_mask_side_effect_matches_reference(ops):
     plain, _ = lp(feats.to(DEV), lbls)
     plain = ops.lp_minmax_normalize_(plain.contiguous()).cpu()
     assert float((plain - fx["preds"]).abs().max()) > 1e-3          # normalising the outputs alone does not reproduce it
+
+
+def test_patch_grid_producer_matches_reference_and_pil(ops):
+    """SURVEY 8f rank 4 (utils/augs.py:59-82): the patch-grid kernel against the reference's own output (golden) and, at the
+    Kinetics shape (256x256 frames -> 49 windows, 8 frames), against PIL / torchvision executed live on every window."""
+    import numpy as np
+    from PIL import Image
+    from sapienza_video_contrastive_b200 import augs
+    c = cases.PG_CASE
+    fx = load("pg_160x128")
+    frame = cases.pg_frame(c)
+    np.random.seed(c["np_seed"])
+    torch.manual_seed(c["torch_seed"])
+    aug = augs.patch_grid(None, shape=(64, 64, 3))                       # the reference's signature: one frame in, (P*3,64,64) CPU out
+    out = aug(frame.numpy())
+    mean, std = torch.tensor(augs.IMG_MEAN)[:, None, None], torch.tensor(augs.IMG_STD)[:, None, None]
+    ref = ((fx["patches_u8"].float().div(255) - mean) / std).view(-1, 64, 64)
+    assert out.shape == ref.shape and not out.is_cuda
+    assert torch.equal(out, ref)
+    # a whole batch of frames in one launch, against PIL on every window
+    g = torch.Generator().manual_seed(2)
+    frames = torch.randint(0, 256, (8, 256, 256, 3), generator=g, dtype=torch.uint8)
+    torch.manual_seed(11)
+    boxes = augs.draw_patch_boxes(8, 49, 64)
+    x = augs.patch_grid_frames(frames.to(DEV), boxes).cpu()
+    assert x.shape == (8, 147, 64, 64)
+    for f in (0, 3, 7):
+        for p in (0, 6, 24, 42, 48):
+            wy, wx = (p // 7) * 32, (p % 7) * 32
+            i, j, h, w = boxes[f, p].tolist()
+            win = frames[f, wy:wy + 64, wx:wx + 64].numpy()
+            pil = np.asarray(Image.fromarray(win).crop((j, i, j + w, i + h)).resize((64, 64), Image.BILINEAR)).copy()
+            want = (torch.from_numpy(pil).permute(2, 0, 1).float().div(255) - mean) / std
+            assert torch.equal(x[f, 3 * p:3 * p + 3], want), (f, p)

@@ -183,3 +183,29 @@ def test_misc_known_answers():
     x = torch.tensor([[-1e20 / 0.07, 0.0, 0.5 / 0.07]])
     e = (torch.exp(x) - 1) ** 2
     assert e[0, 0] == 1 and e[0, 1] == 0
+
+
+def test_patch_grid_matches_reference_and_pil():
+    """utils/augs.py:59-82 run unmodified (tests/golden/pg_160x128.pt) == oracle.patch_grid fed with the crop boxes drawn by the
+    package's host mirror from the same seeds (pins the generator order), and the oracle's restatement of Pillow's BILINEAR
+    resampling == PIL itself on random crops."""
+    import numpy as np
+    from PIL import Image
+    from sapienza_video_contrastive_b200.augs import IMG_MEAN, IMG_STD, draw_patch_boxes
+    c = cases.PG_CASE
+    fx = load("pg_160x128")
+    frame = cases.pg_frame(c)
+    np.random.seed(c["np_seed"])
+    torch.manual_seed(c["torch_seed"])
+    assert np.random.random() * 0.0 + 0.5 == 0.5                     # the reference's stride draw (augs.py:60) consumes one number
+    boxes = draw_patch_boxes(1, 12, 64)[0]
+    out = O.patch_grid(frame.numpy(), boxes.numpy())
+    mean, std = torch.tensor(IMG_MEAN)[:, None, None], torch.tensor(IMG_STD)[:, None, None]
+    ref = ((fx["patches_u8"].float().div(255) - mean) / std).view(-1, 64, 64)
+    assert torch.equal(out, ref)
+    g = np.random.default_rng(1)
+    img = (g.random((64, 64, 3)) * 255).astype(np.uint8)
+    for (i, j, h, w) in [(5, 0, 53, 62), (0, 3, 61, 50), (2, 2, 60, 60), (0, 0, 64, 64), (10, 12, 47, 52)]:
+        pil = np.asarray(Image.fromarray(img).crop((j, i, j + w, i + h)).resize((64, 64), Image.BILINEAR))
+        mine = O.patch_grid(img, np.array([[i, j, h, w]]), 64, 32, 64, (0, 0, 0), (1, 1, 1))
+        assert torch.equal(mine, torch.from_numpy(pil.copy()).permute(2, 0, 1).float().div(255))

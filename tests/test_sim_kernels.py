@@ -627,3 +627,27 @@ def test_head_wgrad_splitk(sim):
     dW = torch.empty(D, C)
     sim.check(sim.crw_head_wgrad(ptr(g), ptr(x), ptr(dW), R, D, C, ptr(ws), nb, None))
     torch.testing.assert_close(dW, g.t() @ x, rtol=1e-4, atol=1e-4)
+
+
+def test_patch_grid_kernel_matches_reference_golden(sim):
+    """crw_patch_grid (csrc/patchgrid.cu) on the host simulator against the reference's own patch_grid output
+    (utils/augs.py:59-82, tests/golden/pg_160x128.pt): bit-exact floats; several frames per launch."""
+    import ctypes
+    import numpy as np
+    from sapienza_video_contrastive_b200.augs import IMG_MEAN, IMG_STD, draw_patch_boxes
+    c = cases.PG_CASE
+    fx = load("pg_160x128")
+    frame = cases.pg_frame(c)
+    np.random.seed(c["np_seed"])
+    torch.manual_seed(c["torch_seed"])
+    boxes = draw_patch_boxes(1, 12, 64)
+    frames = torch.stack([frame, frame.flip(0)]).contiguous()
+    bx = torch.cat([boxes, boxes]).contiguous()
+    out = torch.empty(2, 36, 64, 64)
+    m3, s3 = (ctypes.c_float * 3)(*IMG_MEAN), (ctypes.c_float * 3)(*IMG_STD)
+    sim.check(sim.crw_patch_grid(ptr(frames), ptr(bx), 2, c["H"], c["W"], 64, 32, 64, ctypes.addressof(m3), ctypes.addressof(s3), ptr(out), None))
+    mean, std = torch.tensor(IMG_MEAN)[:, None, None], torch.tensor(IMG_STD)[:, None, None]
+    ref = ((fx["patches_u8"].float().div(255) - mean) / std).view(-1, 64, 64)
+    assert torch.equal(out[0], ref)
+    assert torch.equal(out[1], O.patch_grid(frame.flip(0).numpy(), boxes[0].numpy()))
+    assert sim.crw_patch_grid(ptr(frames), ptr(bx), 2, c["H"], c["W"], 96, 32, 96, ctypes.addressof(m3), ctypes.addressof(s3), ptr(out), None) != 0
