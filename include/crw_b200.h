@@ -99,6 +99,10 @@ int crw_affinity(const float* x1, const float* x2, int BT, int N1, int N2, int D
  * along the last dim. */
 int crw_stoch_mat(float* A, const float* drop_uniform, float rate, float temperature, unsigned flags,
                   int64_t R, int N, int M, float* out, crw_stream_t stream);
+/* Its backward (the reference's stoch_mat / ZeroSoftmax are differentiable torch ops): A as LEFT by the forward call (dropped
+ * entries = -1e20: they get gradient 0), out = the forward result, grad_out -> grad_A, all (R, N, M). */
+int crw_stoch_mat_bwd(const float* A, const float* out, const float* grad_out, float temperature, unsigned flags,
+                      int64_t R, int N, int M, float* grad_A, crw_stream_t stream);
 
 /* ---- a5, Sinkhorn branch: utils/__init__.py:615-641 (sinkhorn_knopp) as called by stoch_mat(do_sinkhorn=True), model.py:83-87 ----
  * A (R, N, M) contiguous, IN PLACE: optionally A <- exp(A / temperature), A <- A / sum(A) per matrix, then sweeps of

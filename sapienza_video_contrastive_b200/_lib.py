@@ -48,6 +48,7 @@ _SIGNATURES = {
     "crw_segmean_dilated_bwd": (c_int, [c_void_p, c_void_p, c_size_t] + [c_int] * 8 + [c_void_p, c_void_p]),
     "crw_affinity": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "crw_stoch_mat": (c_int, [c_void_p, c_void_p, c_float, c_float, c_uint32, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "crw_stoch_mat_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_uint32, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "crw_sinkhorn_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "crw_sinkhorn_knopp": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_walk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_uint32]),

@@ -702,6 +702,50 @@ extern "C" int crw_stoch_mat(float* A, const float* drop_uniform, float rate, fl
     return check_launch("stoch_mat");
 }
 
+// Backward of crw_stoch_mat (model.py:74-90 / utils/__init__.py:414-422 under autograd): A is the tensor AFTER the in-place
+// dropout (dropped entries hold -1e20 and receive no gradient, as index_put_ cuts it in the reference), y the forward output.
+//   softmax:      dA_i = y_i (g_i - sum_j g_j y_j) / tau
+//   ZeroSoftmax:  y_i = e_i / (sum e + eps), e_i = (exp(A_i / tau) - 1)^2:  dA_i = 2 (exp(z_i) - 1) exp(z_i) / (tau S) (g_i - sum_j g_j y_j)
+namespace crw {
+__global__ void __launch_bounds__(256) stoch_rows_bwd_kernel(const float* __restrict__ A, const float* __restrict__ y, const float* __restrict__ g,
+                                                             float* __restrict__ gA, int64_t rows, int M, float tau, int softmax) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < rows; row += nw) {
+        const float* a = A + row * M;
+        const float* yr = y + row * M;
+        const float* gr = g + row * M;
+        float dot = 0.f, S = 0.f;
+        for (int m = lane; m < M; m += 32) {
+            dot = fmaf(gr[m], yr[m], dot);
+            if (!softmax) { const float E = expf(a[m] / tau) - 1.0f; S = fmaf(E, E, S); }
+        }
+        dot = warp_sum(dot);
+        S = warp_sum(S) + kEpsZs;
+        for (int m = lane; m < M; m += 32) {
+            float d;
+            if (softmax) d = yr[m] * (gr[m] - dot) / tau;
+            else {
+                const float ez = expf(a[m] / tau);
+                d = 2.0f * (ez - 1.0f) * ez / (tau * S) * (gr[m] - dot);
+            }
+            gA[row * M + m] = d;
+        }
+    }
+}
+}  // namespace crw
+
+extern "C" int crw_stoch_mat_bwd(const float* A, const float* out, const float* grad_out, float temperature, unsigned flags,
+                                 int64_t R, int N, int M, float* grad_A, crw_stream_t stream) {
+    if (R < 0 || N <= 0 || M <= 0 || !(temperature > 0.f)) { set_error("stoch_mat_bwd: bad shape / temperature"); return CRW_ERR_SHAPE; }
+    const int64_t rows = R * N;
+    if (rows == 0) return CRW_OK;
+    CRW_LAUNCH(stoch_rows_bwd_kernel, rows_grid(rows), 256, 0, stream, A, out, grad_out, grad_A, rows, M, temperature,
+               (flags & CRW_WALK_SOFTMAX) ? 1 : 0);
+    return check_launch("stoch_mat_bwd");
+}
+
 // ---- head weight gradient: dW (D,C) = g^T (D,R) x (R,C), split over R so the small output still fills the GPU ----
 namespace crw {
 // out = beta * out + alpha * sum_j part_j  (alpha = 1, beta = 0: plain reduction, bit-identical to the sum alone)

@@ -25,14 +25,22 @@ EPS = 1e-20
 
 
 class ZeroSoftmax(nn.Module):
-    """code/utils/__init__.py:414-422, evaluated by the stoch_mat kernel (last dim only, eps 1e-5)."""
+    """code/utils/__init__.py:414-422 (eps 1e-5), differentiable, same default `dim=0` as the reference; evaluated by the
+    stoch_mat kernels along the requested dim."""
 
-    def forward(self, x, dim=-1, eps=1e-5):
+    def forward(self, x, dim=0, eps=1e-5):
         if eps != 1e-5:
             raise ValueError("the kernel implements the reference's eps = 1e-5")
-        x = x.transpose(dim, -1) if dim not in (-1, x.dim() - 1) else x
-        y = ops.stoch_mat_(x.contiguous().clone(), 1.0)
-        return y.transpose(dim, -1) if dim not in (-1, x.dim() - 1) else y
+        last = dim in (-1, x.dim() - 1)
+        xt = x if last else x.transpose(dim, -1)
+        if xt.dim() == 1:
+            xt = xt[None]
+            y = ops.stoch_mat(xt[None], 1.0)[0, 0]
+        elif xt.dim() == 2:
+            y = ops.stoch_mat(xt[None], 1.0)[0]
+        else:
+            y = ops.stoch_mat(xt, 1.0)
+        return y if last else y.transpose(dim, -1)
 
 
 class CRW(nn.Module):
@@ -112,7 +120,8 @@ class CRW(nn.Module):
         return A.squeeze(1) if in_t_dim < 4 else A
 
     def stoch_mat(self, A, zero_diagonal=False, do_dropout=True, do_sinkhorn=False):
-        """model.py:74-90.  Like the reference, dropout overwrites the caller's tensor (or view) with -1e20."""
+        """model.py:74-90.  Like the reference, dropout overwrites the caller's tensor (or view) with -1e20, and the result is
+        differentiable with respect to `A` (dropped entries get no gradient)."""
         if zero_diagonal:
             A = self.zeroout_diag(A)
         u = None
@@ -127,16 +136,8 @@ class CRW(nn.Module):
             flat = A.detach().reshape(-1, *A.shape[-2:]) if A.dim() != 3 else A.detach()
             out, _ = ops.sinkhorn_knopp(flat, tol=0.01, max_iter=100, exp_temperature=self.temperature)
             return out.reshape(A.shape)
-        work = A.detach().contiguous()
-        aliased = work.data_ptr() == A.data_ptr()
-        if not aliased:
-            work = work.clone()
-        out = ops.stoch_mat_(work, self.temperature, self.edgedrop_rate if u is not None else 0.0,
-                             softmax=self.use_softmax, uniform=u.contiguous() if u is not None else None)
-        if u is not None and not aliased:
-            with torch.no_grad():
-                A.copy_(work)                          # propagate the in-place side effect through the view
-        return out
+        return ops.stoch_mat(A, self.temperature, self.edgedrop_rate if u is not None else 0.0, softmax=self.use_softmax,
+                             uniform=u.contiguous() if u is not None else None)
 
     def pixels_to_nodes(self, x, featdrop=True):
         """model.py:92-123: x (B,N,C,T,h,w) -> feats (B,128,T,N) unit-norm, maps (B,N,C',T,H,W)."""

@@ -703,6 +703,47 @@ def stoch_mat_(A: torch.Tensor, temperature: float, rate: float = 0.0, softmax: 
     return out
 
 
+class _StochMat(torch.autograd.Function):
+    """model.py:74-90 as a differentiable operator: forward = crw_stoch_mat (the in-place dropout lands in the caller's
+    tensor, as in the reference), backward = crw_stoch_mat_bwd (dropped entries get no gradient)."""
+
+    @staticmethod
+    def forward(ctx, A, temperature, rate, softmax, uniform):
+        _need_cuda(A, uniform)
+        check_device(A.device)
+        if A.dtype != torch.float32:
+            raise TypeError("crw_b200 computes in fp32 (got %s)" % A.dtype)
+        work = A.detach()
+        aliased = work.is_contiguous()
+        if not aliased:
+            work = work.contiguous()                   # a copy: the side effect is written back below
+        out = stoch_mat_(work, temperature, rate, softmax, uniform)
+        if not aliased and rate > 0 and uniform is not None:
+            A.detach().copy_(work)                     # propagate the in-place side effect through the (strided) view
+        ctx.save_for_backward(work, out)
+        ctx.cfg = (float(temperature), bool(softmax))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        work, out = ctx.saved_tensors
+        tau, softmax = ctx.cfg
+        g = _f32c(g)
+        N, M = work.shape[-2:]
+        gA = torch.empty_like(work)
+        L = _lib.lib()
+        L.check(L.crw_stoch_mat_bwd(work.data_ptr(), out.data_ptr(), g.data_ptr(), tau, WALK_SOFTMAX if softmax else 0,
+                                    work.numel() // (N * M), N, M, gA.data_ptr(), _stream()), "stoch_mat_bwd")
+        return gA, None, None, None, None
+
+
+def stoch_mat(A: torch.Tensor, temperature: float, rate: float = 0.0, softmax: bool = False,
+              uniform: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable model.py:74-90 on a (..., N, M) tensor (any strides): in-place dropout to -1e20 where uniform < rate
+    (written into `A`, like the reference), then ZeroSoftmax / softmax of A / temperature along the last dim."""
+    return _StochMat.apply(A, float(temperature), float(rate), bool(softmax), uniform)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # a9-a12: label propagation
 # ------------------------------------------------------------------------------------------------------------------

@@ -294,3 +294,33 @@ def test_patch_grid_producer_matches_reference_and_pil(ops):
             pil = np.asarray(Image.fromarray(win).crop((j, i, j + w, i + h)).resize((64, 64), Image.BILINEAR)).copy()
             want = (torch.from_numpy(pil).permute(2, 0, 1).float().div(255) - mean) / std
             assert torch.equal(x[f, 3 * p:3 * p + 3], want), (f, p)
+
+
+def test_stoch_mat_and_zero_softmax_are_differentiable(ops):
+    """CRW.stoch_mat / ZeroSoftmax must carry gradients like the reference's torch ops (model.py:74-90,
+    utils/__init__.py:414-422, default dim=0), including through a transposed view and with the in-place dropout."""
+    from sapienza_video_contrastive_b200 import CRW
+    from sapienza_video_contrastive_b200.model import ZeroSoftmax
+    from tests.test_gpu_parity import make_args
+    torch.manual_seed(0)
+    x = torch.randn(7, 5, device=DEV, requires_grad=True)
+    y = ZeroSoftmax()(x)                                             # dim = 0, the reference's default
+    xo = x.detach().cpu().requires_grad_(True)
+    yo = (torch.exp(xo) - 1) ** 2
+    yo = yo / (yo.sum(0, keepdim=True) + 1e-5)
+    torch.testing.assert_close(y.cpu(), yo.detach(), rtol=1e-5, atol=1e-7)
+    g = torch.randn(7, 5)
+    y.backward(g.to(DEV))
+    yo.backward(g)
+    assert relmax(x.grad.cpu(), xo.grad) < 1e-5
+    # stoch_mat on the transposed view of an affinity stack, dropout on: gradient flows, dropped edges get none
+    crw = CRW(make_args(dropout=0.3)).to(DEV)
+    q1 = torch.nn.functional.normalize(torch.randn(2, 16, 1, 9, device=DEV), dim=1).requires_grad_(True)
+    q2 = torch.nn.functional.normalize(torch.randn(2, 16, 1, 9, device=DEV), dim=1)
+    A = crw.affinity(q1, q2)[:, 0]                                   # (B, N, N), non-leaf
+    torch.manual_seed(5)
+    P = crw.stoch_mat(A.transpose(-1, -2), do_dropout=True)
+    dropped = A.detach().transpose(-1, -2) == -1e20                  # written through the view
+    assert 0.1 < float(dropped.float().mean()) < 0.5
+    P.sum().backward()
+    assert q1.grad is not None and torch.isfinite(q1.grad).all() and float(q1.grad.abs().max()) > 0

@@ -651,3 +651,24 @@ def test_patch_grid_kernel_matches_reference_golden(sim):
     assert torch.equal(out[0], ref)
     assert torch.equal(out[1], O.patch_grid(frame.flip(0).numpy(), boxes[0].numpy()))
     assert sim.crw_patch_grid(ptr(frames), ptr(bx), 2, c["H"], c["W"], 96, 32, 96, ctypes.addressof(m3), ctypes.addressof(s3), ptr(out), None) != 0
+
+
+@pytest.mark.parametrize("softmax", [False, True])
+def test_stoch_mat_backward_matches_autograd(sim, softmax):
+    """crw_stoch_mat_bwd against torch autograd through the oracle's restatement of model.py:74-90 (dropped edges: no gradient)."""
+    torch.manual_seed(3)
+    R, N, M, tau, rate = 3, 9, 11, 0.07, 0.3
+    A = torch.randn(R, N, M) * 0.3
+    u = torch.rand(R, N, M)
+    g = torch.randn(R, N, M)
+    Ao = A.clone().requires_grad_(True)
+    yo = O.stoch_rows(Ao, u < rate, tau, softmax)
+    yo.backward(g)
+    work, out, gA = A.clone(), torch.empty(R, N, M), torch.empty(R, N, M)
+    flags = 1 if softmax else 0
+    sim.check(sim.crw_stoch_mat(ptr(work), ptr(u), rate, tau, flags, R, N, M, ptr(out), None))
+    torch.testing.assert_close(out, yo.detach(), rtol=1e-5, atol=1e-7)
+    assert bool((work[u < rate] == -1e20).all())
+    sim.check(sim.crw_stoch_mat_bwd(ptr(work), ptr(out), ptr(g), tau, flags, R, N, M, ptr(gA), None))
+    assert float((gA - Ao.grad).abs().max() / Ao.grad.abs().max()) < 1e-5       # (cancellation in g - sum g y: compare at the scale of the row)
+    assert float(gA[u < rate].abs().max()) == 0.0
