@@ -69,3 +69,38 @@ def test_pose_coords_random_shapes(sim):
         for f in range(n):
             ref = O.process_pose(pred[f], torch.zeros(L, 3).numpy(), topk=k)[0]
             assert torch.allclose(coords[f], ref, rtol=0, atol=0, equal_nan=True), (it, n, h, w, L, k)
+
+
+def test_walk_properties_hypothesis(sim):
+    """SURVEY 4 "Property tests" (VERDICT r1 missing #7): hypothesis over clip length, node count, feature width, dropout rate,
+    flip, softmax and EMPTY nodes (all-zero feature rows: zero embedding -> all-zero ZeroSoftmax row), both the fused
+    small-graph kernels and the batched path of the walk (model.py:366-413) against the oracle: loss, per-walk cross-entropies,
+    accuracy up to one near-tie, and the gradient with respect to the un-normalised node vectors."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from tests.test_sim_kernels import run_walk
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(B=st.integers(1, 3), N=st.integers(2, 40), T=st.integers(3, 7), D=st.sampled_from([8, 32, 128]),
+           p=st.sampled_from([0.0, 0.1, 0.5]), flip=st.booleans(), softmax=st.booleans(), general=st.booleans(),
+           n_empty=st.integers(0, 2), seed=st.integers(0, 10 ** 6))
+    def check(B, N, T, D, p, flip, softmax, general, n_empty, seed):
+        g = torch.Generator().manual_seed(seed)
+        f = torch.randn(B, N, T, D, generator=g)
+        for e in range(min(n_empty, N - 1)):                       # empty superpixels: zero vectors in every frame of clip 0
+            f[0, e] = 0
+        u12, u21p = O.draw_uniforms(B, N, T, generator=g)
+        fo = f.clone().requires_grad_(True)
+        qo = (fo / fo.norm(dim=-1, keepdim=True).clamp_min(1e-12)).permute(0, 3, 2, 1)
+        loss_o, xents, accs, _ = O.walk_loss(qo, 0.07, p, u12, u21p, flip=flip, softmax=softmax)
+        loss_o.sum().backward()
+        flags = (1 if softmax else 0) | (2 if flip else 0) | (4 if general else 0)
+        q, xe, ac, gr = run_walk(sim, f, 0.07, p, u12, u21p, flags)
+        cfg = dict(B=B, N=N, T=T, D=D, p=p, flip=flip, softmax=softmax, general=general, n_empty=n_empty, seed=seed)
+        torch.testing.assert_close(q, qo.detach().permute(0, 3, 2, 1), rtol=1e-5, atol=1e-6, msg=str(cfg))
+        torch.testing.assert_close(xe, torch.stack(xents).detach(), rtol=3e-5, atol=1e-6, msg=str(cfg))
+        assert float((ac - torch.stack(accs)).abs().max()) <= 1.0 / (B * N) + 1e-6, cfg
+        scale = float(fo.grad.abs().max())
+        assert float((gr - fo.grad).abs().max()) <= 1e-4 * scale + 1e-9, cfg
+
+    check()

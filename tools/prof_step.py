@@ -13,15 +13,18 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--lp", action="store_true")
 ap.add_argument("--walk-general", action="store_true")
+ap.add_argument("--chain", action="store_true", help="one chain of autograd operators instead of the micro-batch pipeline")
 ap.add_argument("--kineto", action="store_true", help="per-kernel device times in situ from torch.profiler")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 if a.lp:
     bench.LP["n_tgt"] = 2
-    print(bench.label_prop_bench(dev)["ms_per_frame"])
+    print(bench.label_prop_bench(dev, cpu=False, gpu_baseline=False)["ms_per_frame"])
 else:
-    hp = bench.HotPath(dev, 0, use_graph=False)
+    from sapienza_video_contrastive_b200 import ops
+    ops.set_async_wgrad(True)
+    hp = bench.HotPath(dev, 0, use_graph=False, sizes=None if a.chain else [5, 5, 5, 5], pool_sms=0 if a.chain else 108)
     for _ in range(a.steps):
         hp.step()
     torch.cuda.synchronize()
