@@ -27,8 +27,9 @@ UNIT = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 
 
 
 def short(name):
+    name = name.replace("(int)", "")
     for k, v in SHORT:
-        if k in name:
+        if k.replace("(int)", "") in name:
             return v
     return re.sub(r"\(.*", "", name).split("::")[-1][:40]
 
