@@ -162,15 +162,15 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     extern __shared__ unsigned char smem_dyn[];
     const int tiles_x = (a.w + TC_QW - 1) / TC_QW;
     const int tiles = tiles_x * ((a.h + TC_QH - 1) / TC_QH);
-    int n, tile;
-    if (a.list) {                                                 // work list written by the certification pass
-        if (blockIdx.x >= *a.count) return;
-        const int e = a.list[blockIdx.x];
-        n = e / tiles;
-        tile = e - n * tiles;
+    // work items = (target frame, query tile).  Without a list: one per CTA (2-D grid).  With the work list written by the
+    // certification pass: a small fixed grid strides over it (launching one early-exit CTA per possible tile cost 0.57 ms of
+    // block scheduling per call for a list of 21 entries).
+    unsigned work_first, work_end, work_step;
+    if (a.list) {
+        work_first = blockIdx.x; work_end = *a.count; work_step = gridDim.x;
+        if (work_first >= work_end) return;
     } else {
-        n = blockIdx.y;
-        tile = blockIdx.x;
+        work_first = blockIdx.y * (unsigned)tiles + blockIdx.x; work_end = work_first + 1u; work_step = 1u;
     }
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int C = a.C, KC = C / 64, hw = a.h * a.w;
@@ -193,15 +193,6 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     unsigned* tmem_base_smem = reinterpret_cast<unsigned*>(t_empty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qy0 = (tile / tiles_x) * TC_QH, qx0 = (tile % tiles_x) * TC_QW;
-
-    if (threadIdx.x == 0) {
-        mbar_init(q_full, 1);
-        mbar_init(q_ready, 32 * TC_EPI_WARPS);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
-        for (unsigned s = 0; s < ACC_STAGES; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 32 * TC_EPI_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_base_smem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -211,6 +202,22 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     tc_fence_after();
     const unsigned tmem_base = *tmem_base_smem;
     const unsigned tm_qhi = tmem_base, tm_qlo = tmem_base + (unsigned)(C / 2), tm_acc = tmem_base + ACC_BASE;
+
+    for (unsigned work = work_first; work < work_end; work += work_step) {
+    const int wi = a.list ? a.list[work] : (int)work;
+    const int n = wi / tiles, tile = wi - n * tiles;
+    const int qy0 = (tile / tiles_x) * TC_QH, qx0 = (tile % tiles_x) * TC_QW;
+    if (threadIdx.x == 0) {                                       // fresh barriers for every work item (all phases restart at 0)
+        const bool again = work != work_first;
+        const int nb = 2 + 2 * STAGES + 2 * (int)ACC_STAGES;
+        if (again) for (int i = 0; i < nb; ++i) mbar_inval(bars + i);
+        mbar_init(q_full, 1);
+        mbar_init(q_ready, 32 * TC_EPI_WARPS);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+        for (unsigned s = 0; s < ACC_STAGES; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 32 * TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp: one lane per box, so a tile's loads issue in parallel) ==========
@@ -497,9 +504,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         }
     }
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();                                              // every role is done with this work item: smem, TMEM and barriers are free
+    tc_fence_after();
+    }
     if (warp == 1) {
-        tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
     }
 }
@@ -546,15 +554,18 @@ __global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs
         pair1 = npairs;
         stride = (int64_t)gridDim.x * RS_WARPS;
     } else {
-        if (blockIdx.x >= a.hdr[HDR_COUNT]) return;
-        const int e = a.list[blockIdx.x];
+        pair0 = warp;
+        pair1 = TC_M / 2;
+        stride = RS_WARPS;
+    }
+    const unsigned n_items = CHECK ? 1u : a.hdr[HDR_COUNT];
+    for (unsigned item = CHECK ? 0u : blockIdx.x; item < n_items; item += CHECK ? 1u : gridDim.x) {
+    if (!CHECK) {
+        const int e = a.list[item];
         tile_n = e / tiles;
         const int tile = e - tile_n * tiles;
         tile_qy0 = (tile / tiles_x) * TC_QH;
         tile_qx0 = (tile % tiles_x) * TC_QW;
-        pair0 = warp;
-        pair1 = TC_M / 2;
-        stride = RS_WARPS;
     }
     for (int64_t pr = pair0; pr < pair1; pr += stride) {
         // the query of this half-warp
@@ -646,6 +657,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs
             }
         }
     }
+    }
 }
 
 __global__ void lp_fill_list_kernel(int* list, unsigned* count, int n) {
@@ -695,7 +707,8 @@ static int launch_tc_pass(const CUtensorMap& mqh, const CUtensorMap& mql, const 
     auto k = lp_topk_tc_kernel<MODE>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int tiles = lp_tiles(a.h, a.w);
-    dim3 grid = a.list ? dim3((unsigned)(tiles * a.Nt), 1) : dim3((unsigned)tiles, (unsigned)a.Nt);
+    const int listed_grid = tiles * a.Nt < 148 ? tiles * a.Nt : 148;
+    dim3 grid = a.list ? dim3((unsigned)listed_grid, 1) : dim3((unsigned)tiles, (unsigned)a.Nt);
     k<<<grid, TC_THREADS, smem, st>>>(mqh, mql, mkh, mkl, a);
     return check_launch(MODE == MODE_EXACT ? "lp_topk_tc<exact>" : "lp_topk_tc<pre>");
 }
@@ -754,7 +767,7 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
         a.list = list; a.count = hdr + HDR_COUNT;
         e = launch_tc_pass<MODE_EXACT>(mqh, mql, mkh, mkl, a, st);
         if (e != CRW_OK) return e;
-        lp_rescore_kernel<0><<<tiles * a.Nt, 32 * RS_WARPS, 0, st>>>(r);
+        lp_rescore_kernel<0><<<tiles * a.Nt < 148 * 4 ? tiles * a.Nt : 148 * 4, 32 * RS_WARPS, 0, st>>>(r);
         return check_launch("lp_rescore<listed>");
     }
     // every tile on the fp32-faithful path (on request): fill the work list with all tiles first
@@ -762,7 +775,7 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
     e = launch_tc_pass<MODE_EXACT>(mqh, mql, mkh, mkl, a, st);
     if (e != CRW_OK) return e;
     lp_fill_list_kernel<<<(tiles * a.Nt + 255) / 256, 256, 0, st>>>(list, hdr + HDR_COUNT, tiles * a.Nt);
-    lp_rescore_kernel<0><<<tiles * a.Nt, 32 * RS_WARPS, 0, st>>>(r);
+    lp_rescore_kernel<0><<<tiles * a.Nt < 148 * 4 ? tiles * a.Nt : 148 * 4, 32 * RS_WARPS, 0, st>>>(r);
     return check_launch("lp_rescore<all>");
 }
 

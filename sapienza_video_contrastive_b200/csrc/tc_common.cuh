@@ -14,6 +14,9 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -823,6 +823,20 @@ def lp_gather_(lbls: torch.Tensor, key_frames_n: torch.Tensor, Ws_n: torch.Tenso
                             Is_n.contiguous().data_ptr(), hw, Lc, k, int(out_frame), _stream()), "lp_gather")
 
 
+def lp_gather_all_(lbls: torch.Tensor, key_frames: torch.Tensor, Ws: torch.Tensor, Is: torch.Tensor, first_target: int, out_frame0: int) -> None:
+    """test.py:145-157 for every target from `first_target` on, in place, one launch: lbls (Nf,hw,L); key_frames (Nt,S); Ws / Is
+    (Nt,k,hw); target t writes lbls[out_frame0 + t]."""
+    _need_cuda(lbls, key_frames, Ws, Is)
+    if lbls.dtype != torch.float32 or not lbls.is_contiguous():
+        raise ValueError("lbls must be contiguous fp32 (Nf,hw,L)")
+    Nf, hw, Lc = lbls.shape
+    Nt, k = Ws.shape[0], Ws.shape[1]
+    L = _lib.lib()
+    L.check(L.crw_lp_gather_all(lbls.data_ptr(), key_frames.to(torch.int64).contiguous().data_ptr(), _f32c(Ws).data_ptr(),
+                                Is.contiguous().data_ptr(), Nt, key_frames.shape[1], hw, Lc, k, int(first_target), int(out_frame0), _stream()),
+            "lp_gather_all")
+
+
 def lp_minmax_normalize_(maps: torch.Tensor) -> torch.Tensor:
     """test.py:162-164 (--norm_mask) in place on a contiguous (..., L) fp32 tensor: rows -= min; rows /= max."""
     _need_cuda(maps)

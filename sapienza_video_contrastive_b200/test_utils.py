@@ -155,16 +155,19 @@ def propagate_labels(lbls: torch.Tensor, key_indices: torch.Tensor, Ws, Is, n_co
     lb[n_context:] = 0
     lb = lb.view(Nf, h * w, L)
     ki = key_indices.to(device)
-    preds = []
-    for t in range(ki.shape[0]):
-        if t == 0:
-            lb[n_context] = lb[0]                         # test.py:158-160: the first target keeps the ground truth
-            if norm_mask:
-                ops.lp_minmax_normalize_(lb[0])           # ... and --norm_mask then rewrites frame 0 through the view
-            preds.append(lb[0] if norm_mask else lb[n_context])
-        else:
+    Nt = ki.shape[0]
+    stacked = torch.is_tensor(Ws) and torch.is_tensor(Is) and Ws.is_cuda and Is.is_cuda
+    if Nt > 0:
+        lb[n_context] = lb[0]                             # test.py:158-160: the first target keeps the ground truth
+        if norm_mask:
+            ops.lp_minmax_normalize_(lb[0])               # ... and --norm_mask then rewrites frame 0 through the view
+    if stacked:
+        ops.lp_gather_all_(lb, ki, Ws, Is, 1, n_context)  # the whole recurrence in one launch
+    else:                                                 # the reference's lists of per-frame CPU tensors
+        for t in range(1, Nt):
             ops.lp_gather_(lb, ki[t], Ws[t].to(device), Is[t].to(device), t + n_context)
-            preds.append(lb[t + n_context])
+    preds = [lb[0] if norm_mask else lb[n_context]] if Nt > 0 else []
+    preds += [lb[t + n_context] for t in range(1, Nt)]
     out = torch.stack(preds)
     if norm_mask and out.shape[0] > 1:
         ops.lp_minmax_normalize_(out[1:])

@@ -672,3 +672,27 @@ def test_stoch_mat_backward_matches_autograd(sim, softmax):
     sim.check(sim.crw_stoch_mat_bwd(ptr(work), ptr(out), ptr(g), tau, flags, R, N, M, ptr(gA), None))
     assert float((gA - Ao.grad).abs().max() / Ao.grad.abs().max()) < 1e-5       # (cancellation in g - sum g y: compare at the scale of the row)
     assert float(gA[u < rate].abs().max()) == 0.0
+
+
+def test_lp_gather_all_equals_frame_by_frame(sim):
+    """crw_lp_gather_all (the whole loop of test.py:145-157 in one call) == crw_lp_gather applied target by target, bit for bit."""
+    c = cases.LP_CASES["lp_small"]
+    fx = load("lp_small")
+    feats, lbls = cases.lp_inputs(c)
+    hw, L, n_ctx, Nt = c["h"] * c["w"], c["L"], c["n_ctx"], c["n_tgt"]
+    ki = O.context_index_bank(n_ctx, c["long_mem"], Nt)
+    Ws, Is = fx["Ws"].contiguous(), fx["Is"].contiguous()
+    res = []
+    for mode in ("loop", "all"):
+        lb = lbls.clone()
+        lb[n_ctx:] = 0
+        lb = lb.view(-1, hw, L).contiguous()
+        lb[n_ctx] = lb[0]
+        if mode == "loop":
+            for t in range(1, Nt):
+                sim.check(sim.crw_lp_gather(ptr(lb), ptr(ki[t].contiguous()), ptr(Ws[t]), ptr(Is[t]), hw, L, c["k"], t + n_ctx, None))
+        else:
+            sim.check(sim.crw_lp_gather_all(ptr(lb), ptr(ki.contiguous()), ptr(Ws), ptr(Is), Nt, ki.shape[1], hw, L, c["k"], 1, n_ctx, None))
+        res.append(lb[n_ctx:].clone())
+    assert torch.equal(res[0], res[1])
+    torch.testing.assert_close(res[1].view(Nt, c["h"], c["w"], L), fx["preds"], rtol=1e-5, atol=1e-6)

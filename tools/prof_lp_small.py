@@ -24,3 +24,10 @@ lp(fd, ld)
 e1.record()
 torch.cuda.synchronize()
 print("targets", n_tgt, "ms", e0.elapsed_time(e1), lp.stats)
+if "--kineto" in sys.argv:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            lp(fd, ld)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=16, max_name_column_width=60))
