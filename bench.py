@@ -408,7 +408,8 @@ def lp_issued_flops(stats):
         per_tile += ((c["w"] + 7) // 8) * 128 * per_tile_keys * c["C"] * 2
     pre = per_tile * c["n_tgt"]
     tiles = max(stats.get("tiles", 1), 1)
-    return pre + 3 * pre * stats.get("listed_tiles", 0) / tiles
+    redo = stats.get("listed_tiles", 0) if stats.get("uncertified_queries", 0) > 1024 else 0      # (else the open queries are settled on the fp32 pipe)
+    return pre + 3 * pre * redo / tiles
 
 
 def label_prop_bench(dev, cpu=True, gpu_baseline=True):

@@ -253,26 +253,56 @@ __global__ void __launch_bounds__(256) lp_gather_kernel(float* lbls, const int64
 // tiny (hw x L outputs, k gathers each): a single 8-CTA thread-block cluster walks the targets, one cluster barrier per frame
 // (release / acquire: the frame just written is visible to the whole cluster; label reads go to L2, .cg, because another SM wrote
 // them).  36 launches of ~10 us become one of ~60 us.
-constexpr int kGatherCluster = 8, kGatherThreads = 512;
+constexpr int kGatherCluster = 8, kGatherThreads = 512, kGatherMaxK = 16;
 
+// thread = query position: its k (index, weight) pairs are loaded first (coalesced), then the label rows are fetched four ranks
+// at a time (independent loads in flight; accumulation stays in rank order, like the per-frame kernel)
 __global__ void __launch_bounds__(kGatherThreads) lp_gather_all_kernel(float* lbls, const int64_t* __restrict__ key_frames, const float* __restrict__ Ws,
                                                                      const int64_t* __restrict__ Is, int Nt, int S, int hw, int L, int k,
                                                                      int first_target, int64_t out_frame0) {
-    const int64_t total = (int64_t)hw * L;
     const int nthreads = gridDim.x * blockDim.x;
+    const int k4 = (k + 3) & ~3;
     for (int t = first_target; t < Nt; ++t) {
         const int64_t* kf = key_frames + (int64_t)t * S;
         const float* W = Ws + (int64_t)t * k * hw;
         const int64_t* I = Is + (int64_t)t * k * hw;
-        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
-            const int q = (int)(e / L), l = (int)(e - (int64_t)q * L);
-            float s = 0.f;
-            for (int r = 0; r < k; ++r) {
-                const int64_t id = I[(int64_t)r * hw + q];
-                const int64_t slot = id / hw, pos = id - slot * hw;
-                s += ld_cg(lbls + (kf[slot] * hw + pos) * L + l) * W[(int64_t)r * hw + q];
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < hw; q += nthreads) {
+            int off[kGatherMaxK];
+            float wt[kGatherMaxK];
+#pragma unroll
+            for (int r = 0; r < kGatherMaxK; ++r) {
+                off[r] = 0;
+                wt[r] = 0.f;
+                if (r < k) {
+                    const int64_t id = I[(int64_t)r * hw + q];
+                    const int64_t slot = id / hw, pos = id - slot * hw;
+                    off[r] = (int)((kf[slot] * hw + pos) * L);
+                    wt[r] = W[(int64_t)r * hw + q];
+                }
             }
-            lbls[((out_frame0 + t) * hw + q) * L + l] = s;
+            float* dst = lbls + ((out_frame0 + t) * hw + q) * L;
+            for (int l0 = 0; l0 < L; l0 += 4) {
+                float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int r0 = 0; r0 < kGatherMaxK; r0 += 4) {
+                    if (r0 < k4) {
+                        float v[4][4];
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) v[rr][j] = (l0 + j < L) ? ld_cg(lbls + off[r0 + rr] + l0 + j) : 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr)
+                            if (r0 + rr < k) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) s[j] += v[rr][j] * wt[r0 + rr];
+                            }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (l0 + j < L) dst[l0 + j] = s[j];
+            }
         }
 #ifndef CRW_SIM
         __threadfence();
@@ -372,6 +402,13 @@ extern "C" int crw_lp_gather_all(float* lbls, const int64_t* key_frames, const f
                                  int k, int first_target, int64_t out_frame0, crw_stream_t stream) {
     if (Nt < 0 || S <= 0 || hw <= 0 || L <= 0 || k <= 0 || first_target < 0 || out_frame0 < 0) { set_error("lp_gather_all: bad arguments"); return CRW_ERR_SHAPE; }
     if (first_target >= Nt) return CRW_OK;
+    if (k > kGatherMaxK || (int64_t)hw * L * (out_frame0 + Nt + 1) >= 0x7fffffff) {      // rare: one launch per frame
+        for (int t = first_target; t < Nt; ++t) {
+            int e = crw_lp_gather(lbls, key_frames + (int64_t)t * S, Ws + (int64_t)t * k * hw, Is + (int64_t)t * k * hw, hw, L, k, out_frame0 + t, stream);
+            if (e != CRW_OK) return e;
+        }
+        return CRW_OK;
+    }
 #ifdef CRW_SIM
     for (int t = first_target; t < Nt; ++t) {            // the host simulator has no clusters: one launch per frame, same arithmetic
         const int64_t total = (int64_t)hw * L;

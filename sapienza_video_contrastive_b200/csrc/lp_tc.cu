@@ -49,6 +49,7 @@ constexpr int LP_SHORT = 16;     // shortlist length per query
 constexpr int LP_HALF = 12;      // candidates each of a query's two epilogue threads keeps (>= LP_PRE_MAX_K: the k best may all sit in one half)
 constexpr int LP_PRE_MAX_K = 12; // the pre-ranking pass needs spare shortlist entries below the k-th to certify a query
 constexpr int MODE_PRE = 0, MODE_EXACT = 1;
+constexpr unsigned LP_QX_CAP = 1024;   // up to this many uncertified queries are settled one by one (lp_exact_query_kernel)
 // workspace header words
 constexpr int HDR_ERR = 0, HDR_COUNT = 1, HDR_KNORM2 = 2, HDR_MAXABS = 3, HDR_FLAGGED = 4, HDR_BYTES = 1024;
 // |pre-score - exact fp32 score| <= LP_EPS_REL |q| max|k| + LP_EPS_ABS (|q| + max|k|):  2 * 2^-11 (1 + 2^-12) from rounding
@@ -167,6 +168,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     // block scheduling per call for a list of 21 entries).
     unsigned work_first, work_end, work_step;
     if (a.list) {
+        if (a.count[HDR_FLAGGED - HDR_COUNT] <= LP_QX_CAP) return;      // few open queries: lp_exact_query_kernel settles them
         work_first = blockIdx.x; work_end = *a.count; work_step = gridDim.x;
         if (work_first >= work_end) return;
     } else {
@@ -530,9 +532,15 @@ struct LpRescoreArgs {
     unsigned* hdr;               // workspace header
     unsigned* flags;             // (Nt*tiles) tile already listed
     int* list;                   // (Nt*tiles) work list
+    int2* qlist;                 // (LP_QX_CAP) uncertified queries (target, position)
+    int n_unres, restricted, R, r2i;
 };
 
 constexpr int RS_WARPS = 4, RS_CH = 64, RS_LD = RS_CH + 4;
+// Few uncertified queries (distinct frames: ~1 in 10 000) are settled one by one by lp_exact_query_kernel, an exact-fp32
+// evaluation of ALL their admissible keys; only when more than LP_QX_CAP queries are open (replicated frames) is the
+// fp32-faithful tensor-core pass over whole tiles the cheaper way.  Both are always launched; the one out of its regime exits.
+constexpr int QX_WARPS = 8, QX_K = 12;
 
 template <int CHECK>
 __global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs a) {
@@ -558,7 +566,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs
         pair1 = TC_M / 2;
         stride = RS_WARPS;
     }
-    const unsigned n_items = CHECK ? 1u : a.hdr[HDR_COUNT];
+    const unsigned n_items = CHECK ? 1u : (a.hdr[HDR_FLAGGED] <= LP_QX_CAP ? 0u : a.hdr[HDR_COUNT]);
     for (unsigned item = CHECK ? 0u : blockIdx.x; item < n_items; item += CHECK ? 1u : gridDim.x) {
     if (!CHECK) {
         const int e = a.list[item];
@@ -652,7 +660,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs
             if (qok && cand == 0 && !certified) {
                 const int qy = qpos / a.w, qx = qpos - qy * a.w;
                 const int e_ = n * tiles + (qy / TC_QH) * tiles_x + qx / TC_QW;
-                atomicAdd(a.hdr + HDR_FLAGGED, 1u);
+                const unsigned qi = atomicAdd(a.hdr + HDR_FLAGGED, 1u);
+                if (qi < LP_QX_CAP) a.qlist[qi] = make_int2(n, qpos);
                 if (atomicExch(a.flags + e_, 1u) == 0u) a.list[atomicAdd(a.hdr + HDR_COUNT, 1u)] = e_;
             }
         }
@@ -660,10 +669,148 @@ __global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs
     }
 }
 
+// ---- exact evaluation of single queries ---------------------------------------------------------------------------------
+// One CTA = one uncertified query.  Every admissible key (all positions of the long-memory slots, the disc of the restricted
+// ones) is scored in exact fp32 with the same staging and the same sequential fmaf chain as lp_rescore_kernel / lp_simt.cu
+// (lane = key), each lane keeps its k best in registers, the 256 sorted lane lists are merged by k rounds of a block-wide
+// arg-max in (score desc, index asc) order, then the softmax of the SIMT kernel.  ~14 k keys x 1 KB per query: ~0.1 ms.
+__global__ void __launch_bounds__(32 * QX_WARPS) lp_exact_query_kernel(LpRescoreArgs a) {
+    extern __shared__ __align__(16) unsigned char qx_smem[];
+    float (*rows_s)[32][RS_LD] = reinterpret_cast<float (*)[32][RS_LD]>(qx_smem);                       // [warp][32 keys][64 + 4]
+    float* q_s = reinterpret_cast<float*>(qx_smem + sizeof(float) * QX_WARPS * 32 * RS_LD);             // [C]
+    float* lv = q_s + a.C;                                                                              // [256][QX_K]
+    int* li = reinterpret_cast<int*>(lv + 32 * QX_WARPS * QX_K);
+    __shared__ int row_start[32], row_x0[32], row_y[32];
+    __shared__ int n_rows_s, disc_s;
+    __shared__ float red_v[QX_WARPS];
+    __shared__ int red_i[QX_WARPS], red_t[QX_WARPS];
+    __shared__ float win_v[QX_K];
+    __shared__ int win_i[QX_K];
+    const unsigned qcount = a.hdr[HDR_FLAGGED];
+    if (qcount > LP_QX_CAP) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hw = a.h * a.w;
+    for (unsigned item = blockIdx.x; item < qcount; item += gridDim.x) {
+        const int2 nq = a.qlist[item];
+        const int n = nq.x, qpos = nq.y;
+        const int qy = qpos / a.w, qx = qpos - qy * a.w;
+        __syncthreads();
+        if (tid == 0) {
+            int cnt = 0, nr = 0;
+            if (a.restricted)
+                for (int dy = -a.R; dy <= a.R; ++dy) {
+                    const int y = qy + dy, rem = a.r2i - dy * dy;
+                    if (y < 0 || y >= a.h || rem < 0) continue;
+                    const int dxm = (int)sqrtf((float)rem);
+                    const int x0 = max(qx - dxm, 0), x1 = min(qx + dxm, a.w - 1);
+                    row_start[nr] = cnt; row_x0[nr] = x0; row_y[nr] = y;
+                    cnt += x1 - x0 + 1;
+                    ++nr;
+                }
+            n_rows_s = nr;
+            disc_s = cnt;
+        }
+        const float* qrow = a.feats + (a.query_frames[n] * (int64_t)hw + qpos) * a.C;
+        for (int c = tid; c < a.C; c += blockDim.x) q_s[c] = qrow[c];
+        __syncthreads();
+        const int disc = disc_s, nr = n_rows_s;
+        const int64_t total = (int64_t)a.n_unres * hw + (int64_t)(a.S - a.n_unres) * disc;
+        float tv[QX_K];
+        int ti[QX_K];
+#pragma unroll
+        for (int r = 0; r < QX_K; ++r) { tv[r] = -INFINITY; ti[r] = 0x7fffffff; }
+        for (int64_t base = (int64_t)warp * 32; base < total; base += QX_WARPS * 32) {
+            const int64_t c = base + lane;
+            const bool valid = c < total;
+            int slot = 0, pos = 0;
+            if (valid) {
+                if (c < (int64_t)a.n_unres * hw) { slot = (int)(c / hw); pos = (int)(c - (int64_t)slot * hw); }
+                else {
+                    const int64_t c2 = c - (int64_t)a.n_unres * hw;
+                    slot = a.n_unres + (int)(c2 / disc);
+                    const int d = (int)(c2 - (int64_t)(slot - a.n_unres) * disc);
+                    int r = 0;
+                    while (r + 1 < nr && row_start[r + 1] <= d) ++r;
+                    pos = row_y[r] * a.w + row_x0[r] + (d - row_start[r]);
+                }
+            }
+            const float* krow = a.feats + (a.key_frames[(int64_t)n * a.S + slot] * (int64_t)hw + pos) * a.C;
+            float acc = 0.f;
+            for (int c0 = 0; c0 < a.C; c0 += RS_CH) {
+                __syncwarp();
+#pragma unroll 8
+                for (int i = 0; i < 16; ++i) {
+                    const int r = 2 * i + (lane >> 4);
+                    const float* src = reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)krow, r));
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + c0) + (lane & 15));
+                    *reinterpret_cast<float4*>(&rows_s[warp][r][(lane & 15) * 4]) = v;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < RS_CH; cc += 4) {
+                    const float4 kv = *reinterpret_cast<const float4*>(&rows_s[warp][lane][cc]);
+                    const float4 qv = *reinterpret_cast<const float4*>(&q_s[c0 + cc]);
+                    acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc); acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+                }
+            }
+            if (valid) {
+                float x = acc / a.tau;
+                int id = slot * hw + pos;
+                if (x > tv[QX_K - 1]) {                       // ids ascend along a lane's stream: strict > keeps the lower index ahead
+#pragma unroll
+                    for (int r = 0; r < QX_K; ++r) {
+                        const bool better = x > tv[r];
+                        const float ov = tv[r];
+                        const int oi = ti[r];
+                        tv[r] = better ? x : ov;
+                        ti[r] = better ? id : oi;
+                        x = better ? ov : x;
+                        id = better ? oi : id;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < QX_K; ++r) { lv[tid * QX_K + r] = tv[r]; li[tid * QX_K + r] = ti[r]; }
+        int head = 0;
+        for (int r = 0; r < a.k; ++r) {                       // k rounds of a block-wide arg-max over the list heads
+            float v = head < QX_K ? lv[tid * QX_K + head] : -INFINITY;
+            int id = head < QX_K ? li[tid * QX_K + head] : 0x7fffffff;
+            int who = tid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(kFull, v, o);
+                const int oi = __shfl_xor_sync(kFull, id, o), ow = __shfl_xor_sync(kFull, who, o);
+                if (ov > v || (ov == v && oi < id)) { v = ov; id = oi; who = ow; }
+            }
+            if (lane == 0) { red_v[warp] = v; red_i[warp] = id; red_t[warp] = who; }
+            __syncthreads();
+            float bv = red_v[0];
+            int bi = red_i[0], bt = red_t[0];
+            for (int w2 = 1; w2 < QX_WARPS; ++w2)
+                if (red_v[w2] > bv || (red_v[w2] == bv && red_i[w2] < bi)) { bv = red_v[w2]; bi = red_i[w2]; bt = red_t[w2]; }
+            if (tid == bt) ++head;
+            if (tid == 0) { win_v[r] = bv; win_i[r] = bi; }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int64_t o = (int64_t)n * a.k * hw + qpos;
+            float vals[QX_K];
+            float den = 0.f;
+            const float mxv = win_v[0];
+            for (int r = 0; r < a.k; ++r) { vals[r] = expf(win_v[r] - mxv); den += vals[r]; }
+            for (int r = 0; r < a.k; ++r) {
+                a.Ws[o + (int64_t)r * hw] = vals[r] / den;
+                a.Is[o + (int64_t)r * hw] = win_i[r] == 0x7fffffff ? 0 : win_i[r];
+            }
+        }
+    }
+}
+
 __global__ void lp_fill_list_kernel(int* list, unsigned* count, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) list[i] = i;
-    if (i == 0) *count = (unsigned)n;
+    if (i == 0) { count[0] = (unsigned)n; count[HDR_FLAGGED - HDR_COUNT] = LP_QX_CAP + 1u; }      // every tile, on the tensor cores
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
@@ -686,7 +833,7 @@ size_t lp_tc_workspace_bytes(int Nf, int Nt, int h, int w, int C) {
     const size_t plane = align256((size_t)Nf * h * w * C * 2);
     const size_t sl = align256((size_t)Nt * h * w * LP_SHORT * 4);
     const size_t tl = align256((size_t)Nt * lp_tiles(h, w) * 4);
-    return HDR_BYTES + 2 * plane + 2 * sl + 2 * tl;
+    return HDR_BYTES + 2 * plane + 2 * sl + 2 * tl + align256(LP_QX_CAP * sizeof(int2));
 }
 
 bool lp_tc_supported(int C, int k, float radius, int R, bool dense) {
@@ -732,6 +879,7 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
     int* short_i = (int*)(ws + HDR_BYTES + 2 * plane + sl);
     unsigned* flags = (unsigned*)(ws + HDR_BYTES + 2 * plane + 2 * sl);
     int* list = (int*)(ws + HDR_BYTES + 2 * plane + 2 * sl + tl);
+    int2* qlist = (int2*)(ws + HDR_BYTES + 2 * plane + 2 * sl + 2 * tl);
     cudaMemsetAsync(hdr, 0, HDR_BYTES, st);
     cudaMemsetAsync(flags, 0, (size_t)a0.Nt * tiles * 4, st);
     const int64_t rows = (int64_t)Nf * hw;
@@ -752,7 +900,8 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
     LpRescoreArgs r{};
     r.feats = feats; r.key_frames = a.key_frames; r.query_frames = a.query_frames; r.short_v = short_v; r.short_i = short_i;
     r.Nt = a.Nt; r.S = a.S; r.h = a.h; r.w = a.w; r.C = C; r.k = a.k; r.tau = a.tau; r.Ws = a.Ws; r.Is = a.Is;
-    r.hdr = hdr; r.flags = flags; r.list = list;
+    r.hdr = hdr; r.flags = flags; r.list = list; r.qlist = qlist;
+    r.n_unres = a.restricted ? a.n_long : a.S; r.restricted = a.restricted; r.R = a.R; r.r2i = a.r2i;
     const bool pre = !(a.flags & CRW_LP_EXACT_ONLY);
     if (pre) {
         a.list = nullptr; a.count = nullptr;
@@ -764,6 +913,13 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
         lp_rescore_kernel<1><<<rgrid, 32 * RS_WARPS, 0, st>>>(r);
         e = check_launch("lp_rescore<check>");
         if (e != CRW_OK) return e;
+        {   // few open queries: exact fp32, one CTA each
+            const size_t qsm = sizeof(float) * ((size_t)QX_WARPS * 32 * RS_LD + C + 32 * QX_WARPS * QX_K) + sizeof(int) * 32 * QX_WARPS * QX_K;
+            cudaFuncSetAttribute(lp_exact_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm);
+            lp_exact_query_kernel<<<148 * 2, 32 * QX_WARPS, qsm, st>>>(r);
+            e = check_launch("lp_exact_query");
+            if (e != CRW_OK) return e;
+        }
         a.list = list; a.count = hdr + HDR_COUNT;
         e = launch_tc_pass<MODE_EXACT>(mqh, mql, mkh, mkl, a, st);
         if (e != CRW_OK) return e;

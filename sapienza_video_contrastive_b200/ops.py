@@ -806,8 +806,11 @@ def lp_topk(feats_cl: torch.Tensor, key_frames: torch.Tensor, query_frames: torc
             raise _lib.CrwError("lp_topk: tensor-core kernel reported an internal barrier timeout")
         if stats is not None:
             tiles = ((w + 7) // 8) * ((h + 15) // 16) * Nt
-            stats.update(tensor_cores=on_tc, tiles=tiles, listed_tiles=hdr[1] if on_tc else 0,
-                         uncertified_queries=hdr[4] if on_tc else 0)
+            unc = hdr[4] if on_tc else 0
+            stats.update(tensor_cores=on_tc, tiles=tiles, listed_tiles=hdr[1] if on_tc else 0, uncertified_queries=unc,
+                         settled_by=("nothing to settle" if unc == 0 else "exact fp32 evaluation per query" if unc <= 1024
+                                     else "fp32-faithful tensor-core pass over the listed tiles") if on_tc and not exact_only
+                         else ("fp32-faithful tensor-core pass over every tile" if on_tc else "SIMT kernel"))
     return Ws, Is
 
 
