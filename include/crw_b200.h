@@ -237,9 +237,9 @@ int crw_lp_prepare(const float* feats_cf, int C, int Nf, int hw, int normalize, 
 int crw_lp_gather(float* lbls, const int64_t* key_frames_n, const float* Ws_n, const int64_t* Is_n,
                   int hw, int L, int k, int64_t out_frame, crw_stream_t stream);
 
-/* The whole loop test.py:145-157 of one video in one launch: for t = first_target .. Nt-1, lbls[out_frame0 + t] = the gather of
- * target t (key_frames (Nt, S), Ws / Is (Nt, k, hw) as crw_lp_topk returns them).  Sequential in t inside the kernel (a single
- * 8-CTA cluster, one cluster barrier per frame).  The caller handles what precedes first_target (test.py:158-160: the first
+/* The whole loop test.py:145-157 of one video in one call: for t = first_target .. Nt-1, lbls[out_frame0 + t] = the gather of
+ * target t (key_frames (Nt, S), Ws / Is (Nt, k, hw) as crw_lp_topk returns them): one gather launch per frame, enqueued back to
+ * back in stream order (the recurrence is sequential by construction).  The caller handles what precedes first_target (test.py:158-160: the first
  * target keeps the ground truth, so first_target = 1 and out_frame0 = n_context). */
 int crw_lp_gather_all(float* lbls, const int64_t* key_frames, const float* Ws, const int64_t* Is, int Nt, int S, int hw, int L,
                       int k, int first_target, int64_t out_frame0, crw_stream_t stream);

@@ -248,69 +248,6 @@ __global__ void __launch_bounds__(256) lp_gather_kernel(float* lbls, const int64
     }
 }
 
-// ---- the whole propagation loop of a video (test.py:145-157) in ONE launch ------------------------------------------------
-// The recurrence over target frames is sequential (frame t reads the label maps written for earlier targets), but one frame is
-// tiny (hw x L outputs, k gathers each): a single 8-CTA thread-block cluster walks the targets, one cluster barrier per frame
-// (release / acquire: the frame just written is visible to the whole cluster; label reads go to L2, .cg, because another SM wrote
-// them).  36 launches of ~10 us become one of ~60 us.
-constexpr int kGatherCluster = 8, kGatherThreads = 512, kGatherMaxK = 16;
-
-// thread = query position: its k (index, weight) pairs are loaded first (coalesced), then the label rows are fetched four ranks
-// at a time (independent loads in flight; accumulation stays in rank order, like the per-frame kernel)
-__global__ void __launch_bounds__(kGatherThreads) lp_gather_all_kernel(float* lbls, const int64_t* __restrict__ key_frames, const float* __restrict__ Ws,
-                                                                     const int64_t* __restrict__ Is, int Nt, int S, int hw, int L, int k,
-                                                                     int first_target, int64_t out_frame0) {
-    const int nthreads = gridDim.x * blockDim.x;
-    const int k4 = (k + 3) & ~3;
-    for (int t = first_target; t < Nt; ++t) {
-        const int64_t* kf = key_frames + (int64_t)t * S;
-        const float* W = Ws + (int64_t)t * k * hw;
-        const int64_t* I = Is + (int64_t)t * k * hw;
-        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < hw; q += nthreads) {
-            int off[kGatherMaxK];
-            float wt[kGatherMaxK];
-#pragma unroll
-            for (int r = 0; r < kGatherMaxK; ++r) {
-                off[r] = 0;
-                wt[r] = 0.f;
-                if (r < k) {
-                    const int64_t id = I[(int64_t)r * hw + q];
-                    const int64_t slot = id / hw, pos = id - slot * hw;
-                    off[r] = (int)((kf[slot] * hw + pos) * L);
-                    wt[r] = W[(int64_t)r * hw + q];
-                }
-            }
-            float* dst = lbls + ((out_frame0 + t) * hw + q) * L;
-            for (int l0 = 0; l0 < L; l0 += 4) {
-                float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int r0 = 0; r0 < kGatherMaxK; r0 += 4) {
-                    if (r0 < k4) {
-                        float v[4][4];
-#pragma unroll
-                        for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) v[rr][j] = (l0 + j < L) ? ld_cg(lbls + off[r0 + rr] + l0 + j) : 0.f;
-#pragma unroll
-                        for (int rr = 0; rr < 4; ++rr)
-                            if (r0 + rr < k) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) s[j] += v[rr][j] * wt[r0 + rr];
-                            }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (l0 + j < L) dst[l0 + j] = s[j];
-            }
-        }
-#ifndef CRW_SIM
-        __threadfence();
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-#endif
-    }
-}
-
 template <int KCAP>
 static int launch_lp(const LpArgs& a, crw_stream_t stream) {
     const size_t qbytes = (size_t)a.C * (LQ + LPAD) * 4;
@@ -398,44 +335,19 @@ extern "C" int crw_lp_prepare(const float* feats_cf, int C, int Nf, int hw, int 
     return check_launch("lp_prepare");
 }
 
+// The whole propagation loop of a video (test.py:145-157) behind one call: the recurrence over target frames is sequential, one
+// frame is tiny (hw x L outputs, k gathers each) but wants the whole GPU for a few microseconds, so it stays one launch per frame,
+// issued back to back from here (36 launches cost ~0.35 ms of device time; from Python they cost more host time than that).
+// (Measured alternative: the recurrence inside ONE 8-CTA cluster with a cluster barrier per frame - 36 us per frame on 8 SMs
+// against 9.6 us per launch on the whole GPU.)
 extern "C" int crw_lp_gather_all(float* lbls, const int64_t* key_frames, const float* Ws, const int64_t* Is, int Nt, int S, int hw, int L,
                                  int k, int first_target, int64_t out_frame0, crw_stream_t stream) {
     if (Nt < 0 || S <= 0 || hw <= 0 || L <= 0 || k <= 0 || first_target < 0 || out_frame0 < 0) { set_error("lp_gather_all: bad arguments"); return CRW_ERR_SHAPE; }
-    if (first_target >= Nt) return CRW_OK;
-    if (k > kGatherMaxK || (int64_t)hw * L * (out_frame0 + Nt + 1) >= 0x7fffffff) {      // rare: one launch per frame
-        for (int t = first_target; t < Nt; ++t) {
-            int e = crw_lp_gather(lbls, key_frames + (int64_t)t * S, Ws + (int64_t)t * k * hw, Is + (int64_t)t * k * hw, hw, L, k, out_frame0 + t, stream);
-            if (e != CRW_OK) return e;
-        }
-        return CRW_OK;
+    for (int t = first_target; t < Nt; ++t) {
+        int e = crw_lp_gather(lbls, key_frames + (int64_t)t * S, Ws + (int64_t)t * k * hw, Is + (int64_t)t * k * hw, hw, L, k, out_frame0 + t, stream);
+        if (e != CRW_OK) return e;
     }
-#ifdef CRW_SIM
-    for (int t = first_target; t < Nt; ++t) {            // the host simulator has no clusters: one launch per frame, same arithmetic
-        const int64_t total = (int64_t)hw * L;
-        const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-        CRW_LAUNCH(lp_gather_kernel, grid, 256, 0, stream, lbls, key_frames + (int64_t)t * S, Ws + (int64_t)t * k * hw,
-                   Is + (int64_t)t * k * hw, hw, L, k, out_frame0 + t);
-    }
-    return check_launch("lp_gather_all");
-#else
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kGatherCluster);
-    cfg.blockDim = dim3(kGatherThreads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kGatherCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, lp_gather_all_kernel, lbls, key_frames, Ws, Is, Nt, S, hw, L, k, first_target, out_frame0) != cudaSuccess) {
-        set_error("lp_gather_all: %s", cudaGetErrorString(cudaGetLastError()));
-        return CRW_ERR_CUDA;
-    }
-    return check_launch("lp_gather_all");
-#endif
+    return CRW_OK;
 }
 
 extern "C" int crw_lp_gather(float* lbls, const int64_t* key_frames_n, const float* Ws_n, const int64_t* Is_n,

@@ -533,6 +533,9 @@ struct LpRescoreArgs {
     unsigned* flags;             // (Nt*tiles) tile already listed
     int* list;                   // (Nt*tiles) work list
     int2* qlist;                 // (LP_QX_CAP) uncertified queries (target, position)
+    float* qpart_v;              // (LP_QX_CAP, QX_SPLIT, QX_K) partial winners of the per-query kernel
+    int* qpart_i;
+    unsigned* qticket;           // (LP_QX_CAP) CTAs of a query that have delivered
     int n_unres, restricted, R, r2i;
 };
 
@@ -540,7 +543,7 @@ constexpr int RS_WARPS = 4, RS_CH = 64, RS_LD = RS_CH + 4;
 // Few uncertified queries (distinct frames: ~1 in 10 000) are settled one by one by lp_exact_query_kernel, an exact-fp32
 // evaluation of ALL their admissible keys; only when more than LP_QX_CAP queries are open (replicated frames) is the
 // fp32-faithful tensor-core pass over whole tiles the cheaper way.  Both are always launched; the one out of its regime exits.
-constexpr int QX_WARPS = 8, QX_K = 12;
+constexpr int QX_WARPS = 8, QX_K = 12, QX_SPLIT = 8;      // CTAs per open query: each takes every 8th group of 256 keys
 
 template <int CHECK>
 __global__ void __launch_bounds__(32 * RS_WARPS) lp_rescore_kernel(LpRescoreArgs a) {
@@ -690,7 +693,9 @@ __global__ void __launch_bounds__(32 * QX_WARPS) lp_exact_query_kernel(LpRescore
     if (qcount > LP_QX_CAP) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int hw = a.h * a.w;
-    for (unsigned item = blockIdx.x; item < qcount; item += gridDim.x) {
+    __shared__ unsigned last_s;
+    for (unsigned work = blockIdx.x; work < qcount * QX_SPLIT; work += gridDim.x) {
+        const unsigned item = work / QX_SPLIT, part = work - item * QX_SPLIT;
         const int2 nq = a.qlist[item];
         const int n = nq.x, qpos = nq.y;
         const int qy = qpos / a.w, qx = qpos - qy * a.w;
@@ -719,7 +724,7 @@ __global__ void __launch_bounds__(32 * QX_WARPS) lp_exact_query_kernel(LpRescore
         int ti[QX_K];
 #pragma unroll
         for (int r = 0; r < QX_K; ++r) { tv[r] = -INFINITY; ti[r] = 0x7fffffff; }
-        for (int64_t base = (int64_t)warp * 32; base < total; base += QX_WARPS * 32) {
+        for (int64_t base = ((int64_t)part * QX_WARPS + warp) * 32; base < total; base += (int64_t)QX_SPLIT * QX_WARPS * 32) {
             const int64_t c = base + lane;
             const bool valid = c < total;
             int slot = 0, pos = 0;
@@ -793,16 +798,47 @@ __global__ void __launch_bounds__(32 * QX_WARPS) lp_exact_query_kernel(LpRescore
             if (tid == 0) { win_v[r] = bv; win_i[r] = bi; }
             __syncthreads();
         }
+        // deliver this CTA's k winners; the CTA that delivers last merges the QX_SPLIT partial lists (any delivery order gives
+        // the same result: the merge ranks by (score desc, index asc)) and writes the query's output
         if (tid == 0) {
-            const int64_t o = (int64_t)n * a.k * hw + qpos;
+            for (int r = 0; r < a.k; ++r) {
+                a.qpart_v[((size_t)item * QX_SPLIT + part) * QX_K + r] = win_v[r];
+                a.qpart_i[((size_t)item * QX_SPLIT + part) * QX_K + r] = win_i[r];
+            }
+            __threadfence();
+            last_s = atomicAdd(a.qticket + item, 1u) == QX_SPLIT - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (last_s && tid == 0) {
+            __threadfence();
+            const volatile float* pv = a.qpart_v + (size_t)item * QX_SPLIT * QX_K;
+            const volatile int* pi = a.qpart_i + (size_t)item * QX_SPLIT * QX_K;
+            int heads[QX_SPLIT];
+            for (int p2 = 0; p2 < QX_SPLIT; ++p2) heads[p2] = 0;
             float vals[QX_K];
+            int ids[QX_K];
+            for (int r = 0; r < a.k; ++r) {
+                float bv = -INFINITY;
+                int bi = 0x7fffffff, bp = 0;
+                for (int p2 = 0; p2 < QX_SPLIT; ++p2) {
+                    if (heads[p2] >= a.k) continue;
+                    const float v = pv[p2 * QX_K + heads[p2]];
+                    const int id = pi[p2 * QX_K + heads[p2]];
+                    if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; bp = p2; }
+                }
+                heads[bp]++;
+                vals[r] = bv;
+                ids[r] = bi;
+            }
+            const int64_t o = (int64_t)n * a.k * hw + qpos;
             float den = 0.f;
-            const float mxv = win_v[0];
-            for (int r = 0; r < a.k; ++r) { vals[r] = expf(win_v[r] - mxv); den += vals[r]; }
+            const float mxv = vals[0];
+            for (int r = 0; r < a.k; ++r) { vals[r] = expf(vals[r] - mxv); den += vals[r]; }
             for (int r = 0; r < a.k; ++r) {
                 a.Ws[o + (int64_t)r * hw] = vals[r] / den;
-                a.Is[o + (int64_t)r * hw] = win_i[r] == 0x7fffffff ? 0 : win_i[r];
+                a.Is[o + (int64_t)r * hw] = ids[r] == 0x7fffffff ? 0 : ids[r];
             }
+            a.qticket[item] = 0u;                             // ready for the next call
         }
     }
 }
@@ -833,7 +869,8 @@ size_t lp_tc_workspace_bytes(int Nf, int Nt, int h, int w, int C) {
     const size_t plane = align256((size_t)Nf * h * w * C * 2);
     const size_t sl = align256((size_t)Nt * h * w * LP_SHORT * 4);
     const size_t tl = align256((size_t)Nt * lp_tiles(h, w) * 4);
-    return HDR_BYTES + 2 * plane + 2 * sl + 2 * tl + align256(LP_QX_CAP * sizeof(int2));
+    return HDR_BYTES + 2 * plane + 2 * sl + 2 * tl + align256(LP_QX_CAP * sizeof(int2)) + 2 * align256((size_t)LP_QX_CAP * QX_SPLIT * QX_K * 4) +
+           align256(LP_QX_CAP * 4);
 }
 
 bool lp_tc_supported(int C, int k, float radius, int R, bool dense) {
@@ -879,7 +916,13 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
     int* short_i = (int*)(ws + HDR_BYTES + 2 * plane + sl);
     unsigned* flags = (unsigned*)(ws + HDR_BYTES + 2 * plane + 2 * sl);
     int* list = (int*)(ws + HDR_BYTES + 2 * plane + 2 * sl + tl);
-    int2* qlist = (int2*)(ws + HDR_BYTES + 2 * plane + 2 * sl + 2 * tl);
+    unsigned char* qbase = ws + HDR_BYTES + 2 * plane + 2 * sl + 2 * tl;
+    int2* qlist = (int2*)qbase;
+    const size_t qp = align256((size_t)LP_QX_CAP * QX_SPLIT * QX_K * 4);
+    float* qpart_v = (float*)(qbase + align256(LP_QX_CAP * sizeof(int2)));
+    int* qpart_i = (int*)(qbase + align256(LP_QX_CAP * sizeof(int2)) + qp);
+    unsigned* qticket = (unsigned*)(qbase + align256(LP_QX_CAP * sizeof(int2)) + 2 * qp);
+    cudaMemsetAsync(qticket, 0, LP_QX_CAP * 4, st);
     cudaMemsetAsync(hdr, 0, HDR_BYTES, st);
     cudaMemsetAsync(flags, 0, (size_t)a0.Nt * tiles * 4, st);
     const int64_t rows = (int64_t)Nf * hw;
@@ -900,7 +943,7 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
     LpRescoreArgs r{};
     r.feats = feats; r.key_frames = a.key_frames; r.query_frames = a.query_frames; r.short_v = short_v; r.short_i = short_i;
     r.Nt = a.Nt; r.S = a.S; r.h = a.h; r.w = a.w; r.C = C; r.k = a.k; r.tau = a.tau; r.Ws = a.Ws; r.Is = a.Is;
-    r.hdr = hdr; r.flags = flags; r.list = list; r.qlist = qlist;
+    r.hdr = hdr; r.flags = flags; r.list = list; r.qlist = qlist; r.qpart_v = qpart_v; r.qpart_i = qpart_i; r.qticket = qticket;
     r.n_unres = a.restricted ? a.n_long : a.S; r.restricted = a.restricted; r.R = a.R; r.r2i = a.r2i;
     const bool pre = !(a.flags & CRW_LP_EXACT_ONLY);
     if (pre) {
@@ -916,7 +959,7 @@ int launch_lp_tc(const float* feats, int Nf, const LpTcArgs& a0, void* workspace
         {   // few open queries: exact fp32, one CTA each
             const size_t qsm = sizeof(float) * ((size_t)QX_WARPS * 32 * RS_LD + C + 32 * QX_WARPS * QX_K) + sizeof(int) * 32 * QX_WARPS * QX_K;
             cudaFuncSetAttribute(lp_exact_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm);
-            lp_exact_query_kernel<<<148 * 2, 32 * QX_WARPS, qsm, st>>>(r);
+            lp_exact_query_kernel<<<148 * 4, 32 * QX_WARPS, qsm, st>>>(r);
             e = check_launch("lp_exact_query");
             if (e != CRW_OK) return e;
         }
