@@ -207,7 +207,7 @@ class HotPath:
     parts >= 2: pipeline.PatchWalkPipeline - the clips split into micro-batches on staggered streams so that the HBM-bound pooling
     of one micro-batch runs beside the latency-bound walk of another (pooling confined to `pool_sms` SMs)."""
 
-    def __init__(self, dev, rank, use_graph=True, parts=1, pool_sms=0, sizes=None):
+    def __init__(self, dev, rank, use_graph=True, parts=1, pool_sms=0, sizes=None, head_splits=1, walk_flags=0):
         from sapienza_video_contrastive_b200 import ops
         from sapienza_video_contrastive_b200.pipeline import PatchWalkPipeline
         self.ops, self.dev = ops, dev
@@ -233,7 +233,7 @@ class HotPath:
         else:
             self.maps_parts = self._split(self.maps, clone=True)
             self.pipe = PatchWalkPipeline(self.head.weight, c["B"], c["N"], c["T"], c["tau"], c["p"], pool_sms=pool_sms, seed=123,
-                                          device=dev, sizes=self.sizes)
+                                          device=dev, sizes=self.sizes, head_splits=head_splits, walk_flags=walk_flags)
             self.gmaps, self.ghead = None, None
 
     def _split(self, maps, clone=False):
@@ -291,9 +291,35 @@ class HotPath:
                 self._step_eager()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._static_loss = self._step_eager()
+        # Capture, then check the instantiated graph: with several concurrent branches the same capture occasionally comes up in a
+        # slow mode (measured: ~0.35 instead of 0.25 ms per replay for one instantiation in five with 5 micro-batches on 108 SMs,
+        # profiles/r02_split_sweep.jsonl) - the branch-to-hardware-queue assignment differs between instantiations.  Keep the best
+        # of up to four instantiations (all outside the timed region).
+        best, seen = None, []
+        for attempt in range(4 if self.pipe is not None else 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._step_eager()
+            torch.cuda.synchronize()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            seen.append(ms)
+            if best is None or ms < best[0]:
+                best = (ms, g, loss)
+            two = sorted(seen)[:2]
+            if len(two) == 2 and two[1] <= 1.05 * two[0]:
+                break                                   # two instantiations agree on the fast mode
+        self.capture_trials = seen
+        self.graph, self._static_loss = best[1], best[2]
+        self.capture_ms = best[0]
         torch.cuda.synchronize()
 
     def step(self):
@@ -668,7 +694,7 @@ def run_ours(args, rank, world, local_rank):
     sizes = [int(x) for x in args.part_sizes.split(",")] if args.part_sizes else None
     if sizes is None and args.parts == 1:
         args.pool_sms = 0
-    hp = HotPath(dev, rank, use_graph=not args.eager, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes)
+    hp = HotPath(dev, rank, use_graph=not args.eager, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes, head_splits=args.head_splits)
     hp.prepare()
     grads = torch.zeros(RESNET18_GRAD_FLOATS, device=dev) if world > 1 else None
     pending = []
@@ -706,7 +732,7 @@ def run_ours(args, rank, world, local_rank):
     h2d = host[0].numel() * 4
     d2h = 4 + ghead_host.numel() * 4
 
-    e2e = HotPath(dev, rank, use_graph=False, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes)      # same operators, eager, on uploaded inputs
+    e2e = HotPath(dev, rank, use_graph=False, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes, head_splits=args.head_splits)   # same operators, eager, on uploaded inputs
     e2e.head = hp.head
 
     def e2e_loop(n):
@@ -762,7 +788,7 @@ def run_ours(args, rank, world, local_rank):
     out = {"metric": "crw_walk_fwd_bwd_clips_per_s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-           "launch": "eager" if args.eager else "cuda_graph", "parts": hp.sizes or [c["B"]], "pool_sms": args.pool_sms, "schedule": step_desc,
+           "launch": "eager" if args.eager else "cuda_graph", "parts": hp.sizes or [c["B"]], "pool_sms": args.pool_sms, "schedule": step_desc, "graph_instantiations_ms": getattr(hp, "capture_trials", None),
            "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": n_e2e,
                    "ms_timed": ms_e2e,
@@ -815,9 +841,10 @@ def main():
     ap.add_argument("--no-lp", action="store_true", help="skip the label-propagation leg")
     ap.add_argument("--no-extras", action="store_true", help="headline line only (no label_prop / superpixel / sweep / baselines on the GPU)")
     ap.add_argument("--parts", type=int, default=1, help="with --part-sizes '': equal micro-batches per step (1 = one chain of autograd operators)")
-    ap.add_argument("--part-sizes", default="5,5,5,5", help="clips per micro-batch on staggered streams (pipeline.PatchWalkPipeline), must add up to "
+    ap.add_argument("--head-splits", type=int, default=4, help="split-K slices of the head forward GEMM of a micro-batch")
+    ap.add_argument("--part-sizes", default="4,4,4,4,4", help="clips per micro-batch on staggered streams (pipeline.PatchWalkPipeline), must add up to "
                                                            "20; '' = use --parts.  Default: the best of the measured sweep (profiles/r02_split_sweep.jsonl)")
-    ap.add_argument("--pool-sms", type=int, default=108, help="SMs the pooling kernels are confined to while micro-batches overlap (0 = all)")
+    ap.add_argument("--pool-sms", type=int, default=100, help="SMs the pooling kernels are confined to while micro-batches overlap (0 = all)")
     ap.add_argument("--nccl-ctas", type=int, default=16, help="NCCL_MAX_CTAS for the gradient all-reduce (several GPUs)")
     ap.add_argument("--e2e-module", action="store_true", help="also time CRW(args)(x) with the ResNet-18 (DDP when several GPUs)")
     args = ap.parse_args()

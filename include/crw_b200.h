@@ -168,6 +168,11 @@ int crw_head_wgrad(const float* grad_out, const float* x, float* dW, int64_t R, 
 /* dW = beta * dW + alpha * grad_out^T x: accumulation of micro-batch contributions (pipeline.py) without a separate pass. */
 int crw_head_wgrad_axpby(const float* grad_out, const float* x, float* dW, int64_t R, int D, int C, float alpha, float beta,
                          void* workspace, size_t workspace_bytes, crw_stream_t stream);
+/* Head forward with the K = C contraction split into `splits` slices (a batched product into the workspace, summed in fixed
+ * order): for micro-batches whose few row tiles would otherwise run one long serial K loop each.  splits <= 1 = crw_head_fwd. */
+size_t crw_head_fwd_splitk_workspace_bytes(int64_t R, int D, int splits);
+int crw_head_fwd_splitk(const float* x, const float* weight, float* out, int64_t R, int D, int C, int splits, void* workspace,
+                        size_t workspace_bytes, unsigned* err_word, crw_stream_t stream);
 
 /* L2 normalisation of rows (F.normalize, eps 1e-12; model.py:118,329): q = f / max(|f|, eps).  inv_norm and norm
  * (rows each) are kept for the backward, which overwrites grad in place: g <- (g - q (q.g)) * inv_norm. */

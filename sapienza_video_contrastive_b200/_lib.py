@@ -75,6 +75,8 @@ _SIGNATURES = {
     "crw_head_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "crw_head_wgrad_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "crw_patch_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "crw_head_fwd_splitk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "crw_head_fwd_splitk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "crw_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "crw_lp_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -841,6 +841,32 @@ extern "C" int crw_head_fwd(const float* x, const float* weight, float* out, int
     return gemm_tf32_run(c, err_word, stream);
 }
 
+// Split-K variant for short row counts (a micro-batch of 5 clips is 980 rows = 8 row tiles: one K loop of 16 chunks per CTA is a
+// 20 us latency chain): `splits` slices of K = C / splits channels as a batched product into the workspace, summed in fixed order.
+extern "C" size_t crw_head_fwd_splitk_workspace_bytes(int64_t R, int D, int splits) { return sizeof(float) * (size_t)R * D * (splits > 1 ? splits : 1) + 256; }
+
+extern "C" int crw_head_fwd_splitk(const float* x, const float* weight, float* out, int64_t R, int D, int C, int splits, void* workspace,
+                                   size_t workspace_bytes, unsigned* err_word, crw_stream_t stream) {
+    if (R <= 0 || D <= 0 || C <= 0 || R > 0x7fffffff) { set_error("head_fwd: bad shape"); return CRW_ERR_SHAPE; }
+    if (splits <= 1) return crw_head_fwd(x, weight, out, R, D, C, err_word, stream);
+    if (C % splits != 0 || !workspace || workspace_bytes < crw_head_fwd_splitk_workspace_bytes(R, D, splits)) {
+        set_error("head_fwd_splitk: C %% splits != 0 or workspace too small");
+        return CRW_ERR_SHAPE;
+    }
+    const int Ks = C / splits;
+    const int64_t n = R * D;
+    TcGemmCall c{};
+    c.ngroups = 1; c.nterms = 1; c.K[0] = Ks; c.M = (int)R; c.N = D; c.nb = splits; c.nj = 1;
+    c.grp[0].A[0] = TcOperand{x, Ks, 0, C, 1};                       // slice z: channels [z Ks, (z+1) Ks) of x (R, C)
+    c.grp[0].B[0] = TcOperand{weight, Ks, 0, 1, C};                  // B(k, d) = weight[d * C + z Ks + k]
+    c.grp[0].C = (float*)workspace; c.grp[0].csb = n; c.grp[0].csj = 0; c.grp[0].ldc = D; c.grp[0].accumulate = 0;
+    if (!gemm_tf32_eligible(c)) { set_error("head_fwd_splitk: shape not addressable by the tensor-core path"); return CRW_ERR_UNSUPPORTED; }
+    int e = gemm_tf32_run(c, err_word, stream);
+    if (e != CRW_OK) return e;
+    CRW_LAUNCH(splitk_reduce_kernel, (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8), 256, 0, stream, (const float*)workspace, out, n, splits, 1.0f, 0.0f);
+    return check_launch("head_fwd_splitk_reduce");
+}
+
 extern "C" int crw_head_dgrad(const float* grad_out, const float* weight, float* grad_x, int64_t R, int D, int C, unsigned* err_word,
                               crw_stream_t stream) {
     if (R <= 0 || D <= 0 || C <= 0 || R > 0x7fffffff) { set_error("head_dgrad: bad shape"); return CRW_ERR_SHAPE; }

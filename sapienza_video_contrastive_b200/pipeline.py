@@ -34,7 +34,8 @@ from . import _lib, ops
 
 class PatchWalkPipeline:
     def __init__(self, head_weight: torch.Tensor, clips: int, nodes: int, frames: int, temperature: float, dropout: float,
-                 n_parts: int = 2, pool_sms: int = 0, seed: int = 123, device=None, sizes: Optional[Sequence[int]] = None):
+                 n_parts: int = 2, pool_sms: int = 0, seed: int = 123, device=None, sizes: Optional[Sequence[int]] = None,
+                 head_splits: int = 1, walk_flags: int = 0):
         if sizes is None:
             if clips % n_parts:
                 raise ValueError("clips (%d) must divide evenly into %d micro-batches (or pass `sizes`)" % (clips, n_parts))
@@ -45,6 +46,8 @@ class PatchWalkPipeline:
         self.w = head_weight
         self.B, self.N, self.T, self.tau, self.p = clips, nodes, frames, float(temperature), float(dropout)
         self.sizes, self.n_parts, self.pool_sms = sizes, len(sizes), int(pool_sms)
+        self.head_splits = int(head_splits)
+        self.walk_flags = int(walk_flags)               # e.g. _lib.WALK_NO_CLUSTER: one CTA per clip for the chain instead of a 4-CTA cluster
         dev = torch.device(device if device is not None else head_weight.device)
         ops.check_device(dev)
         self.dev = dev
@@ -66,12 +69,14 @@ class PatchWalkPipeline:
         self.buf = []
         for b in sizes:
             R = b * nodes * frames
-            wsb = L.crw_walk_workspace_bytes(b, nodes, frames, D, 0)
+            wsb = L.crw_walk_workspace_bytes(b, nodes, frames, D, self.walk_flags)
             wgb = L.crw_head_wgrad_workspace_bytes(R, D, C)
+            hfb = L.crw_head_fwd_splitk_workspace_bytes(R, D, self.head_splits)
             self.buf.append(dict(
                 R=R, pooled=torch.empty(R, C, **f32), f=torch.empty(R, D, **f32), q=torch.empty(R, D, **f32),
                 gf=torch.empty(R, D, **f32), gpooled=torch.empty(R, C, **f32),
                 ws=torch.zeros(max(wsb, 256), dtype=torch.uint8, device=dev), wgws=torch.zeros(max(wgb, 256), dtype=torch.uint8, device=dev),
+                hfws=torch.zeros(max(hfb, 256), dtype=torch.uint8, device=dev),
                 thr=ops.torch_rand_threads(b * nodes * nodes, dev), gmaps=None))
 
     def step(self, parts: Sequence[torch.Tensor]):
@@ -106,9 +111,10 @@ class PatchWalkPipeline:
             L.check(L.crw_pool_patch_fwd_sm(m.data_ptr(), bf["pooled"].data_ptr(), R * self.C, hw, self.pool_sms, st), "pool_patch_fwd")
             prev_pool = torch.cuda.Event()
             prev_pool.record(s)
-            L.check(L.crw_head_fwd(bf["pooled"].data_ptr(), w.data_ptr(), bf["f"].data_ptr(), R, self.D, self.C, self.err.data_ptr(), st), "head_fwd")
+            L.check(L.crw_head_fwd_splitk(bf["pooled"].data_ptr(), w.data_ptr(), bf["f"].data_ptr(), R, self.D, self.C, self.head_splits,
+                                          bf["hfws"].data_ptr(), bf["hfws"].numel(), self.err.data_ptr(), st), "head_fwd")
             L.check(L.crw_walk_fwd_bwd(bf["f"].data_ptr(), b, self.N, self.T, self.D, self.tau, self.p, None, None, 0, 0, bf["thr"],
-                                       self.rng_states[i].data_ptr() if self.p > 0 else None, 0, bf["q"].data_ptr(),
+                                       self.rng_states[i].data_ptr() if self.p > 0 else None, self.walk_flags, bf["q"].data_ptr(),
                                        self.xent[i].data_ptr(), self.acc[i].data_ptr(), bf["gf"].data_ptr(), bf["ws"].data_ptr(),
                                        bf["ws"].numel(), st), "walk_fwd_bwd")
             fork = torch.cuda.Event()

@@ -155,8 +155,8 @@ def test_label_prop_davis_shape_tensor_core_vs_oracle(ops):
     assert int(bad.sum()) <= 50 * len(where), (int(bad.sum()), len(where))
 
 
-@pytest.mark.parametrize("sizes,pool_sms", [(None, 0), ([5, 5, 5, 5], 108), ([13, 7], 108)])
-def test_bench_hot_path_graph_replay_matches_oracle(ops, sizes, pool_sms):
+@pytest.mark.parametrize("sizes,pool_sms,head_splits", [(None, 0, 1), ([4, 4, 4, 4, 4], 100, 4), ([5, 5, 5, 5], 108, 1), ([13, 7], 108, 2)])
+def test_bench_hot_path_graph_replay_matches_oracle(ops, sizes, pool_sms, head_splits):
     """the configuration bench.py times - rng='device', the whole step replayed as a CUDA graph, chain on
     4-CTA clusters, weight gradient on a side stream; by default the stream-staggered micro-batch pipeline (pipeline.py) - against
     the oracle (model.py:92-123, 366-413) on the WHOLE 20-clip batch, fed with the Philox draws the device-side generator states
@@ -165,7 +165,8 @@ def test_bench_hot_path_graph_replay_matches_oracle(ops, sizes, pool_sms):
     import bench
     ops.set_async_wgrad(True)
     try:
-        hp = bench.HotPath(torch.device(DEV, torch.cuda.current_device()), 0, use_graph=True, sizes=sizes, pool_sms=pool_sms)
+        hp = bench.HotPath(torch.device(DEV, torch.cuda.current_device()), 0, use_graph=True, sizes=sizes, pool_sms=pool_sms,
+                           head_splits=head_splits)
         hp.prepare()
         assert hp.graph is not None
         c = bench.CFG

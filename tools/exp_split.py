@@ -26,17 +26,14 @@ for sms in (0,):
     print(json.dumps({"pool_sms": sms, "fwd_us": f * 1e3, "fwd_gbs": gb / f, "bwd_us": b * 1e3, "bwd_gbs": gb / b}), flush=True)
 del maps, pooled
 torch.cuda.empty_cache()
-configs = [(None, 0), ([20], 0), ([10, 10], 108), ([4, 4, 4, 4, 4], 116), ([5, 5, 5, 5], 116), ([5, 5, 4, 3, 3], 112), ([6, 5, 4, 3, 2], 112), ([13, 7], 108), ([14, 6], 116), ([8, 8, 4], 108), ([8, 8, 4], 116), ([6, 6, 6, 2], 108),
-           ([6, 6, 4, 4], 116), ([5, 5, 5, 5], 108), ([4, 4, 4, 4, 4], 108), ([6, 6, 4, 2, 2], 116), ([4, 4, 4, 4, 2, 2], 120), ([8, 8, 4], 0),
-           ([8, 8, 4], 128), ([8, 8, 4], 96)]
-for sizes, sms in configs:
-    try:
-        hp = bench.HotPath(dev, 0, use_graph=True, parts=1, pool_sms=sms, sizes=sizes)
+configs = [([4] * 5, 100, 4, 0), ([4] * 5, 108, 4, 0), ([5] * 4, 100, 1, 0), ([5] * 4, 108, 1, 0), ([4] * 5, 108, 4, 32), ([5] * 4, 108, 2, 32), ([4] * 5, 92, 4, 0)]
+for sizes, sms, hs, wf in configs:
+    res = []
+    for trial in range(6):
+        hp = bench.HotPath(dev, 0, use_graph=True, parts=1, pool_sms=sms, sizes=sizes, head_splits=hs, walk_flags=wf)
         hp.prepare()
-        ms, n, tot = bench.timed_median(hp.step)
-        print(json.dumps({"sizes": sizes, "pool_sms": sms, "ms_per_step": ms, "clips_per_s": c["B"] / ms * 1e3, "steps": n,
-                          "loss": (hp.step(), hp.loss_value())[1]}), flush=True)
+        ms, n, tot = bench.timed_median(hp.step, min_ms=30.0)
+        res.append(round(ms, 4))
         del hp
         torch.cuda.empty_cache()
-    except Exception as e:
-        print(json.dumps({"sizes": sizes, "pool_sms": sms, "error": repr(e)[:300]}), flush=True)
+    print(json.dumps({"sizes": sizes, "pool_sms": sms, "head_splits": hs, "walk_flags": wf, "ms_per_step_trials": res}), flush=True)

@@ -24,7 +24,8 @@ if a.lp:
 else:
     from sapienza_video_contrastive_b200 import ops
     ops.set_async_wgrad(True)
-    hp = bench.HotPath(dev, 0, use_graph=False, sizes=None if a.chain else [5, 5, 5, 5], pool_sms=0 if a.chain else 108)
+    hp = bench.HotPath(dev, 0, use_graph=False, sizes=None if a.chain else [4, 4, 4, 4, 4], pool_sms=0 if a.chain else 100,
+                       head_splits=1 if a.chain else 4)
     for _ in range(a.steps):
         hp.step()
     torch.cuda.synchronize()
