@@ -207,7 +207,7 @@ class HotPath:
     parts >= 2: pipeline.PatchWalkPipeline - the clips split into micro-batches on staggered streams so that the HBM-bound pooling
     of one micro-batch runs beside the latency-bound walk of another (pooling confined to `pool_sms` SMs)."""
 
-    def __init__(self, dev, rank, use_graph=True, parts=1, pool_sms=0, sizes=None, head_splits=1, walk_flags=0):
+    def __init__(self, dev, rank, use_graph=True, parts=1, pool_sms=0, sizes=None, head_splits=1, walk_flags=0, pool_sms_bwd=None):
         from sapienza_video_contrastive_b200 import ops
         from sapienza_video_contrastive_b200.pipeline import PatchWalkPipeline
         self.ops, self.dev = ops, dev
@@ -233,7 +233,7 @@ class HotPath:
         else:
             self.maps_parts = self._split(self.maps, clone=True)
             self.pipe = PatchWalkPipeline(self.head.weight, c["B"], c["N"], c["T"], c["tau"], c["p"], pool_sms=pool_sms, seed=123,
-                                          device=dev, sizes=self.sizes, head_splits=head_splits, walk_flags=walk_flags)
+                                          device=dev, sizes=self.sizes, head_splits=head_splits, walk_flags=walk_flags, pool_sms_bwd=pool_sms_bwd)
             self.gmaps, self.ghead = None, None
 
     def _split(self, maps, clone=False):
@@ -361,7 +361,7 @@ def time_gpu_steps(fn, steps, warmup, world, after=None, finish=None):
     return ms
 
 
-def kernel_roofline(dev, clips=None, sms=0):
+def kernel_roofline(dev, clips=None, sms=0, sms_bwd=0):
     """The dominant kernels of the step are the two HBM streams over the 514 MB of maps, launched per micro-batch of `clips`
     clips on `sms` SMs (0 = all) exactly as the step launches them.  Timed live, alone, with CUDA events on the launching stream
     (>= 50 ms each), cycling over as many distinct micro-batch buffers as the step has (together > L2, so every launch finds its
@@ -385,25 +385,45 @@ def kernel_roofline(dev, clips=None, sms=0):
 
     def bwd():
         i[0] = (i[0] + 1) % nbuf
-        L.crw_pool_patch_bwd_sm(pooled.data_ptr(), gms[i[0]].data_ptr(), rows, hw, sms, st)
+        L.crw_pool_patch_bwd_sm(pooled.data_ptr(), gms[i[0]].data_ptr(), rows, hw, sms_bwd, st)
 
     for name, fn in (("pool_patch_fwd", fwd), ("pool_patch_bwd", bwd)):
         for _ in range(2 * nbuf):
             fn()
         torch.cuda.synchronize()
+        # the launches are replayed from a CUDA graph, as in the step (no host launch gaps between 20-us kernels)
+        per_graph = 4 * nbuf
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            st_side = side.cuda_stream
+            if name == "pool_patch_fwd":
+                launch = lambda j: L.crw_pool_patch_fwd_sm(maps[j % nbuf].data_ptr(), pooled.data_ptr(), rows, hw, sms, st_side)
+            else:
+                launch = lambda j: L.crw_pool_patch_bwd_sm(pooled.data_ptr(), gms[j % nbuf].data_ptr(), rows, hw, sms_bwd, st_side)
+            launch(0)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                st_side = torch.cuda.current_stream().cuda_stream
+                for j in range(per_graph):
+                    launch(j)
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
         n, total = 0, 0.0
         while total < MIN_MS:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(4 * nbuf):
-                fn()
+            graph.replay()
             e1.record()
             torch.cuda.synchronize()
             total += e0.elapsed_time(e1)
-            n += 4 * nbuf
+            n += per_graph
         ms = total / n
         bytes_alg = rows * hw * 4 + rows * 4
-        res[name] = {"us": ms * 1e3, "launches_timed": n, "clips_per_launch": clips, "sms": sms or 148, "buffers": nbuf,
+        res[name] = {"us": ms * 1e3, "launches_timed": n, "clips_per_launch": clips,
+                     "sms": (sms if name == "pool_patch_fwd" else sms_bwd) or 148, "buffers": nbuf,
                      "algorithmic_bytes": bytes_alg, "gbs": bytes_alg / ms / 1e6}
     return res
 
@@ -693,8 +713,9 @@ def run_ours(args, rank, world, local_rank):
     ops.set_async_wgrad(True)
     sizes = [int(x) for x in args.part_sizes.split(",")] if args.part_sizes else None
     if sizes is None and args.parts == 1:
-        args.pool_sms = 0
-    hp = HotPath(dev, rank, use_graph=not args.eager, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes, head_splits=args.head_splits)
+        args.pool_sms = args.pool_sms_bwd = 0
+    hp = HotPath(dev, rank, use_graph=not args.eager, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes, head_splits=args.head_splits,
+                 pool_sms_bwd=args.pool_sms_bwd)
     hp.prepare()
     grads = torch.zeros(RESNET18_GRAD_FLOATS, device=dev) if world > 1 else None
     pending = []
@@ -732,7 +753,8 @@ def run_ours(args, rank, world, local_rank):
     h2d = host[0].numel() * 4
     d2h = 4 + ghead_host.numel() * 4
 
-    e2e = HotPath(dev, rank, use_graph=False, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes, head_splits=args.head_splits)   # same operators, eager, on uploaded inputs
+    e2e = HotPath(dev, rank, use_graph=False, parts=args.parts, pool_sms=args.pool_sms, sizes=sizes, head_splits=args.head_splits,
+                  pool_sms_bwd=args.pool_sms_bwd)   # same operators, eager, on uploaded inputs
     e2e.head = hp.head
 
     def e2e_loop(n):
@@ -779,7 +801,8 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     hbm, tf, src = peaks()
-    kr = kernel_roofline(dev, clips=max(hp.sizes) if hp.pipe is not None else None, sms=args.pool_sms if hp.pipe is not None else 0)
+    kr = kernel_roofline(dev, clips=max(hp.sizes) if hp.pipe is not None else None, sms=args.pool_sms if hp.pipe is not None else 0,
+                         sms_bwd=args.pool_sms_bwd if hp.pipe is not None else 0)
     dom = max(kr, key=lambda k: kr[k]["us"])
     traffic, traffic_src = ncu_traffic(dom)
     n_ours, n_other, knames = count_kernels(hp._step_eager)
@@ -788,7 +811,7 @@ def run_ours(args, rank, world, local_rank):
     out = {"metric": "crw_walk_fwd_bwd_clips_per_s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-           "launch": "eager" if args.eager else "cuda_graph", "parts": hp.sizes or [c["B"]], "pool_sms": args.pool_sms, "schedule": step_desc, "graph_instantiations_ms": getattr(hp, "capture_trials", None),
+           "launch": "eager" if args.eager else "cuda_graph", "parts": hp.sizes or [c["B"]], "pool_sms": args.pool_sms, "pool_sms_bwd": args.pool_sms_bwd, "schedule": step_desc, "graph_instantiations_ms": getattr(hp, "capture_trials", None),
            "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": n_e2e,
                    "ms_timed": ms_e2e,
@@ -844,6 +867,7 @@ def main():
     ap.add_argument("--head-splits", type=int, default=4, help="split-K slices of the head forward GEMM of a micro-batch")
     ap.add_argument("--part-sizes", default="4,4,4,4,4", help="clips per micro-batch on staggered streams (pipeline.PatchWalkPipeline), must add up to "
                                                            "20; '' = use --parts.  Default: the best of the measured sweep (profiles/r02_split_sweep.jsonl)")
+    ap.add_argument("--pool-sms-bwd", type=int, default=0, help="SMs of the pooling BACKWARD kernels (store-bound: 0 = all SMs measured best)")
     ap.add_argument("--pool-sms", type=int, default=100, help="SMs the pooling kernels are confined to while micro-batches overlap (0 = all)")
     ap.add_argument("--nccl-ctas", type=int, default=16, help="NCCL_MAX_CTAS for the gradient all-reduce (several GPUs)")
     ap.add_argument("--e2e-module", action="store_true", help="also time CRW(args)(x) with the ResNet-18 (DDP when several GPUs)")

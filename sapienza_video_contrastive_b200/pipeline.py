@@ -35,7 +35,7 @@ from . import _lib, ops
 class PatchWalkPipeline:
     def __init__(self, head_weight: torch.Tensor, clips: int, nodes: int, frames: int, temperature: float, dropout: float,
                  n_parts: int = 2, pool_sms: int = 0, seed: int = 123, device=None, sizes: Optional[Sequence[int]] = None,
-                 head_splits: int = 1, walk_flags: int = 0):
+                 head_splits: int = 1, walk_flags: int = 0, pool_sms_bwd: Optional[int] = None):
         if sizes is None:
             if clips % n_parts:
                 raise ValueError("clips (%d) must divide evenly into %d micro-batches (or pass `sizes`)" % (clips, n_parts))
@@ -47,6 +47,7 @@ class PatchWalkPipeline:
         self.B, self.N, self.T, self.tau, self.p = clips, nodes, frames, float(temperature), float(dropout)
         self.sizes, self.n_parts, self.pool_sms = sizes, len(sizes), int(pool_sms)
         self.head_splits = int(head_splits)
+        self.pool_sms_bwd = self.pool_sms if pool_sms_bwd is None else int(pool_sms_bwd)   # the store-bound backward wants more SMs
         self.walk_flags = int(walk_flags)               # e.g. _lib.WALK_NO_CLUSTER: one CTA per clip for the chain instead of a 4-CTA cluster
         dev = torch.device(device if device is not None else head_weight.device)
         ops.check_device(dev)
@@ -124,7 +125,7 @@ class PatchWalkPipeline:
                                            b / self.B, 0.0 if i == 0 else 1.0, bf["wgws"].data_ptr(), bf["wgws"].numel(), sd.cuda_stream),
                     "head_wgrad")
             L.check(L.crw_head_dgrad(bf["gf"].data_ptr(), w.data_ptr(), bf["gpooled"].data_ptr(), R, self.D, self.C, self.err.data_ptr(), st), "head_dgrad")
-            L.check(L.crw_pool_patch_bwd_scaled(bf["gpooled"].data_ptr(), bf["gmaps"].data_ptr(), R * self.C, hw, b / self.B, self.pool_sms, st),
+            L.check(L.crw_pool_patch_bwd_scaled(bf["gpooled"].data_ptr(), bf["gmaps"].data_ptr(), R * self.C, hw, b / self.B, self.pool_sms_bwd, st),
                     "pool_patch_bwd")
         for s in self.streams[1:]:
             cur.wait_stream(s)

@@ -166,7 +166,7 @@ def test_bench_hot_path_graph_replay_matches_oracle(ops, sizes, pool_sms, head_s
     ops.set_async_wgrad(True)
     try:
         hp = bench.HotPath(torch.device(DEV, torch.cuda.current_device()), 0, use_graph=True, sizes=sizes, pool_sms=pool_sms,
-                           head_splits=head_splits)
+                           head_splits=head_splits, pool_sms_bwd=0 if head_splits == 4 else None)
         hp.prepare()
         assert hp.graph is not None
         c = bench.CFG

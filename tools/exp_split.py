@@ -26,14 +26,14 @@ for sms in (0,):
     print(json.dumps({"pool_sms": sms, "fwd_us": f * 1e3, "fwd_gbs": gb / f, "bwd_us": b * 1e3, "bwd_gbs": gb / b}), flush=True)
 del maps, pooled
 torch.cuda.empty_cache()
-configs = [([4] * 5, 100, 4, 0), ([4] * 5, 108, 4, 0), ([5] * 4, 100, 1, 0), ([5] * 4, 108, 1, 0), ([4] * 5, 108, 4, 32), ([5] * 4, 108, 2, 32), ([4] * 5, 92, 4, 0)]
-for sizes, sms, hs, wf in configs:
+configs = [([4] * 5, 100, 4, 100), ([4] * 5, 100, 4, 116), ([4] * 5, 100, 4, 132), ([4] * 5, 100, 4, 0), ([4] * 5, 108, 4, 124), ([5] * 4, 100, 4, 124), ([4] * 5, 92, 4, 124)]
+for sizes, sms, hs, sb in configs:
     res = []
-    for trial in range(6):
-        hp = bench.HotPath(dev, 0, use_graph=True, parts=1, pool_sms=sms, sizes=sizes, head_splits=hs, walk_flags=wf)
+    for trial in range(4):
+        hp = bench.HotPath(dev, 0, use_graph=True, parts=1, pool_sms=sms, sizes=sizes, head_splits=hs, pool_sms_bwd=sb)
         hp.prepare()
         ms, n, tot = bench.timed_median(hp.step, min_ms=30.0)
         res.append(round(ms, 4))
         del hp
         torch.cuda.empty_cache()
-    print(json.dumps({"sizes": sizes, "pool_sms": sms, "head_splits": hs, "walk_flags": wf, "ms_per_step_trials": res}), flush=True)
+    print(json.dumps({"sizes": sizes, "pool_sms": sms, "head_splits": hs, "pool_sms_bwd": sb, "ms_per_step_trials": res}), flush=True)

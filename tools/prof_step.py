@@ -25,7 +25,7 @@ else:
     from sapienza_video_contrastive_b200 import ops
     ops.set_async_wgrad(True)
     hp = bench.HotPath(dev, 0, use_graph=False, sizes=None if a.chain else [4, 4, 4, 4, 4], pool_sms=0 if a.chain else 100,
-                       head_splits=1 if a.chain else 4)
+                       head_splits=1 if a.chain else 4, pool_sms_bwd=0)
     for _ in range(a.steps):
         hp.step()
     torch.cuda.synchronize()
