@@ -430,10 +430,16 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 // lower index, so it must get in - nextafter turns ">=" into the single ">" the mask loop evaluates)
                 thr = fmaxf(thr, nextafterf(*thr_other, -INFINITY));
                 // candidate mask: bit j = sign(thr - score_j), shifted in from the top column down (two instructions per key)
-                unsigned cm = 0u;
+                // (four independent 8-bit chains: one 32-long chain of dependent shifts stalled the two warps of a scheduler)
+                unsigned c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
 #pragma unroll
-                for (int j = 31; j >= 0; --j) cm = __funnelshift_l(__float_as_uint(thr - sv[j]), cm, 1);
-                cm &= adm;
+                for (int j = 7; j >= 0; --j) {
+                    c0 = __funnelshift_l(__float_as_uint(thr - sv[j]), c0, 1);
+                    c1 = __funnelshift_l(__float_as_uint(thr - sv[8 + j]), c1, 1);
+                    c2 = __funnelshift_l(__float_as_uint(thr - sv[16 + j]), c2, 1);
+                    c3 = __funnelshift_l(__float_as_uint(thr - sv[24 + j]), c3, 1);
+                }
+                unsigned cm = (c0 | (c1 << 8) | (c2 << 16) | (c3 << 24)) & adm;
                 if (__any_sync(kFull, cm != 0u)) {
                     __syncwarp();
 #pragma unroll
