@@ -280,6 +280,22 @@ int crw_lp_pose_coords(const float* pred, int n, int h, int w, int L, int topk, 
 int crw_patch_grid(const unsigned char* frames, const int* boxes, int F, int H, int W, int win, int stride, int out_size,
                    const float* mean3, const float* std3, float* out, crw_stream_t stream);
 
+/* ---- f4, second half: the superpixel label-map producer, code/data/superpixels.py:9-16 (compute_sp_slic) for every frame of a
+ * clip (compute_mask, superpixels.py:24-63) ----------------------------------------------------------------------------------
+ * video (F, 3, H, W) fp32, DEVICE (the (T, C, H, W) clip compute_mask receives; it permutes each frame to HWC on the host).
+ * Per frame: cv2.normalize(0, 255, NORM_MINMAX, CV_8U) (bit-exact with OpenCV 4.x) -> skimage.segmentation.slic(img,
+ * n_segments[f], compactness): Lab, regular grid of centres, n_iter (the reference: 10) rounds of windowed nearest-centre
+ * assignment and centre update, then - connectivity != 0, the reference's default - the scan-order breadth-first
+ * enforce_connectivity pass.  labels (F, H, W) int32, DEVICE, starting at 1 (0 only where enforce_connectivity found nothing
+ * to merge into, as in scikit-image).  n_segments: HOST array of F counts (--randomise-superpixels draws one per frame).
+ * scikit-image is not in this image, so the definition is oracle/slic_oracle.py's restatement of its published algorithm
+ * (deviations listed there: 2^-24 feature quantisation, fixed Newton cube root, empty segments stay empty): parity with
+ * scikit-image itself is UNPINNED.  At most 2048 grid centres per frame.  Workspace: crw_slic_workspace_bytes (0 = bad
+ * arguments). */
+size_t crw_slic_workspace_bytes(int F, int H, int W, const int* n_segments, int n_iter);
+int crw_slic(const float* video, int F, int H, int W, const int* n_segments, double compactness, int n_iter, int connectivity,
+             int* labels, void* workspace, size_t workspace_bytes, crw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import glob
 import os
 import subprocess
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
@@ -75,6 +75,8 @@ _SIGNATURES = {
     "crw_head_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "crw_head_wgrad_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "crw_patch_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "crw_slic_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_void_p, c_int]),
+    "crw_slic": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_head_fwd_splitk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "crw_head_fwd_splitk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "crw_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
