@@ -296,6 +296,14 @@ size_t crw_slic_workspace_bytes(int F, int H, int W, const int* n_segments, int 
 int crw_slic(const float* video, int F, int H, int W, const int* n_segments, double compactness, int n_iter, int connectivity,
              int* labels, void* workspace, size_t workspace_bytes, crw_stream_t stream);
 
+/* The connectivity pass of crw_slic on its own (scikit-image _enforce_label_connectivity_cython, called at the end of slic()):
+ * segments (F, H, W) int32 DEVICE, any labelling -> labels (F, H, W) int32: 4-connected components relabelled from 1 in scan
+ * order, components below min_size merged into the last labelled neighbour the breadth-first search met (0 if none), the search
+ * cut at max_size pixels.  Workspace: crw_label_connectivity_workspace_bytes. */
+size_t crw_label_connectivity_workspace_bytes(int F, int H, int W);
+int crw_label_connectivity(const int* segments, int F, int H, int W, int min_size, int max_size, int* labels, void* workspace,
+                           size_t workspace_bytes, crw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ _SIGNATURES = {
     "crw_patch_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "crw_slic_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_void_p, c_int]),
     "crw_slic": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crw_label_connectivity_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "crw_label_connectivity": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crw_head_fwd_splitk_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "crw_head_fwd_splitk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "crw_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),

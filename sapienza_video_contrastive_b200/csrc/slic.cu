@@ -16,8 +16,8 @@
 //                  integer sums) in shared memory, each thread finds the nearest centre of its pixels among those whose
 //                  2-step window holds the pixel (centres in increasing order, strict comparison = the sequential scatter of
 //                  _slic.pyx), and the pixel is added to that centre's sums (shared-memory then global 64-bit atomics)
-//   slic_connect   enforce_connectivity: the scan-order breadth-first relabelling is inherently sequential per frame, one thread
-//                  per frame does it (frames in parallel), labels and queue L2-resident
+//   slic_connect   enforce_connectivity: the scan-order breadth-first relabelling depends on the queue order, which one warp per
+//                  frame reproduces exactly while popping 32 queue entries at a time (frames in parallel, state L2-resident)
 #include <math.h>
 
 #include "common.cuh"
@@ -132,11 +132,13 @@ __global__ void __launch_bounds__(SLIC_THREADS) slic_features_kernel(const float
 // sums layout per frame and iteration: [K][6] u64 = {n, sum y, sum x, sum f0, sum f1, sum f2} (two's complement)
 __global__ void __launch_bounds__(SLIC_THREADS) slic_assign_kernel(SlicFrames fr, int frame0, int H, int W, int it, int Kmax,
                                                                      const double* __restrict__ feat, const unsigned long long* __restrict__ prev,
-                                                                     unsigned long long* __restrict__ next, int* __restrict__ nearest) {
+                                                                     unsigned long long* __restrict__ next, int* __restrict__ nearest,
+                                                                     int* __restrict__ kinfo) {
     CRW_DYN_SMEM(smem);
     const int fl = blockIdx.y, f = frame0 + fl;
     const SlicGrid g = fr.g[fl];
     const int K = g.ny * g.nx, hw = H * W;
+    if (it == 0 && blockIdx.x == 0 && threadIdx.x == 0) kinfo[f] = K;          // for the connectivity pass
     int* win = reinterpret_cast<int*>(smem);                                         // [K][4]: ya, yb, xa, xb (16-byte rows)
     double* cen = reinterpret_cast<double*>(win + (size_t)K * 4);                    // [K][5]: y, x, c0, c1, c2
     unsigned long long* acc = reinterpret_cast<unsigned long long*>(cen + (size_t)K * 5);   // [K][6]
@@ -212,49 +214,104 @@ __global__ void slic_offset_kernel(const int* __restrict__ nearest, int64_t n, i
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) labels[i] = nearest[i] + 1;
 }
 
-// _enforce_label_connectivity_cython, one thread per frame.  con (= the output labels) starts at -1.
-__global__ void slic_connect_kernel(SlicFrames fr, int frame0, int H, int W, const int* __restrict__ nearest, int* __restrict__ queue,
-                                    int* __restrict__ labels) {
-    if (threadIdx.x != 0) return;
-    const int fl = blockIdx.x, f = frame0 + fl, hw = H * W;
-    const int K = fr.g[fl].ny * fr.g[fl].nx;
-    const double seg_size = (double)hw / (double)K;
-    const int min_size = (int)(0.5 * seg_size), max_size = (int)(3.0 * seg_size);
+__device__ __forceinline__ int ld_cg_i(const int* p) {
+#ifdef CRW_SIM
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
+
+// _enforce_label_connectivity_cython, one WARP per frame.  con (= the output labels) starts at -1, claim at INT_MAX-ish.
+// The reference algorithm is a scan-order breadth-first search whose result depends on the queue order (the max_size cut, the
+// "last labelled neighbour met" merge rule), so the queue order is reproduced exactly: the warp pops up to 32 queue entries at
+// once (lane = pop order), every lane looks at its 4 neighbours (x+1, x-1, y+1, y-1), and a pixel reachable from several pops is
+// pushed by the earliest (lane, neighbour) - an atomicMin on claim[] decides -, at the queue position a prefix sum over that
+// order assigns.  Pushes only turn con from -1 into the current label, which the merge rule ignores, so looking at the 32 pops
+// side by side reads the same values as one after the other.
+__global__ void __launch_bounds__(32) slic_connect_kernel(const int* __restrict__ kinfo, int min_size, int max_size, int H, int W,
+                                                          const int* __restrict__ nearest, int* __restrict__ queue, int* __restrict__ claim,
+                                                          int* __restrict__ labels) {
+    const int f = blockIdx.x, lane = threadIdx.x, hw = H * W;
+    if (kinfo) {                                                  // slic(): 0.5 and 3 times the mean segment size
+        const double seg_size = (double)hw / (double)kinfo[f];
+        min_size = (int)(0.5 * seg_size);
+        max_size = (int)(3.0 * seg_size);
+    }
     const int* seg = nearest + (int64_t)f * hw;
     int* con = labels + (int64_t)f * hw;
     int* q = queue + (int64_t)f * hw;
-    int new_label = 1;
-    for (int p0 = 0; p0 < hw; ++p0) {
-        if (con[p0] >= 0) continue;
-        int adjacent = 0;
+    int* cl = claim + (int64_t)f * hw;
+    int new_label = 1, scan = 0;
+    while (true) {
+        int p0 = -1;                                              // next pixel in scan order without a label
+        while (scan < hw) {
+            const int p = scan + lane;
+            const unsigned m = __ballot_sync(kFull, p < hw && con[p] < 0);
+            if (m) { p0 = scan + __ffs((int)m) - 1; break; }
+            scan += 32;
+        }
+        if (p0 < 0) break;
+        scan = p0 + 1;
         const int label = seg[p0];
-        con[p0] = new_label;
-        int size = 1, visited = 0;
-        q[0] = p0;
+        if (lane == 0) { con[p0] = new_label; q[0] = p0; }
+        __syncwarp();
+        int size = 1, visited = 0, adjacent = 0;
         while (visited < size && size < max_size) {
-            const int p = q[visited];
-            const int y = p / W, x = p - y * W;
+            const int nb = size - visited < 32 ? size - visited : 32;
+            int cand[4] = {-1, -1, -1, -1};
+            int adj = -1;
+            if (lane < nb) {
+                const int p = q[visited + lane];
+                const int y = p / W, x = p - y * W;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int xx = x + (i == 0 ? 1 : (i == 1 ? -1 : 0)), yy = y + (i == 2 ? 1 : (i == 3 ? -1 : 0));
-                if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
-                const int pp = yy * W + xx;
-                const int c = con[pp];
-                if (c == -1 && seg[pp] == label) {
-                    con[pp] = new_label;
-                    q[size++] = pp;
-                    if (size >= max_size) break;
-                } else if (c >= 0 && c != new_label) {
-                    adjacent = c;
+                for (int i = 0; i < 4; ++i) {
+                    const int xx = x + (i == 0 ? 1 : (i == 1 ? -1 : 0)), yy = y + (i == 2 ? 1 : (i == 3 ? -1 : 0));
+                    if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+                    const int pp = yy * W + xx;
+                    const int c = con[pp];
+                    if (c == -1) {
+                        if (seg[pp] == label) { cand[i] = pp; atomicMin(cl + pp, lane * 4 + i); }
+                    } else if (c != new_label) {
+                        adj = c;
+                    }
                 }
             }
-            ++visited;
+            __syncwarp();
+            bool win[4];
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                win[i] = cand[i] >= 0 && ld_cg_i(cl + cand[i]) == lane * 4 + i;
+                cnt += win[i] ? 1 : 0;
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(kFull, incl, 31);
+            int pos = size + incl - cnt;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!win[i]) continue;
+                if (pos < max_size) { con[cand[i]] = new_label; q[pos] = cand[i]; }
+                else cl[cand[i]] = 0x7f7f7f7f;                    // cut by max_size: the pixel stays free for a later segment
+                ++pos;
+            }
+            const unsigned am = __ballot_sync(kFull, adj >= 0);
+            if (am) adjacent = __shfl_sync(kFull, adj, 31 - __clz((int)am));
+            size = size + total < max_size ? size + total : max_size;
+            visited += nb;
+            __syncwarp();
         }
-        if (size < min_size) {
-            for (int i = 0; i < size; ++i) con[q[i]] = adjacent;
+        if (size < min_size) {                                    // too small: merged into the last labelled neighbour met
+            for (int i = lane; i < size; i += 32) con[q[i]] = adjacent;
         } else {
             ++new_label;
         }
+        __syncwarp();
     }
 }
 
@@ -312,7 +369,7 @@ static const double* slic_lin_table() {
     return t.v;
 }
 
-struct SlicLayout { size_t mm, table, feat, nearest, queue, sums, total; int Kmax; };
+struct SlicLayout { size_t mm, kinfo, table, feat, nearest, queue, claim, sums, total; int Kmax; };
 
 static int slic_layout(int F, int H, int W, const int* n_segments, int n_iter, SlicLayout& L) {
     int Kmax = 1;
@@ -328,10 +385,12 @@ static int slic_layout(int F, int H, int W, const int* n_segments, int n_iter, S
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     L.mm = off; off += up((size_t)F * 2 * sizeof(unsigned));
+    L.kinfo = off; off += up((size_t)F * sizeof(int));
     L.table = off; off += up(256 * sizeof(double));
     L.feat = off; off += up((size_t)F * 3 * hw * sizeof(double));
     L.nearest = off; off += up((size_t)F * hw * sizeof(int));
     L.queue = off; off += up((size_t)F * hw * sizeof(int));
+    L.claim = off; off += up((size_t)F * hw * sizeof(int));
     L.sums = off; off += up((size_t)n_iter * F * Kmax * 6 * sizeof(unsigned long long));
     L.total = off;
     L.Kmax = Kmax;
@@ -370,13 +429,18 @@ extern "C" int crw_slic(const float* video, int F, int H, int W, const int* n_se
     double* feat = reinterpret_cast<double*>(w + L.feat);
     int* nearest = reinterpret_cast<int*>(w + L.nearest);
     int* queue = reinterpret_cast<int*>(w + L.queue);
+    int* claim = reinterpret_cast<int*>(w + L.claim);
+    int* kinfo = reinterpret_cast<int*>(w + L.kinfo);
     unsigned long long* sums = reinterpret_cast<unsigned long long*>(w + L.sums);
     const int hw = H * W;
     const size_t sums_per_iter = (size_t)F * L.Kmax * 6;
     cudaMemsetAsync(mm, 0, (size_t)F * 2 * sizeof(unsigned), st);
     cudaMemsetAsync(nearest, 0, (size_t)F * hw * sizeof(int), st);
     cudaMemsetAsync(sums, 0, (size_t)n_iter * sums_per_iter * sizeof(unsigned long long), st);
-    if (connectivity) cudaMemsetAsync(labels, 0xff, (size_t)F * hw * sizeof(int), st);
+    if (connectivity) {
+        cudaMemsetAsync(labels, 0xff, (size_t)F * hw * sizeof(int), st);
+        cudaMemsetAsync(claim, 0x7f, (size_t)F * hw * sizeof(int), st);
+    }
     cudaMemcpyAsync(table, slic_lin_table(), 256 * sizeof(double), cudaMemcpyHostToDevice, st);
     int blocks = (hw * 3 + SLIC_THREADS * 8 - 1) / (SLIC_THREADS * 8);
     if (blocks > 64) blocks = 64;
@@ -396,10 +460,35 @@ extern "C" int crw_slic(const float* video, int F, int H, int W, const int* n_se
         for (int it = 0; it < n_iter; ++it) {
             const unsigned long long* prev = sums + (size_t)(it > 0 ? it - 1 : 0) * sums_per_iter;
             CRW_LAUNCH(slic_assign_kernel, dim3(tiles, nf), SLIC_THREADS, smem, st, fr, f0, H, W, it, L.Kmax, feat, prev,
-                       sums + (size_t)it * sums_per_iter, nearest);
+                       sums + (size_t)it * sums_per_iter, nearest, kinfo);
         }
-        if (connectivity) CRW_LAUNCH(slic_connect_kernel, dim3(nf), 32, 0, st, fr, f0, H, W, nearest, queue, labels);
     }
-    if (!connectivity) CRW_LAUNCH(slic_offset_kernel, dim3(296), 256, 0, st, nearest, (int64_t)F * hw, labels);
+    if (connectivity) CRW_LAUNCH(slic_connect_kernel, dim3(F), 32, 0, st, kinfo, 0, 0, H, W, nearest, queue, claim, labels);
+    else CRW_LAUNCH(slic_offset_kernel, dim3(296), 256, 0, st, nearest, (int64_t)F * hw, labels);
     return check_launch("crw_slic");
+}
+
+extern "C" size_t crw_label_connectivity_workspace_bytes(int F, int H, int W) {
+    if (F < 1 || H < 1 || W < 1) return 0;
+    return (size_t)2 * F * H * W * sizeof(int);
+}
+
+extern "C" int crw_label_connectivity(const int* segments, int F, int H, int W, int min_size, int max_size, int* labels, void* ws,
+                                      size_t ws_bytes, void* stream) {
+    if (F < 1 || H < 1 || W < 1 || (int64_t)H * W > (1 << 30)) {
+        set_error("crw_label_connectivity: bad arguments (F=%d H=%d W=%d)", F, H, W);
+        return 1;
+    }
+    if (ws_bytes < crw_label_connectivity_workspace_bytes(F, H, W)) {
+        set_error("crw_label_connectivity: workspace too small (%zu bytes)", ws_bytes);
+        return 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)F * H * W;
+    int* queue = static_cast<int*>(ws);
+    int* claim = queue + n;
+    cudaMemsetAsync(labels, 0xff, n * sizeof(int), st);
+    cudaMemsetAsync(claim, 0x7f, n * sizeof(int), st);
+    CRW_LAUNCH(slic_connect_kernel, dim3(F), 32, 0, st, (const int*)nullptr, min_size, max_size, H, W, segments, queue, claim, labels);
+    return check_launch("crw_label_connectivity");
 }

@@ -158,6 +158,53 @@ def test_sim_constant_frame_and_bad_arguments(sim):
     assert sim.crw_slic(t.data_ptr(), 1, 32, 32, ns, 0.0, 10, 1, out.data_ptr(), out.data_ptr(), 1 << 30, None) != 0  # compactness
 
 
+def random_label_maps(F, H, W, n_labels, seed, blobs):
+    """Label maps with components of every size: blurred noise quantised into n_labels levels (blobs) or raw noise."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(F):
+        v = rng.standard_normal((H, W)).astype(np.float32)
+        if blobs:
+            v = cv2.GaussianBlur(v, (0, 0), blobs)
+        r = np.argsort(np.argsort(v.ravel())).reshape(H, W)
+        out.append((r * n_labels // (H * W)).astype(np.int32))
+    return np.stack(out)
+
+
+CONNECT_CASES = [   # F, H, W, labels, min_size, max_size, blur
+    (2, 24, 31, 3, 4, 40, 2.0),        # big blobs against a small max_size: the search is cut again and again
+    (2, 24, 31, 5, 6, 10_000, 1.0),    # no cut, many merges
+    (1, 40, 40, 2, 0, 7, 3.0),         # min_size 0: nothing merges, segments of at most 7 pixels
+    (1, 16, 16, 4, 3, 3, 0),           # salt and pepper, max_size == min_size
+    (1, 33, 65, 1, 1, 100, 0),         # one label everywhere: a frontier much wider than a warp
+    (1, 8, 8, 2, 100, 1, 0),           # max_size 1: no search at all, every pixel merges into its predecessor
+]
+
+
+def run_connect(lib, seg, mn, mx, device=None):
+    F, H, W = seg.shape
+    t = torch.from_numpy(seg)
+    if device is not None:
+        t = t.to(device)
+    wb = lib.crw_label_connectivity_workspace_bytes(F, H, W)
+    ws = torch.zeros(wb, dtype=torch.uint8, device=t.device)
+    out = torch.zeros(F, H, W, dtype=torch.int32, device=t.device)
+    for _ in range(2):
+        lib.check(lib.crw_label_connectivity(t.data_ptr(), F, H, W, mn, mx, out.data_ptr(), ws.data_ptr(), wb, None), "connectivity")
+    if device is not None:
+        torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("F,H,W,nl,mn,mx,blobs", CONNECT_CASES)
+def test_sim_connectivity_matches_oracle(sim, F, H, W, nl, mn, mx, blobs):
+    seg = random_label_maps(F, H, W, nl, seed=H * W + nl, blobs=blobs)
+    got = run_connect(sim, seg, mn, mx)
+    for f in range(F):
+        assert np.array_equal(got[f], SO.enforce_connectivity(seg[f].astype(np.int64), mn, mx))
+
+
 # ---- the kernels on the GPU ---------------------------------------------------------------------------------------------
 
 @pytest.mark.gpu
@@ -197,3 +244,13 @@ def test_gpu_compute_mask_mirror():
     assert np.array_equal(one.cpu().numpy(), want[0] if counts[0] == 16 else oracle_labels(vid.numpy()[:1], [16], 30.0, 1)[0])
     with pytest.raises(NotImplementedError):
         SP.compute_mask(vid, "fh", 16, 1.0, False, 0, 30.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("F,H,W,nl,mn,mx,blobs", CONNECT_CASES + [(3, 128, 96, 6, 50, 700, 3.0), (1, 256, 256, 4, 300, 4000, 6.0)])
+def test_gpu_connectivity_matches_oracle(F, H, W, nl, mn, mx, blobs):
+    from sapienza_video_contrastive_b200 import _lib
+    seg = random_label_maps(F, H, W, nl, seed=H * W + nl, blobs=blobs)
+    got = run_connect(_lib.lib(), seg, mn, mx, device="cuda")
+    for f in range(F):
+        assert np.array_equal(got[f], SO.enforce_connectivity(seg[f].astype(np.int64), mn, mx))
