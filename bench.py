@@ -596,6 +596,57 @@ def superpixel_bench(dev):
             "dilated_L1_51_fwd_ms": dil_fwd, "dilated_L1_51_fwd_bwd_ms": dil, "dilated_clips_per_s": B / dil * 1e3}
 
 
+# ---- the data-loader producers (patch grid, superpixel label maps) ---------------------------------------
+def producers_bench(dev, cpu=True):
+    """The inputs of the two walk variants for one training batch of CFG's shape (B clips x T frames of 256 x 256): the patch grid
+    (augs.py:59-82: 49 crops + PIL bilinear resizes per frame) and the SLIC label maps (data/superpixels.py:9-63, --num-sp 30
+    --compactness 200 defaults), produced on the GPU; beside them the reference's per-frame CPU procedure on one host core (a
+    DataLoader worker), timed on a few frames."""
+    from sapienza_video_contrastive_b200 import augs, superpixels
+    hbm, _, _ = peaks()
+    F, size = CFG["B"] * CFG["T"], 256
+    g = torch.Generator(device="cpu").manual_seed(0)
+    frames = torch.randint(0, 256, (F, size, size, 3), dtype=torch.uint8, generator=g)
+    torch.manual_seed(0)
+    P = ((size - 64) // 32 + 1) ** 2
+    boxes = augs.draw_patch_boxes(F, P, 64).to(dev)
+    fr_d = frames.to(dev)
+    pg_ms, n_pg, _ = timed_median(lambda: augs.patch_grid_frames(fr_d, boxes, 64, 32, 64))
+    pg_bytes = F * P * 3 * 64 * 64 * 4 + frames.numel()
+    vid = torch.nn.functional.avg_pool2d(torch.randn(F, 3, size, size, generator=g), 9, 1, 4).to(dev)
+    sl_ms, n_sl, _ = timed_median(lambda: superpixels.slic_frames(vid, 30, 200.0), min_iters=3)
+    sl_nc_ms, _, _ = timed_median(lambda: superpixels.slic_frames(vid, 30, 200.0, enforce_connectivity=False), min_iters=3)
+    out = {"config": "%d frames of %dx%d (B=%d clips x T=%d)" % (F, size, size, CFG["B"], CFG["T"]),
+           "patch_grid": {"ms": pg_ms, "frames_per_s": F / pg_ms * 1e3, "gbs": pg_bytes / pg_ms / 1e6, "hbm_frac": pg_bytes / pg_ms / 1e6 / hbm,
+                          "windows_per_frame": P, "parity": "bit-exact with Pillow (tests)"},
+           "slic": {"ms": sl_ms, "frames_per_s": F / sl_ms * 1e3, "clustering_only_ms": sl_nc_ms, "n_segments": 30, "compactness": 200.0,
+                    "parity": "unpinned (scikit-image absent): bit-exact with oracle/slic_oracle.py's restatement"}}
+    if cpu:
+        from PIL import Image
+        import numpy as np
+        nf = 4
+        bx = boxes[:nf].cpu().numpy()
+        mean, std = np.array(augs.IMG_MEAN, dtype=np.float32), np.array(augs.IMG_STD, dtype=np.float32)
+        t0 = time.perf_counter()
+        for f in range(nf):                                       # augs.py:70-80, window by window
+            x = frames[f].numpy()
+            for p in range(P):
+                wy, wx = (p // 7) * 32, (p % 7) * 32
+                i, j, h, w = (int(v) for v in bx[f, p])
+                im = Image.fromarray(x[wy:wy + 64, wx:wx + 64]).crop((j, i, j + w, i + h)).resize((64, 64), Image.BILINEAR)
+                _ = ((np.asarray(im, dtype=np.float32) / 255.0 - mean) / std).transpose(2, 0, 1)
+        cpu_pg = nf / (time.perf_counter() - t0)
+        out["patch_grid"]["cpu_baseline"] = {"value": cpu_pg, "unit": "frames/s", "cores": 1, "kind": "port",
+                                             "sample": "%d frames, the reference's per-window PIL crop + resize + normalise loop" % nf}
+        from oracle import slic_oracle
+        t0 = time.perf_counter()
+        slic_oracle.slic_labels(np.moveaxis(vid[0].cpu().numpy(), 0, -1), 30, 200.0)
+        out["slic"]["cpu_baseline"] = {"value": 1.0 / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                                       "sample": "1 frame through oracle/slic_oracle.py (numpy + a Python flood fill; scikit-image's Cython "
+                                                 "is not in this image and would be faster)"}
+    return out
+
+
 # ---- configs[4]: sweep points ------------------------------------------------------------------------------------------------
 def sweep_bench(dev):
     from sapienza_video_contrastive_b200 import ops
@@ -842,6 +893,7 @@ def run_ours(args, rank, world, local_rank):
                         ("label_prop", lambda: label_prop_bench(dev, cpu=not args.no_cpu)),
                         ("superpixel", lambda: superpixel_bench(dev)),
                         ("sweep", lambda: sweep_bench(dev)),
+                        ("producers", lambda: producers_bench(dev, cpu=not args.no_cpu)),
                         ("e2e_module", (lambda: module_e2e(dev, 1)) if mod is None else None)):
             if fn is None or (key == "label_prop" and args.no_lp):
                 continue

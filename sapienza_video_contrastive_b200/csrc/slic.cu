@@ -4,10 +4,10 @@
 // superpixel pooling consumes (model.py:136-200).
 //
 // scikit-image is a dependency that is not in this image: the kernels follow the PUBLISHED algorithm (scikit-image >= 0.19
-// slic_superpixels.py / _slic.pyx / _regular_grid.py; Achanta et al., TPAMI 2012) as restated by oracle/slic_oracle.py, with the
-// deviations listed there (features quantised to 2^-24 so that the centre update is an exact integer sum; a fixed Newton cube
+// slic_superpixels.py / _slic.pyx / _regular_grid.py; Achanta et al., TPAMI 2012) (the tests hold a CPU restatement of it), with the
+// deviations DESIGN.md section 2 lists (features quantised to 2^-24 so that the centre update is an exact integer sum; a fixed Newton cube
 // root; empty segments stay empty).  All floating-point work is IEEE double with explicit, unfused operations in a fixed order,
-// so that the label maps are the oracle's bit for bit.
+// so that the label maps are that restatement's bit for bit.
 //
 //   slic_minmax    global min / max of each frame (ordered-integer atomics)
 //   slic_features  min-max normalise to 8 bit (OpenCV's single-rounding float multiply-add), sRGB -> linear by table, XYZ, Lab,
@@ -354,7 +354,7 @@ static void slic_regular_grid(int H, int W, int n, SlicGrid& g, double& sw) {
     sw = 1.0 / ((double)step * (double)step);
 }
 
-// skimage.color.rgb2xyz's gamma expansion of the 256 possible inputs (libm pow, as the oracle)
+// skimage.color.rgb2xyz's gamma expansion of the 256 possible inputs (libm pow, as the CPU restatement)
 struct SlicLinTable {
     double v[256];
     SlicLinTable() {

@@ -4,7 +4,7 @@ skimage.segmentation.slic per frame -> stack -> repeat over 3 channels).  Here o
 clips on the GPU (csrc/slic.cu); the per-frame segment counts of --randomise-superpixels stay on the host and are drawn with
 the reference's own generator calls.
 
-The segmentation follows scikit-image's published SLIC as restated by oracle/slic_oracle.py (scikit-image itself is not in
+The segmentation follows scikit-image's published SLIC (DESIGN.md sections 2 and 4 list the deviations; scikit-image itself is not in
 this image, so parity with it is unpinned; the min-max normalisation is bit-exact with OpenCV).  Felzenszwalb ("fh") is not
 built: `compute_mask` raises for it rather than falling back to anything.
 """
