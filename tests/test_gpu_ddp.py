@@ -91,8 +91,10 @@ def test_ddp_gradients_equal_single_gpu_on_concatenated_batch(tmp_path, world):
     assert abs(float(r["loss"]) - float(r["loss1"])) <= 1e-5 * abs(float(r["loss1"]))
     # (1) the data-parallel plumbing: N ranks == the shards accumulated on one GPU, to rounding (same kernel shapes everywhere)
     assert rel(r["ghead"], r["ghead2"]) < 1e-5
-    assert rel(r["glast"], r["glast2"]) < 1e-5
-    assert rel(r["gconv1"], r["gconv12"]) < 1e-3        # (cuDNN's weight gradient of the first convolution reduces with atomics: 1.3e-4 measured)
+    # the encoder's weight gradients come from cuDNN kernels that reduce with atomics (run-to-run noise): measured 3.7e-5 on the
+    # last convolution, 1.3e-4 on the first; the head's gradient (this repository's kernels, deterministic) holds 1e-5 above
+    assert rel(r["glast"], r["glast2"]) < 2e-4
+    assert rel(r["gconv1"], r["gconv12"]) < 1e-3
     # (2) == the concatenated batch in one call.  The loss agrees to 1e-5 above; the gradients pass through cuDNN convolutions
     # whose algorithms differ between batch 2 and batch 4, and at random initialisation the walk's gradient is a small
     # difference of nearly equal terms (all node embeddings are almost parallel), which amplifies that 1e-6 feature noise
