@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi0, const __grid_constant__ CUtensorMap a_lo0,
                const __grid_constant__ CUtensorMap b_hi0, const __grid_constant__ CUtensorMap b_lo0, GtArgs g) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);     // stays in the shared state space: LDS / STS, not generic LD / ST
     constexpr unsigned kTile = GT_M * 128;                 // one plane of one operand: 128 rows x 128 B
     constexpr unsigned kStage = 4 * kTile;                 // A hi, A lo, B hi, B lo
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * kStage);

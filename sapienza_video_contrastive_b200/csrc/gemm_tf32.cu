@@ -68,7 +68,7 @@ __device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__f
 
 __global__ void __launch_bounds__(G3_THREADS, 1) gemm_tf32_kernel(const __grid_constant__ G3Maps maps, G3Args g) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);     // stays in the shared state space: LDS / STS, not generic LD / ST
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G3_STAGES * kG3Stage);
     uint64_t* full = bars;                             // TMA landed
     uint64_t* conv = bars + G3_STAGES;                 // converters done

@@ -174,7 +174,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     } else {
         work_first = blockIdx.y * (unsigned)tiles + blockIdx.x; work_end = work_first + 1u; work_step = 1u;
     }
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);     // stays in the shared state space: LDS / STS, not generic LD / ST
     const int C = a.C, KC = C / 64, hw = a.h * a.w;
     const unsigned q_chunk = (unsigned)TC_M * 128;                // staged query tile: one 64-channel chunk = 128 rows x 128 B
     const unsigned q_plane = (unsigned)KC * q_chunk;

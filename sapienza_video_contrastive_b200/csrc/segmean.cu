@@ -11,6 +11,8 @@
 //      cp.async pipeline and reduces it per label with the accumulators in registers; the epilogue divides by the sizes;
 //   4. segmean_bwd mirrors 3 as a gather over the per-cell lists (deterministic).
 // Neither the one-hot nor the broadcast product is ever materialised; forward and backward are deterministic.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace crw {
@@ -779,8 +781,16 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     return seg_fwd_tail(maps, ws, B, C, T, cells, SP, out, stream);
 }
 
+#include "segmean_tc.cuh"
+
 static int seg_fwd_tail(const float* maps, const SegWs& ws, int B, int C, int T, int cells, int SP, float* out, crw_stream_t stream) {
     int e;
+#ifndef CRW_SIM
+    static const bool force_simt = getenv("CRW_SEGMEAN_SIMT") != nullptr;     // A/B switch for tests and profiles
+    if (!force_simt && seg_mma_eligible(maps, out, C, cells, SP))          // the tensor-core forward consumes the per-cell lists directly
+        return C % 256 == 0 && !getenv("CRW_SEG_NCH128") ? seg_mma_launch<256>(maps, ws, B, C, T, cells, SP, out, stream)
+                            : seg_mma_launch<128>(maps, ws, B, C, T, cells, SP, out, stream);
+#endif
     if (cells > 1024 || SP > 1024 || (size_t)SP * 33 * 4 > 200 * 1024) {
         set_error("segmean_fwd: unsupported size (cells=%d, SP=%d)", cells, SP);
         return CRW_ERR_UNSUPPORTED;

@@ -325,3 +325,32 @@ def test_stoch_mat_and_zero_softmax_are_differentiable(ops):
     assert 0.1 < float(dropped.float().mean()) < 0.5
     P.sum().backward()
     assert q1.grad is not None and torch.isfinite(q1.grad).all() and float(q1.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,T,C,Hm,scale,SP", [(2, 3, 256, 32, 8, 196), (1, 2, 512, 32, 8, 256), (1, 3, 128, 16, 8, 129), (2, 1, 256, 32, 4, 128),
+                                               (1, 2, 384, 32, 8, 7), (1, 1, 256, 8, 8, 60)])
+def test_segmean_tensor_core_forward_vs_oracle(B, T, C, Hm, scale, SP):
+    """The tcgen05 forward of the superpixel pooling (segmean_tc.cuh: cells % 32 == 0, C % 128 == 0, SP <= 256) against the oracle:
+    one and two M-tiles, 128 / 256 channels per CTA, labels out of range, empty labels, and the gradient still flows through the
+    per-cell lists the forward left in the workspace."""
+    from sapienza_video_contrastive_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + SP + C)
+    maps = torch.randn(B, C, T, Hm, Hm, generator=g) * 3 + 0.5
+    lab = cases.voronoi_labels(B, T, max(SP - 2, 1), Hm * scale, g, one_based=False)       # the last labels stay empty
+    lab[:, :, :3, :5] = SP + 2
+    lab[:, :, -2:, :] = -1
+    md = maps.to(DEV).requires_grad_(True)
+    out = ops.segment_mean(md, lab.to(DEV), SP)
+    ref = O.segment_mean(maps, lab, SP)
+    torch.testing.assert_close(out.detach().cpu().transpose(1, 2), ref, rtol=1e-5, atol=2e-6)
+    if SP > 2:
+        assert float(out[:, SP - 1].abs().max()) == 0.0                                  # an empty label is an exact zero row
+    gout = torch.randn(B, SP, T, C, generator=g)
+    out.backward(gout.to(DEV))
+    m2 = maps.clone().requires_grad_(True)                  # autograd through a one-hot restatement of model.py:296-325
+    up = m2.repeat_interleave(scale, -1).repeat_interleave(scale, -2)
+    ok = (lab >= 0) & (lab < SP)
+    oh = torch.nn.functional.one_hot(lab.clamp(0, SP - 1), SP).float() * ok[..., None]
+    ref = torch.einsum("bcthw,bthws->btsc", up, oh) / (oh.sum((2, 3))[..., None] + 1e-20)
+    ref.backward(gout.transpose(1, 2))
+    torch.testing.assert_close(md.grad.cpu(), m2.grad, rtol=1e-4, atol=1e-6)
