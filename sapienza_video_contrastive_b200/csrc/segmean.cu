@@ -788,7 +788,7 @@ static int seg_fwd_tail(const float* maps, const SegWs& ws, int B, int C, int T,
 #ifndef CRW_SIM
     static const bool force_simt = getenv("CRW_SEGMEAN_SIMT") != nullptr;     // A/B switch for tests and profiles
     if (!force_simt && seg_mma_eligible(maps, out, C, cells, SP))          // the tensor-core forward consumes the per-cell lists directly
-        return C % 256 == 0 && !getenv("CRW_SEG_NCH128") ? seg_mma_launch<256>(maps, ws, B, C, T, cells, SP, out, stream)
+        return C % 256 == 0 ? seg_mma_launch<256>(maps, ws, B, C, T, cells, SP, out, stream)
                             : seg_mma_launch<128>(maps, ws, B, C, T, cells, SP, out, stream);
 #endif
     if (cells > 1024 || SP > 1024 || (size_t)SP * 33 * 4 > 200 * 1024) {

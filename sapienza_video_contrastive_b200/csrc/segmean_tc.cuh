@@ -42,7 +42,6 @@ template <int NCH> static SgLayout sg_layout(int SP) {
     const size_t fixed = 1024 + kSgMisc + 2 * (size_t)SgCfg<NCH>::kB + 2 * (size_t)L.cnt_bytes;
     int r = (int)((kSgSmemMax - fixed) / SgCfg<NCH>::kB);
     L.raw_stages = r > SG_MAX_RAW ? SG_MAX_RAW : r;
-    if (getenv("CRW_SEG_R") && atoi(getenv("CRW_SEG_R")) >= 1 && atoi(getenv("CRW_SEG_R")) < L.raw_stages) L.raw_stages = atoi(getenv("CRW_SEG_R"));   // profiling only
     L.smem = fixed + (size_t)L.raw_stages * SgCfg<NCH>::kB;
     return L;
 }
