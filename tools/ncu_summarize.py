@@ -14,7 +14,8 @@ SHORT = [("pool_fwd_kernel", "pool_patch_fwd"), ("pool_bwd_kernel", "pool_patch_
          ("walk_chain_cluster", "walk_chain_cluster"), ("walk_pairs_bwd", "walk_pairs_bwd"), ("gemm_tf32_kernel", "gemm_tf32"),
          ("splitk_reduce", "splitk_reduce"), ("lp_topk_tc_kernel<(int)0>", "lp_topk_tc_pre"), ("lp_topk_tc_kernel<(int)1>", "lp_topk_tc_exact"),
          ("lp_rescore_kernel<(int)1>", "lp_rescore_check"), ("lp_rescore_kernel<(int)0>", "lp_rescore_listed"), ("lp_split_kernel", "lp_split"),
-         ("lp_prepare_kernel", "lp_prepare"), ("lp_gather_kernel", "lp_gather"), ("segmean_accum_tma", "segmean_accum_tma"),
+         ("lp_prepare_kernel", "lp_prepare"), ("lp_gather_kernel", "lp_gather"), ("segmean_accum_tma", "segmean_accum_tma"), ("segmean_mma_kernel", "segmean_mma"), ("segdil_runs", "segdil_runs"),
+         ("slic_assign", "slic_assign"), ("slic_connect", "slic_connect"), ("slic_features", "slic_features"), ("slic_minmax", "slic_minmax"),
          ("segmean_count", "segmean_count"), ("segmean_csr", "segmean_csr"), ("segmean_bwd", "segmean_bwd"), ("segdil_count", "segdil_count"),
          ("gemm_tc_kernel", "gemm_tc"), ("tc_split_kernel", "tc_split"), ("patch_grid_kernel", "patch_grid"), ("lp_post_kernel", "lp_post")]
 WANT = {"gpu__time_duration.sum": "us", "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
