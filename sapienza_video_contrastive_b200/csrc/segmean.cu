@@ -112,6 +112,56 @@ __global__ void __launch_bounds__(256) segmean_count_kernel(const int64_t* __res
     }
 }
 
+// Thread-per-cell variant for unit-stride label rows (the common case: sp_mask[:, :, 0] of a contiguous mask): a warp's lanes are
+// 32 neighbouring cells, so at every (row, pixel) step the warp reads one 8-byte label per lane out of the same few cache lines,
+// and the cell's list is built in registers (run-length shortcut, four slots, an array in local memory beyond that).  Same
+// lists in the same order as segmean_count_kernel (entries by first occurrence in pixel order).
+__global__ void __launch_bounds__(256) segmean_count_cell_kernel(const int64_t* __restrict__ labels, int64_t ls_b, int64_t ls_t, int64_t ls_y,
+                                                                 int T, int Hm, int Wm, int sy, int sx, int SP, SegWs ws, int64_t total_cells) {
+    const int cells = Hm * Wm;
+    for (int64_t gc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gc < total_cells; gc += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bt = gc / cells;
+        const int cell = (int)(gc - bt * cells);
+        const int b = (int)(bt / T), t = (int)(bt - (int64_t)b * T);
+        const int cy = cell / Wm, cx = cell - cy * Wm;
+        const int64_t* base = labels + b * ls_b + t * ls_t + (int64_t)(cy * sy) * ls_y + (int64_t)(cx * sx);
+        int l0 = -1, l1 = -1, l2 = -1, l3 = -1, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        int xl[kSegMaxEnt], xc[kSegMaxEnt];            // entries beyond the four slots (rare: a cell on a junction of many segments)
+        int nx = 0;
+        for (int py = 0; py < sy; ++py) {
+            const int64_t* row = base + (int64_t)py * ls_y;
+            for (int px = 0; px < sx; ++px) {
+                const int64_t L64 = row[px];
+                if (L64 < 0 || L64 >= SP) continue;    // labels outside [0,SP) never match a one-hot plane (model.py:299-301)
+                const int L = (int)L64;
+                if (L == l0) ++c0;
+                else if (L == l1) ++c1;
+                else if (L == l2) ++c2;
+                else if (L == l3) ++c3;
+                else if (l0 < 0) { l0 = L; c0 = 1; }
+                else if (l1 < 0) { l1 = L; c1 = 1; }
+                else if (l2 < 0) { l2 = L; c2 = 1; }
+                else if (l3 < 0) { l3 = L; c3 = 1; }
+                else {
+                    int j = 0;
+                    while (j < nx && xl[j] != L) ++j;
+                    if (j == nx) { xl[nx] = L; xc[nx] = 0; ++nx; }
+                    ++xc[j];
+                }
+            }
+        }
+        unsigned* e = ws.ent + (int64_t)bt * ws.cap * cells + cell;
+        int* size = ws.size + bt * SP;
+        int n = 0;
+        if (l0 >= 0) { e[(int64_t)n++ * cells] = ((unsigned)l0 << 8) | (unsigned)c0; atomicAdd(size + l0, c0); }
+        if (l1 >= 0) { e[(int64_t)n++ * cells] = ((unsigned)l1 << 8) | (unsigned)c1; atomicAdd(size + l1, c1); }
+        if (l2 >= 0) { e[(int64_t)n++ * cells] = ((unsigned)l2 << 8) | (unsigned)c2; atomicAdd(size + l2, c2); }
+        if (l3 >= 0) { e[(int64_t)n++ * cells] = ((unsigned)l3 << 8) | (unsigned)c3; atomicAdd(size + l3, c3); }
+        for (int j = 0; j < nx; ++j) { e[(int64_t)n++ * cells] = ((unsigned)xl[j] << 8) | (unsigned)xc[j]; atomicAdd(size + xl[j], xc[j]); }
+        ws.nent[bt * cells + cell] = (unsigned char)n;
+    }
+}
+
 // ---- dilated superpixel masks (model.py:303-309, utils/__init__.py:590-608) -------------------------------
 // The reference dilates every label's one-hot mask with a 51..55-pixel structuring element (a depthwise 55 x 55 convolution
 // over T*SP channels, thresholded at > 0), so masks overlap and a pixel carries a SET of labels.  Here the element is
@@ -775,7 +825,12 @@ extern "C" int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t
     cudaMemsetAsync(ws.size, 0, sizeof(int) * (size_t)B * T * SP, (cudaStream_t)stream);
     const int64_t total = (int64_t)B * T * cells;
     const int grid1 = (int)((total + 7) / 8 < 148 * 8 ? (total + 7) / 8 : 148 * 8);
-    CRW_LAUNCH(segmean_count_kernel, grid1, 256, 0, stream, labels, ls_b, ls_t, ls_y, ls_x, T, Hm, Wm, h / Hm, w / Wm, SP, ws, total);
+    if (ls_x == 1) {
+        const int gridc = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        CRW_LAUNCH(segmean_count_cell_kernel, gridc, 256, 0, stream, labels, ls_b, ls_t, ls_y, T, Hm, Wm, h / Hm, w / Wm, SP, ws, total);
+    } else {
+        CRW_LAUNCH(segmean_count_kernel, grid1, 256, 0, stream, labels, ls_b, ls_t, ls_y, ls_x, T, Hm, Wm, h / Hm, w / Wm, SP, ws, total);
+    }
     e = check_launch("segmean_count");
     if (e != CRW_OK) return e;
     return seg_fwd_tail(maps, ws, B, C, T, cells, SP, out, stream);

@@ -323,9 +323,15 @@ static int seg_mma_launch(const float* maps, const SegWs& ws, int B, int C, int 
     }
     auto k = segmean_mma_kernel<NCH>;
     const SgLayout L = sg_layout<NCH>(SP);
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSgSmemMax) != cudaSuccess) {
-        set_error("segmean_fwd: %s", cudaGetErrorString(cudaGetLastError()));
-        return CRW_ERR_CUDA;
+    static thread_local int attr_device = -1;          // the opt-in is per device and sticky: ask once per thread and device
+    int device = 0;
+    cudaGetDevice(&device);
+    if (attr_device != device) {
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSgSmemMax) != cudaSuccess) {
+            set_error("segmean_fwd: %s", cudaGetErrorString(cudaGetLastError()));
+            return CRW_ERR_CUDA;
+        }
+        attr_device = device;
     }
     static const int dbg = getenv("CRW_SEG_DBG") ? atoi(getenv("CRW_SEG_DBG")) : 0;     // profiling only: 1 no MMAs, 2 no split, 4 no scatter
     k<<<dim3(C / NCH, B * T), SG_THREADS, L.smem, (cudaStream_t)stream>>>(fmap, ws, C, T, cells, SP, L.raw_stages, L.cnt_bytes, dbg, out);
