@@ -52,15 +52,27 @@ __device__ __forceinline__ void pg_coeffs(int in_size, int out_size, int xx, int
 
 __device__ __forceinline__ unsigned char pg_clip8(int v) { return (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
-__global__ void __launch_bounds__(256) patch_grid_kernel(PgArgs a) {
+constexpr int PG_THREADS = 2 * PG_MAX * 3;         // two groups of (column, channel) threads, alternating rows
+
+__global__ void __launch_bounds__(PG_THREADS) patch_grid_kernel(PgArgs a) {
     __shared__ unsigned char crop[PG_MAX * PG_MAX * 3];
     __shared__ unsigned char tmp[PG_MAX * PG_MAX * 3];
-    __shared__ int kx[PG_MAX][PG_TAPS + 1], ky[PG_MAX][PG_TAPS + 1];      // [.][3] = first tap
+    __shared__ __align__(16) int kx[PG_MAX][PG_TAPS + 1], ky[PG_MAX][PG_TAPS + 1];      // [.][3] = first tap
+    __shared__ float lut[3][256];                       // ToTensor + Normalize of the 256 possible bytes per channel
     const int p = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const int* b = a.boxes + ((int64_t)f * a.P + p) * 4;
     const int top = b[0], left = b[1], ch = b[2], cw = b[3];
     const int wy = (p / a.nwx) * a.stride, wx = (p % a.nwx) * a.stride;
     const int ps = a.ps;
+    // the two thread groups take alternate rows; inside a group a thread owns one byte column (pixel column x channel)
+    const int grp = tid >= PG_MAX * 3 ? 1 : 0, col = tid - grp * (PG_MAX * 3);
+    const int rowb = cw * 3, outb = ps * 3;
+    const unsigned char* src = a.frames + (((int64_t)f * a.H + wy + top) * a.W + wx + left) * 3;
+    if (col < rowb) {
+#pragma unroll 8
+        for (int r = grp; r < ch; r += 2) crop[r * rowb + col] = src[(int64_t)r * a.W * 3 + col];     // (independent loads, in flight together)
+    }
+    // the resampling coefficients (double arithmetic, Pillow's) and the value table are computed while the crop travels
     if (tid < ps) {
         int lo, n, k[PG_TAPS];
         pg_coeffs(cw, ps, tid, lo, n, k);
@@ -70,38 +82,37 @@ __global__ void __launch_bounds__(256) patch_grid_kernel(PgArgs a) {
         pg_coeffs(ch, ps, tid - 64, lo, n, k);
         ky[tid - 64][0] = k[0]; ky[tid - 64][1] = k[1]; ky[tid - 64][2] = k[2]; ky[tid - 64][3] = lo;
     }
-    const unsigned char* src = a.frames + (((int64_t)f * a.H + wy + top) * a.W + wx + left) * 3;
-    for (int e = tid; e < ch * cw * 3; e += blockDim.x) {
-        const int r = e / (cw * 3), c = e - r * (cw * 3);
-        crop[e] = src[(int64_t)r * a.W * 3 + c];
+    for (int e = tid; e < 768; e += PG_THREADS) {
+        const int c = e >> 8;
+        lut[c][e & 255] = ((float)(e & 255) / 255.0f - a.mean[c]) / a.stdv[c];
     }
     __syncthreads();
     // horizontal pass: (ch rows) x (ps columns) x 3, 8-bit result
-    for (int e = tid; e < ch * ps * 3; e += blockDim.x) {
-        const int r = e / (ps * 3), rem = e - r * (ps * 3), xx = rem / 3, c = rem - xx * 3;
-        const int lo = kx[xx][3];
-        int acc = 1 << 21;
-#pragma unroll
-        for (int t = 0; t < PG_TAPS; ++t) {
-            const int x = lo + t < cw ? lo + t : cw - 1;                    // (taps past the edge carry weight 0)
-            acc += (int)crop[(r * cw + x) * 3 + c] * kx[xx][t];
+    if (col < outb) {
+        const int xx = col / 3, c = col - xx * 3;
+        const int lo = kx[xx][3], k0 = kx[xx][0], k1 = kx[xx][1], k2 = kx[xx][2];
+        // (taps past the edge carry weight 0)
+        const int o0 = (lo < cw ? lo : cw - 1) * 3 + c, o1 = (lo + 1 < cw ? lo + 1 : cw - 1) * 3 + c, o2 = (lo + 2 < cw ? lo + 2 : cw - 1) * 3 + c;
+        for (int r = grp; r < ch; r += 2) {
+            const unsigned char* q = crop + r * rowb;
+            const int acc = (1 << 21) + (int)q[o0] * k0 + (int)q[o1] * k1 + (int)q[o2] * k2;
+            tmp[r * outb + col] = pg_clip8(acc >> 22);
         }
-        tmp[e] = pg_clip8(acc >> 22);
     }
     __syncthreads();
-    // vertical pass + ToTensor + Normalize, channel-first output
-    float* dst = a.out + ((int64_t)f * a.P + p) * 3 * ps * ps;
-    for (int e = tid; e < 3 * ps * ps; e += blockDim.x) {
-        const int c = e / (ps * ps), rem = e - c * (ps * ps), yy = rem / ps, xx = rem - yy * ps;
-        const int lo = ky[yy][3];
-        int acc = 1 << 21;
-#pragma unroll
-        for (int t = 0; t < PG_TAPS; ++t) {
-            const int y = lo + t < ch ? lo + t : ch - 1;
-            acc += (int)tmp[(y * ps + xx) * 3 + c] * ky[yy][t];
+    // vertical pass + ToTensor + Normalize, channel-first output: a thread owns (channel, column), a warp stores 32 neighbouring columns
+    if (col < outb) {
+        const int c = col / ps, xx = col - c * ps;
+        const unsigned char* q = tmp + xx * 3 + c;
+        float* dst = a.out + (((int64_t)f * a.P + p) * 3 + c) * ps * ps + xx;
+        const float* lc = lut[c];
+        for (int yy = grp; yy < ps; yy += 2) {
+            const int4 k = *reinterpret_cast<const int4*>(ky[yy]);
+            const int lo = k.w;
+            const int y0 = lo < ch ? lo : ch - 1, y1 = lo + 1 < ch ? lo + 1 : ch - 1, y2 = lo + 2 < ch ? lo + 2 : ch - 1;
+            const int acc = (1 << 21) + (int)q[y0 * outb] * k.x + (int)q[y1 * outb] * k.y + (int)q[y2 * outb] * k.z;
+            dst[yy * ps] = lc[pg_clip8(acc >> 22)];
         }
-        const float v = (float)pg_clip8(acc >> 22) / 255.0f;
-        dst[e] = (v - a.mean[c]) / a.stdv[c];
     }
 }
 
@@ -123,6 +134,6 @@ extern "C" int crw_patch_grid(const unsigned char* frames, const int* boxes, int
     a.P = a.nwx * ((H - win) / stride + 1);
     for (int c = 0; c < 3; ++c) { a.mean[c] = mean3[c]; a.stdv[c] = std3[c]; }
     dim3 grid(a.P, F);
-    CRW_LAUNCH(patch_grid_kernel, grid, 256, 0, stream, a);
+    CRW_LAUNCH(patch_grid_kernel, grid, PG_THREADS, 0, stream, a);
     return check_launch("patch_grid");
 }
