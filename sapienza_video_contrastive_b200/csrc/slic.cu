@@ -179,30 +179,55 @@ __global__ void __launch_bounds__(SLIC_THREADS) slic_assign_kernel(SlicFrames fr
 #pragma unroll 1
     for (int j = 0; j < SLIC_PIX; ++j) {
         const int p = base + j * SLIC_THREADS + threadIdx.x;
-        if (p >= hw) break;
-        const int y = p / W, x = p - y * W;
-        const double f0 = ft[p], f1 = ft[(int64_t)hw + p], f2 = ft[(int64_t)2 * hw + p];
-        double best = 1.7976931348623157e308;
-        int bk = -1;
-        for (int k = 0; k < K; ++k) {
-            const int4 w4 = *reinterpret_cast<const int4*>(win + k * 4);
-            if (y < w4.x || y >= w4.y || x < w4.z || x >= w4.w) continue;
-            const double* c = cen + k * 5;
-            const double dy = dsub(c[0], (double)y), dx = dsub(c[1], (double)x);
-            double d = dmul(dadd(dmul(dy, dy), dmul(dx, dx)), sw);
-            const double e0 = dsub(f0, c[2]), e1 = dsub(f1, c[3]), e2 = dsub(f2, c[4]);
-            d = dadd(d, dadd(dadd(dmul(e0, e0), dmul(e1, e1)), dmul(e2, e2)));
-            if (best > d) { best = d; bk = k; }
+        const bool valid = p < hw;                                 // (no early exit: the warp reduces together below)
+        int y = 0, x = 0, bk = -1;
+        long long q0 = 0, q1 = 0, q2 = 0;
+        if (valid) {
+            y = p / W; x = p - y * W;
+            const double f0 = ft[p], f1 = ft[(int64_t)hw + p], f2 = ft[(int64_t)2 * hw + p];
+            double best = 1.7976931348623157e308;
+            for (int k = 0; k < K; ++k) {
+                const int4 w4 = *reinterpret_cast<const int4*>(win + k * 4);
+                if (y < w4.x || y >= w4.y || x < w4.z || x >= w4.w) continue;
+                const double* c = cen + k * 5;
+                const double dy = dsub(c[0], (double)y), dx = dsub(c[1], (double)x);
+                double d = dmul(dadd(dmul(dy, dy), dmul(dx, dx)), sw);
+                const double e0 = dsub(f0, c[2]), e1 = dsub(f1, c[3]), e2 = dsub(f2, c[4]);
+                d = dadd(d, dadd(dadd(dmul(e0, e0), dmul(e1, e1)), dmul(e2, e2)));
+                if (best > d) { best = d; bk = k; }
+            }
+            if (bk < 0) bk = nr[p];                  // no window holds the pixel: it keeps its segment
+            else nr[p] = bk;
+            q0 = d2ll_rn(dmul(f0, (double)(1 << SLIC_QBITS)));
+            q1 = d2ll_rn(dmul(f1, (double)(1 << SLIC_QBITS)));
+            q2 = d2ll_rn(dmul(f2, (double)(1 << SLIC_QBITS)));
         }
-        if (bk < 0) bk = nr[p];                      // no window holds the pixel: it keeps its segment
-        else nr[p] = bk;
-        unsigned long long* a = acc + bk * 6;
-        atomicAdd(a, 1ull);
-        atomicAdd(a + 1, (unsigned long long)y);
-        atomicAdd(a + 2, (unsigned long long)x);
-        atomicAdd(a + 3, (unsigned long long)d2ll_rn(dmul(f0, (double)(1 << SLIC_QBITS))));
-        atomicAdd(a + 4, (unsigned long long)d2ll_rn(dmul(f1, (double)(1 << SLIC_QBITS))));
-        atomicAdd(a + 5, (unsigned long long)d2ll_rn(dmul(f2, (double)(1 << SLIC_QBITS))));
+        // a warp is 32 neighbouring pixels: one segment, sometimes two or three.  Per segment present the warp adds up first and
+        // one lane issues the six shared-memory atomics (64-bit shared atomics are compare-and-swap loops: 32 lanes on one
+        // address serialise completely); the sums are integers, so the order does not matter.
+        unsigned todo = __ballot_sync(kFull, valid);
+        while (todo) {
+            const int leader = __ffs((int)todo) - 1;
+            const int bkl = __shfl_sync(kFull, bk, leader);
+            const bool mine = valid && bk == bkl;
+            const unsigned m = __ballot_sync(kFull, mine);
+            long long sy = mine ? y : 0, sx = mine ? x : 0, s0 = mine ? q0 : 0, s1 = mine ? q1 : 0, s2 = mine ? q2 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sy += __shfl_xor_sync(kFull, sy, o); sx += __shfl_xor_sync(kFull, sx, o);
+                s0 += __shfl_xor_sync(kFull, s0, o); s1 += __shfl_xor_sync(kFull, s1, o); s2 += __shfl_xor_sync(kFull, s2, o);
+            }
+            if ((int)(threadIdx.x & 31) == leader) {
+                unsigned long long* a = acc + bkl * 6;
+                atomicAdd(a, (unsigned long long)__popc(m));
+                atomicAdd(a + 1, (unsigned long long)sy);
+                atomicAdd(a + 2, (unsigned long long)sx);
+                atomicAdd(a + 3, (unsigned long long)s0);
+                atomicAdd(a + 4, (unsigned long long)s1);
+                atomicAdd(a + 5, (unsigned long long)s2);
+            }
+            todo &= ~m;
+        }
     }
     __syncthreads();
     unsigned long long* nx = next + (int64_t)f * Kmax * 6;
