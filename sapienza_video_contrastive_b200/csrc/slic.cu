@@ -247,16 +247,20 @@ __device__ __forceinline__ int ld_cg_i(const int* p) {
 #endif
 }
 
-// _enforce_label_connectivity_cython, one WARP per frame.  con (= the output labels) starts at -1, claim at INT_MAX-ish.
+// _enforce_label_connectivity_cython, one WARP per frame.  con (= the output labels) starts at -1.
 // The reference algorithm is a scan-order breadth-first search whose result depends on the queue order (the max_size cut, the
 // "last labelled neighbour met" merge rule), so the queue order is reproduced exactly: the warp pops up to 32 queue entries at
 // once (lane = pop order), every lane looks at its 4 neighbours (x+1, x-1, y+1, y-1), and a pixel reachable from several pops is
-// pushed by the earliest (lane, neighbour) - an atomicMin on claim[] decides -, at the queue position a prefix sum over that
+// pushed by the earliest (lane, neighbour) - a small shared-memory table keyed by pixel decides -, at the queue position a prefix sum over that
 // order assigns.  Pushes only turn con from -1 into the current label, which the merge rule ignores, so looking at the 32 pops
 // side by side reads the same values as one after the other.
+constexpr int SLIC_QSMEM = 11264;       // queue entries kept in shared memory (a larger max_size uses the workspace in global memory)
+constexpr int SLIC_HASH = 256;          // slots of the per-batch pixel table (at most 128 candidates)
+
 __global__ void __launch_bounds__(32) slic_connect_kernel(const int* __restrict__ kinfo, int min_size, int max_size, int H, int W,
-                                                          const int* __restrict__ nearest, int* __restrict__ queue, int* __restrict__ claim,
-                                                          int* __restrict__ labels) {
+                                                          const int* __restrict__ nearest, int* __restrict__ queue, int* __restrict__ labels) {
+    __shared__ int qs[SLIC_QSMEM];
+    __shared__ int hkey[SLIC_HASH], hord[SLIC_HASH];
     const int f = blockIdx.x, lane = threadIdx.x, hw = H * W;
     if (kinfo) {                                                  // slic(): 0.5 and 3 times the mean segment size
         const double seg_size = (double)hw / (double)kinfo[f];
@@ -265,8 +269,9 @@ __global__ void __launch_bounds__(32) slic_connect_kernel(const int* __restrict_
     }
     const int* seg = nearest + (int64_t)f * hw;
     int* con = labels + (int64_t)f * hw;
-    int* q = queue + (int64_t)f * hw;
-    int* cl = claim + (int64_t)f * hw;
+    int* q = max_size <= SLIC_QSMEM ? qs : queue + (int64_t)f * hw;      // the search never holds more than max_size pixels
+    for (int i = lane; i < SLIC_HASH; i += 32) { hkey[i] = -1; hord[i] = 0x7fffffff; }
+    __syncwarp();
     int new_label = 1, scan = 0;
     while (true) {
         int p0 = -1;                                              // next pixel in scan order without a label
@@ -284,19 +289,38 @@ __global__ void __launch_bounds__(32) slic_connect_kernel(const int* __restrict_
         int size = 1, visited = 0, adjacent = 0;
         while (visited < size && size < max_size) {
             const int nb = size - visited < 32 ? size - visited : 32;
-            int cand[4] = {-1, -1, -1, -1};
+            int cand[4] = {-1, -1, -1, -1}, slot[4] = {0, 0, 0, 0};
             int adj = -1;
             if (lane < nb) {
                 const int p = q[visited + lane];
                 const int y = p / W, x = p - y * W;
+                int pps[4], cs[4], ss[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                     // all eight loads first: one round trip to L2, not two
+                    const int xx = x + (i == 0 ? 1 : (i == 1 ? -1 : 0)), yy = y + (i == 2 ? 1 : (i == 3 ? -1 : 0));
+                    const bool in = xx >= 0 && xx < W && yy >= 0 && yy < H;
+                    pps[i] = in ? yy * W + xx : -1;
+                    cs[i] = in ? con[pps[i]] : 0;
+                    ss[i] = in ? seg[pps[i]] : -1;
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int xx = x + (i == 0 ? 1 : (i == 1 ? -1 : 0)), yy = y + (i == 2 ? 1 : (i == 3 ? -1 : 0));
-                    if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
-                    const int pp = yy * W + xx;
-                    const int c = con[pp];
+                    if (pps[i] < 0) continue;
+                    const int pp = pps[i], c = cs[i];
                     if (c == -1) {
-                        if (seg[pp] == label) { cand[i] = pp; atomicMin(cl + pp, lane * 4 + i); }
+                        if (ss[i] == label) {
+                            // a pixel several pops can reach is pushed by the earliest (pop, neighbour): find or claim the pixel's
+                            // slot in the batch table, then the smallest order wins (shared-memory atomics: no trip to L2)
+                            cand[i] = pp;
+                            int h = (int)(((unsigned)pp * 2654435761u) >> 24);
+                            while (true) {
+                                const int old = atomicCAS(hkey + h, -1, pp);
+                                if (old == -1 || old == pp) break;
+                                h = (h + 1) & (SLIC_HASH - 1);
+                            }
+                            slot[i] = h;
+                            atomicMin(hord + h, lane * 4 + i);
+                        }
                     } else if (c != new_label) {
                         adj = c;
                     }
@@ -307,9 +331,13 @@ __global__ void __launch_bounds__(32) slic_connect_kernel(const int* __restrict_
             int cnt = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                win[i] = cand[i] >= 0 && ld_cg_i(cl + cand[i]) == lane * 4 + i;
+                win[i] = cand[i] >= 0 && hord[slot[i]] == lane * 4 + i;
                 cnt += win[i] ? 1 : 0;
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (cand[i] >= 0) { hkey[slot[i]] = -1; hord[slot[i]] = 0x7fffffff; }      // the table is empty again for the next batch
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -321,8 +349,7 @@ __global__ void __launch_bounds__(32) slic_connect_kernel(const int* __restrict_
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (!win[i]) continue;
-                if (pos < max_size) { con[cand[i]] = new_label; q[pos] = cand[i]; }
-                else cl[cand[i]] = 0x7f7f7f7f;                    // cut by max_size: the pixel stays free for a later segment
+                if (pos < max_size) { con[cand[i]] = new_label; q[pos] = cand[i]; }      // beyond max_size: the pixel stays free for a later segment
                 ++pos;
             }
             const unsigned am = __ballot_sync(kFull, adj >= 0);
@@ -394,7 +421,7 @@ static const double* slic_lin_table() {
     return t.v;
 }
 
-struct SlicLayout { size_t mm, kinfo, table, feat, nearest, queue, claim, sums, total; int Kmax; };
+struct SlicLayout { size_t mm, kinfo, table, feat, nearest, queue, sums, total; int Kmax; };
 
 static int slic_layout(int F, int H, int W, const int* n_segments, int n_iter, SlicLayout& L) {
     int Kmax = 1;
@@ -415,7 +442,6 @@ static int slic_layout(int F, int H, int W, const int* n_segments, int n_iter, S
     L.feat = off; off += up((size_t)F * 3 * hw * sizeof(double));
     L.nearest = off; off += up((size_t)F * hw * sizeof(int));
     L.queue = off; off += up((size_t)F * hw * sizeof(int));
-    L.claim = off; off += up((size_t)F * hw * sizeof(int));
     L.sums = off; off += up((size_t)n_iter * F * Kmax * 6 * sizeof(unsigned long long));
     L.total = off;
     L.Kmax = Kmax;
@@ -454,7 +480,6 @@ extern "C" int crw_slic(const float* video, int F, int H, int W, const int* n_se
     double* feat = reinterpret_cast<double*>(w + L.feat);
     int* nearest = reinterpret_cast<int*>(w + L.nearest);
     int* queue = reinterpret_cast<int*>(w + L.queue);
-    int* claim = reinterpret_cast<int*>(w + L.claim);
     int* kinfo = reinterpret_cast<int*>(w + L.kinfo);
     unsigned long long* sums = reinterpret_cast<unsigned long long*>(w + L.sums);
     const int hw = H * W;
@@ -464,7 +489,6 @@ extern "C" int crw_slic(const float* video, int F, int H, int W, const int* n_se
     cudaMemsetAsync(sums, 0, (size_t)n_iter * sums_per_iter * sizeof(unsigned long long), st);
     if (connectivity) {
         cudaMemsetAsync(labels, 0xff, (size_t)F * hw * sizeof(int), st);
-        cudaMemsetAsync(claim, 0x7f, (size_t)F * hw * sizeof(int), st);
     }
     cudaMemcpyAsync(table, slic_lin_table(), 256 * sizeof(double), cudaMemcpyHostToDevice, st);
     int blocks = (hw * 3 + SLIC_THREADS * 8 - 1) / (SLIC_THREADS * 8);
@@ -488,14 +512,14 @@ extern "C" int crw_slic(const float* video, int F, int H, int W, const int* n_se
                        sums + (size_t)it * sums_per_iter, nearest, kinfo);
         }
     }
-    if (connectivity) CRW_LAUNCH(slic_connect_kernel, dim3(F), 32, 0, st, kinfo, 0, 0, H, W, nearest, queue, claim, labels);
+    if (connectivity) CRW_LAUNCH(slic_connect_kernel, dim3(F), 32, 0, st, kinfo, 0, 0, H, W, nearest, queue, labels);
     else CRW_LAUNCH(slic_offset_kernel, dim3(296), 256, 0, st, nearest, (int64_t)F * hw, labels);
     return check_launch("crw_slic");
 }
 
 extern "C" size_t crw_label_connectivity_workspace_bytes(int F, int H, int W) {
     if (F < 1 || H < 1 || W < 1) return 0;
-    return (size_t)2 * F * H * W * sizeof(int);
+    return (size_t)F * H * W * sizeof(int);
 }
 
 extern "C" int crw_label_connectivity(const int* segments, int F, int H, int W, int min_size, int max_size, int* labels, void* ws,
@@ -511,9 +535,7 @@ extern "C" int crw_label_connectivity(const int* segments, int F, int H, int W, 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)F * H * W;
     int* queue = static_cast<int*>(ws);
-    int* claim = queue + n;
     cudaMemsetAsync(labels, 0xff, n * sizeof(int), st);
-    cudaMemsetAsync(claim, 0x7f, n * sizeof(int), st);
-    CRW_LAUNCH(slic_connect_kernel, dim3(F), 32, 0, st, (const int*)nullptr, min_size, max_size, H, W, segments, queue, claim, labels);
+    CRW_LAUNCH(slic_connect_kernel, dim3(F), 32, 0, st, (const int*)nullptr, min_size, max_size, H, W, segments, queue, labels);
     return check_launch("crw_label_connectivity");
 }

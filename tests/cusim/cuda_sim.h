@@ -173,6 +173,7 @@ static inline unsigned long long atomicOr(unsigned long long* p, unsigned long l
 static inline int atomicMax(int* p, int v) { int o = *p; *p = o > v ? o : v; return o; }
 static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = o > v ? o : v; return o; }
 static inline int atomicMin(int* p, int v) { int o = *p; *p = o < v ? o : v; return o; }
+static inline int atomicCAS(int* p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
 static inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *p = (o >= lim) ? 0 : o + 1; return o; }
 static inline unsigned atomicExch(unsigned* p, unsigned v) { unsigned o = *p; *p = v; return o; }
 
