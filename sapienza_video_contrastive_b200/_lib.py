@@ -117,12 +117,29 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    """Digest of everything the library is compiled from.  The library is current iff the digest written next to it at build time
+    matches: modification times do not survive a copy of the tree to another machine in any useful order."""
+    import hashlib
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(os.path.dirname(PKG), "include", "crw_b200.h")]
+    h = hashlib.sha1()
+    for d in deps:
+        if os.path.exists(d):
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    h.update(" ".join(ARCH_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(PKG), "include", "crw_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -133,6 +150,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise CrwError("nvcc not found at %s and %s is missing or stale" % (NVCC, LIB_PATH))
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
+    # one builder at a time across PROCESSES (the ranks of a torchrun job all import this module at once)
+    import fcntl
+    with open(os.path.join(objdir, ".lock"), "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():          # another process built it while this one waited
+                return LIB_PATH
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir: str, verbose: bool) -> str:
+    digest = _source_hash()
     procs, objs = [], []
     for s in sources():
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
@@ -152,9 +183,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print("\n".join(log))
     if failed:
         raise CrwError("nvcc failed, see log above")
-    tmp = LIB_PATH + ".tmp"
+    tmp = "%s.%d.tmp" % (LIB_PATH, os.getpid())
     subprocess.check_call([NVCC, "-shared", "-o", tmp] + ARCH_FLAGS + objs)
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH + ".tmp", "w") as f:
+        f.write(digest + "\n")
+    os.replace(HASH_PATH + ".tmp", HASH_PATH)
     return LIB_PATH
 
 

@@ -190,3 +190,29 @@ def test_small_test_utils_mirrors():
     ref /= ref.sum(0)[None]
     assert torch.equal(hard_prop(neg), ref)
     assert list(infer_downscale()) == [8, 8]
+
+
+def test_library_staleness_is_by_content_not_by_mtime(tmp_path):
+    """The built library travels to other machines by copy (modification times arrive in any order) and is imported by all ranks of
+    a torchrun job at once: `_lib` decides by a digest of the sources written next to the library, and builds under a file lock."""
+    import time
+    from sapienza_video_contrastive_b200 import _lib
+    _lib.build()
+    assert not _lib._stale()
+    src = _lib.sources()[0]
+    st = os.stat(src)
+    try:
+        os.utime(src, (time.time() + 3600, time.time() + 3600))          # "newer" than the library: still current
+        assert not _lib._stale()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    with open(_lib.HASH_PATH) as f:
+        good = f.read()
+    try:
+        with open(_lib.HASH_PATH, "w") as f:
+            f.write("0" * 40 + "\n")
+        assert _lib._stale()                                            # a library built from other sources is stale
+    finally:
+        with open(_lib.HASH_PATH, "w") as f:
+            f.write(good)
+    assert not _lib._stale()
