@@ -182,7 +182,7 @@ CONNECT_CASES = [   # F, H, W, labels, min_size, max_size, blur
 ]
 
 
-def run_connect(lib, seg, mn, mx, device=None):
+def run_connect(lib, seg, mn, mx, device=None, reps=2):
     F, H, W = seg.shape
     t = torch.from_numpy(seg)
     if device is not None:
@@ -190,7 +190,7 @@ def run_connect(lib, seg, mn, mx, device=None):
     wb = lib.crw_label_connectivity_workspace_bytes(F, H, W)
     ws = torch.zeros(wb, dtype=torch.uint8, device=t.device)
     out = torch.zeros(F, H, W, dtype=torch.int32, device=t.device)
-    for _ in range(2):
+    for _ in range(reps):
         lib.check(lib.crw_label_connectivity(t.data_ptr(), F, H, W, mn, mx, out.data_ptr(), ws.data_ptr(), wb, None), "connectivity")
     if device is not None:
         torch.cuda.synchronize()
@@ -254,3 +254,30 @@ def test_gpu_connectivity_matches_oracle(F, H, W, nl, mn, mx, blobs):
     got = run_connect(_lib.lib(), seg, mn, mx, device="cuda")
     for f in range(F):
         assert np.array_equal(got[f], SO.enforce_connectivity(seg[f].astype(np.int64), mn, mx))
+
+
+# ---- randomised: the connectivity pass on the simulator, host-mirror argument handling -------------------------------------
+
+def test_sim_connectivity_random_maps(sim):
+    """hypothesis over small label maps and size limits: the warp-parallel queue must reproduce the sequential scan-order search
+    (cuts at max_size, merges below min_size, the "last labelled neighbour met" rule) exactly."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(3, 14), st.integers(3, 40), st.integers(1, 5), st.integers(0, 12), st.integers(1, 70), st.integers(0, 2 ** 31 - 1),
+           st.sampled_from([0.0, 1.0, 2.5]))
+    def run(H, W, nl, mn, mx, seed, blobs):
+        seg = random_label_maps(1, H, W, nl, seed=seed, blobs=blobs)
+        got = run_connect(sim, seg, mn, mx, reps=1)
+        assert np.array_equal(got[0], SO.enforce_connectivity(seg[0].astype(np.int64), mn, mx))
+
+    run()
+
+
+def test_compute_mask_rejects_other_methods_before_touching_the_gpu():
+    from sapienza_video_contrastive_b200 import superpixels as SP
+    vid = torch.zeros(2, 3, 16, 16)
+    with pytest.raises(NotImplementedError):
+        SP.compute_mask(vid, "fh", 8, 1.0, False, 0, 10.0)
+    with pytest.raises(RuntimeError):
+        SP.slic_frames(vid, 8, 10.0)                       # CPU tensor: there is no CPU path
