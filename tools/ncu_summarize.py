@@ -53,11 +53,12 @@ def main():
                     ent[v] = val * UNIT.get(u[k], 1.0) if v in ("us", "dram_read", "dram_write") else val
             if "dram_read" in ent:
                 ent["dram_bytes_per_launch"] = ent.pop("dram_read") + ent.pop("dram_write", 0.0)
-            if name in out:                          # several launches of one kernel: keep the longest, count them
+            if name in out and out[name].get("report") == ent["report"]:      # several launches in one report: keep the longest, count them
                 out[name]["launches_captured"] = out[name].get("launches_captured", 1) + 1
                 if ent.get("us", 0) <= out[name].get("us", 0):
                     continue
                 ent["launches_captured"] = out[name]["launches_captured"]
+            # (a kernel that also appears in an EARLIER report is replaced: reports are listed oldest first)
             out[name] = ent
     with open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
