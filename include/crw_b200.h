@@ -63,7 +63,10 @@ int crw_pool_patch_bwd_scaled(const float* gpooled, float* gmaps, int64_t rows, 
  * maps (B,C,T,Hm,Wm) contiguous; labels int64 addressed as labels[b*ls_b + t*ls_t + y*ls_y + x*ls_x]
  * (so channel 0 of the (B,T,3,h,w) mask is passed without a copy, model.py:298); h = sy*Hm, w = sx*Wm.
  * out (B,SP,T,C) (node-major, the layout the walk consumes): mean of maps[b,:,t,y/sy,x/sx] over pixels labelled s; labels outside [0,SP) ignored;
- * empty segments -> 0.  The workspace keeps the per-cell label histogram for the backward. */
+ * empty segments -> 0.  The workspace keeps the per-cell label histogram for the backward.
+ * Hm*Wm a multiple of 32, C a multiple of 128 and SP <= 256 (BASELINE configs[2]) run as a tcgen05 product of the window-count
+ * matrix with the map (fp32-faithful: TF32 big/small split, fp32 accumulation; summation order differs from the scatter-reduce
+ * other shapes take, results agree to 1e-6); both paths are deterministic. */
 size_t crw_segmean_workspace_bytes(int B, int T, int Hm, int Wm, int h, int w, int SP);
 int crw_segmean_fwd(const float* maps, const int64_t* labels, int64_t ls_b, int64_t ls_t, int64_t ls_y, int64_t ls_x,
                     int B, int C, int T, int Hm, int Wm, int h, int w, int SP,
