@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) segmean_mma_kernel(const __grid
 // shapes the tensor-core forward takes: whole 32-cell slabs, whole channel blocks, at most two 128-label M-tiles, every cell's
 // list complete (cap entries), TMA-addressable maps and 16-byte aligned output rows
 static bool seg_mma_eligible(const float* maps, const float* out, int C, int cells, int SP) {
-    return cells % SG_K == 0 && C % 128 == 0 && SP <= 256 && (reinterpret_cast<uintptr_t>(maps) & 15) == 0 &&
+    return cells % SG_K == 0 && cells >= 2 * SG_K && C % 128 == 0 && SP <= 256 && (reinterpret_cast<uintptr_t>(maps) & 15) == 0 &&
            (reinterpret_cast<uintptr_t>(out) & 15) == 0;
 }
 
