@@ -128,26 +128,45 @@ __global__ void __launch_bounds__(256) segmean_count_cell_kernel(const int64_t* 
         int l0 = -1, l1 = -1, l2 = -1, l3 = -1, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         int xl[kSegMaxEnt], xc[kSegMaxEnt];            // entries beyond the four slots (rare: a cell on a junction of many segments)
         int nx = 0;
-        for (int py = 0; py < sy; ++py) {
-            const int64_t* row = base + (int64_t)py * ls_y;
-            for (int px = 0; px < sx; ++px) {
-                const int64_t L64 = row[px];
-                if (L64 < 0 || L64 >= SP) continue;    // labels outside [0,SP) never match a one-hot plane (model.py:299-301)
-                const int L = (int)L64;
-                if (L == l0) ++c0;
-                else if (L == l1) ++c1;
-                else if (L == l2) ++c2;
-                else if (L == l3) ++c3;
-                else if (l0 < 0) { l0 = L; c0 = 1; }
-                else if (l1 < 0) { l1 = L; c1 = 1; }
-                else if (l2 < 0) { l2 = L; c2 = 1; }
-                else if (l3 < 0) { l3 = L; c3 = 1; }
-                else {
-                    int j = 0;
-                    while (j < nx && xl[j] != L) ++j;
-                    if (j == nx) { xl[nx] = L; xc[nx] = 0; ++nx; }
-                    ++xc[j];
+        auto take = [&](int64_t L64) {
+            if (L64 < 0 || L64 >= SP) return;          // labels outside [0,SP) never match a one-hot plane (model.py:299-301)
+            const int L = (int)L64;
+            if (L == l0) ++c0;
+            else if (L == l1) ++c1;
+            else if (L == l2) ++c2;
+            else if (L == l3) ++c3;
+            else if (l0 < 0) { l0 = L; c0 = 1; }
+            else if (l1 < 0) { l1 = L; c1 = 1; }
+            else if (l2 < 0) { l2 = L; c2 = 1; }
+            else if (l3 < 0) { l3 = L; c3 = 1; }
+            else {
+                int j = 0;
+                while (j < nx && xl[j] != L) ++j;
+                if (j == nx) { xl[nx] = L; xc[nx] = 0; ++nx; }
+                ++xc[j];
+            }
+        };
+        if (sx <= 8) {
+            // a row of the cell is at most 8 labels: all of them are requested before any is looked at, and the next row is on its
+            // way while this one is counted (the loads are what this kernel waits for when the label map comes from DRAM)
+            int64_t cur[8], nxt[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+#pragma unroll
+            for (int px = 0; px < 8; ++px) cur[px] = px < sx ? base[px] : -1;
+            for (int py = 0; py < sy; ++py) {
+                if (py + 1 < sy) {
+                    const int64_t* row = base + (int64_t)(py + 1) * ls_y;
+#pragma unroll
+                    for (int px = 0; px < 8; ++px) nxt[px] = px < sx ? row[px] : -1;
                 }
+#pragma unroll
+                for (int px = 0; px < 8; ++px) take(cur[px]);
+#pragma unroll
+                for (int px = 0; px < 8; ++px) cur[px] = nxt[px];
+            }
+        } else {
+            for (int py = 0; py < sy; ++py) {
+                const int64_t* row = base + (int64_t)py * ls_y;
+                for (int px = 0; px < sx; ++px) take(row[px]);
             }
         }
         unsigned* e = ws.ent + (int64_t)bt * ws.cap * cells + cell;
