@@ -15,9 +15,11 @@
 //   slic_assign    one launch per iteration: every CTA rebuilds the K centres (from the grid, or from the previous iteration's
 //                  integer sums) in shared memory, each thread finds the nearest centre of its pixels among those whose
 //                  2-step window holds the pixel (centres in increasing order, strict comparison = the sequential scatter of
-//                  _slic.pyx), and the pixel is added to that centre's sums (shared-memory then global 64-bit atomics)
+//                  _slic.pyx), and the pixel is added to that centre's integer sums (warp reduction per segment, then shared-memory
+//                  and global 64-bit atomics)
 //   slic_connect   enforce_connectivity: the scan-order breadth-first relabelling depends on the queue order, which one warp per
-//                  frame reproduces exactly while popping 32 queue entries at a time (frames in parallel, state L2-resident)
+//                  frame reproduces exactly while popping 32 queue entries at a time (frames in parallel; queue and the per-batch
+//                  pixel table in shared memory)
 #include <math.h>
 
 #include "common.cuh"
